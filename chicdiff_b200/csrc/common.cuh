@@ -1,0 +1,241 @@
+// common.cuh -- shared definitions for the chicdiff_b200 CUDA path (sm_100a).
+//
+// Matrix layout everywhere: "sample-major" = R's column-major n x S matrix, element
+// (region i, sample s) at [s*n + i], so a warp of consecutive regions reads every
+// per-sample column fully coalesced.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define CD_MAXS 32          // samples (replicates over both conditions)
+#define CD_MAXP 4           // design columns
+
+// per-region status bits (cd_results.flags)
+#define CD_FLAG_ALLZERO 1          // every count is zero: all outputs NA (DESeq2 allZero)
+#define CD_FLAG_GENE_GRID 2        // gene-wise estimate refitted on the grid (fitDispGrid)
+#define CD_FLAG_MAP_GRID 4         // MAP estimate refitted on the grid
+#define CD_FLAG_BETA_NOCONV 8      // IRLS did not converge: the reference would switch to optim()
+#define CD_FLAG_OUTLIER 16         // dispersion outlier: final dispersion = gene-wise estimate
+#define CD_FLAG_GENE_NOINCREASE 32 // line search did not raise the posterior: kept the start value
+#define CD_FLAG_COOKS_KEEP 64      // >= 3 counts above the max-Cook's sample (results() heuristic)
+
+struct CdDesign {
+    int S, p;
+    int linear_mu;                   // #distinct design rows == p: mu by hat-matrix projection
+    int ncell, any3;
+    double X[CD_MAXS * CD_MAXP];     // S x p, row-major
+    double hat[CD_MAXS * CD_MAXS];   // X (X'X)^-1 X'
+    double ls[CD_MAXP * CD_MAXS];    // (X'X)^-1 X'  (p x S): least-squares start for IRLS
+    int cell[CD_MAXS];               // design cell of each sample
+    int cell_size[CD_MAXS];
+};
+
+namespace cd {
+
+constexpr double kMinDisp = 1e-8;
+constexpr double kMinMu = 0.5;
+constexpr double kLnSqrt2Pi = 0.918938533204672741780329736406;
+constexpr double kLn2Pi = 1.837877066409345483560659472811;
+constexpr double kLn2 = 0.693147180559945309417232121458;
+constexpr double kLog2e = 1.442695040888963407359924681002;
+
+// ---------------------------------------------------------------------------------------
+// special functions (FP64)
+// ---------------------------------------------------------------------------------------
+
+// digamma(x), x > 0.  Recurrence to x >= 10 with pairwise-combined reciprocals, then the
+// asymptotic expansion (truncation < 5e-17 at x = 10).
+__device__ __forceinline__ double digamma_pos(double x)
+{
+    double acc = 0.0;
+    while (x < 9.0) {               // two steps per division
+        acc -= (2.0 * x + 1.0) / (x * (x + 1.0));
+        x += 2.0;
+    }
+    if (x < 10.0) { acc -= 1.0 / x; x += 1.0; }
+    const double xi = 1.0 / x;
+    const double f = xi * xi;
+    double t = -1.0 / 12.0;
+    t = fma(f, t, 691.0 / 32760.0);
+    t = fma(f, t, -1.0 / 132.0);
+    t = fma(f, t, 1.0 / 240.0);
+    t = fma(f, t, -1.0 / 252.0);
+    t = fma(f, t, 1.0 / 120.0);
+    t = fma(f, t, -1.0 / 12.0);
+    return acc + log(x) - 0.5 * xi + f * t;
+}
+
+__device__ __forceinline__ double trigamma_pos(double x)
+{
+    double acc = 0.0;
+    while (x < 10.0) { acc += 1.0 / (x * x); x += 1.0; }
+    const double xi = 1.0 / x;
+    const double f = xi * xi;
+    double t = 7.0 / 6.0;
+    t = fma(f, t, -691.0 / 2730.0);
+    t = fma(f, t, 5.0 / 66.0);
+    t = fma(f, t, -1.0 / 30.0);
+    t = fma(f, t, 1.0 / 42.0);
+    t = fma(f, t, -1.0 / 30.0);
+    t = fma(f, t, 1.0 / 6.0);
+    return acc + xi + 0.5 * f + xi * f * t;
+}
+
+// Saddle-point pieces of the binomial/negative-binomial density (Loader 2000), in the
+// branch structure R's nmath uses so that the deviance follows dnbinom_mu().
+__device__ const double kSferrHalves[31] = {
+    0.0, 0.1534264097200273452913848, 0.0810614667953272582196702,
+    0.0548141210519176538961390, 0.0413406959554092940938221,
+    0.03316287351993628748511048, 0.02767792568499833914878929,
+    0.02374616365629749597132920, 0.02079067210376509311152277,
+    0.01848845053267318523077934, 0.01664469118982119216319487,
+    0.01513497322191737887351255, 0.01387612882307074799874573,
+    0.01281046524292022692424986, 0.01189670994589177009505572,
+    0.01110455975820691732662991, 0.010411265261972096497478567,
+    0.009799416126158803298389475, 0.009255462182712732917728637,
+    0.008768700134139385462952823, 0.008330563433362871256469318,
+    0.007934114564314020547248100, 0.007573675487951840794972024,
+    0.007244554301320383179543912, 0.006942840107209529865664152,
+    0.006665247032707682442354394, 0.006408994188004207068439631,
+    0.006171712263039457647532867, 0.005951370112758847735624416,
+    0.005746216513010115682023589, 0.005554733551962801371038690};
+
+__device__ __forceinline__ double stirlerr(double n)
+{
+    if (n <= 15.0) {
+        const double nn = n + n;
+        if (nn == (double)(int)nn) return kSferrHalves[(int)nn];
+        return lgamma(n + 1.0) - (n + 0.5) * log(n) + n - kLnSqrt2Pi;
+    }
+    const double nn = n * n;
+    const double S0 = 1.0 / 12.0, S1 = 1.0 / 360.0, S2 = 1.0 / 1260.0, S3 = 1.0 / 1680.0, S4 = 1.0 / 1188.0;
+    if (n > 500.0) return (S0 - S1 / nn) / n;
+    if (n > 80.0) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35.0) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+__device__ __forceinline__ double bd0(double x, double np)
+{
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np);
+        double s = (x - np) * v;
+        if (fabs(s) < 2.2250738585072014e-308) return s;
+        double ej = 2.0 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            const double s1 = s + ej / (double)((j << 1) + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+// log dnbinom(y; size, mu) split into the part that does not depend on mu (computed once
+// per row and sample: nb_const) and the part that does (nb_var, evaluated in every IRLS
+// iteration).  kind: 0 = y == 0, 1 = tiny y / size (Poisson-like expansion), 2 = general.
+struct NbConst { double c; int kind; };
+
+__device__ __forceinline__ NbConst nb_const(double y, double size)
+{
+    NbConst r;
+    if (y == 0.0) { r.c = 0.0; r.kind = 0; return r; }
+    if (y < 1e-10 * size) {
+        r.c = -lgamma(y + 1.0) + log1p(y * (y - 1.0) / (2.0 * size));
+        r.kind = 1;
+        return r;
+    }
+    const double n = y + size;
+    // log(size/(size+y)) + [stirlerr(n) - stirlerr(size) - stirlerr(y)] - 0.5*[ln 2pi + log(size) + log1p(-size/n)]
+    r.c = log(size / n) + (stirlerr(n) - stirlerr(size) - stirlerr(y)) -
+          0.5 * (kLn2Pi + log(size) + log1p(-size / n));
+    r.kind = 2;
+    return r;
+}
+
+__device__ __forceinline__ double nb_var(double y, double size, double mu, NbConst k)
+{
+    if (k.kind == 0)
+        return size * (size < mu ? log(size / (size + mu)) : log1p(-mu / (size + mu)));
+    if (k.kind == 1) {
+        const double p = (size < mu ? log(size / (1.0 + size / mu)) : log(mu / (1.0 + mu / size)));
+        return y * p - mu + k.c;
+    }
+    const double n = y + size;
+    const double pp = size / (size + mu), qq = mu / (size + mu);
+    return k.c - bd0(size, n * pp) - bd0(y, n * qq);
+}
+
+__device__ __forceinline__ double dnbinom_mu_log(double y, double size, double mu)
+{
+    return nb_var(y, size, mu, nb_const(y, size));
+}
+
+// ---------------------------------------------------------------------------------------
+// tiny SPD algebra, P <= CD_MAXP.  Symmetric matrices are stored packed lower:
+// index(a, b) = a*(a+1)/2 + b for b <= a.
+// ---------------------------------------------------------------------------------------
+template <int P> struct Sym { double v[P * (P + 1) / 2]; };
+
+template <int P> __device__ __forceinline__ int sidx(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// in-place Cholesky A = L L'; returns log det A (NaN if not positive definite)
+template <int P> __device__ __forceinline__ double chol_logdet(Sym<P>& A)
+{
+    double det = 1.0;
+#pragma unroll
+    for (int j = 0; j < P; j++) {
+        double d = A.v[sidx<P>(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= A.v[sidx<P>(j, k)] * A.v[sidx<P>(j, k)];
+        det *= d;
+        const double l = sqrt(d);
+        A.v[sidx<P>(j, j)] = l;
+#pragma unroll
+        for (int i = j + 1; i < P; i++) {
+            double s = A.v[sidx<P>(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= A.v[sidx<P>(i, k)] * A.v[sidx<P>(j, k)];
+            A.v[sidx<P>(i, j)] = s / l;
+        }
+    }
+    return log(det);
+}
+
+// solve L L' x = b given the Cholesky factor
+template <int P> __device__ __forceinline__ void chol_solve(const Sym<P>& L, double* x)
+{
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+        double s = x[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L.v[sidx<P>(i, k)] * x[k];
+        x[i] = s / L.v[sidx<P>(i, i)];
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; i--) {
+        double s = x[i];
+#pragma unroll
+        for (int k = i + 1; k < P; k++) s -= L.v[sidx<P>(k, i)] * x[k];
+        x[i] = s / L.v[sidx<P>(i, i)];
+    }
+}
+
+// explicit inverse (packed) from the Cholesky factor
+template <int P> __device__ __forceinline__ void chol_inverse(const Sym<P>& L, Sym<P>& inv)
+{
+#pragma unroll
+    for (int c = 0; c < P; c++) {
+        double e[P];
+#pragma unroll
+        for (int k = 0; k < P; k++) e[k] = (k == c) ? 1.0 : 0.0;
+        chol_solve<P>(L, e);
+#pragma unroll
+        for (int r = c; r < P; r++) inv.v[sidx<P>(r, c)] = e[r];
+    }
+}
+
+}  // namespace cd

@@ -1,0 +1,800 @@
+// context.cu -- the C ABI (include/chicdiff_b200.h) and the orchestration of the hot path:
+// DESeq2Wrap's numeric core (chicdiff.R:1540-1674) as a sequence of sm_100a kernels on one
+// stream, with the few global steps (size-factor medians, dispersion trend, MAD, theta grid)
+// driven from the host and, in a sharded run, joined across ranks by NCCL.
+#include "../../include/chicdiff_b200.h"
+#include "kernels.h"
+#include "comm.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace cd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+};
+
+bool invert_small(const double* A, int p, double* inv)
+{
+    double a[CD_MAXP][2 * CD_MAXP];
+    for (int i = 0; i < p; i++)
+        for (int j = 0; j < p; j++) { a[i][j] = A[i * p + j]; a[i][p + j] = (i == j) ? 1.0 : 0.0; }
+    for (int k = 0; k < p; k++) {
+        int piv = k;
+        for (int i = k + 1; i < p; i++) if (fabs(a[i][k]) > fabs(a[piv][k])) piv = i;
+        if (fabs(a[piv][k]) < 1e-12) return false;
+        if (piv != k) for (int j = 0; j < 2 * p; j++) std::swap(a[k][j], a[piv][j]);
+        const double d = a[k][k];
+        for (int j = 0; j < 2 * p; j++) a[k][j] /= d;
+        for (int i = 0; i < p; i++) if (i != k) {
+            const double f = a[i][k];
+            if (f != 0.0) for (int j = 0; j < 2 * p; j++) a[i][j] -= f * a[k][j];
+        }
+    }
+    for (int i = 0; i < p; i++) for (int j = 0; j < p; j++) inv[i * p + j] = a[i][p + j];
+    return true;
+}
+
+bool build_design(int S, int p, const double* X, CdDesign& d)
+{
+    memset(&d, 0, sizeof(d));
+    d.S = S; d.p = p;
+    for (int i = 0; i < S * p; i++) d.X[i] = X[i];
+    double xtx[CD_MAXP * CD_MAXP], inv[CD_MAXP * CD_MAXP];
+    for (int a = 0; a < p; a++)
+        for (int b = 0; b < p; b++) {
+            double s = 0;
+            for (int j = 0; j < S; j++) s += X[j * p + a] * X[j * p + b];
+            xtx[a * p + b] = s;
+        }
+    if (!invert_small(xtx, p, inv)) return false;          // not full rank
+    for (int u = 0; u < p; u++)
+        for (int j = 0; j < S; j++) {
+            double s = 0;
+            for (int v = 0; v < p; v++) s += inv[u * p + v] * X[j * p + v];
+            d.ls[u * S + j] = s;
+        }
+    for (int a = 0; a < S; a++)
+        for (int b = 0; b < S; b++) {
+            double s = 0;
+            for (int u = 0; u < p; u++) s += X[a * p + u] * d.ls[u * S + b];
+            d.hat[a * S + b] = s;
+        }
+    d.ncell = 0;
+    for (int j = 0; j < S; j++) {
+        int found = -1;
+        for (int k = 0; k < j && found < 0; k++) {
+            bool same = true;
+            for (int u = 0; u < p; u++) if (X[j * p + u] != X[k * p + u]) same = false;
+            if (same) found = d.cell[k];
+        }
+        if (found < 0) { found = d.ncell++; d.cell_size[found] = 0; }
+        d.cell[j] = found;
+        d.cell_size[found]++;
+    }
+    d.linear_mu = (d.ncell == p);
+    d.any3 = 0;
+    for (int c = 0; c < d.ncell; c++) if (d.cell_size[c] >= 3) d.any3 = 1;
+    return true;
+}
+
+double trigamma_host(double x)
+{
+    double r = 0.0;
+    while (x < 10.0) { r += 1.0 / (x * x); x += 1.0; }
+    const double f = 1.0 / (x * x);
+    return r + 1.0 / x + 0.5 * f +
+           (1.0 / x) * f * (1.0 / 6.0 + f * (-1.0 / 30.0 + f * (1.0 / 42.0 + f * (-1.0 / 30.0 +
+           f * (5.0 / 66.0 + f * (-691.0 / 2730.0 + f * (7.0 / 6.0)))))));
+}
+
+// xim = mean_s 1 / (colsum_s / count)   (momentsDispEstimate)
+__global__ void xim_kernel(int S, const double* __restrict__ sums, double* __restrict__ xim)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double cnt = sums[S];
+        double acc = 0.0;
+        for (int s = 0; s < S; s++) acc += 1.0 / (sums[s] / cnt);
+        *xim = acc / S;
+    }
+}
+
+__global__ void count_finite_kernel(int64_t n, const double* __restrict__ v, unsigned long long* __restrict__ cnt)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool f = (i < n) && isfinite(v[i]);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, (unsigned long long)__popc(m));
+}
+
+// R median of the finite prefix of an ascending-sorted array; out = exp(median) if do_exp
+__global__ void median_sorted_kernel(const double* __restrict__ sorted, const unsigned long long* __restrict__ cnt,
+                                     double* __restrict__ out, int do_exp, double scale)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long m = *cnt;
+        double med = NAN;
+        if (m > 0) med = (m & 1ull) ? sorted[m / 2] : 0.5 * (sorted[m / 2 - 1] + sorted[m / 2]);
+        med *= scale;
+        *out = do_exp ? exp(med) : med;
+    }
+}
+
+__global__ void abs_dev_dev_kernel(int64_t n, const double* __restrict__ v, const double* __restrict__ center,
+                                   double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = v[i];
+    out[i] = isinf(x) ? INFINITY : fabs(x - *center);
+}
+
+__global__ void count_flags_kernel(int64_t n, const uint8_t* __restrict__ flags, unsigned long long* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t f = (i < n) ? flags[i] : (uint8_t)CD_FLAG_ALLZERO;
+    const unsigned nz = __ballot_sync(0xffffffffu, (i < n) && !(f & CD_FLAG_ALLZERO));
+    const unsigned gg = __ballot_sync(0xffffffffu, (i < n) && (f & CD_FLAG_GENE_GRID));
+    const unsigned mg = __ballot_sync(0xffffffffu, (i < n) && (f & CD_FLAG_MAP_GRID));
+    const unsigned bn = __ballot_sync(0xffffffffu, (i < n) && (f & CD_FLAG_BETA_NOCONV));
+    if ((threadIdx.x & 31) == 0) {
+        if (nz) atomicAdd(out + 0, (unsigned long long)__popc(nz));
+        if (gg) atomicAdd(out + 1, (unsigned long long)__popc(gg));
+        if (mg) atomicAdd(out + 2, (unsigned long long)__popc(mg));
+        if (bn) atomicAdd(out + 3, (unsigned long long)__popc(bn));
+    }
+}
+
+}  // namespace
+
+struct cd_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    Comm comm;
+
+    // design
+    bool have_design = false;
+    CdDesign des{}, des1{};          // user design and the intercept-only design of the theta grid
+    // regions / rows
+    int64_t n = 0, R = 0;
+    bool have_regions = false, have_agg = false, rows_borrowed = false;
+    std::vector<uint8_t> sample_set;
+    DevBuf<int64_t> row_off;
+    DevBuf<int32_t> N_rows;
+    DevBuf<double> FM_rows;
+    const int32_t* N_rows_p = nullptr;
+    const double* FM_rows_p = nullptr;
+    DevBuf<int32_t> K;               // S x n
+    DevBuf<double> FM;               // S x n
+    // work buffers (local shard)
+    DevBuf<double> nf, mu, baseVar, rough, alpha_init, log_alpha, initial_lp, last_lp, dispMAP, dispersion,
+        beta, betaSE, stat, pvalue, deviance, maxCooks;
+    DevBuf<int32_t> dispGeneIter, dispIter, betaIter, refit_list;
+    // global (all ranks) buffers: baseMean, dispGeneEst, flags, dispFit, resid ; local slice at g_off
+    DevBuf<double> g_baseMean, g_dispGeneEst, g_dispFit, g_resid, g_sortbuf, g_sortbuf2;
+    DevBuf<uint8_t> g_flags;
+    DevBuf<int32_t> g_K;             // gathered counts for the size factors (sharded run only)
+    DevBuf<double> g_LR;
+    DevBuf<unsigned char> cub_tmp;
+    DevBuf<double> partial, scal;    // reduction scratch ; device scalars
+    DevBuf<unsigned long long> counters;
+    DevBuf<int32_t> refit_count;
+    double* h_pinned = nullptr;      // pinned host scratch (64 doubles)
+    std::vector<int64_t> shard_n, shard_off;
+    int64_t n_tot = 0, g_off = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CD_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return (ctx)->fail(CD_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CD_LAUNCHN(ctx, k, call)                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        (ctx)->launches += (k);                                                                     \
+        if (e_ != cudaSuccess) return (ctx)->fail(CD_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CD_COMM(ctx, call)                                                                          \
+    do {                                                                                            \
+        std::string m_ = (call);                                                                    \
+        if (!m_.empty()) return (ctx)->fail(CD_ECOMM, "%s", m_.c_str());                            \
+    } while (0)
+
+extern "C" {
+
+const char* cd_version(void) { return "chicdiff_b200 0.1 (sm_100a)"; }
+
+const char* cd_last_error(const cd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cd_create(cd_ctx** out, int device)
+{
+    if (!out) return CD_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                         " (chicdiff_b200 has no CPU fallback)";
+        return CD_ECUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device ordinal out of range"; return CD_EINVAL; }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return CD_ECUDA; }
+    cd_ctx* c = new (std::nothrow) cd_ctx();
+    if (!c) return CD_ENOMEM;
+    c->device = device;
+    if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return CD_ECUDA;
+    }
+    for (int k = 0; k < 4; k++) cudaEventCreate(&c->ev[k]);
+    *out = c;
+    return CD_OK;
+}
+
+void cd_destroy(cd_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    cudaStream_t st = ctx->st;
+    delete ctx;
+    if (st) cudaStreamDestroy(st);
+}
+
+int cd_comm_unique_id(cd_ctx* ctx, char id[128])
+{
+    if (!ctx || !id) return CD_EINVAL;
+    CD_COMM(ctx, ctx->comm.unique_id(id));
+    return CD_OK;
+}
+
+int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128])
+{
+    if (!ctx || !id) return CD_EINVAL;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_COMM(ctx, ctx->comm.init(nranks, rank, id));
+    return CD_OK;
+}
+
+int cd_plan_shards(int64_t n, const int32_t* region_bait, const int64_t* row_off, int nshards, int64_t* bounds)
+{
+    if (n < 0 || nshards < 1 || !bounds || (n > 0 && (!region_bait || !row_off))) return CD_EINVAL;
+    bounds[0] = 0;
+    const int64_t total = n > 0 ? row_off[n] - row_off[0] : 0;
+    int64_t i = 0;
+    for (int k = 1; k < nshards; k++) {
+        const int64_t target = row_off ? row_off[0] + (total * k) / nshards : 0;
+        // first region whose rows start at or after the target ...
+        int64_t lo = i, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (row_off[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        i = lo;
+        // ... moved forward to the next bait boundary
+        while (i > 0 && i < n && region_bait[i] == region_bait[i - 1]) i++;
+        bounds[k] = i;
+    }
+    bounds[nshards] = n;
+    for (int k = 1; k <= nshards; k++) if (bounds[k] < bounds[k - 1]) bounds[k] = bounds[k - 1];
+    return CD_OK;
+}
+
+int cd_set_design(cd_ctx* ctx, int S, int p, const double* X)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!X || S < 2 || S > CD_MAXS || p < 1 || p > CD_MAXP)
+        return ctx->fail(CD_EINVAL, "cd_set_design: need 2 <= S <= %d and 1 <= p <= %d", CD_MAXS, CD_MAXP);
+    if (S <= p) return ctx->fail(CD_EINVAL, "cd_set_design: S <= p: no residual degrees of freedom (DESeq2 stops here too)");
+    if (!build_design(S, p, X, ctx->des)) return ctx->fail(CD_EINVAL, "cd_set_design: the model matrix is not full rank");
+    double ones[CD_MAXS];
+    for (int j = 0; j < S; j++) ones[j] = 1.0;
+    build_design(S, 1, ones, ctx->des1);
+    ctx->have_design = true;
+    ctx->have_regions = ctx->have_agg = false;
+    ctx->sample_set.assign((size_t)S, 0);
+    return CD_OK;
+}
+
+int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_design) return ctx->fail(CD_EINVAL, "cd_set_regions: call cd_set_design first");
+    if (n < 0 || n > 2000000000LL || !row_off) return ctx->fail(CD_EINVAL, "cd_set_regions: bad n / row_off");
+    for (int64_t i = 0; i < n; i++)
+        if (row_off[i + 1] < row_off[i]) return ctx->fail(CD_EINVAL, "cd_set_regions: row_off must be non-decreasing");
+    if (row_off[0] != 0) return ctx->fail(CD_EINVAL, "cd_set_regions: row_off[0] must be 0");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->row_off.ensure((size_t)n + 1));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->row_off.p, row_off, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->n = n;
+    ctx->R = row_off[n];
+    ctx->have_regions = true;
+    ctx->have_agg = false;
+    ctx->rows_borrowed = false;
+    ctx->N_rows_p = nullptr; ctx->FM_rows_p = nullptr;
+    std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 0);
+    return CD_OK;
+}
+
+int cd_set_sample_rows(cd_ctx* ctx, int s, int64_t R, const int32_t* N, const double* fullmean)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions) return ctx->fail(CD_EINVAL, "cd_set_sample_rows: call cd_set_regions first");
+    const int S = ctx->des.S;
+    if (s < 0 || s >= S || R != ctx->R || (R > 0 && (!N || !fullmean)))
+        return ctx->fail(CD_EINVAL, "cd_set_sample_rows: sample index or row count does not match the regions");
+    if (ctx->rows_borrowed) return ctx->fail(CD_EINVAL, "cd_set_sample_rows: rows were set with cd_set_rows_device");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R));
+    CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->N_rows.p + (size_t)s * R, N, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->FM_rows.p + (size_t)s * R, fullmean, sizeof(double) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
+    ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
+    ctx->sample_set[(size_t)s] = 1;
+    ctx->have_agg = false;
+    return CD_OK;            // the copies are ordered before any kernel on the context's stream
+}
+
+int cd_set_rows_device(cd_ctx* ctx, int64_t R, const int32_t* N_dev, const double* fullmean_dev)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions) return ctx->fail(CD_EINVAL, "cd_set_rows_device: call cd_set_regions first");
+    if (R != ctx->R || (R > 0 && (!N_dev || !fullmean_dev))) return ctx->fail(CD_EINVAL, "cd_set_rows_device: row count mismatch");
+    ctx->N_rows_p = N_dev; ctx->FM_rows_p = fullmean_dev;
+    ctx->rows_borrowed = true;
+    std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 1);
+    ctx->have_agg = false;
+    return CD_OK;
+}
+
+int cd_set_aggregated(cd_ctx* ctx, int64_t n, const int32_t* K, const double* fullmean)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_design) return ctx->fail(CD_EINVAL, "cd_set_aggregated: call cd_set_design first");
+    if (n < 0 || (n > 0 && (!K || !fullmean))) return ctx->fail(CD_EINVAL, "cd_set_aggregated: bad arguments");
+    const int S = ctx->des.S;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->K.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, ctx->FM.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->K.p, K, sizeof(int32_t) * (size_t)S * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->FM.p, fullmean, sizeof(double) * (size_t)S * (size_t)n, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->n = n;
+    ctx->have_agg = true;
+    return CD_OK;
+}
+
+int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions) return ctx->fail(CD_EINVAL, "cd_aggregate: call cd_set_regions first");
+    const int S = ctx->des.S;
+    for (int s = 0; s < S; s++)
+        if (!ctx->sample_set[(size_t)s]) return ctx->fail(CD_EINVAL, "cd_aggregate: rows of sample %d were never set", s);
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n;
+    CD_CUDA(ctx, ctx->K.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, ctx->FM.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->st));
+    CD_LAUNCHN(ctx, n > 0 ? 1 : 0, launch_aggregate(n, S, ctx->row_off.p, ctx->R, ctx->N_rows_p, ctx->FM_rows_p, ctx->K.p, ctx->FM.p, ctx->st));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->st));
+    if (K_out) CD_CUDA(ctx, cudaMemcpyAsync(K_out, ctx->K.p, sizeof(int32_t) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM.p, sizeof(double) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timings[0] = ms;
+    ctx->have_agg = true;
+    return CD_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// global steps
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// ascending sort of n doubles (src -> dst) with CUB; +inf entries end up last
+int sort_doubles(cd_ctx* ctx, const double* src, double* dst, int64_t n)
+{
+    size_t bytes = 0;
+    CD_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, bytes, src, dst, (int)n, 0, 64, ctx->st));
+    CD_CUDA(ctx, ctx->cub_tmp.ensure(bytes));
+    CD_LAUNCHN(ctx, 0, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, bytes, src, dst, (int)n, 0, 64, ctx->st));
+    return CD_OK;
+}
+
+// median of the finite entries of v (length n) -> device scalar out (exp / scale applied)
+int median_finite(cd_ctx* ctx, const double* v, int64_t n, double* out_dev, int do_exp, double scale)
+{
+    CD_CUDA(ctx, ctx->g_sortbuf.ensure((size_t)n));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 8, 0, sizeof(unsigned long long), ctx->st));
+    if (n > 0) {
+        count_finite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(n, v, ctx->counters.p + 8);
+        ctx->launches++;
+        int rc = sort_doubles(ctx, v, ctx->g_sortbuf.p, n);
+        if (rc != CD_OK) return rc;
+    }
+    median_sorted_kernel<<<1, 32, 0, ctx->st>>>(ctx->g_sortbuf.p, ctx->counters.p + 8, out_dev, do_exp, scale);
+    ctx->launches++;
+    CD_CUDA(ctx, cudaGetLastError());
+    return CD_OK;
+}
+
+// estimateSizeFactors over ALL regions (gathers the counts in a sharded run) -> scal[0..S)
+int size_factors(cd_ctx* ctx, double* sf_host)
+{
+    const int S = ctx->des.S;
+    const int64_t n = ctx->n, nt = ctx->n_tot;
+    const int32_t* Kall = ctx->K.p;
+    if (ctx->comm.active()) {
+        CD_CUDA(ctx, ctx->g_K.ensure((size_t)S * (size_t)nt));
+        for (int s = 0; s < S; s++)
+            CD_COMM(ctx, ctx->comm.allgatherv(ctx->K.p + (size_t)s * n, ctx->g_K.p + (size_t)s * nt, ctx->shard_n,
+                                              ctx->shard_off, sizeof(int32_t), ctx->st));
+        Kall = ctx->g_K.p;
+    }
+    CD_CUDA(ctx, ctx->g_LR.ensure((size_t)S * (size_t)nt));
+    CD_LAUNCHN(ctx, 1, launch_log_ratios(nt, S, Kall, ctx->g_LR.p, ctx->st));
+    for (int s = 0; s < S; s++) {
+        int rc = median_finite(ctx, ctx->g_LR.p + (size_t)s * nt, nt, ctx->scal.p + s, 1, 1.0);
+        if (rc != CD_OK) return rc;
+    }
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    for (int s = 0; s < S; s++) {
+        sf_host[s] = ctx->h_pinned[s];
+        if (std::isnan(sf_host[s]))
+            return ctx->fail(CD_ENUMERIC, "every gene contains at least one zero, cannot compute log geometric means");
+    }
+    return CD_OK;
+}
+
+// parametricDispersionFit on the global arrays; coefs out.  Mirrors glm.fit's IRLS with step halving.
+int trend_fit(cd_ctx* ctx, double coefs[2])
+{
+    const int64_t nt = ctx->n_tot;
+    double c0 = 0.1, c1 = 1.0;
+    int iter = 0;
+    auto pass = [&](double oc0, double oc1, double b0, double b1, double* v) -> int {
+        CD_LAUNCHN(ctx, 2, launch_trend_pass(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, oc0, oc1, b0, b1,
+                                             ctx->partial.p, ctx->scal.p + 40, ctx->st));
+        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 40, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+        for (int k = 0; k < 8; k++) v[k] = ctx->h_pinned[k];
+        return CD_OK;
+    };
+    while (true) {
+        double v[8];
+        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
+        int rc = pass(c0, c1, b0, b1, v);
+        if (rc != CD_OK) return rc;
+        if (v[7] < 2.0) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (fewer than 2 usable regions); the reference would switch to a local fit, which is not implemented");
+        if (v[6] > 0.0) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (invalid starting values); the reference would switch to a local fit, which is not implemented");
+        double devold = v[5];
+        bool conv = false;
+        for (int it = 0; it < 25; it++) {
+            const double det = v[0] * v[2] - v[1] * v[1];
+            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
+            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
+            double w[8];
+            int halv = 0;
+            while (true) {
+                rc = pass(c0, c1, nb0, nb1, w);
+                if (rc != CD_OK) return rc;
+                if (w[6] == 0.0 && std::isfinite(w[5])) break;
+                if (++halv > 25) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (no valid step); local fit not implemented");
+                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
+            }
+            b0 = nb0; b1 = nb1;
+            for (int k = 0; k < 8; k++) v[k] = w[k];
+            const double dev = w[5];
+            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
+            devold = dev; ob0 = b0; ob1 = b1;
+        }
+        const double oc0 = c0, oc1 = c1;
+        c0 = b0; c1 = b1;
+        if (!(c0 > 0.0 && c1 > 0.0)) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (non-positive coefficients); local fit not implemented");
+        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
+        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
+        iter++;
+        if (iter > 10) return ctx->fail(CD_ENUMERIC, "dispersion fit did not converge; local fit not implemented");
+    }
+    coefs[0] = c0; coefs[1] = c1;
+    return CD_OK;
+}
+
+struct PipeOut { double a0, a1, varLogDispEsts, dispPriorVar, sum_deviance; };
+
+// estimateDispersions + nbinomWaldTest for one normalisation (mode / theta) and one design
+int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, double prior_var_override, int grid_len,
+                 bool want_cooks, PipeOut& po)
+{
+    const int S = des.S, p = des.p;
+    const int64_t n = ctx->n, nt = ctx->n_tot, off = ctx->g_off;
+    cudaStream_t st = ctx->st;
+    const int df = S - p;
+    if (std::isnan(prior_var_override) && df <= 3)
+        return ctx->fail(CD_ENUMERIC, "S - p = %d <= 3: DESeq2 estimates the dispersion prior variance by a seeded Monte-Carlo "
+                                      "match here (set.seed(2), rchisq, loess), which is not implemented; pass disp_prior_var", df);
+    CD_CUDA(ctx, set_design_dispersion(des, st));
+    CD_CUDA(ctx, set_design_wald(des, st));
+    double* baseMean = ctx->g_baseMean.p + off;
+    double* dispGeneEst = ctx->g_dispGeneEst.p + off;
+    double* dispFit = ctx->g_dispFit.p + off;
+    uint8_t* flags = ctx->g_flags.p + off;
+    double* sf_dev = ctx->scal.p;                 // size factors live in scal[0..S)
+    double* sums_dev = ctx->scal.p + 48;          // S + 1 offsets sums
+    double* xim_dev = ctx->scal.p + 47;
+
+    CD_LAUNCHN(ctx, 1, launch_norm_factors(n, S, ctx->FM.p, sf_dev, mode, theta, ctx->nf.p, st));
+    CD_LAUNCHN(ctx, 1, launch_base_stats(n, S, ctx->K.p, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, st));
+    CD_LAUNCHN(ctx, 2, launch_masked_colsums(n, S, ctx->nf.p, flags, ctx->partial.p, sums_dev, st));
+    CD_COMM(ctx, ctx->comm.allreduce_sum(sums_dev, (size_t)S + 1, st));
+    xim_kernel<<<1, 32, 0, st>>>(S, sums_dev, xim_dev);
+    ctx->launches++;
+    CD_LAUNCHN(ctx, 1, launch_gene_init(n, S, ctx->K.p, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev,
+                                        ctx->alpha_init.p, ctx->mu.p, st));
+    if (!des.linear_mu) {
+        // mu from an NB GLM fitted with the rough dispersion (fitNbinomGLMs(alpha_hat = alpha_init)$mu)
+        CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->alpha_init.p, flags, nullptr, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, ctx->mu.p, st));
+    }
+    CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
+                                       ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    CD_LAUNCHN(ctx, 1, launch_gene_post(n, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
+                                        ctx->last_lp.p, flags, dispGeneEst, ctx->refit_list.p, ctx->refit_count.p, st));
+    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, nullptr, 1.0,
+                                            grid_len, dispGeneEst, nullptr, flags, dispGeneEst, st));
+    if (ctx->comm.active()) {
+        CD_COMM(ctx, ctx->comm.allgatherv(baseMean, ctx->g_baseMean.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
+        CD_COMM(ctx, ctx->comm.allgatherv(dispGeneEst, ctx->g_dispGeneEst.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
+        CD_COMM(ctx, ctx->comm.allgatherv(flags, ctx->g_flags.p, ctx->shard_n, ctx->shard_off, sizeof(uint8_t), st));
+    }
+    // trend + MAD on the global arrays (every rank computes the same numbers)
+    double coefs[2];
+    int rc = trend_fit(ctx, coefs);
+    if (rc != CD_OK) return rc;
+    CD_LAUNCHN(ctx, 1, launch_trend_apply(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, coefs[0], coefs[1],
+                                          ctx->g_dispFit.p, ctx->g_resid.p, st));
+    double* med_dev = ctx->scal.p + 44;
+    rc = median_finite(ctx, ctx->g_resid.p, nt, med_dev, 0, 1.0);
+    if (rc != CD_OK) return rc;
+    CD_CUDA(ctx, ctx->g_sortbuf2.ensure((size_t)nt));
+    if (nt > 0) {
+        abs_dev_dev_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(nt, ctx->g_resid.p, med_dev, ctx->g_sortbuf2.p);
+        ctx->launches++;
+    }
+    rc = median_finite(ctx, ctx->g_sortbuf2.p, nt, ctx->scal.p + 45, 0, 1.4826);
+    if (rc != CD_OK) return rc;
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    const double mad = ctx->h_pinned[0];
+    if (std::isnan(mad))
+        return ctx->fail(CD_ENUMERIC, "all gene-wise dispersion estimates are within 2 orders of magnitude of the minimum");
+    const double varLogDispEsts = mad * mad;
+    double dispPriorVar;
+    if (!std::isnan(prior_var_override)) dispPriorVar = prior_var_override;
+    else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
+
+    // MAP
+    CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, dispGeneEst, dispFit, dispPriorVar, ctx->log_alpha.p,
+                                       ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    CD_LAUNCHN(ctx, 1, launch_map_post(n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, 2.0 * sqrt(varLogDispEsts),
+                                       flags, ctx->dispMAP.p, ctx->dispersion.p, ctx->refit_list.p, ctx->refit_count.p, st));
+    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, dispFit,
+                                            dispPriorVar, grid_len, ctx->dispMAP.p, ctx->dispersion.p, flags, dispGeneEst, st));
+    // NB GLM + Wald
+    CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->dispersion.p, flags, ctx->beta.p, ctx->betaSE.p, ctx->stat.p,
+                                   ctx->pvalue.p, ctx->deviance.p, want_cooks ? ctx->maxCooks.p : nullptr, ctx->betaIter.p,
+                                   nullptr, st));
+    CD_LAUNCHN(ctx, 2, launch_sum_nan(n, ctx->deviance.p, ctx->partial.p, ctx->scal.p + 46, st));
+    CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + 46, 1, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 46, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    po.a0 = coefs[0]; po.a1 = coefs[1]; po.varLogDispEsts = varLogDispEsts; po.dispPriorVar = dispPriorVar;
+    po.sum_deviance = ctx->h_pinned[0];
+    return CD_OK;
+}
+
+template <typename T>
+int d2h(cd_ctx* ctx, T* dst, const T* src, size_t count)
+{
+    if (!dst || count == 0) return CD_OK;
+    CD_CUDA(ctx, cudaMemcpyAsync(dst, src, sizeof(T) * count, cudaMemcpyDeviceToHost, ctx->st));
+    return CD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!opt || !out) return ctx->fail(CD_EINVAL, "cd_region_test: null options / results");
+    if (!ctx->have_agg) return ctx->fail(CD_EINVAL, "cd_region_test: call cd_aggregate (or cd_set_aggregated) first");
+    if (opt->norm < 0 || opt->norm > 2) return ctx->fail(CD_EINVAL, "DESeq2Wrap error: Unknown normalisation method.");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int S = ctx->des.S, p = ctx->des.p;
+    const int64_t n = ctx->n;
+    cudaStream_t st = ctx->st;
+    const int grid_len = opt->disp_grid_len > 0 ? opt->disp_grid_len : 20;
+    if (grid_len < 2 || grid_len > 32) return ctx->fail(CD_EINVAL, "disp_grid_len must be in [2, 32]");
+
+    // shard geometry
+    CD_COMM(ctx, ctx->comm.allgather_i64(n, ctx->shard_n, st));
+    ctx->shard_off.assign(ctx->shard_n.size(), 0);
+    int64_t tot = 0;
+    for (size_t r = 0; r < ctx->shard_n.size(); r++) { ctx->shard_off[r] = tot; tot += ctx->shard_n[r]; }
+    ctx->n_tot = tot;
+    ctx->g_off = ctx->shard_off[(size_t)ctx->comm.rank];
+    if (tot > 2147483647LL) return ctx->fail(CD_EINVAL, "more than 2^31-1 regions in total");
+
+    const size_t sn = (size_t)S * (size_t)n;
+    CD_CUDA(ctx, ctx->nf.ensure(sn));
+    CD_CUDA(ctx, ctx->mu.ensure(sn));
+    CD_CUDA(ctx, ctx->baseVar.ensure((size_t)n)); CD_CUDA(ctx, ctx->rough.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->alpha_init.ensure((size_t)n)); CD_CUDA(ctx, ctx->log_alpha.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->initial_lp.ensure((size_t)n)); CD_CUDA(ctx, ctx->last_lp.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->dispMAP.ensure((size_t)n)); CD_CUDA(ctx, ctx->dispersion.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->beta.ensure((size_t)CD_MAXP * (size_t)n)); CD_CUDA(ctx, ctx->betaSE.ensure((size_t)CD_MAXP * (size_t)n));
+    CD_CUDA(ctx, ctx->stat.ensure((size_t)n)); CD_CUDA(ctx, ctx->pvalue.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->deviance.ensure((size_t)n)); CD_CUDA(ctx, ctx->maxCooks.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->dispGeneIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->dispIter.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->betaIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->refit_list.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->g_baseMean.ensure((size_t)tot)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure((size_t)tot));
+    CD_CUDA(ctx, ctx->g_dispFit.ensure((size_t)tot)); CD_CUDA(ctx, ctx->g_resid.ensure((size_t)tot));
+    CD_CUDA(ctx, ctx->g_flags.ensure((size_t)tot));
+    CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * (CD_MAXS + 8)));
+    CD_CUDA(ctx, ctx->scal.ensure(128));
+    CD_CUDA(ctx, ctx->counters.ensure(16));
+    CD_CUDA(ctx, ctx->refit_count.ensure(1));
+
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    memset(out->sizeFactors, 0, sizeof(out->sizeFactors));
+    int rc = size_factors(ctx, out->sizeFactors);
+    if (rc != CD_OK) return rc;
+
+    int norm = opt->norm;
+    double theta = opt->theta;
+    out->n_deviances = 0;
+    if (!std::isnan(theta)) {
+        // chicdiff.R:1511-1521: theta = 1 is "standard", theta = 0 is "fullmean"
+        if (theta == 1.0 && norm != CD_NORM_STANDARD) norm = CD_NORM_STANDARD;
+        if (theta == 0.0 && norm != CD_NORM_FULLMEAN) norm = CD_NORM_FULLMEAN;
+    }
+    PipeOut po{};
+    if (norm == CD_NORM_COMBINED && std::isnan(theta)) {
+        static const double default_grid[5] = {0.0, 0.25, 0.5, 0.75, 1.0};
+        const double* grid = opt->theta_grid ? opt->theta_grid : default_grid;
+        const int ng = opt->theta_grid ? opt->n_theta_grid : 5;
+        if (ng < 1 || ng > 16) return ctx->fail(CD_EINVAL, "theta grid must have 1..16 values");
+        int best = -1, nbest = 0;
+        for (int k = 0; k < ng; k++) {
+            rc = run_pipeline(ctx, ctx->des1, CD_NORM_COMBINED, grid[k], opt->disp_prior_var_grid, grid_len, false, po);
+            if (rc != CD_OK) return rc;
+            out->deviances[k] = po.sum_deviance;
+            if (std::isnan(po.sum_deviance))
+                return ctx->fail(CD_ENUMERIC, "theta grid: total deviance is NA (an all-zero region is present and chicdiff.R:1647 "
+                                              "sums without na.rm); pass theta explicitly, as chicdiffPipeline does for the control set");
+        }
+        out->n_deviances = ng;
+        for (int k = 0; k < ng; k++) {
+            if (best < 0 || out->deviances[k] < out->deviances[best]) { best = k; nbest = 1; }
+            else if (out->deviances[k] == out->deviances[best]) nbest++;
+        }
+        if (nbest != 1) return ctx->fail(CD_ENUMERIC, "theta grid: the minimum total deviance is tied");
+        theta = grid[best];
+    }
+    rc = run_pipeline(ctx, ctx->des, norm, std::isnan(theta) ? 0.0 : theta, opt->disp_prior_var, grid_len, true, po);
+    if (rc != CD_OK) return rc;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+
+    out->theta = (norm == CD_NORM_COMBINED) ? theta : NAN;
+    out->trend_a0 = po.a0; out->trend_a1 = po.a1;
+    out->varLogDispEsts = po.varLogDispEsts; out->dispPriorVar = po.dispPriorVar;
+
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+    const uint8_t* flags = ctx->g_flags.p + ctx->g_off;
+    if (n > 0) {
+        count_flags_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, flags, ctx->counters.p);
+        ctx->launches++;
+    }
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    CD_CUDA(ctx, cudaMemcpyAsync(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    const size_t nn = (size_t)n;
+    if ((rc = d2h(ctx, out->baseMean, ctx->g_baseMean.p + ctx->g_off, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->baseVar, ctx->baseVar.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispGeneEst, ctx->g_dispGeneEst.p + ctx->g_off, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispFit, ctx->g_dispFit.p + ctx->g_off, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispMAP, ctx->dispMAP.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispersion, ctx->dispersion.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->log2FoldChange, ctx->beta.p + (size_t)(p - 1) * nn, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->lfcSE, ctx->betaSE.p + (size_t)(p - 1) * nn, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->beta, ctx->beta.p, (size_t)p * nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->betaSE, ctx->betaSE.p, (size_t)p * nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->stat, ctx->stat.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->pvalue, ctx->pvalue.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->deviance, ctx->deviance.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->maxCooks, ctx->maxCooks.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->normFactors, ctx->nf.p, sn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->mu, ctx->mu.p, sn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispGeneIter, ctx->dispGeneIter.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->dispIter, ctx->dispIter.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->betaIter, ctx->betaIter.p, nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->flags, flags, nn)) != CD_OK) return rc;
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    out->n_nonzero = (int64_t)hc[0]; out->n_gene_grid = (int64_t)hc[1];
+    out->n_map_grid = (int64_t)hc[2]; out->n_beta_noconv = (int64_t)hc[3];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    ctx->timings[1] = ms;
+    return CD_OK;
+}
+
+int64_t cd_launch_count(const cd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmean_dev)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_agg) return ctx->fail(CD_EINVAL, "cd_device_buffers: nothing aggregated yet");
+    if (K_dev) *K_dev = ctx->K.p;
+    if (fullmean_dev) *fullmean_dev = ctx->FM.p;
+    return CD_OK;
+}
+
+int cd_last_timings(const cd_ctx* ctx, double out_ms[8])
+{
+    if (!ctx || !out_ms) return CD_EINVAL;
+    for (int k = 0; k < 8; k++) out_ms[k] = ctx->timings[k];
+    return CD_OK;
+}
+
+}  // extern "C"

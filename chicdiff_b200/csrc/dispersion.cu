@@ -1,0 +1,456 @@
+// dispersion.cu -- stage 4: gene-wise Cox-Reid dispersion line search, grid refit, MAP.
+//
+// Restates, for the GPU, what DESeq2's estimateDispersionsGeneEst / estimateDispersionsMAP
+// do when Chicdiff calls estimateDispersions() (chicdiff.R:1573,1602,1643,1673): rough and
+// moments starting values, mu from the hat-matrix projection, the Armijo line search on
+// log(alpha) over the Cox-Reid adjusted profile likelihood (DESeq2.cpp fitDisp), and the
+// two-level grid refit (fitDispGrid) for rows whose search did not converge.
+//
+// Mapping: one thread per region; per-sample columns are read coalesced from the
+// sample-major matrices and the region's replicates (y_j, mu_j) are staged per thread in a
+// conflict-free shared-memory column.
+#include "kernels.h"
+
+namespace cd {
+
+__constant__ CdDesign c_des;
+
+cudaError_t set_design_dispersion(const CdDesign& d, cudaStream_t st)
+{
+    return cudaMemcpyToSymbolAsync(c_des, &d, sizeof(CdDesign), 0, cudaMemcpyHostToDevice, st);
+}
+
+static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------
+// base statistics, linear mu, rough dispersion
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+base_stats_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                  double* __restrict__ baseMean, double* __restrict__ baseVar,
+                  double* __restrict__ rough, uint8_t* __restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q[CD_MAXS];
+    double sum = 0.0;
+    int64_t tot = 0;
+    for (int j = 0; j < S; j++) {
+        const int32_t k = K[(int64_t)j * n + i];
+        q[j] = (double)k / nf[(int64_t)j * n + i];
+        sum += q[j];
+        tot += k;
+    }
+    const double m = sum / S;
+    double v = 0.0;
+    for (int j = 0; j < S; j++) v += (q[j] - m) * (q[j] - m);
+    baseMean[i] = m;
+    baseVar[i] = v / (S - 1);
+    flags[i] = (tot == 0) ? CD_FLAG_ALLZERO : 0;
+    // roughDispEstimate: linearModelMu on normalised counts, floored at 1
+    double est = 0.0;
+    for (int a = 0; a < S; a++) {
+        double mul = 0.0;
+        for (int b = 0; b < S; b++) mul += c_des.hat[a * S + b] * q[b];
+        const double mm = fmax(1.0, mul);
+        est += ((q[a] - mm) * (q[a] - mm) - mm) / (mm * mm);
+    }
+    rough[i] = fmax(est / (S - c_des.p), 0.0);
+}
+
+cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf, double* baseMean,
+                              double* baseVar, double* rough, uint8_t* flags, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    base_stats_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, baseMean, baseVar, rough, flags);
+    return cudaGetLastError();
+}
+
+// alpha_init = clamp(min(rough, moments)); mu = linearModelMu(q) * nf floored at minmu
+__global__ void __launch_bounds__(256)
+gene_init_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                 const double* __restrict__ baseMean, const double* __restrict__ baseVar,
+                 const double* __restrict__ rough, const uint8_t* __restrict__ flags,
+                 const double* __restrict__ xim_dev, double* __restrict__ alpha_init,
+                 double* __restrict__ mu)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] & CD_FLAG_ALLZERO) {
+        alpha_init[i] = NAN;
+        if (mu) for (int j = 0; j < S; j++) mu[(int64_t)j * n + i] = NAN;
+        return;
+    }
+    const double xim = *xim_dev;
+    const double bm = baseMean[i], bv = baseVar[i];
+    const double moments = (bv - xim * bm) / (bm * bm);
+    const double maxDisp = fmax(10.0, (double)S);
+    alpha_init[i] = fmin(fmax(kMinDisp, fmin(rough[i], moments)), maxDisp);
+    if (!mu) return;
+    double q[CD_MAXS];
+    for (int j = 0; j < S; j++) q[j] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
+    for (int a = 0; a < S; a++) {
+        double mul = 0.0;
+        for (int b = 0; b < S; b++) mul += c_des.hat[a * S + b] * q[b];
+        mu[(int64_t)a * n + i] = fmax(mul * nf[(int64_t)a * n + i], kMinMu);
+    }
+}
+
+cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* nf, const double* baseMean,
+                             const double* baseVar, const double* rough, const uint8_t* flags,
+                             const double* xim_dev, double* alpha_init, double* mu, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, baseMean, baseVar, rough, flags,
+                                                       xim_dev, alpha_init, mu);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// Cox-Reid adjusted profile log-posterior of log(alpha) and its derivative
+// (DESeq2.cpp log_posterior / dlog_posterior).  ys / mus point at the region's replicates
+// in shared memory, element j at [j * stride].
+// ---------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ double eval_lp(double a, const double* ys, const double* mus, int stride, int S,
+                                          double prior_mean, double prior_sigmasq, bool use_prior)
+{
+    const double alpha = exp(a);
+    const double r = 1.0 / alpha;
+    const double lgr = lgamma(r);
+    Sym<P> B;
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) B.v[k] = 0.0;
+    double ll = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < S; j++) {
+        const double yj = ys[j * stride], muj = mus[j * stride];
+        const double w = 1.0 / (1.0 / muj + alpha);
+#pragma unroll
+        for (int u = 0; u < P; u++)
+#pragma unroll
+            for (int v = 0; v <= u; v++)
+                B.v[u * (u + 1) / 2 + v] += w * c_des.X[j * P + u] * c_des.X[j * P + v];
+        // lgamma(0 + r) - lgamma(r) is exactly zero: skip both calls for zero counts
+        double t = (yj != 0.0) ? lgamma(yj + r) - lgr : 0.0;
+        t = (t - yj * log(muj + r)) - r * log(1.0 + muj * alpha);
+        ll += t;
+    }
+    const double cr = -0.5 * chol_logdet<P>(B);
+    double pr = 0.0;
+    if (use_prior) {
+        const double d = a - prior_mean;
+        pr = -0.5 * d * d / prior_sigmasq;
+    }
+    return ll + pr + cr;
+}
+
+template <int P>
+__device__ __forceinline__ double eval_dlp(double a, const double* ys, const double* mus, int stride, int S,
+                                           double prior_mean, double prior_sigmasq, bool use_prior)
+{
+    const double alpha = exp(a);
+    const double r = 1.0 / alpha;
+    const double an2 = 1.0 / (alpha * alpha);
+    const double dgr = digamma_pos(r);
+    Sym<P> B, dB;
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) { B.v[k] = 0.0; dB.v[k] = 0.0; }
+    double s = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < S; j++) {
+        const double yj = ys[j * stride], muj = mus[j * stride];
+        const double t = 1.0 / muj + alpha;
+        const double w = 1.0 / t;
+        const double dw = -w * w;
+#pragma unroll
+        for (int u = 0; u < P; u++)
+#pragma unroll
+            for (int v = 0; v <= u; v++) {
+                const double xx = c_des.X[j * P + u] * c_des.X[j * P + v];
+                B.v[u * (u + 1) / 2 + v] += w * xx;
+                dB.v[u * (u + 1) / 2 + v] += dw * xx;
+            }
+        const double ma = muj * alpha;
+        double term = log(1.0 + ma) - ma / (1.0 + ma);
+        // digamma(r) - digamma(0 + r) is exactly zero: skip both calls for zero counts
+        if (yj != 0.0) term = ((dgr + term) - digamma_pos(yj + r)) + yj / (muj + r);
+        s += term;
+    }
+    const double ll = an2 * s;
+    chol_logdet<P>(B);
+    Sym<P> Bi;
+    chol_inverse<P>(B, Bi);
+    double tr = 0.0;
+#pragma unroll
+    for (int u = 0; u < P; u++)
+#pragma unroll
+        for (int v = 0; v < P; v++) tr += Bi.v[sidx<P>(u, v)] * dB.v[sidx<P>(v, u)];
+    const double cr = -0.5 * tr;
+    double pr = 0.0;
+    if (use_prior) pr = -1.0 * (a - prior_mean) / prior_sigmasq;
+    return (ll + cr) * alpha + pr;
+}
+
+// ---------------------------------------------------------------------------------------
+// fitDisp line search, one thread per region; the region's replicates are staged once into
+// a conflict-free shared-memory column ([j][thread]) so that the sample loop stays rolled
+// (the special-function bodies are large) without spilling to local memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kFitDispThreads = 128;
+
+template <int P>
+__global__ void __launch_bounds__(kFitDispThreads)
+fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
+                const uint8_t* __restrict__ flags, const double* __restrict__ disp_init,
+                const double* __restrict__ prior_mean_disp, double prior_sigmasq,
+                double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
+                double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out)
+{
+    extern __shared__ double smem[];
+    const int stride = kFitDispThreads;
+    double* ys = smem + threadIdx.x;
+    double* mus = smem + (size_t)S * stride + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] & CD_FLAG_ALLZERO) {
+        log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
+        return;
+    }
+    for (int j = 0; j < S; j++) {
+        ys[j * stride] = (double)K[(int64_t)j * n + i];
+        mus[j * stride] = mu_g[(int64_t)j * n + i];
+    }
+    const bool use_prior = (prior_mean_disp != nullptr);
+    double a, prior_mean = 0.0;
+    if (use_prior) {
+        // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more than an
+        // order of magnitude below the trend
+        const double ft = prior_mean_disp[i], ge = disp_init[i];
+        a = log((ge > 0.1 * ft) ? ge : ft);
+        prior_mean = log(ft);
+    } else {
+        a = log(disp_init[i]);
+    }
+    const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
+    const double min_log_alpha = log(kMinDisp / 10.0);
+    const int maxit = 100;
+    double lp = eval_lp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+    double dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+    const double lp0 = lp;
+    double kappa = kappa_0;
+    int iter = 0, iter_accept = 0;
+    for (int t = 0; t < maxit; t++) {
+        iter++;
+        const double a_propose = a + kappa * dlp;
+        if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
+        if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
+        const double a_new = a + kappa * dlp;
+        // fitDisp evaluates the posterior at a_new twice (Armijo test, then "lpnew"); the two
+        // arguments are the same double, so one evaluation serves both
+        const double lpnew = eval_lp<P>(a_new, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+        const double theta_kappa = -1.0 * lpnew;
+        const double theta_hat_kappa = -1.0 * lp - kappa * epsilon * (dlp * dlp);
+        if (theta_kappa <= theta_hat_kappa) {
+            iter_accept++;
+            a = a_new;
+            const double change = lpnew - lp;
+            if (change < tol) { lp = lpnew; break; }
+            if (a < min_log_alpha) break;
+            lp = lpnew;
+            dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+            kappa = fmin(kappa * 1.1, kappa_0);
+            if (iter_accept % 5 == 0) kappa = kappa / 2.0;
+        } else {
+            kappa = kappa / 2.0;
+        }
+    }
+    log_alpha_out[i] = a;
+    iter_out[i] = iter;
+    initial_lp_out[i] = lp0;
+    last_lp_out[i] = lp;
+}
+
+cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu, const uint8_t* flags,
+                            const double* disp_init, const double* prior_mean_disp, double prior_sigmasq,
+                            double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const int threads = kFitDispThreads;
+    const int blocks = blocks_for(n, threads);
+    const size_t smem = (size_t)2 * S * threads * sizeof(double);
+#define CD_LAUNCH(P_)                                                                                        \
+    fit_disp_kernel<P_><<<blocks, threads, smem, st>>>(n, S, K, mu, flags, disp_init, prior_mean_disp,      \
+                                                       prior_sigmasq, log_alpha, iter, initial_lp, last_lp)
+    switch (p) {
+        case 1: CD_LAUNCH(1); break;
+        case 2: CD_LAUNCH(2); break;
+        case 3: CD_LAUNCH(3); break;
+        case 4: CD_LAUNCH(4); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef CD_LAUNCH
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// post-processing
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gene_post_kernel(int64_t n, int S, const double* __restrict__ alpha_init, const double* __restrict__ log_alpha,
+                 const int32_t* __restrict__ iter, const double* __restrict__ initial_lp,
+                 const double* __restrict__ last_lp, uint8_t* __restrict__ flags,
+                 double* __restrict__ dispGeneEst, int32_t* __restrict__ refit_list,
+                 int32_t* __restrict__ refit_count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t f = flags[i];
+    if (f & CD_FLAG_ALLZERO) { dispGeneEst[i] = NAN; return; }
+    const double maxDisp = fmax(10.0, (double)S);
+    double disp = fmin(exp(log_alpha[i]), maxDisp);
+    const double l0 = initial_lp[i];
+    if (last_lp[i] < l0 + fabs(l0) / 1e6) { disp = alpha_init[i]; f |= CD_FLAG_GENE_NOINCREASE; }
+    const int it = iter[i];
+    const bool conv = (it < 100) && (it != 1);
+    if (!conv && disp > kMinDisp * 10.0) {
+        f |= CD_FLAG_GENE_GRID;
+        const int32_t slot = atomicAdd(refit_count, 1);
+        refit_list[slot] = (int32_t)i;
+    }
+    dispGeneEst[i] = fmin(fmax(disp, kMinDisp), maxDisp);
+    flags[i] = f;
+}
+
+cudaError_t launch_gene_post(int64_t n, int S, const double* alpha_init, const double* log_alpha, const int32_t* iter,
+                             const double* initial_lp, const double* last_lp, uint8_t* flags, double* dispGeneEst,
+                             int32_t* refit_list, int32_t* refit_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(refit_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess || n == 0) return e;
+    gene_post_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, alpha_init, log_alpha, iter, initial_lp, last_lp,
+                                                       flags, dispGeneEst, refit_list, refit_count);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+map_post_kernel(int64_t n, int S, const double* __restrict__ log_alpha, const int32_t* __restrict__ iter,
+                const double* __restrict__ dispGeneEst, const double* __restrict__ dispFit, double outlier_thr,
+                uint8_t* __restrict__ flags, double* __restrict__ dispMAP, double* __restrict__ dispersion,
+                int32_t* __restrict__ refit_list, int32_t* __restrict__ refit_count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t f = flags[i];
+    if (f & CD_FLAG_ALLZERO) { dispMAP[i] = NAN; dispersion[i] = NAN; return; }
+    const double maxDisp = fmax(10.0, (double)S);
+    if (!(iter[i] < 100)) {
+        f |= CD_FLAG_MAP_GRID;
+        const int32_t slot = atomicAdd(refit_count, 1);
+        refit_list[slot] = (int32_t)i;
+    }
+    const double dmap = fmin(fmax(exp(log_alpha[i]), kMinDisp), maxDisp);
+    const double ge = dispGeneEst[i], ft = dispFit[i];
+    const bool outl = log(ge) > log(ft) + outlier_thr;
+    if (outl) f |= CD_FLAG_OUTLIER;
+    dispMAP[i] = dmap;
+    dispersion[i] = outl ? ge : dmap;
+    flags[i] = f;
+}
+
+cudaError_t launch_map_post(int64_t n, int S, const double* log_alpha, const int32_t* iter, const double* dispGeneEst,
+                            const double* dispFit, double outlier_thr, uint8_t* flags, double* dispMAP,
+                            double* dispersion, int32_t* refit_list, int32_t* refit_count, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(refit_count, 0, sizeof(int32_t), st);
+    if (e != cudaSuccess || n == 0) return e;
+    map_post_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, log_alpha, iter, dispGeneEst, dispFit, outlier_thr,
+                                                      flags, dispMAP, dispersion, refit_list, refit_count);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// fitDispGrid: one warp per listed row, lane = grid point (grid_len <= 32)
+// ---------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(128)
+fit_disp_grid_kernel(int64_t n, int S, const int32_t* __restrict__ n_list_dev, const int32_t* __restrict__ list,
+                     const int32_t* __restrict__ K, const double* __restrict__ mu_g,
+                     const double* __restrict__ prior_mean_disp, double prior_sigmasq, int grid_len,
+                     double* __restrict__ disp_out, double* __restrict__ dispersion_out,
+                     const uint8_t* __restrict__ flags, const double* __restrict__ dispGeneEst)
+{
+    __shared__ double sh[4][2 * CD_MAXS];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int n_list = *n_list_dev;
+    double* ys = sh[wib];
+    double* mus = sh[wib] + CD_MAXS;
+    for (int w = blockIdx.x * warps_per_block + wib; w < n_list; w += gridDim.x * warps_per_block) {
+        const int64_t i = list[w];
+        __syncwarp();
+        if (lane < S) {
+            ys[lane] = (double)K[(int64_t)lane * n + i];
+            mus[lane] = mu_g[(int64_t)lane * n + i];
+        }
+        __syncwarp();
+        const bool use_prior = (prior_mean_disp != nullptr);
+        const double prior_mean = use_prior ? log(prior_mean_disp[i]) : 0.0;
+        const double maxDisp = fmax(10.0, (double)S);
+        const double lo = log(1e-8), hi = log(maxDisp);
+        const double step = (hi - lo) / (grid_len - 1);
+        double best_a = lo;
+        double from = lo, to = hi, by = step;
+        for (int level = 0; level < 2; level++) {
+            const double a = (lane == grid_len - 1) ? to : from + lane * by;
+            double v = -INFINITY;
+            if (lane < grid_len) v = eval_lp<P>(a, ys, mus, 1, S, prior_mean, prior_sigmasq, use_prior);
+            int idx = lane;
+            // arg max, first maximum wins
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+                if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+            }
+            best_a = (idx == grid_len - 1) ? to : from + idx * by;
+            if (level == 0) {
+                const double delta = (lo + step) - lo;
+                from = best_a - delta;
+                to = best_a + delta;
+                by = (to - from) / (grid_len - 1);
+            }
+        }
+        if (lane == 0) {
+            const double d = fmin(fmax(exp(best_a), kMinDisp), maxDisp);
+            disp_out[i] = d;
+            if (dispersion_out) dispersion_out[i] = (flags[i] & CD_FLAG_OUTLIER) ? dispGeneEst[i] : d;
+        }
+    }
+}
+
+cudaError_t launch_fit_disp_grid(int64_t n, int S, int p, const int32_t* n_list_dev, const int32_t* list,
+                                 const int32_t* K, const double* mu, const double* prior_mean_disp,
+                                 double prior_sigmasq, int grid_len, double* disp_out, double* dispersion_out,
+                                 const uint8_t* flags, const double* dispGeneEst, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    if (grid_len < 2 || grid_len > 32) return cudaErrorInvalidValue;
+    const int threads = 128, blocks = 148 * 4;
+#define CD_LAUNCH(P_)                                                                                          \
+    fit_disp_grid_kernel<P_><<<blocks, threads, 0, st>>>(n, S, n_list_dev, list, K, mu, prior_mean_disp,       \
+                                                         prior_sigmasq, grid_len, disp_out, dispersion_out,    \
+                                                         flags, dispGeneEst)
+    switch (p) {
+        case 1: CD_LAUNCH(1); break;
+        case 2: CD_LAUNCH(2); break;
+        case 3: CD_LAUNCH(3); break;
+        case 4: CD_LAUNCH(4); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef CD_LAUNCH
+    return cudaGetLastError();
+}
+
+}  // namespace cd

@@ -1,0 +1,84 @@
+// kernels.h -- host-callable launchers of the hand-written sm_100a kernels.
+// Every launcher enqueues on `st` and returns the cudaGetLastError() of its launches.
+// All pointers are device pointers; matrices are sample-major (see common.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace cd {
+
+// design constants live in __constant__ memory of each translation unit that needs them
+cudaError_t set_design_dispersion(const CdDesign& d, cudaStream_t st);
+cudaError_t set_design_wald(const CdDesign& d, cudaStream_t st);
+
+// ---- stage 1: aggregation (chicdiff.R:1540-1547) --------------------------------------
+cudaError_t launch_aggregate(int64_t n, int S, const int64_t* row_off, int64_t R,
+                             const int32_t* N_rows, const double* FM_rows,
+                             int32_t* K, double* FM, cudaStream_t st);
+
+// ---- size factors + stage 2: offsets (chicdiff.R:1561-1562, 1583-1589, 1635-1638) ------
+cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR /*S x n, +inf = excluded*/,
+                              cudaStream_t st);
+cudaError_t launch_norm_factors(int64_t n, int S, const double* FMagg, const double* sf /*S, device*/,
+                                int mode, double theta, double* nf, cudaStream_t st);
+
+// ---- deterministic reductions -----------------------------------------------------------
+// column sums of a sample-major S x n matrix over rows where mask[i]==0 (mask may be null);
+// out[s] (device, S doubles) and, if count != null, the number of unmasked rows
+cudaError_t launch_masked_colsums(int64_t n, int S, const double* M, const uint8_t* mask,
+                                  double* partial /*>= kReduceBlocks*(S+1)*/, double* out, cudaStream_t st);
+cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* out /*[0]=sum incl. NaN*/,
+                           cudaStream_t st);
+constexpr int kReduceBlocks = 592;      // 148 SMs x 4
+
+// ---- stage 4a: gene-wise dispersion -----------------------------------------------------
+cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf,
+                              double* baseMean, double* baseVar, double* rough, uint8_t* flags,
+                              cudaStream_t st);
+cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* nf,
+                             const double* baseMean, const double* baseVar, const double* rough,
+                             const uint8_t* flags, const double* xim_dev, double* alpha_init, double* mu,
+                             cudaStream_t st);
+// line search; prior_mean == null => no prior (gene-wise); log_alpha0 in/out
+cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu,
+                            const uint8_t* flags, const double* disp_init /*alpha scale*/,
+                            const double* prior_mean_disp /*alpha scale or null*/, double prior_sigmasq,
+                            double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
+                            cudaStream_t st);
+// post-processing of the gene-wise fit + compaction of rows needing the grid
+cudaError_t launch_gene_post(int64_t n, int S, const double* alpha_init, const double* log_alpha,
+                             const int32_t* iter, const double* initial_lp, const double* last_lp,
+                             uint8_t* flags, double* dispGeneEst, int32_t* refit_list, int32_t* refit_count,
+                             cudaStream_t st);
+cudaError_t launch_map_post(int64_t n, int S, const double* log_alpha, const int32_t* iter,
+                            const double* dispGeneEst, const double* dispFit, double outlier_thr,
+                            uint8_t* flags, double* dispMAP, double* dispersion,
+                            int32_t* refit_list, int32_t* refit_count, cudaStream_t st);
+// grid refit of listed rows, one warp per row; writes disp_out[row] (clamped) and, for MAP,
+// re-applies the outlier rule through dispersion_out
+cudaError_t launch_fit_disp_grid(int64_t n, int S, int p, const int32_t* n_list_dev, const int32_t* list,
+                                 const int32_t* K, const double* mu, const double* prior_mean_disp,
+                                 double prior_sigmasq, int grid_len, double* disp_out,
+                                 double* dispersion_out /*null for gene-wise*/, const uint8_t* flags,
+                                 const double* dispGeneEst, cudaStream_t st);
+
+// ---- stage 4b: trend ---------------------------------------------------------------------
+// one pass of the Gamma(identity) IRLS: at coefficients b, over rows with !allZero,
+// dispGeneEst > 1e-6 and residual ratio (w.r.t. outer coefs c) in (1e-4, 15):
+// out[0..4] = s00,s01,s11,t0,t1 ; out[5] = deviance ; out[6] = #invalid mu ; out[7] = #rows used
+cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* dispGeneEst,
+                              const uint8_t* flags, double c0, double c1, double b0, double b1,
+                              double* partial, double* out, cudaStream_t st);
+// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded
+cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst,
+                               const uint8_t* flags, double a0, double a1, double* dispFit, double* resid,
+                               cudaStream_t st);
+
+// ---- stages 3 + 5: NB GLM, Cook's, Wald --------------------------------------------------
+// also used for the IRLS-mu variant of the gene-wise step (mu_out != null => only mu is written)
+cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double* nf,
+                        const double* dispersion, uint8_t* flags,
+                        double* beta /*p x n, log2*/, double* betaSE, double* stat, double* pvalue,
+                        double* deviance, double* maxCooks, int32_t* betaIter, double* mu_out,
+                        cudaStream_t st);
+
+}  // namespace cd

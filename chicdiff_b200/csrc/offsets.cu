@@ -1,0 +1,219 @@
+// offsets.cu -- size factors, stage 2 (per-region normalisation offsets), the parametric
+// dispersion trend passes and the deterministic reductions they need.
+//
+//   chicdiff.R:1561-1562  estimateSizeFactors: log-ratio matrix (medians are taken by the host
+//                         orchestration after a device sort)
+//   chicdiff.R:1583-1589  FullMean scaling factors, rows with NA replaced by the size factors
+//   chicdiff.R:1614-1615, theta mix with the size factors and row geometric-mean rescale
+//              1635-1638
+//   DESeq2 parametricDispersionFit / dispersionFunction<-: Gamma(identity) IRLS sums, fitted
+//                         trend and log residuals
+//
+// All reductions are two-stage with a fixed block count and fixed summation order, so results
+// are bit-reproducible from run to run (no floating-point atomics).
+#include "kernels.h"
+
+namespace cd {
+
+static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* dst)
+{
+    __shared__ double sh[NV][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) sh[k][wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double x = 0.0;
+        const int nw = blockDim.x >> 5;
+        for (int w = 0; w < nw; w++) x += sh[threadIdx.x][w];
+        dst[threadIdx.x] = x;
+    }
+    __syncthreads();
+}
+
+// final stage: out[k] = sum_b partial[b*NVrt + k], b ascending
+__global__ void final_reduce_kernel(int nblocks, int nv, const double* __restrict__ partial, double* __restrict__ out)
+{
+    const int k = threadIdx.x;
+    if (k >= nv) return;
+    double x = 0.0;
+    for (int b = 0; b < nblocks; b++) x += partial[(size_t)b * nv + k];
+    out[k] = x;
+}
+
+// ---------------------------------------------------------------------------------------
+// masked column sums: out[s] = sum_i M[s][i] over rows with mask[i] == 0 ; out[S] = #rows
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+masked_colsums_kernel(int64_t n, int S, const double* __restrict__ M, const uint8_t* __restrict__ mask,
+                      double* __restrict__ partial)
+{
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
+    for (int s = 0; s <= S; s++) {
+        double v[1] = {0.0};
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const bool use = (mask == nullptr) || ((mask[i] & CD_FLAG_ALLZERO) == 0);
+            if (use) v[0] += (s < S) ? M[(int64_t)s * n + i] : 1.0;
+        }
+        block_reduce_store<1>(v, partial + (size_t)blockIdx.x * (S + 1) + s);
+    }
+}
+
+cudaError_t launch_masked_colsums(int64_t n, int S, const double* M, const uint8_t* mask, double* partial,
+                                  double* out, cudaStream_t st)
+{
+    masked_colsums_kernel<<<kReduceBlocks, 256, 0, st>>>(n, S, M, mask, partial);
+    final_reduce_kernel<<<1, 64, 0, st>>>(kReduceBlocks, S + 1, partial, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* out, cudaStream_t st)
+{
+    return launch_masked_colsums(n, 1, v, nullptr, partial, out, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// size factors: LR[s][i] = log K[s][i] - mean_s' log K[s'][i] for rows with every K > 0,
+// +inf otherwise (sorted to the end; the host reads the median of the finite prefix)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+log_ratios_kernel(int64_t n, int S, const int32_t* __restrict__ K, double* __restrict__ LR)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    bool ok = true;
+    for (int s = 0; s < S; s++) {
+        const int32_t k = K[(int64_t)s * n + i];
+        ok = ok && (k > 0);
+        acc += log((double)k);
+    }
+    const double lgm = acc / S;
+    for (int s = 0; s < S; s++)
+        LR[(int64_t)s * n + i] = ok ? log((double)K[(int64_t)s * n + i]) - lgm : INFINITY;
+}
+
+cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    log_ratios_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, LR);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 2: normalisation factors.  mode 0 standard, 1 fullmean, 2 combined(theta)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+norm_factors_kernel(int64_t n, int S, const double* __restrict__ FMagg, const double* __restrict__ sf,
+                    int mode, double theta, double* __restrict__ nf)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mode == 0) {
+        for (int s = 0; s < S; s++) nf[(int64_t)s * n + i] = sf[s];
+        return;
+    }
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) acc += log(FMagg[(int64_t)s * n + i]);
+    const double g = exp(acc / S);
+    bool anyna = false;
+    for (int s = 0; s < S; s++) {
+        const double m3 = FMagg[(int64_t)s * n + i] / g;
+        anyna = anyna || isnan(m3);
+    }
+    if (mode == 1) {
+        for (int s = 0; s < S; s++) nf[(int64_t)s * n + i] = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
+        return;
+    }
+    double acc2 = 0.0;
+    for (int s = 0; s < S; s++) {
+        const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
+        acc2 += log(m3 * (1.0 - theta) + sf[s] * theta);
+    }
+    const double g2 = exp(acc2 / S);
+    for (int s = 0; s < S; s++) {
+        const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
+        nf[(int64_t)s * n + i] = (m3 * (1.0 - theta) + sf[s] * theta) / g2;
+    }
+}
+
+cudaError_t launch_norm_factors(int64_t n, int S, const double* FMagg, const double* sf, int mode, double theta,
+                                double* nf, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    norm_factors_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, FMagg, sf, mode, theta, nf);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
+// parametric trend: one pass of glm.fit(family = Gamma(link = "identity")) at coefficients b
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+trend_pass_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
+                  const uint8_t* __restrict__ flags, double c0, double c1, double b0, double b1,
+                  double* __restrict__ partial)
+{
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (flags[i] & CD_FLAG_ALLZERO) continue;
+        const double d = dispGeneEst[i];
+        if (!(d > 100.0 * kMinDisp)) continue;
+        const double x = 1.0 / baseMean[i];
+        const double r = d / (c0 + c1 * x);
+        if (!((r > 1e-4) && (r < 15.0))) continue;
+        const double mu = b0 + b1 * x;
+        v[7] += 1.0;
+        if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; continue; }
+        const double w = 1.0 / (mu * mu);
+        v[0] += w; v[1] += w * x; v[2] += w * x * x;
+        v[3] += w * d; v[4] += w * x * d;
+        v[5] += -2.0 * (log(d / mu) - (d - mu) / mu);
+    }
+    block_reduce_store<8>(v, partial + (size_t)blockIdx.x * 8);
+}
+
+cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+                              double c0, double c1, double b0, double b1, double* partial, double* out,
+                              cudaStream_t st)
+{
+    trend_pass_kernel<<<kReduceBlocks, 256, 0, st>>>(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial);
+    final_reduce_kernel<<<1, 64, 0, st>>>(kReduceBlocks, 8, partial, out);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+trend_apply_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
+                   const uint8_t* __restrict__ flags, double a0, double a1, double* __restrict__ dispFit,
+                   double* __restrict__ resid)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] & CD_FLAG_ALLZERO) { dispFit[i] = NAN; resid[i] = INFINITY; return; }
+    const double f = a0 + a1 / baseMean[i];
+    const double d = dispGeneEst[i];
+    dispFit[i] = f;
+    resid[i] = (d >= 100.0 * kMinDisp) ? log(d) - log(f) : INFINITY;
+}
+
+cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+                               double a0, double a1, double* dispFit, double* resid, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, baseMean, dispGeneEst, flags, a0, a1, dispFit, resid);
+    return cudaGetLastError();
+}
+
+}  // namespace cd

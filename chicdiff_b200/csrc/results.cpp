@@ -1,0 +1,232 @@
+// results.cpp -- cd_results_adjust: the part of DESeq2 results() that Chicdiff's output table needs
+// (chicdiff.R:1721,1730,1739): Cook's-distance cutoff qf(.99, p, m - p) with the two-level-factor
+// heuristic, independent filtering on baseMean (50 quantile cut-offs, BH at each, lowess(f = 1/5)
+// threshold rule, alpha = 0.1) and the Benjamini-Hochberg adjusted p-values.
+// Global over all regions and O(n log n): host code, outside the five timed stages.
+#include "../../include/chicdiff_b200.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+namespace {
+
+double betacf(double a, double b, double x)
+{
+    const double tiny = 1e-300;
+    const double qab = a + b, qap = a + 1, qam = a - 1;
+    double c = 1, d = 1 - qab * x / qap;
+    if (std::fabs(d) < tiny) d = tiny;
+    d = 1 / d;
+    double h = d;
+    for (int m = 1; m <= 500; m++) {
+        const int m2 = 2 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1 + aa * d; if (std::fabs(d) < tiny) d = tiny;
+        c = 1 + aa / c; if (std::fabs(c) < tiny) c = tiny;
+        d = 1 / d; h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1 + aa * d; if (std::fabs(d) < tiny) d = tiny;
+        c = 1 + aa / c; if (std::fabs(c) < tiny) c = tiny;
+        d = 1 / d;
+        const double del = d * c;
+        h *= del;
+        if (std::fabs(del - 1) < 1e-16) break;
+    }
+    return h;
+}
+
+double pbeta(double x, double a, double b)
+{
+    if (x <= 0) return 0;
+    if (x >= 1) return 1;
+    const double bt = std::exp(std::lgamma(a + b) - std::lgamma(a) - std::lgamma(b) + a * std::log(x) + b * std::log1p(-x));
+    if (x < (a + 1) / (a + b + 2)) return bt * betacf(a, b, x) / a;
+    return 1 - bt * betacf(b, a, 1 - x) / b;
+}
+
+double qf(double prob, double df1, double df2)
+{
+    double lo = 0, hi = 1;
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (pbeta(mid, 0.5 * df1, 0.5 * df2) < prob) lo = mid; else hi = mid;
+    }
+    const double x = 0.5 * (lo + hi);
+    return (df2 * x) / (df1 * (1 - x));
+}
+
+// stats::lowess (Cleveland), x ascending
+void lowess(const std::vector<double>& x, const std::vector<double>& y, double f, int nsteps, double delta,
+            std::vector<double>& ys)
+{
+    const int n = (int)x.size();
+    ys.assign(n, 0.0);
+    if (n < 2) { if (n == 1) ys[0] = y[0]; return; }
+    std::vector<double> rw(n, 1.0), res(n, 0.0), w(n, 0.0);
+    const int ns = std::max(2, std::min(n, (int)(f * n + 1e-7)));
+    auto lowest = [&](double xs, int nleft, int nright, bool userw, double& out) -> bool {
+        const double range = x[n - 1] - x[0];
+        const double h = std::max(xs - x[nleft], x[nright] - xs);
+        const double h9 = .999 * h, h1 = .001 * h;
+        double a = 0.0;
+        int j = nleft;
+        while (j < n) {
+            w[j] = 0.0;
+            const double r = std::fabs(x[j] - xs);
+            if (r <= h9) {
+                if (r <= h1) w[j] = 1.0;
+                else { const double q = r / h; const double t = 1.0 - q * q * q; w[j] = t * t * t; }
+                if (userw) w[j] *= rw[j];
+                a += w[j];
+            } else if (x[j] > xs) break;
+            j++;
+        }
+        const int nrt = j - 1;
+        if (a <= 0.0) return false;
+        for (j = nleft; j <= nrt; j++) w[j] /= a;
+        if (h > 0.0) {
+            a = 0.0;
+            for (j = nleft; j <= nrt; j++) a += w[j] * x[j];
+            double b = xs - a, c = 0.0;
+            for (j = nleft; j <= nrt; j++) c += w[j] * (x[j] - a) * (x[j] - a);
+            if (std::sqrt(c) > .001 * range) {
+                b /= c;
+                for (j = nleft; j <= nrt; j++) w[j] *= (b * (x[j] - a) + 1.0);
+            }
+        }
+        out = 0.0;
+        for (j = nleft; j <= nrt; j++) out += w[j] * y[j];
+        return true;
+    };
+    for (int iter = 0; iter <= nsteps; iter++) {
+        int nleft = 0, nright = ns - 1, last = -1, i = 0;
+        while (true) {
+            if (nright < n - 1) {
+                const double d1 = x[i] - x[nleft], d2 = x[nright + 1] - x[i];
+                if (d1 > d2) { nleft++; nright++; continue; }
+            }
+            double v;
+            if (lowest(x[i], nleft, nright, iter > 0, v)) ys[i] = v; else ys[i] = y[i];
+            if (last < i - 1) {
+                const double denom = x[i] - x[last];
+                for (int j = last + 1; j < i; j++) {
+                    const double alpha = (x[j] - x[last]) / denom;
+                    ys[j] = alpha * ys[i] + (1.0 - alpha) * ys[last];
+                }
+            }
+            last = i;
+            const double cut = x[last] + delta;
+            for (i = last + 1; i < n; i++) {
+                if (x[i] > cut) break;
+                if (x[i] == x[last]) { ys[i] = ys[last]; last = i; }
+            }
+            i = std::max(last + 1, i - 1);
+            if (last >= n - 1) break;
+        }
+        for (int k = 0; k < n; k++) res[k] = y[k] - ys[k];
+        double sc = 0.0;
+        for (int k = 0; k < n; k++) sc += std::fabs(res[k]);
+        sc /= n;
+        if (iter >= nsteps) break;
+        for (int k = 0; k < n; k++) rw[k] = std::fabs(res[k]);
+        std::vector<double> srt(rw);
+        std::sort(srt.begin(), srt.end());
+        const int m1 = n / 2;
+        double cmad;
+        if (n % 2 == 0) { const int m2 = n - m1 - 1; cmad = 3.0 * (srt[m1] + srt[m2]); }
+        else cmad = 6.0 * srt[m1];
+        if (cmad < 1e-7 * sc) break;
+        const double c9 = .999 * cmad, c1 = .001 * cmad;
+        for (int k = 0; k < n; k++) {
+            const double r = std::fabs(res[k]);
+            if (r <= c1) rw[k] = 1.0;
+            else if (r <= c9) { const double q = r / cmad; rw[k] = (1.0 - q * q) * (1.0 - q * q); }
+            else rw[k] = 0.0;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const double* maxCooks,
+                                 const uint8_t* flags, double* pvalue, double* padj, double* scalars_out)
+{
+    if (n < 0 || S <= p || p < 1 || (n > 0 && (!baseMean || !pvalue || !padj))) return CD_EINVAL;
+    const double alpha = 0.1;
+    const double cutoff = qf(0.99, (double)p, (double)(S - p));
+    if (maxCooks) {
+        for (int64_t i = 0; i < n; i++) {
+            if (maxCooks[i] > cutoff) {                               // NaN compares false
+                const bool keep = flags && (flags[i] & CD_FLAG_COOKS_KEEP) && p == 2;
+                if (!keep) pvalue[i] = NAN;
+            }
+        }
+    }
+    // independent filtering
+    int64_t nzero = 0;
+    for (int64_t i = 0; i < n; i++) nzero += (baseMean[i] == 0.0);
+    const double lower = n > 0 ? (double)nzero / (double)n : 0.0;
+    const double upper = lower < .95 ? .95 : 1.0;
+    const int NT = 50;
+    std::vector<double> theta(NT), cut(NT);
+    for (int k = 0; k < NT; k++) theta[k] = (k == NT - 1) ? upper : lower + k * ((upper - lower) / (NT - 1));
+    std::vector<double> fs(baseMean, baseMean + n);
+    std::sort(fs.begin(), fs.end());
+    for (int k = 0; k < NT; k++) {
+        if (n == 0) { cut[k] = NAN; continue; }
+        const double index = (double)(n - 1) * theta[k];             // 0-based version of 1 + (n-1) p
+        const int64_t lo = (int64_t)std::floor(index), hi = (int64_t)std::ceil(index);
+        double q = fs[lo];
+        if (index > (double)lo && fs[hi] != q) {
+            const double h = index - (double)lo;
+            q = (1.0 - h) * q + h * fs[hi];
+        }
+        cut[k] = q;
+    }
+    // rows with a p-value, ascending by p (stable, so ties keep row order like R's order())
+    std::vector<int64_t> ord;
+    ord.reserve((size_t)n);
+    for (int64_t i = 0; i < n; i++) if (!std::isnan(pvalue[i])) ord.push_back(i);
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return pvalue[a] < pvalue[b]; });
+    std::vector<double> numRej(NT, 0.0);
+    for (int k = 0; k < NT; k++) {
+        int64_t m = 0;
+        for (int64_t i : ord) m += (baseMean[i] >= cut[k]);
+        int64_t rank = 0, best = 0;
+        for (int64_t i : ord) {
+            if (!(baseMean[i] >= cut[k])) continue;
+            rank++;
+            if ((double)m / (double)rank * pvalue[i] < alpha) best = rank;
+        }
+        numRej[k] = (double)best;
+    }
+    std::vector<double> lo_fit;
+    lowess(theta, numRej, 1.0 / 5.0, 3, 0.01 * (theta[NT - 1] - theta[0]), lo_fit);
+    int j = 0;
+    const double maxRej = *std::max_element(numRej.begin(), numRej.end());
+    if (maxRej > 10.0) {
+        double ss = 0.0; int cnt = 0;
+        for (int k = 0; k < NT; k++) if (numRej[k] > 0) { const double r = numRej[k] - lo_fit[k]; ss += r * r; cnt++; }
+        const double thresh = *std::max_element(lo_fit.begin(), lo_fit.end()) - std::sqrt(ss / cnt);
+        for (int k = 0; k < NT; k++) if (numRej[k] > thresh) { j = k; break; }
+    }
+    // BH at the chosen cut-off
+    for (int64_t i = 0; i < n; i++) padj[i] = NAN;
+    int64_t m = 0;
+    for (int64_t i : ord) m += (baseMean[i] >= cut[j]);
+    double running = INFINITY;
+    int64_t rank = m;
+    for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
+        const int64_t i = *it;
+        if (!(baseMean[i] >= cut[j])) continue;
+        const double v = (double)m / (double)rank * pvalue[i];
+        running = std::min(running, v);
+        padj[i] = std::min(1.0, running);
+        rank--;
+    }
+    if (scalars_out) {
+        scalars_out[0] = cutoff; scalars_out[1] = cut[j]; scalars_out[2] = theta[j]; scalars_out[3] = (double)(j + 1);
+    }
+    return CD_OK;
+}

@@ -1,0 +1,243 @@
+"""ctypes binding of libchicdiff_b200.so (include/chicdiff_b200.h).
+
+This is the Python stand-in for the R ``.Call`` glue (R/r_glue.c): it only marshals NumPy
+arrays to the C ABI.  There is no CPU implementation behind it: if the shared library or a
+CUDA device is missing every call raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libchicdiff_b200.so")
+_lib = None
+
+CD_NORM = {"standard": 0, "fullmean": 1, "combined": 2}
+FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLAG_GENE_NOINCREASE, FLAG_COOKS_KEEP = \
+    1, 2, 4, 8, 16, 32, 64
+
+EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init",
+            "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
+            "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
+            "cd_device_buffers", "cd_last_timings"]
+
+
+class ChicdiffError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("chicdiff_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CdOptions(C.Structure):
+    _fields_ = [("norm", C.c_int), ("theta", C.c_double), ("theta_grid", C.POINTER(C.c_double)),
+                ("n_theta_grid", C.c_int), ("disp_prior_var", C.c_double), ("disp_prior_var_grid", C.c_double),
+                ("disp_grid_len", C.c_int)]
+
+
+_RES_PTRS = ["baseMean", "baseVar", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "log2FoldChange", "lfcSE",
+             "beta", "betaSE", "stat", "pvalue", "deviance", "maxCooks", "normFactors", "mu",
+             "dispGeneIter", "dispIter", "betaIter", "flags"]
+
+
+class CdResults(C.Structure):
+    _fields_ = ([(k, C.c_void_p) for k in _RES_PTRS] +
+                [("sizeFactors", C.c_double * 32), ("theta", C.c_double), ("deviances", C.c_double * 16),
+                 ("n_deviances", C.c_int), ("trend_a0", C.c_double), ("trend_a1", C.c_double),
+                 ("varLogDispEsts", C.c_double), ("dispPriorVar", C.c_double), ("n_nonzero", C.c_int64),
+                 ("n_gene_grid", C.c_int64), ("n_map_grid", C.c_int64), ("n_beta_noconv", C.c_int64)])
+
+
+def load_library():
+    """Loads the in-tree shared library; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ChicdiffError(-2, "libchicdiff_b200.so is not built (run `python -m chicdiff_b200.build`); "
+                                "there is no CPU fallback")
+    L = C.CDLL(_LIB_PATH)
+    L.cd_version.restype = C.c_char_p
+    L.cd_last_error.restype = C.c_char_p
+    L.cd_last_error.argtypes = [C.c_void_p]
+    L.cd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.cd_destroy.argtypes = [C.c_void_p]
+    L.cd_destroy.restype = None
+    L.cd_comm_unique_id.argtypes = [C.c_void_p, C.c_char_p]
+    L.cd_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    L.cd_plan_shards.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.cd_set_design.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.cd_set_regions.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.cd_set_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_set_rows_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_set_aggregated.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_region_test.argtypes = [C.c_void_p, C.POINTER(CdOptions), C.POINTER(CdResults)]
+    L.cd_results_adjust.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]
+    L.cd_launch_count.argtypes = [C.c_void_p]
+    L.cd_launch_count.restype = C.c_int64
+    L.cd_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.cd_last_timings.argtypes = [C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def plan_shards(region_bait, row_off, nshards):
+    """Contiguous, bait-aligned, row-balanced partition of the regions (cd_plan_shards)."""
+    L = load_library()
+    region_bait = np.ascontiguousarray(region_bait, dtype=np.int32)
+    row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+    bounds = np.zeros(nshards + 1, np.int64)
+    rc = L.cd_plan_shards(len(region_bait), _ptr(region_bait), _ptr(row_off), nshards, _ptr(bounds))
+    if rc != 0:
+        raise ChicdiffError(rc, "cd_plan_shards: bad arguments")
+    return bounds
+
+
+def results_adjust(baseMean, maxCooks, flags, pvalue, S, p):
+    """DESeq2 results(): Cook's cutoff, independent filtering and BH (cd_results_adjust)."""
+    L = load_library()
+    baseMean = np.ascontiguousarray(baseMean, dtype=np.float64)
+    n = len(baseMean)
+    pv = np.array(pvalue, dtype=np.float64, copy=True)
+    mc = None if maxCooks is None else np.ascontiguousarray(maxCooks, dtype=np.float64)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
+    padj = np.empty(n, np.float64)
+    sc = np.zeros(4, np.float64)
+    rc = L.cd_results_adjust(n, S, p, _ptr(baseMean), _ptr(mc), _ptr(fl), _ptr(pv), _ptr(padj), _ptr(sc))
+    if rc != 0:
+        raise ChicdiffError(rc, "cd_results_adjust: bad arguments")
+    return dict(pvalue=pv, padj=padj, cooksCutoff=sc[0], filterThreshold=sc[1], filterTheta=sc[2], filterIndex=int(sc[3]))
+
+
+class Engine:
+    """One context = one GPU (cd_ctx)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.cd_create(C.byref(h), device)
+        if rc != 0:
+            raise ChicdiffError(rc, self._L.cd_last_error(None).decode())
+        self._h = h
+        self.S = self.p = None
+        self.n = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ChicdiffError(rc, self._L.cd_last_error(self._h).decode())
+
+    # -- multi-GPU -------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._check(self._L.cd_comm_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        self._check(self._L.cd_comm_init(self._h, nranks, rank, C.create_string_buffer(uid, 128)))
+
+    # -- setup ------------------------------------------------------------------------------
+    def set_design(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self.S, self.p = X.shape
+        self._check(self._L.cd_set_design(self._h, self.S, self.p, _ptr(X)))
+
+    def set_regions(self, row_off):
+        row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+        self.n = len(row_off) - 1
+        self._check(self._L.cd_set_regions(self._h, self.n, _ptr(row_off)))
+
+    def set_sample_rows(self, s, N, fullmean):
+        N = np.ascontiguousarray(N, dtype=np.int32)
+        fullmean = np.ascontiguousarray(fullmean, dtype=np.float64)
+        self._keep = [N, fullmean]        # the copy is asynchronous on the context's stream
+        self._check(self._L.cd_set_sample_rows(self._h, s, len(N), _ptr(N), _ptr(fullmean)))
+
+    def set_sample_rows_ptr(self, s, R, N_ptr, fm_ptr):
+        self._check(self._L.cd_set_sample_rows(self._h, s, R, C.c_void_p(N_ptr), C.c_void_p(fm_ptr)))
+
+    def set_rows_device(self, R, N_dev_ptr, fm_dev_ptr):
+        self._check(self._L.cd_set_rows_device(self._h, R, C.c_void_p(N_dev_ptr), C.c_void_p(fm_dev_ptr)))
+
+    def set_aggregated(self, K, fullmean):
+        K = np.ascontiguousarray(K, dtype=np.int32)
+        fullmean = np.ascontiguousarray(fullmean, dtype=np.float64)
+        self.n = K.shape[1]
+        self._check(self._L.cd_set_aggregated(self._h, self.n, _ptr(K), _ptr(fullmean)))
+
+    # -- stages -----------------------------------------------------------------------------
+    def aggregate(self, fetch=True):
+        if fetch:
+            K = np.empty((self.S, self.n), np.int32)
+            FM = np.empty((self.S, self.n), np.float64)
+            self._check(self._L.cd_aggregate(self._h, _ptr(K), _ptr(FM)))
+            return K, FM
+        self._check(self._L.cd_aggregate(self._h, None, None))
+        return None
+
+    def region_test(self, norm="combined", theta=None, theta_grid=None, disp_prior_var=None,
+                    disp_prior_var_grid=None, disp_grid_len=20, fetch="all"):
+        """cd_region_test.  fetch: "all" | "table" (columns of the output table only) | "none"."""
+        n, S, p = self.n, self.S, self.p
+        opt = CdOptions()
+        opt.norm = CD_NORM[norm]
+        opt.theta = float("nan") if theta is None else float(theta)
+        grid = None
+        if theta_grid is not None:
+            grid = np.ascontiguousarray(theta_grid, dtype=np.float64)
+            opt.theta_grid = grid.ctypes.data_as(C.POINTER(C.c_double))
+            opt.n_theta_grid = len(grid)
+        opt.disp_prior_var = float("nan") if disp_prior_var is None else float(disp_prior_var)
+        opt.disp_prior_var_grid = float("nan") if disp_prior_var_grid is None else float(disp_prior_var_grid)
+        opt.disp_grid_len = disp_grid_len
+        res = CdResults()
+        arrays = {}
+        shapes = dict(beta=(p, n), betaSE=(p, n), normFactors=(S, n), mu=(S, n))
+        dtypes = dict(dispGeneIter=np.int32, dispIter=np.int32, betaIter=np.int32, flags=np.uint8)
+        if fetch == "all":
+            want = _RES_PTRS
+        elif fetch == "table":
+            want = ["baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "maxCooks", "flags"]
+        else:
+            want = []
+        for k in want:
+            arrays[k] = np.empty(shapes.get(k, (n,)), dtypes.get(k, np.float64))
+            setattr(res, k, arrays[k].ctypes.data)
+        self._check(self._L.cd_region_test(self._h, C.byref(opt), C.byref(res)))
+        out = dict(arrays)
+        out["sizeFactors"] = np.array(res.sizeFactors[:S])
+        out["theta"] = None if res.theta != res.theta else res.theta
+        out["deviances"] = np.array(res.deviances[:res.n_deviances]) if res.n_deviances else None
+        for k in ("trend_a0", "trend_a1", "varLogDispEsts", "dispPriorVar", "n_nonzero", "n_gene_grid", "n_map_grid",
+                  "n_beta_noconv"):
+            out[k] = getattr(res, k)
+        return out
+
+    # -- introspection ------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._L.cd_launch_count(self._h))
+
+    def last_timings(self):
+        t = np.zeros(8, np.float64)
+        self._L.cd_last_timings(self._h, _ptr(t))
+        return t

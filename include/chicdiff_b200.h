@@ -1,0 +1,159 @@
+/*
+ * chicdiff_b200.h -- C ABI of libchicdiff_b200.so: the B200-native implementation of Chicdiff's
+ * region-test hot path (aggregation -> normalisation offsets -> NB GLM -> dispersion -> Wald).
+ *
+ * The reference (RegulatoryGenomicsGroup/chicdiff, Chicdiff/R/chicdiff.R) is pure R and exposes no
+ * FFI; the drop-in boundary is the numeric core of two exported R functions, which an R front
+ * end reaches through .Call -> R/r_glue.c -> the entry points below (INTEGRATION.md shows the
+ * binding):
+ *
+ *   DESeq2Wrap(chicdiff.settings, RU, FullRegionData, suffix, theta)       chicdiff.R:1494-1777
+ *     :1540-1547  by=(baitID, regionID, sample) sums of N and FullMean      -> cd_aggregate
+ *     :1561-1562  estimateSizeFactors                                       -> cd_region_test (sizeFactors)
+ *     :1583-1589, FullMean scaling factors, NA rows, theta mix, rescale     -> cd_region_test (norm, theta)
+ *      1614-1615, 1635-1638, 1666-1669
+ *     :1619-1662  theta grid: 5 intercept-only fits, argmin sum(deviance)   -> cd_region_test (theta = NaN)
+ *     :1573-1574, estimateDispersions + nbinomWaldTest                      -> cd_region_test
+ *      1602-1603, 1643-1644, 1673-1674
+ *     :1721,1730,1739  results(): Cook's cutoff, independent filtering, BH  -> cd_results_adjust
+ *   getFullRegionData(chicdiff.settings, RU, RUcontrol, suffix)            chicdiff.R:1460-1478
+ *     supplies the per-row N / FullMean columns                            -> cd_set_sample_rows
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only.  Every function returns 0 on success or a negative
+ *     CD_E* code; cd_last_error() returns a message.  Nothing aborts or throws across the ABI,
+ *     and there is no CPU fallback: without a CUDA device every compute call fails with CD_ECUDA.
+ *   - Host buffers are owned by the caller; the library owns its device memory inside cd_ctx.
+ *     Calls are synchronous unless the name says otherwise.
+ *   - Matrices are "sample-major" = R's column-major n x S layout: element (region i, sample s)
+ *     at [s*n + i].  An R numeric/integer matrix can be passed without transposition.
+ *   - NA: integer NA is INT32_MIN (R's NA_integer_); floating NA is any NaN (R's NA_real_ is a
+ *     NaN; is.na() is true for both).  All-zero regions get NaN in every output column, as in
+ *     DESeq2.
+ *   - One context drives one GPU.  For several GPUs run one process per GPU, shard the regions
+ *     by bait (cd_plan_shards) and join the contexts with cd_comm_init; the few global steps
+ *     (size-factor medians, dispersion trend, theta-grid deviances) then use NCCL over NVLink.
+ */
+#ifndef CHICDIFF_B200_H
+#define CHICDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cd_ctx cd_ctx;
+
+#define CD_OK 0
+#define CD_EINVAL (-1)      /* bad argument / call order */
+#define CD_ECUDA (-2)       /* CUDA runtime error (message has the CUDA error string) */
+#define CD_ENOMEM (-3)
+#define CD_ECOMM (-4)       /* NCCL error / NCCL not loadable */
+#define CD_ENUMERIC (-5)    /* numerical failure the reference also stops on, or a reference fallback
+                               that is not implemented (local dispersion fit, Monte-Carlo prior) */
+
+/* per-region status bits returned in cd_results.flags */
+#define CD_FLAG_ALLZERO 1
+#define CD_FLAG_GENE_GRID 2
+#define CD_FLAG_MAP_GRID 4
+#define CD_FLAG_BETA_NOCONV 8
+#define CD_FLAG_OUTLIER 16
+#define CD_FLAG_GENE_NOINCREASE 32
+#define CD_FLAG_COOKS_KEEP 64
+
+#define CD_NORM_STANDARD 0
+#define CD_NORM_FULLMEAN 1
+#define CD_NORM_COMBINED 2
+
+const char* cd_version(void);
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int cd_create(cd_ctx** out, int device);
+void cd_destroy(cd_ctx* ctx);
+const char* cd_last_error(const cd_ctx* ctx);      /* ctx may be NULL: last error of cd_create */
+
+/* ---- multi-GPU: one process per GPU, NCCL communicator over NVLink --------------------- */
+/* rank 0 calls cd_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ * (the Python host uses torch.distributed); every rank then calls cd_comm_init. */
+int cd_comm_unique_id(cd_ctx* ctx, char id[128]);
+int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128]);
+/* contiguous bait-balanced partition of regions (region_bait must be non-decreasing):
+ * shard k owns regions [bounds[k], bounds[k+1]); cuts fall only between baits and balance rows. */
+int cd_plan_shards(int64_t n, const int32_t* region_bait, const int64_t* row_off, int nshards,
+                   int64_t* bounds /* nshards + 1 */);
+
+/* ---- problem setup ---------------------------------------------------------------------- */
+/* design: model.matrix of the reference's `~ condition` (chicdiff.R:1559) or `~ batch + condition`;
+ * X is S x p row-major, column 0 the intercept, the LAST column the tested coefficient. */
+int cd_set_design(cd_ctx* ctx, int S, int p, const double* X);
+/* regions as CSR segments over region-contiguous rows (sorted by regionID, then otherEndID) */
+int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off /* n + 1 */);
+/* per-replicate columns of the long table: N (chicdiff.R:853) and FullMean = Bmean + Tmean
+ * (chicdiff.R:896), R = row_off[n] rows, host pointers (copied to the device) */
+int cd_set_sample_rows(cd_ctx* ctx, int s, int64_t R, const int32_t* N, const double* fullmean);
+/* same, but the pointers are device pointers holding ALL samples sample-major (S x R); the
+ * context borrows them (no copy) until the next cd_set_regions / cd_destroy */
+int cd_set_rows_device(cd_ctx* ctx, int64_t R, const int32_t* N_dev, const double* fullmean_dev);
+/* skip stage 1: provide already aggregated matrices (host, sample-major S x n) */
+int cd_set_aggregated(cd_ctx* ctx, int64_t n, const int32_t* K, const double* fullmean);
+
+/* ---- stage 1 ----------------------------------------------------------------------------- */
+/* K_out / fullmean_out: host S x n sample-major, either may be NULL (results stay on the device) */
+int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out);
+
+/* ---- stages 2-5 -------------------------------------------------------------------------- */
+typedef struct {
+    int norm;                    /* CD_NORM_*; reference default "combined" */
+    double theta;                /* NaN = choose on theta_grid by minimum total deviance */
+    const double* theta_grid;    /* NULL = {0, .25, .5, .75, 1} */
+    int n_theta_grid;
+    double disp_prior_var;       /* NaN = estimate (closed form needs S - p > 3) */
+    double disp_prior_var_grid;  /* same for the intercept-only theta-grid fits (needs S - 1 > 3) */
+    int disp_grid_len;           /* fitDispGrid length; 0 = 20 */
+} cd_options;
+
+typedef struct {
+    /* per region, length n, host, any pointer may be NULL */
+    double* baseMean; double* baseVar;
+    double* dispGeneEst; double* dispFit; double* dispMAP; double* dispersion;
+    double* log2FoldChange; double* lfcSE;      /* tested (last) coefficient */
+    double* beta; double* betaSE;               /* all coefficients, p x n, log2 scale */
+    double* stat; double* pvalue; double* deviance; double* maxCooks;
+    double* normFactors;                        /* S x n, the offsets used by the final fit */
+    double* mu;                                 /* S x n, fitted means of the gene-wise step */
+    int32_t* dispGeneIter; int32_t* dispIter; int32_t* betaIter;
+    uint8_t* flags;
+    /* scalars, filled by the call */
+    double sizeFactors[32];
+    double theta;                               /* NaN when norm != combined */
+    double deviances[16];                       /* theta-grid total deviances */
+    int n_deviances;
+    double trend_a0, trend_a1;                  /* asymptDisp, extraPois */
+    double varLogDispEsts, dispPriorVar;
+    int64_t n_nonzero, n_gene_grid, n_map_grid, n_beta_noconv;
+} cd_results;
+
+/* DESeq2Wrap numerics on the aggregated matrices of this context (this rank's shard) */
+int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out);
+
+/* results(): Cook's cutoff (+ two-level-factor heuristic via CD_FLAG_COOKS_KEEP), independent
+ * filtering on baseMean (alpha = 0.1), BH.  Global over all regions: in a sharded run gather
+ * first.  pvalue is updated in place (outliers -> NaN); padj is written.  scalars_out (may be
+ * NULL) receives {cooksCutoff, filterThreshold, filterTheta, filterIndex(1-based)}. */
+int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const double* maxCooks,
+                      const uint8_t* flags, double* pvalue, double* padj, double* scalars_out);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* number of kernel launches issued by this context since creation */
+int64_t cd_launch_count(const cd_ctx* ctx);
+/* device pointers of the aggregated matrices (S x n): for device-resident pipelines */
+int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmean_dev);
+/* time of the last cd_aggregate / cd_region_test kernels in ms, measured with CUDA events on the
+ * context's stream: [0] aggregate, [1] region_test total, [2] fit_disp kernels, [3] wald kernels */
+int cd_last_timings(const cd_ctx* ctx, double out_ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,331 @@
+"""ctypes front end of the CPU oracle (oracle/chicdiff_oracle.c) plus the NumPy restatement
+of DESeq2 ``results()`` (Cook's cutoff, independent filtering, BH).
+
+TEST INFRASTRUCTURE -- see the header of chicdiff_oracle.c.  PARITY UNPINNED at the DESeq2
+boundary; pinned pieces are listed there.  Imported only by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLAG_GENE_NOINCREASE = 1, 2, 4, 8, 16, 32
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        d = C.c_double
+        for name, nargs in [("orc_lgamma", 1), ("orc_digamma", 1), ("orc_trigamma", 1), ("orc_wald_pvalue", 1)]:
+            getattr(L, name).restype = d
+            getattr(L, name).argtypes = [d] * nargs
+        L.orc_dnbinom_mu_log.restype = d
+        L.orc_dnbinom_mu_log.argtypes = [d, d, d]
+        L.orc_qf.restype = d
+        L.orc_qf.argtypes = [d, d, d]
+        for name in ("orc_log_posterior", "orc_dlog_posterior"):
+            f = getattr(L, name)
+            f.restype = d
+            f.argtypes = [d, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, d, d, C.c_int, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _OrcOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in (
+        "baseMean", "baseVar", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "beta", "betaSE",
+        "stat", "pvalue", "deviance", "maxCooks", "mu", "H", "cooks", "dispGeneIter", "dispIter",
+        "betaIter", "allZero", "dispOutlier", "betaConv", "flags", "scalars")]
+
+
+def aggregate(row_off, N_rows, FM_rows):
+    """row_off int64[n+1]; N_rows int32[S, R]; FM_rows float64[S, R] -> K int32[S, n], FM float64[S, n]."""
+    row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+    N_rows = np.ascontiguousarray(N_rows, dtype=np.int32)
+    FM_rows = np.ascontiguousarray(FM_rows, dtype=np.float64)
+    S, R = N_rows.shape
+    n = len(row_off) - 1
+    K = np.empty((S, n), np.int32)
+    FM = np.empty((S, n), np.float64)
+    rc = lib().orc_aggregate(C.c_int64(n), C.c_int(S), _p(row_off), C.c_int64(R), _p(N_rows), _p(FM_rows), _p(K), _p(FM))
+    assert rc == 0
+    return K, FM
+
+
+def size_factors(K):
+    K = np.ascontiguousarray(K, dtype=np.int32)
+    S, n = K.shape
+    sf = np.empty(S, np.float64)
+    rc = lib().orc_size_factors(C.c_int64(n), C.c_int(S), _p(K), _p(sf))
+    if rc != 0:
+        raise ValueError("every gene contains at least one zero, cannot compute log geometric means")
+    return sf
+
+
+NORM_MODES = {"standard": 0, "fullmean": 1, "combined": 2}
+
+
+def norm_factors(FMagg, sf, norm, theta=0.0):
+    FMagg = np.ascontiguousarray(FMagg, dtype=np.float64)
+    sf = np.ascontiguousarray(sf, dtype=np.float64)
+    S, n = FMagg.shape
+    nf = np.empty((S, n), np.float64)
+    lib().orc_norm_factors(C.c_int64(n), C.c_int(S), _p(FMagg), _p(sf), C.c_int(NORM_MODES[norm]),
+                           C.c_double(theta), _p(nf))
+    return nf
+
+
+def deseq(K, nf, X, prior_var=float("nan"), grid_n=20, nthreads=0):
+    """estimateDispersions + nbinomWaldTest.  K int32[S,n], nf float64[S,n], X float64[S,p]."""
+    K = np.ascontiguousarray(K, dtype=np.int32)
+    nf = np.ascontiguousarray(nf, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    S, n = K.shape
+    p = X.shape[1]
+    f8 = lambda *sh: np.full(sh, np.nan, np.float64)
+    res = dict(
+        baseMean=f8(n), baseVar=f8(n), dispGeneEst=f8(n), dispFit=f8(n), dispMAP=f8(n), dispersion=f8(n),
+        beta=f8(p, n), betaSE=f8(p, n), stat=f8(n), pvalue=f8(n), deviance=f8(n), maxCooks=f8(n),
+        mu=f8(S, n), H=f8(S, n), cooks=f8(S, n),
+        dispGeneIter=np.zeros(n, np.int32), dispIter=np.zeros(n, np.int32), betaIter=np.zeros(n, np.int32),
+        allZero=np.zeros(n, np.uint8), dispOutlier=np.zeros(n, np.uint8), betaConv=np.zeros(n, np.uint8),
+        flags=np.zeros(n, np.uint8), scalars=f8(16))
+    out = _OrcOut(**{k: _p(v) for k, v in res.items()})
+    rc = lib().orc_deseq(C.c_int64(n), C.c_int(S), C.c_int(p), _p(X), _p(K), _p(nf), C.c_double(prior_var),
+                         C.c_int(grid_n), C.c_int(nthreads), C.byref(out))
+    res["rc"] = rc
+    sc = res["scalars"]
+    res.update(trend_a0=sc[0], trend_a1=sc[1], varLogDispEsts=sc[2], dispPriorVar=sc[3], trend_status=int(sc[4]) if sc[4] == sc[4] else -1,
+               lp_evals=sc[8], dlp_evals=sc[9], irls_iters=sc[10], sum_deviance=sc[11], n_nonzero=sc[12])
+    if rc != 0:
+        raise RuntimeError({-1: "bad design (S<=p or too large)", -2: "S-p<=3 needs dispPriorVar (Monte-Carlo path not restated)",
+                            -3: "parametric dispersion trend failed (local fit not restated)"}.get(rc, "rc=%d" % rc))
+    return res
+
+
+def region_test(K, FMagg, X, norm="combined", theta=None, theta_grid=(0, .25, .5, .75, 1), prior_var=float("nan"),
+                prior_var_grid=float("nan"), nthreads=0):
+    """DESeq2Wrap numerics (chicdiff.R:1551-1674): size factors, offsets, theta grid, final fit."""
+    S, n = K.shape
+    sf = size_factors(K)
+    out = {"sizeFactors": sf, "deviances": None}
+    if norm == "combined" and theta is not None:
+        if theta == 1:
+            norm = "standard"
+        elif theta == 0:
+            norm = "fullmean"
+    if norm == "combined" and theta is None:
+        devs = []
+        X1 = np.ones((S, 1))
+        for tt in theta_grid:
+            nf = norm_factors(FMagg, sf, "combined", tt)
+            r = deseq(K, nf, X1, prior_var=prior_var_grid, nthreads=nthreads)
+            devs.append(r["sum_deviance"])
+        devs = np.asarray(devs)
+        out["deviances"] = devs
+        if np.any(np.isnan(devs)):
+            raise ValueError("theta grid: NA deviance (all-zero region present; chicdiff.R:1647 has no na.rm)")
+        w = np.flatnonzero(devs == devs.min())
+        if len(w) != 1:
+            raise ValueError("theta grid: tied minimum")
+        theta = float(theta_grid[w[0]])
+    out["theta"] = theta
+    nf = norm_factors(FMagg, sf, norm, 0.0 if theta is None else theta)
+    out["nf"] = nf
+    out.update(deseq(K, nf, X, prior_var=prior_var, nthreads=nthreads))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# DESeq2 results(): Cook's cutoff, independent filtering (genefilter::filtered_p + lowess), BH.
+# Pinned by tests/test_golden.py against the shipped golden table.
+# ---------------------------------------------------------------------------------------------
+
+def p_adjust_bh(p):
+    p = np.asarray(p, dtype=np.float64)
+    out = np.full(p.shape, np.nan)
+    ok = ~np.isnan(p)
+    pv = p[ok]
+    m = len(pv)
+    if m == 0:
+        return out
+    o = np.argsort(-pv, kind="stable")          # decreasing
+    ranks = np.arange(m, 0, -1)
+    adj = np.minimum(1.0, np.minimum.accumulate(m / ranks * pv[o]))
+    res = np.empty(m)
+    res[o] = adj
+    out[ok] = res
+    return out
+
+
+def quantile7(x, probs):
+    xs = np.sort(np.asarray(x, dtype=np.float64))
+    n = len(xs)
+    h = (n - 1) * np.asarray(probs, dtype=np.float64)
+    lo = np.floor(h + 4 * np.finfo(float).eps).astype(np.int64)     # R's fuzz
+    lo = np.clip(lo, 0, n - 1)
+    hi = np.clip(lo + 1, 0, n - 1)
+    frac = h - lo
+    frac = np.where(np.abs(frac) < 4 * np.finfo(float).eps, 0.0, frac)
+    return xs[lo] + frac * (xs[hi] - xs[lo])
+
+
+def lowess(x, y, f=2.0 / 3.0, nsteps=3, delta=None):
+    """Cleveland's lowess as in R stats::lowess (x must be sorted ascending)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(x)
+    if delta is None:
+        delta = 0.01 * (x[-1] - x[0])
+    ys = np.zeros(n)
+    rw = np.ones(n)
+    res = np.zeros(n)
+    if n < 2:
+        return y.copy()
+    ns = max(2, min(n, int(f * n + 1e-7)))
+
+    def lowest(xs, nleft, nright, userw):
+        rng = x[n - 1] - x[0]
+        h = max(xs - x[nleft], x[nright] - xs)
+        h9, h1 = .999 * h, .001 * h
+        w = np.zeros(n)
+        a = 0.0
+        j = nleft
+        while j < n:
+            r = abs(x[j] - xs)
+            if r <= h9:
+                w[j] = 1.0 if r <= h1 else (1.0 - (r / h) ** 3) ** 3
+                if userw:
+                    w[j] *= rw[j]
+                a += w[j]
+            elif x[j] > xs:
+                break
+            j += 1
+        nrt = j - 1
+        if a <= 0:
+            return None
+        w[nleft:nrt + 1] /= a
+        if h > 0:
+            a = float(np.sum(w[nleft:nrt + 1] * x[nleft:nrt + 1]))
+            b = xs - a
+            c = float(np.sum(w[nleft:nrt + 1] * (x[nleft:nrt + 1] - a) ** 2))
+            if np.sqrt(c) > .001 * rng:
+                b /= c
+                w[nleft:nrt + 1] *= (b * (x[nleft:nrt + 1] - a) + 1.0)
+        return float(np.sum(w[nleft:nrt + 1] * y[nleft:nrt + 1]))
+
+    for it in range(nsteps + 1):
+        nleft, nright, last, i = 0, ns - 1, -1, 0
+        while True:
+            if nright < n - 1:
+                d1 = x[i] - x[nleft]
+                d2 = x[nright + 1] - x[i]
+                if d1 > d2:
+                    nleft += 1
+                    nright += 1
+                    continue
+            v = lowest(x[i], nleft, nright, it > 0)
+            ys[i] = y[i] if v is None else v
+            if last < i - 1:
+                denom = x[i] - x[last]
+                for j in range(last + 1, i):
+                    alpha = (x[j] - x[last]) / denom
+                    ys[j] = alpha * ys[i] + (1.0 - alpha) * ys[last]
+            last = i
+            cut = x[last] + delta
+            i = last + 1
+            while i < n:
+                if x[i] > cut:
+                    break
+                if x[i] == x[last]:
+                    ys[i] = ys[last]
+                    last = i
+                i += 1
+            i = max(last + 1, i - 1)
+            if last >= n - 1:
+                break
+        res = y - ys
+        sc = np.sum(np.abs(res)) / n
+        if it >= nsteps:
+            break
+        rw = np.abs(res)
+        srt = np.sort(rw)
+        m1 = n // 2
+        if n % 2 == 0:
+            m2 = n - m1 - 1
+            cmad = 3.0 * (srt[m1] + srt[m2])
+        else:
+            cmad = 6.0 * srt[m1]
+        if cmad < 1e-7 * sc:
+            break
+        c9, c1 = .999 * cmad, .001 * cmad
+        r = np.abs(res)
+        rw = np.where(r <= c1, 1.0, np.where(r <= c9, (1.0 - (r / cmad) ** 2) ** 2, 0.0))
+    return ys
+
+
+def independent_filtering(base_mean, pvalue, alpha=0.1):
+    """DESeq2 pvalueAdjustment (independentFiltering=TRUE, filter=baseMean).  Returns dict."""
+    flt = np.asarray(base_mean, dtype=np.float64)
+    p = np.asarray(pvalue, dtype=np.float64)
+    lower = np.mean(flt == 0)
+    upper = .95 if lower < .95 else 1.0
+    theta = np.linspace(lower, upper, 50)
+    cut = quantile7(flt, theta)
+    padj_mat = np.full((len(p), 50), np.nan)
+    for k in range(50):
+        use = flt >= cut[k]
+        if use.any():
+            padj_mat[use, k] = p_adjust_bh(p[use])
+    with np.errstate(invalid="ignore"):
+        num_rej = np.sum(padj_mat < alpha, axis=0)
+    lo = lowess(theta, num_rej.astype(np.float64), f=1 / 5)
+    if num_rej.max() <= 10:
+        j = 0
+    else:
+        pos = num_rej > 0
+        resid = num_rej[pos] - lo[pos]
+        thresh = lo.max() - np.sqrt(np.mean(resid ** 2))
+        w = np.flatnonzero(num_rej > thresh)
+        j = int(w[0]) if len(w) else 0
+    return dict(padj=padj_mat[:, j], j=j, theta=theta[j], cutoff=cut[j], num_rej=num_rej, lowess=lo)
+
+
+def results(res, K, X, alpha=0.1):
+    """DESeq2 results() defaults on the output of deseq(): Cook's outlier NA + independent filtering."""
+    S, n = K.shape
+    p = X.shape[1]
+    pvalue = res["pvalue"].copy()
+    max_cooks = res["maxCooks"]
+    cutoff = lib().orc_qf(0.99, float(p), float(S - p))
+    with np.errstate(invalid="ignore"):
+        outlier = max_cooks > cutoff
+    # two-level single-factor heuristic: keep rows where >= 3 counts exceed the max-Cook's sample's count
+    two_level = (p == 2 and set(np.unique(X[:, 0])) == {1.0} and len(np.unique(X[:, 1])) == 2)
+    if outlier.any() and two_level:
+        idx = np.flatnonzero(outlier)
+        worst = np.argmax(res["cooks"][:, idx], axis=0)
+        out_count = K[worst, idx]
+        keep = (K[:, idx] > out_count[None, :]).sum(axis=0) >= 3
+        outlier[idx[keep]] = False
+    pvalue[outlier] = np.nan
+    f = independent_filtering(res["baseMean"], pvalue, alpha)
+    return dict(baseMean=res["baseMean"], log2FoldChange=res["beta"][p - 1], lfcSE=res["betaSE"][p - 1],
+                stat=res["stat"], pvalue=pvalue, padj=f["padj"], cooksCutoff=cutoff, cooksOutlier=outlier,
+                filterThreshold=f["cutoff"], filterTheta=f["theta"], filterIndex=f["j"])
