@@ -119,6 +119,20 @@ __global__ void xim_kernel(int S, const double* __restrict__ sums, double* __res
     }
 }
 
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double m, double* __restrict__ sink)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double c = 1e-9;
+#pragma unroll 16
+    for (int k = 0; k < iters; k++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) *sink = r;
+}
+
 __global__ void count_finite_kernel(int64_t n, const double* __restrict__ v, unsigned long long* __restrict__ cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,6 +220,31 @@ struct cd_ctx {
     std::vector<int64_t> shard_n, shard_off;
     int64_t n_tot = 0, g_off = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_user[2] = {nullptr, nullptr};
+    // per-section device timing: pairs of events recorded around launches, summed after the final sync
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_slot;            // section of pair k
+    size_t ev_used = 0;
+    void tm_begin(int slot)
+    {
+        if (ev_used + 2 > ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            ev_pool.push_back(a); ev_pool.push_back(b);
+            ev_slot.push_back(slot);
+        }
+        ev_slot[ev_used / 2] = slot;
+        cudaEventRecord(ev_pool[ev_used], st);
+    }
+    void tm_end() { cudaEventRecord(ev_pool[ev_used + 1], st); ev_used += 2; }
+    void tm_collect()
+    {
+        for (size_t k = 0; k < ev_used; k += 2) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[k], ev_pool[k + 1]) == cudaSuccess) timings[ev_slot[k / 2]] += ms;
+        }
+        ev_used = 0;
+    }
 
     int fail(int code, const char* fmt, ...)
     {
@@ -268,6 +307,7 @@ int cd_create(cd_ctx** out, int device)
         return CD_ECUDA;
     }
     for (int k = 0; k < 4; k++) cudaEventCreate(&c->ev[k]);
+    for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev_user[k]);
     *out = c;
     return CD_OK;
 }
@@ -278,6 +318,8 @@ void cd_destroy(cd_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 2; k++) if (ctx->ev_user[k]) cudaEventDestroy(ctx->ev_user[k]);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStream_t st = ctx->st;
     delete ctx;
@@ -586,12 +628,16 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
         CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->alpha_init.p, flags, nullptr, nullptr, nullptr, nullptr,
                                        nullptr, nullptr, nullptr, ctx->mu.p, st));
     }
+    ctx->tm_begin(2);
     CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
                                        ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    ctx->tm_end();
     CD_LAUNCHN(ctx, 1, launch_gene_post(n, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
                                         ctx->last_lp.p, flags, dispGeneEst, ctx->refit_list.p, ctx->refit_count.p, st));
+    ctx->tm_begin(4);
     CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, nullptr, 1.0,
                                             grid_len, dispGeneEst, nullptr, flags, dispGeneEst, st));
+    ctx->tm_end();
     if (ctx->comm.active()) {
         CD_COMM(ctx, ctx->comm.allgatherv(baseMean, ctx->g_baseMean.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
         CD_COMM(ctx, ctx->comm.allgatherv(dispGeneEst, ctx->g_dispGeneEst.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
@@ -599,6 +645,7 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     }
     // trend + MAD on the global arrays (every rank computes the same numbers)
     double coefs[2];
+    ctx->tm_begin(5);
     int rc = trend_fit(ctx, coefs);
     if (rc != CD_OK) return rc;
     CD_LAUNCHN(ctx, 1, launch_trend_apply(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, coefs[0], coefs[1],
@@ -613,6 +660,7 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     }
     rc = median_finite(ctx, ctx->g_sortbuf2.p, nt, ctx->scal.p + 45, 0, 1.4826);
     if (rc != CD_OK) return rc;
+    ctx->tm_end();
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaStreamSynchronize(st));
     const double mad = ctx->h_pinned[0];
@@ -624,16 +672,22 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
 
     // MAP
+    ctx->tm_begin(2);
     CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, dispGeneEst, dispFit, dispPriorVar, ctx->log_alpha.p,
                                        ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    ctx->tm_end();
     CD_LAUNCHN(ctx, 1, launch_map_post(n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, 2.0 * sqrt(varLogDispEsts),
                                        flags, ctx->dispMAP.p, ctx->dispersion.p, ctx->refit_list.p, ctx->refit_count.p, st));
+    ctx->tm_begin(4);
     CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, dispFit,
                                             dispPriorVar, grid_len, ctx->dispMAP.p, ctx->dispersion.p, flags, dispGeneEst, st));
+    ctx->tm_end();
     // NB GLM + Wald
+    ctx->tm_begin(3);
     CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->dispersion.p, flags, ctx->beta.p, ctx->betaSE.p, ctx->stat.p,
                                    ctx->pvalue.p, ctx->deviance.p, want_cooks ? ctx->maxCooks.p : nullptr, ctx->betaIter.p,
                                    nullptr, st));
+    ctx->tm_end();
     CD_LAUNCHN(ctx, 2, launch_sum_nan(n, ctx->deviance.p, ctx->partial.p, ctx->scal.p + 46, st));
     CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + 46, 1, st));
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 46, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -676,6 +730,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     ctx->n_tot = tot;
     ctx->g_off = ctx->shard_off[(size_t)ctx->comm.rank];
     if (tot > 2147483647LL) return ctx->fail(CD_EINVAL, "more than 2^31-1 regions in total");
+    if (tot < 1) return ctx->fail(CD_EINVAL, "cd_region_test: no regions");
 
     const size_t sn = (size_t)S * (size_t)n;
     CD_CUDA(ctx, ctx->nf.ensure(sn));
@@ -699,8 +754,12 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
 
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     memset(out->sizeFactors, 0, sizeof(out->sizeFactors));
+    for (int k = 2; k < 8; k++) ctx->timings[k] = 0.0;
+    ctx->ev_used = 0;
+    ctx->tm_begin(6);
     int rc = size_factors(ctx, out->sizeFactors);
     if (rc != CD_OK) return rc;
+    ctx->tm_end();
 
     int norm = opt->norm;
     double theta = opt->theta;
@@ -776,10 +835,52 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
     ctx->timings[1] = ms;
+    ctx->tm_collect();
     return CD_OK;
 }
 
 int64_t cd_launch_count(const cd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cd_timer_start(cd_ctx* ctx)
+{
+    if (!ctx) return CD_EINVAL;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev_user[0], ctx->st));
+    return CD_OK;
+}
+
+int cd_timer_stop(cd_ctx* ctx, double* ms_out)
+{
+    if (!ctx || !ms_out) return CD_EINVAL;
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev_user[1], ctx->st));
+    CD_CUDA(ctx, cudaEventSynchronize(ctx->ev_user[1]));
+    float ms = 0;
+    CD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_user[0], ctx->ev_user[1]));
+    *ms_out = ms;
+    return CD_OK;
+}
+
+int cd_measure_fp64_peak(cd_ctx* ctx, double* tflops_out)
+{
+    if (!ctx || !tflops_out) return CD_EINVAL;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->scal.ensure(128));
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CD_CUDA(ctx, cudaEventRecord(ctx->ev_user[0], ctx->st));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->st>>>(iters, 1.0000001, ctx->scal.p + 100);
+        ctx->launches++;
+        CD_CUDA(ctx, cudaEventRecord(ctx->ev_user[1], ctx->st));
+        CD_CUDA(ctx, cudaEventSynchronize(ctx->ev_user[1]));
+        float ms = 0;
+        CD_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_user[0], ctx->ev_user[1]));
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops_out = best;
+    return CD_OK;
+}
 
 int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmean_dev)
 {

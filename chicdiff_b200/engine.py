@@ -19,7 +19,7 @@ FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLA
 EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
-            "cd_device_buffers", "cd_last_timings"]
+            "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak"]
 
 
 class ChicdiffError(RuntimeError):
@@ -78,6 +78,9 @@ def load_library():
     L.cd_launch_count.restype = C.c_int64
     L.cd_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.cd_last_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.cd_timer_start.argtypes = [C.c_void_p]
+    L.cd_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.cd_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -236,6 +239,19 @@ class Engine:
     # -- introspection ------------------------------------------------------------------------
     def launch_count(self):
         return int(self._L.cd_launch_count(self._h))
+
+    def timer_start(self):
+        self._check(self._L.cd_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._check(self._L.cd_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        self._check(self._L.cd_measure_fp64_peak(self._h, C.byref(t)))
+        return t.value
 
     def last_timings(self):
         t = np.zeros(8, np.float64)

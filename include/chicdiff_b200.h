@@ -149,9 +149,15 @@ int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const dou
 int64_t cd_launch_count(const cd_ctx* ctx);
 /* device pointers of the aggregated matrices (S x n): for device-resident pipelines */
 int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmean_dev);
-/* time of the last cd_aggregate / cd_region_test kernels in ms, measured with CUDA events on the
- * context's stream: [0] aggregate, [1] region_test total, [2] fit_disp kernels, [3] wald kernels */
+/* device time of the last cd_aggregate / cd_region_test in ms, measured with CUDA events on the context's
+ * stream: [0] aggregation kernel, [1] region_test total, [2] fitDisp line-search kernels (all fits),
+ * [3] NB GLM / Wald kernels, [4] grid refits, [5] trend fit + MAD, [6] size factors */
 int cd_last_timings(const cd_ctx* ctx, double out_ms[8]);
+/* CUDA-event stopwatch on the context's stream (what bench.py brackets its timed region with) */
+int cd_timer_start(cd_ctx* ctx);
+int cd_timer_stop(cd_ctx* ctx, double* ms_out);      /* synchronises */
+/* DFMA micro-benchmark: the FP64 roofline denominator measured on this GPU, in TFLOP/s (FMA = 2 flop) */
+int cd_measure_fp64_peak(cd_ctx* ctx, double* tflops_out);
 
 #ifdef __cplusplus
 }

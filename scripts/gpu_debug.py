@@ -58,3 +58,14 @@ e_, nb = rel(adj["padj"], resO["padj"])
 print("padj max rel %.3e nan mismatch %d ; sig set equal %s (%d)" % (e_.max(), nb,
       np.array_equal(adj["padj"] < 0.05, resO["padj"] < 0.05), np.nansum(resO["padj"] < 0.05)))
 print("filter idx", adj["filterIndex"], resO["filterIndex"] + 1, "cooks outliers", int(np.isnan(adj["pvalue"]).sum() - np.isnan(r["pvalue"]).sum()), int(resO["cooksOutlier"].sum()))
+# mismatching gene-wise estimates in detail
+e_, _ = rel(r["dispGeneEst"], ro["dispGeneEst"])
+bad = np.flatnonzero(e_ > 1e-6)
+print("gene-est mismatches: %d ; of which oracle est > 1e-6: %d ; gpu est > 1e-6: %d" % (
+    len(bad), (ro["dispGeneEst"][bad] > 1e-6).sum(), (r["dispGeneEst"][bad] > 1e-6).sum()))
+order = bad[np.argsort(-np.maximum(ro["dispGeneEst"][bad], r["dispGeneEst"][bad]))]
+for i in order[:25]:
+    print(i, "K", Ko[:, i].tolist(), "gpu est %.6e it %d fl %d | orc est %.6e it %d fl %d | fit %.3e" % (
+        r["dispGeneEst"][i], r["dispGeneIter"][i], r["flags"][i], ro["dispGeneEst"][i], ro["dispGeneIter"][i], ro["flags"][i], ro["dispFit"][i]))
+np.savez_compressed("gpurun_out/debug_%s.npz" % name, bad=bad, K=Ko[:, bad], mu=ro["mu"][:, bad], gpu_est=r["dispGeneEst"][bad],
+                    orc_est=ro["dispGeneEst"][bad], gpu_it=r["dispGeneIter"][bad], orc_it=ro["dispGeneIter"][bad], flags=ro["flags"][bad])

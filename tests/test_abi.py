@@ -1,0 +1,87 @@
+"""CPU-side checks of the boundary: the shared library loads without a GPU, exports every symbol that
+include/chicdiff_b200.h declares, fails loudly (no CPU fallback) when there is no device, and its host-only
+entry points (shard planner, results adjustment) behave."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "chicdiff_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cd_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from chicdiff_b200 import engine
+    L = engine.load_library()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for nm in names:
+        assert hasattr(L, nm), nm
+    assert sorted(engine.EXPORTED) == names
+    assert b"sm_100a" in L.cd_version()
+
+
+def test_no_cpu_fallback_without_device(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from chicdiff_b200 import engine
+    with pytest.raises(engine.ChicdiffError) as ei:
+        engine.Engine(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "chicdiff_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.lower() or f == "synth.py" and "oracle" not in txt, (dp, f)
+
+
+def test_plan_shards_is_bait_aligned_and_balanced(built):
+    from chicdiff_b200 import engine, synth
+    d = synth.generate("c1")
+    for k in (1, 2, 3, 8):
+        b = engine.plan_shards(d.region_bait, d.row_off, k)
+        assert b[0] == 0 and b[-1] == d.n and np.all(np.diff(b) >= 0)
+        for c in b[1:-1]:
+            assert 0 < c < d.n and d.region_bait[c] != d.region_bait[c - 1]      # cuts only between baits
+        rows = np.diff(d.row_off[b])
+        assert rows.max() <= 1.15 * rows.mean() + 11 * 600                       # balanced up to one bait
+    # degenerate inputs
+    assert engine.plan_shards(np.zeros(0, np.int32), np.zeros(1, np.int64), 4).tolist() == [0, 0, 0, 0, 0]
+    one_bait = engine.plan_shards(np.full(10, 7, np.int32), np.arange(11, dtype=np.int64) * 3, 2)
+    assert one_bait.tolist() in ([0, 10, 10], [0, 0, 10])
+
+
+def test_results_adjust_matches_oracle_restatement(built):
+    from chicdiff_b200 import engine
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    n = 5000
+    base = np.exp(rng.normal(3, 1.5, n))
+    base[:40] = 0
+    z = rng.normal(0, 1, n) + (rng.random(n) < 0.1) * rng.normal(0, 4, n) * np.sqrt(np.minimum(base, 50) / 10)
+    p = np.array([O.lib().orc_wald_pvalue(v) for v in z])
+    p[:40] = np.nan
+    mc = rng.random(n) * 10
+    mc[100:110] = 50.0
+    flags = np.zeros(n, np.uint8)
+    flags[105:110] = engine.FLAG_COOKS_KEEP
+    adj = engine.results_adjust(base, mc, flags, p, 6, 2)
+    assert abs(adj["cooksCutoff"] - 18.0) < 1e-9
+    assert np.isnan(adj["pvalue"][100:105]).all() and not np.isnan(adj["pvalue"][105:110]).any()
+    f = O.independent_filtering(base, adj["pvalue"])
+    assert adj["filterIndex"] == f["j"] + 1
+    assert np.array_equal(np.isnan(adj["padj"]), np.isnan(f["padj"]))
+    ok = ~np.isnan(f["padj"])
+    assert np.max(np.abs(adj["padj"][ok] - f["padj"][ok])) < 1e-15

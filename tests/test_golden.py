@@ -1,0 +1,87 @@
+"""Pins the oracle (and the product's host-side results() step) against the golden table shipped with the
+reference: ChicdiffData/inst/extdata/CD4_Mono_results/test_results.Rds (fixture tests/golden/chr19_golden.npz,
+made by tests/golden/make_golden.py).  The inputs of that run are not in the mount, so what the table pins is
+the output identities of SURVEY.md Appendix D."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def test_stat_is_lfc_over_se(golden):
+    assert np.array_equal(golden["stat"], golden["log2FoldChange"] / golden["lfcSE"])
+
+
+def test_wald_pvalue_formula(golden):
+    L = O.lib()
+    pv = np.array([L.orc_wald_pvalue(z) for z in golden["stat"]])
+    rel = np.abs(pv - golden["pvalue"]) / golden["pvalue"]
+    assert golden["pvalue"].min() < 1e-50          # deep tail is exercised
+    assert rel.max() < 1e-12
+
+
+def test_independent_filtering_reproduces_golden_padj(golden):
+    f = O.independent_filtering(golden["baseMean"], golden["pvalue"])
+    assert f["j"] == 5                               # k = 6 in R's 1-based indexing
+    assert abs(f["theta"] - 0.09693877551020408) < 1e-15
+    assert abs(f["cutoff"] - 4.796776) < 1e-6
+    gp = golden["padj"]
+    assert np.array_equal(np.isnan(gp), np.isnan(f["padj"]))
+    assert np.isnan(gp).sum() == 2411
+    ok = ~np.isnan(gp)
+    assert np.max(np.abs(f["padj"][ok] - gp[ok]) / gp[ok]) < 1e-14
+    assert (gp[ok] < 0.05).sum() == 2792
+
+
+def test_bh_on_weighted_pvalues(golden):
+    wp = O.p_adjust_bh(golden["weighted_pvalue"])
+    assert np.nanmax(np.abs(wp - golden["weighted_padj"])) < 1e-15
+    assert (golden["weighted_padj"] < 0.05).sum() == 2759
+
+
+def test_ihw_weight_identities(golden):
+    w = golden["avWeights"] / golden["avWeights"].mean()
+    assert np.max(np.abs(w - golden["weight"])) < 1e-12
+    assert np.max(np.abs(golden["pvalue"] / golden["weight"] - golden["weighted_pvalue"])) < 1e-15
+
+
+def test_annotation_lookups(golden):
+    rid, rs, re_ = golden["rmap_id"], golden["rmap_start"], golden["rmap_end"]
+    assert np.array_equal(np.diff(rid), np.ones(len(rid) - 1, dtype=rid.dtype))     # contiguous IDs
+    base = rid[0]
+    assert np.array_equal(golden["OEstart"], rs[golden["minOE"] - base])
+    assert np.array_equal(golden["OEend"], re_[golden["maxOE"] - base])
+    assert np.array_equal(golden["baitstart"], rs[golden["baitID"] - base])
+    assert np.array_equal(golden["baitend"], re_[golden["baitID"] - base])
+
+
+def test_region_width_law(golden):
+    """.expandAvoidBait (chicdiff.R:353-367) with RUexpand = 5: widths 6..11, never touching bait +- 1."""
+    from chicdiff_b200 import synth
+    s = int(golden["settings_RUexpand"][0])
+    width = golden["maxOE"] - golden["minOE"] + 1
+    assert width.min() >= s + 1 and width.max() == 2 * s + 1
+    assert (width == 2 * s + 1).sum() == 24449
+    bait = golden["baitID"].astype(np.int64)
+    assert not np.any((golden["minOE"] <= bait + 1) & (golden["maxOE"] >= bait - 1))
+    # every golden window is what expand_avoid_bait yields for some seed, up to chromosome-end trimming
+    lo, hi = golden["minOE"].astype(np.int64), golden["maxOE"].astype(np.int64)
+    right = lo > bait
+    seed = np.where(right, hi - s, lo + s)
+    elo, ehi = synth.expand_avoid_bait(bait, seed, s)
+    last = golden["rmap_id"].max()
+    ehi = np.minimum(ehi, last)
+    assert np.array_equal(elo[right], lo[right]) or np.all((elo[right] == lo[right]) | (lo[right] == bait[right] + 2))
+    assert np.array_equal(ehi[~right], hi[~right]) or np.all((ehi[~right] == hi[~right]) | (hi[~right] == bait[~right] - 2))
+
+
+def test_product_results_adjust_matches_golden(golden, built):
+    """cd_results_adjust is host code (no GPU needed): independent filtering + BH of the product."""
+    from chicdiff_b200 import engine
+    adj = engine.results_adjust(golden["baseMean"], None, None, golden["pvalue"], 4, 2)
+    gp = golden["padj"]
+    assert adj["filterIndex"] == 6
+    assert abs(adj["filterThreshold"] - 4.796776) < 1e-6
+    assert np.array_equal(np.isnan(gp), np.isnan(adj["padj"]))
+    ok = ~np.isnan(gp)
+    assert np.max(np.abs(adj["padj"][ok] - gp[ok]) / gp[ok]) < 1e-14
