@@ -44,17 +44,45 @@ constexpr double kLog2e = 1.442695040888963407359924681002;
 // special functions (FP64)
 // ---------------------------------------------------------------------------------------
 
-// digamma(x), x > 0.  Recurrence to x >= 10 with pairwise-combined reciprocals, then the
-// asymptotic expansion (truncation < 5e-17 at x = 10).
+// Branch-free special functions for the line-search inner loop.  libdevice's lgamma() picks one
+// of several argument-range code paths; with one region per lane the lanes of a warp hold
+// unrelated arguments (y_j + 1/alpha), so those paths serialise.  The versions below run the same
+// instruction sequence for every positive argument: shift by a fixed count with the recurrence
+// (products instead of a data-dependent loop), then the asymptotic series.
+//
+// lgamma_c(x) = log Gamma(x) - 0.5*log(2*pi), x > 0 (the constant cancels in every use:
+// lgamma(y + r) - lgamma(r)).  Shift 8: Gamma(x) = Gamma(x + 8) / (x (x+1) ... (x+7)); Stirling
+// series at x + 8 >= 8 truncated after the x^-15 term (next term < 1e-16).
+__device__ __forceinline__ double lgamma_c(double x)
+{
+    const double p = ((x * (x + 1.0)) * ((x + 2.0) * (x + 3.0))) * (((x + 4.0) * (x + 5.0)) * ((x + 6.0) * (x + 7.0)));
+    const double xs = x + 8.0;
+    const double xi = 1.0 / xs;
+    const double f = xi * xi;
+    double t = -3617.0 / 122400.0;
+    t = fma(f, t, 1.0 / 156.0);
+    t = fma(f, t, -691.0 / 360360.0);
+    t = fma(f, t, 1.0 / 1188.0);
+    t = fma(f, t, -1.0 / 1680.0);
+    t = fma(f, t, 1.0 / 1260.0);
+    t = fma(f, t, -1.0 / 360.0);
+    t = fma(f, t, 1.0 / 12.0);
+    return (((xs - 0.5) * log(xs) - xs) + xi * t) - log(p);
+}
+
+// digamma(x), x > 0.  Shift 10: psi(x) = psi(x + 10) - sum_{k<10} 1/(x + k), the sum formed as one
+// rational num/den; asymptotic series at x + 10 (truncation < 5e-17).
 __device__ __forceinline__ double digamma_pos(double x)
 {
-    double acc = 0.0;
-    while (x < 9.0) {               // two steps per division
-        acc -= (2.0 * x + 1.0) / (x * (x + 1.0));
-        x += 2.0;
+    double num = 1.0, den = x;
+#pragma unroll
+    for (int k = 1; k < 10; k++) {
+        const double t = x + (double)k;
+        num = fma(num, t, den);
+        den *= t;
     }
-    if (x < 10.0) { acc -= 1.0 / x; x += 1.0; }
-    const double xi = 1.0 / x;
+    const double xs = x + 10.0;
+    const double xi = 1.0 / xs;
     const double f = xi * xi;
     double t = -1.0 / 12.0;
     t = fma(f, t, 691.0 / 32760.0);
@@ -63,7 +91,7 @@ __device__ __forceinline__ double digamma_pos(double x)
     t = fma(f, t, -1.0 / 252.0);
     t = fma(f, t, 1.0 / 120.0);
     t = fma(f, t, -1.0 / 12.0);
-    return acc + log(x) - 0.5 * xi + f * t;
+    return ((log(xs) - 0.5 * xi) + f * t) - num / den;
 }
 
 __device__ __forceinline__ double trigamma_pos(double x)

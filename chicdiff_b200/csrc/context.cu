@@ -216,6 +216,10 @@ struct cd_ctx {
     DevBuf<double> partial, scal;    // reduction scratch ; device scalars
     DevBuf<unsigned long long> counters;
     DevBuf<int32_t> refit_count;
+    DevBuf<int64_t> park_row;
+    DevBuf<double> park_d;           // 5 x capacity
+    DevBuf<int32_t> park_i;          // 2 x capacity
+    FitDispPark park{};
     double* h_pinned = nullptr;      // pinned host scratch (64 doubles)
     std::vector<int64_t> shard_n, shard_off;
     int64_t n_tot = 0, g_off = 0;
@@ -629,8 +633,8 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
                                        nullptr, nullptr, nullptr, ctx->mu.p, st));
     }
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
-                                       ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
+                                       ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
     CD_LAUNCHN(ctx, 1, launch_gene_post(n, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
                                         ctx->last_lp.p, flags, dispGeneEst, ctx->refit_list.p, ctx->refit_count.p, st));
@@ -673,8 +677,8 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
 
     // MAP
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 1, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, dispGeneEst, dispFit, dispPriorVar, ctx->log_alpha.p,
-                                       ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, st));
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, dispGeneEst, dispFit, dispPriorVar, ctx->log_alpha.p,
+                                       ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
     CD_LAUNCHN(ctx, 1, launch_map_post(n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, 2.0 * sqrt(varLogDispEsts),
                                        flags, ctx->dispMAP.p, ctx->dispersion.p, ctx->refit_list.p, ctx->refit_count.p, st));
@@ -751,6 +755,17 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->scal.ensure(128));
     CD_CUDA(ctx, ctx->counters.ensure(16));
     CD_CUDA(ctx, ctx->refit_count.ensure(1));
+    {
+        const int64_t cap = n / 4 + 4096;
+        CD_CUDA(ctx, ctx->park_row.ensure((size_t)cap));
+        CD_CUDA(ctx, ctx->park_d.ensure((size_t)cap * 5));
+        CD_CUDA(ctx, ctx->park_i.ensure((size_t)cap * 2));
+        FitDispPark& pk = ctx->park;
+        pk.capacity = cap; pk.row = ctx->park_row.p;
+        pk.a = ctx->park_d.p; pk.lp = pk.a + cap; pk.dlp = pk.lp + cap; pk.kappa = pk.dlp + cap; pk.lp0 = pk.kappa + cap;
+        pk.iter = ctx->park_i.p; pk.iter_accept = pk.iter + cap;
+        pk.count = ctx->counters.p + 14;
+    }
 
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     memset(out->sizeFactors, 0, sizeof(out->sizeFactors));

@@ -117,7 +117,7 @@ __device__ __forceinline__ double eval_lp(double a, const double* ys, const doub
 {
     const double alpha = exp(a);
     const double r = 1.0 / alpha;
-    const double lgr = lgamma(r);
+    const double lgr = lgamma_c(r);
     Sym<P> B;
 #pragma unroll
     for (int k = 0; k < P * (P + 1) / 2; k++) B.v[k] = 0.0;
@@ -131,8 +131,8 @@ __device__ __forceinline__ double eval_lp(double a, const double* ys, const doub
 #pragma unroll
             for (int v = 0; v <= u; v++)
                 B.v[u * (u + 1) / 2 + v] += w * c_des.X[j * P + u] * c_des.X[j * P + v];
-        // lgamma(0 + r) - lgamma(r) is exactly zero: skip both calls for zero counts
-        double t = (yj != 0.0) ? lgamma(yj + r) - lgr : 0.0;
+        // same instruction sequence for every lane; for a zero count the difference is exactly zero
+        double t = lgamma_c(yj + r) - lgr;
         t = (t - yj * log(muj + r)) - r * log(1.0 + muj * alpha);
         ll += t;
     }
@@ -172,9 +172,9 @@ __device__ __forceinline__ double eval_dlp(double a, const double* ys, const dou
                 dB.v[u * (u + 1) / 2 + v] += dw * xx;
             }
         const double ma = muj * alpha;
-        double term = log(1.0 + ma) - ma / (1.0 + ma);
-        // digamma(r) - digamma(0 + r) is exactly zero: skip both calls for zero counts
-        if (yj != 0.0) term = ((dgr + term) - digamma_pos(yj + r)) + yj / (muj + r);
+        // digamma(r) - digamma(y + r) first: it is exactly zero for a zero count and it keeps the
+        // small log / ratio terms from being absorbed by digamma(r) when 1/alpha is huge
+        const double term = ((dgr - digamma_pos(yj + r)) + (log(1.0 + ma) - ma / (1.0 + ma))) + yj / (muj + r);
         s += term;
     }
     const double ll = an2 * s;
@@ -193,95 +193,204 @@ __device__ __forceinline__ double eval_dlp(double a, const double* ys, const dou
 }
 
 // ---------------------------------------------------------------------------------------
-// fitDisp line search, one thread per region; the region's replicates are staged once into
-// a conflict-free shared-memory column ([j][thread]) so that the sample loop stays rolled
-// (the special-function bodies are large) without spilling to local memory.
+// fitDisp line search.  One lane works on one region at a time and the kernel is persistent:
+// iteration counts are very uneven (most regions stop after 5-15 trips, ~2 % run all 100), so
+// a lane that finishes its region immediately pulls the next one from a global work counter
+// (one warp-aggregated atomic per refill) instead of idling until the slowest lane of its warp
+// is done.  Every trip of a lane has the same shape -- one posterior evaluation, then
+// optionally one derivative evaluation -- whether the lane is initialising a fresh region or
+// is inside the line search, so lanes in different states do not serialise each other.
+// The region's replicates (y_j, mu_j) live in a conflict-free shared-memory column per lane.
 // ---------------------------------------------------------------------------------------
 constexpr int kFitDispThreads = 128;
+constexpr int kFitDispTripCap = 24;     // first pass: a region still searching after this many trips is parked
 
-template <int P>
+// Two passes.  ~2-3 % of the regions run the full 100 trips while the average is below 10; in a
+// single persistent pass such a region pulled near the end keeps its warp alive long after the
+// work queue is empty.  Pass 1 therefore parks every region that is still searching after
+// kFitDispTripCap trips (its scalar search state goes to the FitDispPark arrays); pass 2 resumes
+// all parked regions at once, one per lane, so the long searches overlap each other.
+template <int P, bool RESUME>
 __global__ void __launch_bounds__(kFitDispThreads)
 fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
                 const uint8_t* __restrict__ flags, const double* __restrict__ disp_init,
                 const double* __restrict__ prior_mean_disp, double prior_sigmasq,
                 double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
-                double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out)
+                double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
+                unsigned long long* __restrict__ work_counter, FitDispPark park)
 {
     extern __shared__ double smem[];
     const int stride = kFitDispThreads;
     double* ys = smem + threadIdx.x;
     double* mus = smem + (size_t)S * stride + threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (flags[i] & CD_FLAG_ALLZERO) {
-        log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
-        return;
-    }
-    for (int j = 0; j < S; j++) {
-        ys[j * stride] = (double)K[(int64_t)j * n + i];
-        mus[j * stride] = mu_g[(int64_t)j * n + i];
-    }
+    const unsigned lane = threadIdx.x & 31u;
     const bool use_prior = (prior_mean_disp != nullptr);
-    double a, prior_mean = 0.0;
-    if (use_prior) {
-        // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more than an
-        // order of magnitude below the trend
-        const double ft = prior_mean_disp[i], ge = disp_init[i];
-        a = log((ge > 0.1 * ft) ? ge : ft);
-        prior_mean = log(ft);
-    } else {
-        a = log(disp_init[i]);
-    }
     const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
     const double min_log_alpha = log(kMinDisp / 10.0);
     const int maxit = 100;
-    double lp = eval_lp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-    double dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-    const double lp0 = lp;
-    double kappa = kappa_0;
+    int64_t n_work = n;
+    if (RESUME) {
+        const unsigned long long parked = *park.count;
+        n_work = (int64_t)(parked < (unsigned long long)park.capacity ? parked : (unsigned long long)park.capacity);
+    }
+
+    bool active = false, exhausted = false, fresh = false;
+    int64_t i = 0;
+    double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0;
     int iter = 0, iter_accept = 0;
-    for (int t = 0; t < maxit; t++) {
-        iter++;
-        const double a_propose = a + kappa * dlp;
-        if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
-        if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
-        const double a_new = a + kappa * dlp;
-        // fitDisp evaluates the posterior at a_new twice (Armijo test, then "lpnew"); the two
-        // arguments are the same double, so one evaluation serves both
-        const double lpnew = eval_lp<P>(a_new, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-        const double theta_kappa = -1.0 * lpnew;
-        const double theta_hat_kappa = -1.0 * lp - kappa * epsilon * (dlp * dlp);
-        if (theta_kappa <= theta_hat_kappa) {
-            iter_accept++;
-            a = a_new;
-            const double change = lpnew - lp;
-            if (change < tol) { lp = lpnew; break; }
-            if (a < min_log_alpha) break;
-            lp = lpnew;
-            dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-            kappa = fmin(kappa * 1.1, kappa_0);
-            if (iter_accept % 5 == 0) kappa = kappa / 2.0;
-        } else {
-            kappa = kappa / 2.0;
+
+    while (true) {
+        // ---- refill idle lanes ----
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(0xffffffffu, want);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                const int64_t w = (int64_t)(base + __popc(need & ((1u << lane) - 1u)));
+                if (w >= n_work) {
+                    exhausted = true;
+                } else if (RESUME) {
+                    i = park.row[w];
+                    a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
+                    iter = park.iter[w]; iter_accept = park.iter_accept[w];
+                    if (use_prior) prior_mean = log(prior_mean_disp[i]);
+                    for (int j = 0; j < S; j++) {
+                        ys[j * stride] = (double)K[(int64_t)j * n + i];
+                        mus[j * stride] = mu_g[(int64_t)j * n + i];
+                    }
+                    active = true; fresh = false;
+                } else {
+                    i = w;
+                    if (flags[i] & CD_FLAG_ALLZERO) {
+                        log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
+                    } else {
+                        for (int j = 0; j < S; j++) {
+                            ys[j * stride] = (double)K[(int64_t)j * n + i];
+                            mus[j * stride] = mu_g[(int64_t)j * n + i];
+                        }
+                        if (use_prior) {
+                            // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more
+                            // than an order of magnitude below the trend
+                            const double ft = prior_mean_disp[i], ge = disp_init[i];
+                            a = log((ge > 0.1 * ft) ? ge : ft);
+                            prior_mean = log(ft);
+                        } else {
+                            a = log(disp_init[i]);
+                        }
+                        active = true; fresh = true;
+                        iter = 0; iter_accept = 0; kappa = kappa_0;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !active)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        // ---- phase 1: one posterior evaluation per active lane ----
+        // (the explicit __syncwarp()s make the lanes reconverge before each of the two heavy
+        //  evaluations; without them the branches above tail-merge into separate passes)
+        double x = a, lpx = 0.0;
+        if (active && !fresh) {
+            iter++;
+            const double a_propose = a + kappa * dlp;
+            if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
+            if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
+            x = a + kappa * dlp;
+        }
+        __syncwarp();
+        if (active) {
+            // fitDisp evaluates the posterior at the proposal twice (Armijo test, then "lpnew"); the
+            // two arguments are the same double, so one evaluation serves both
+            lpx = eval_lp<P>(x, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+        }
+        // ---- decision ----
+        bool need_dlp = false, finished = false;
+        if (active) {
+            if (fresh) {
+                lp = lp0 = lpx;
+                need_dlp = true;
+            } else {
+                const double theta_kappa = -1.0 * lpx;
+                const double theta_hat_kappa = -1.0 * lp - kappa * epsilon * (dlp * dlp);
+                if (theta_kappa <= theta_hat_kappa) {
+                    iter_accept++;
+                    a = x;
+                    const double change = lpx - lp;
+                    if (change < tol) { lp = lpx; finished = true; }
+                    else if (a < min_log_alpha) { finished = true; }
+                    else { lp = lpx; need_dlp = true; }
+                } else {
+                    kappa = kappa / 2.0;
+                }
+                if (iter >= maxit) { finished = true; need_dlp = false; }
+            }
+        }
+        // ---- phase 2: derivative where the search continues from a new point ----
+        __syncwarp();
+        if (need_dlp) dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
+        __syncwarp();
+        if (need_dlp) {
+            if (!fresh) {
+                kappa = fmin(kappa * 1.1, kappa_0);
+                if (iter_accept % 5 == 0) kappa = kappa / 2.0;
+            }
+            fresh = false;
+        }
+        if (finished) {
+            log_alpha_out[i] = a;
+            iter_out[i] = iter;
+            initial_lp_out[i] = lp0;
+            last_lp_out[i] = lp;
+            active = false;
+        } else if (!RESUME && active && iter >= kFitDispTripCap) {
+            const unsigned long long slot = atomicAdd(park.count, 1ull);
+            if (slot < (unsigned long long)park.capacity) {
+                park.row[slot] = i;
+                park.a[slot] = a; park.lp[slot] = lp; park.dlp[slot] = dlp; park.kappa[slot] = kappa; park.lp0[slot] = lp0;
+                park.iter[slot] = iter; park.iter_accept[slot] = iter_accept;
+                active = false;
+            }                                   // park full: this lane simply keeps searching
         }
     }
-    log_alpha_out[i] = a;
-    iter_out[i] = iter;
-    initial_lp_out[i] = lp0;
-    last_lp_out[i] = lp;
 }
 
 cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu, const uint8_t* flags,
                             const double* disp_init, const double* prior_mean_disp, double prior_sigmasq,
-                            double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp, cudaStream_t st)
+                            double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
+                            unsigned long long* work_counter, const FitDispPark& park, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    // work_counter[0]: pass-1 queue head, work_counter[1]: pass-2 queue head ; park.count: parked regions
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(park.count, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
     const int threads = kFitDispThreads;
-    const int blocks = blocks_for(n, threads);
+    const int64_t want = (n + threads - 1) / threads;
     const size_t smem = (size_t)2 * S * threads * sizeof(double);
-#define CD_LAUNCH(P_)                                                                                        \
-    fit_disp_kernel<P_><<<blocks, threads, smem, st>>>(n, S, K, mu, flags, disp_init, prior_mean_disp,      \
-                                                       prior_sigmasq, log_alpha, iter, initial_lp, last_lp)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // persistent grids: exactly the number of CTAs that are resident at once
+#define CD_LAUNCH(P_)                                                                                          \
+    {                                                                                                          \
+        int per_sm = 1;                                                                                        \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_disp_kernel<P_, false>, threads, smem); \
+        if (e != cudaSuccess) return e;                                                                        \
+        const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                     \
+        const int blocks = (int)(want < resident ? want : resident);                                           \
+        fit_disp_kernel<P_, false><<<blocks, threads, smem, st>>>(n, S, K, mu, flags, disp_init,               \
+            prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);         \
+        const int64_t want2 = (park.capacity + threads - 1) / threads;                                         \
+        const int blocks2 = (int)(want2 < resident ? want2 : resident);                                        \
+        fit_disp_kernel<P_, true><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, S, K, mu, flags,        \
+            disp_init, prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter + 1, \
+            park);                                                                                             \
+    }
     switch (p) {
         case 1: CD_LAUNCH(1); break;
         case 2: CD_LAUNCH(2); break;

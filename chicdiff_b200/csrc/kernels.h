@@ -38,11 +38,20 @@ cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* n
                              const double* baseMean, const double* baseVar, const double* rough,
                              const uint8_t* flags, const double* xim_dev, double* alpha_init, double* mu,
                              cudaStream_t st);
+// scalar search state of regions parked by the first line-search pass (see dispersion.cu)
+struct FitDispPark {
+    int64_t capacity;
+    int64_t* row;
+    double *a, *lp, *dlp, *kappa, *lp0;
+    int32_t *iter, *iter_accept;
+    unsigned long long* count;
+};
 // line search; prior_mean == null => no prior (gene-wise); log_alpha0 in/out
 cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu,
                             const uint8_t* flags, const double* disp_init /*alpha scale*/,
                             const double* prior_mean_disp /*alpha scale or null*/, double prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
+                            unsigned long long* work_counter /*device scratch, 2 words*/, const FitDispPark& park,
                             cudaStream_t st);
 // post-processing of the gene-wise fit + compaction of rows needing the grid
 cudaError_t launch_gene_post(int64_t n, int S, const double* alpha_init, const double* log_alpha,

@@ -39,14 +39,17 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* dst)
     __syncthreads();
 }
 
-// final stage: out[k] = sum_b partial[b*NVrt + k], b ascending
-__global__ void final_reduce_kernel(int nblocks, int nv, const double* __restrict__ partial, double* __restrict__ out)
+// final stage: out[k] = sum_b partial[b*nv + k]; one warp per value, lanes stride over the blocks
+// and a fixed shuffle tree joins them, so the summation order never changes
+__global__ void __launch_bounds__(32) final_reduce_kernel(int nblocks, int nv, const double* __restrict__ partial,
+                                                          double* __restrict__ out)
 {
-    const int k = threadIdx.x;
-    if (k >= nv) return;
+    const int k = blockIdx.x;
     double x = 0.0;
-    for (int b = 0; b < nblocks; b++) x += partial[(size_t)b * nv + k];
-    out[k] = x;
+    for (int b = threadIdx.x; b < nblocks; b += 32) x += partial[(size_t)b * nv + k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+    if (threadIdx.x == 0) out[k] = x;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -73,7 +76,7 @@ cudaError_t launch_masked_colsums(int64_t n, int S, const double* M, const uint8
                                   double* out, cudaStream_t st)
 {
     masked_colsums_kernel<<<kReduceBlocks, 256, 0, st>>>(n, S, M, mask, partial);
-    final_reduce_kernel<<<1, 64, 0, st>>>(kReduceBlocks, S + 1, partial, out);
+    final_reduce_kernel<<<S + 1, 32, 0, st>>>(kReduceBlocks, S + 1, partial, out);
     return cudaGetLastError();
 }
 
@@ -190,7 +193,7 @@ cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* d
                               cudaStream_t st)
 {
     trend_pass_kernel<<<kReduceBlocks, 256, 0, st>>>(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial);
-    final_reduce_kernel<<<1, 64, 0, st>>>(kReduceBlocks, 8, partial, out);
+    final_reduce_kernel<<<8, 32, 0, st>>>(kReduceBlocks, 8, partial, out);
     return cudaGetLastError();
 }
 

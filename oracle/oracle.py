@@ -145,7 +145,8 @@ def region_test(K, FMagg, X, norm="combined", theta=None, theta_grid=(0, .25, .5
         if len(w) != 1:
             raise ValueError("theta grid: tied minimum")
         theta = float(theta_grid[w[0]])
-    out["theta"] = theta
+    # chicdiff.R:1759: the theta attribute exists only when the "combined" branch assigned `tt`
+    out["theta"] = theta if norm == "combined" else None
     nf = norm_factors(FMagg, sf, norm, 0.0 if theta is None else theta)
     out["nf"] = nf
     out.update(deseq(K, nf, X, prior_var=prior_var, nthreads=nthreads))
