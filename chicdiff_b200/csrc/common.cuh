@@ -44,35 +44,63 @@ constexpr double kLog2e = 1.442695040888963407359924681002;
 // special functions (FP64)
 // ---------------------------------------------------------------------------------------
 
-// Branch-free special functions for the line-search inner loop.  libdevice's lgamma() picks one
-// of several argument-range code paths; with one region per lane the lanes of a warp hold
-// unrelated arguments (y_j + 1/alpha), so those paths serialise.  The versions below run the same
-// instruction sequence for every positive argument: shift by a fixed count with the recurrence
-// (products instead of a data-dependent loop), then the asymptotic series.
-//
-// lgamma_c(x) = log Gamma(x) - 0.5*log(2*pi), x > 0 (the constant cancels in every use:
-// lgamma(y + r) - lgamma(r)).  Shift 8: Gamma(x) = Gamma(x + 8) / (x (x+1) ... (x+7)); Stirling
-// series at x + 8 >= 8 truncated after the x^-15 term (next term < 1e-16).
-__device__ __forceinline__ double lgamma_c(double x)
+// ---- building blocks of the line-search inner loop ----------------------------------------------
+// Polynomial coefficients live in __constant__ memory so that the DFMAs take them as constant-bank
+// operands; as literals every 64-bit coefficient costs two UMOV issue slots per use (measured: 20 %
+// of all issued instructions in the first version of the kernel).
+static __constant__ double kLogC[9] = {
+    6.93147180369123816490e-01,   // ln2_hi
+    1.90821492927058770002e-10,   // ln2_lo
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+// Stirling series of log Gamma in 1/x (odd powers): B_2k / (2k (2k-1)), k = 1..7
+static __constant__ double kLgamC[7] = {1.0 / 12.0, -1.0 / 360.0, 1.0 / 1260.0, -1.0 / 1680.0, 1.0 / 1188.0,
+                                        -691.0 / 360360.0, 1.0 / 156.0};
+// asymptotic series of digamma in 1/x^2: -B_2k / (2k), k = 1..7
+static __constant__ double kDigamC[7] = {-1.0 / 12.0, 1.0 / 120.0, -1.0 / 252.0, 1.0 / 240.0, -1.0 / 132.0,
+                                         691.0 / 32760.0, -1.0 / 12.0};
+
+// 1/b for a positive normal b: MUFU.RCP64H seed + two Newton steps (no slow-path branch; the
+// arguments here are never zero, denormal, infinite or NaN)
+__device__ __forceinline__ double rcp_pos(double b)
 {
-    const double p = ((x * (x + 1.0)) * ((x + 2.0) * (x + 3.0))) * (((x + 4.0) * (x + 5.0)) * ((x + 6.0) * (x + 7.0)));
-    const double xs = x + 8.0;
-    const double xi = 1.0 / xs;
-    const double f = xi * xi;
-    double t = -3617.0 / 122400.0;
-    t = fma(f, t, 1.0 / 156.0);
-    t = fma(f, t, -691.0 / 360360.0);
-    t = fma(f, t, 1.0 / 1188.0);
-    t = fma(f, t, -1.0 / 1680.0);
-    t = fma(f, t, 1.0 / 1260.0);
-    t = fma(f, t, -1.0 / 360.0);
-    t = fma(f, t, 1.0 / 12.0);
-    return (((xs - 0.5) * log(xs) - xs) + xi * t) - log(p);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = fma(-b, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-b, r, 1.0);
+    return fma(r, e, r);
 }
 
-// digamma(x), x > 0.  Shift 10: psi(x) = psi(x + 10) - sum_{k<10} 1/(x + k), the sum formed as one
-// rational num/den; asymptotic series at x + 10 (truncation < 5e-17).
-__device__ __forceinline__ double digamma_pos(double x)
+// natural log of a positive normal x (< 1 ulp): x = 2^k m with m in [sqrt(1/2), sqrt(2)),
+// log m = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f), f = m - 1   (the classic fdlibm scheme)
+__device__ __forceinline__ double log_pos(double x)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int i = (hi + 0x95f64) & 0x100000;
+    hi |= (i ^ 0x3ff00000);
+    k += (i >> 20);
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * rcp_pos(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, kLogC[7], kLogC[5]), kLogC[3]);
+    const double t2 = z * fma(w, fma(w, fma(w, kLogC[8], kLogC[6]), kLogC[4]), kLogC[2]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * kLogC[0] - ((hfsq - fma(s, hfsq + R, dk * kLogC[1])) - f);
+}
+
+// log Gamma(x) - 0.5 log(2 pi) and digamma(x) for x > 0 in one go, same instruction sequence for every
+// argument (libdevice's lgamma picks an argument-range code path; with one region per lane the lanes of a
+// warp hold unrelated arguments y_j + 1/alpha, so those paths serialise).  Shift by 10 with the
+// recurrence, the ten factors kept as one rational:  Gamma(x) = Gamma(x + 10) / prod (x + k),
+// psi(x) = psi(x + 10) - sum 1/(x + k) = psi(x + 10) - num/den; asymptotic series at x + 10 >= 10
+// (truncation < 1e-16).  log(x + 10) and 1/(x + 10) are shared by the two functions.
+__device__ __forceinline__ void lgamma_digamma_pos(double x, double& lg, double& dg)
 {
     double num = 1.0, den = x;
 #pragma unroll
@@ -82,16 +110,32 @@ __device__ __forceinline__ double digamma_pos(double x)
         den *= t;
     }
     const double xs = x + 10.0;
-    const double xi = 1.0 / xs;
+    const double xi = rcp_pos(xs);
     const double f = xi * xi;
-    double t = -1.0 / 12.0;
-    t = fma(f, t, 691.0 / 32760.0);
-    t = fma(f, t, -1.0 / 132.0);
-    t = fma(f, t, 1.0 / 240.0);
-    t = fma(f, t, -1.0 / 252.0);
-    t = fma(f, t, 1.0 / 120.0);
-    t = fma(f, t, -1.0 / 12.0);
-    return ((log(xs) - 0.5 * xi) + f * t) - num / den;
+    const double lxs = log_pos(xs);
+    double t = kLgamC[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) t = fma(f, t, kLgamC[k]);
+    lg = (((xs - 0.5) * lxs - xs) + xi * t) - log_pos(den);
+    double u = kDigamC[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) u = fma(f, u, kDigamC[k]);
+    dg = ((lxs - 0.5 * xi) + f * u) - num * rcp_pos(den);
+}
+
+// log Gamma(x) - 0.5 log(2 pi) alone (same scheme as above)
+__device__ __forceinline__ double lgamma_c_pos(double x)
+{
+    double den = x;
+#pragma unroll
+    for (int k = 1; k < 10; k++) den *= x + (double)k;
+    const double xs = x + 10.0;
+    const double xi = rcp_pos(xs);
+    const double f = xi * xi;
+    double t = kLgamC[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) t = fma(f, t, kLgamC[k]);
+    return (((xs - 0.5) * log_pos(xs) - xs) + xi * t) - log_pos(den);
 }
 
 __device__ __forceinline__ double trigamma_pos(double x)

@@ -220,6 +220,9 @@ struct cd_ctx {
     DevBuf<double> park_d;           // 5 x capacity
     DevBuf<int32_t> park_i;          // 2 x capacity
     FitDispPark park{};
+    DevBuf<double> wald_c, wald_b0, wald_b;
+    DevBuf<int32_t> wald_iter;
+    WaldScratch wald_ws{};
     double* h_pinned = nullptr;      // pinned host scratch (64 doubles)
     std::vector<int64_t> shard_n, shard_off;
     int64_t n_tot = 0, g_off = 0;
@@ -629,8 +632,8 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
                                         ctx->alpha_init.p, ctx->mu.p, st));
     if (!des.linear_mu) {
         // mu from an NB GLM fitted with the rough dispersion (fitNbinomGLMs(alpha_hat = alpha_init)$mu)
-        CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->alpha_init.p, flags, nullptr, nullptr, nullptr, nullptr,
-                                       nullptr, nullptr, nullptr, ctx->mu.p, st));
+        CD_LAUNCHN(ctx, 3, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->alpha_init.p, flags, ctx->wald_ws, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, ctx->mu.p, st));
     }
     ctx->tm_begin(2);
     CD_LAUNCHN(ctx, 2, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
@@ -688,7 +691,7 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     ctx->tm_end();
     // NB GLM + Wald
     ctx->tm_begin(3);
-    CD_LAUNCHN(ctx, 1, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->dispersion.p, flags, ctx->beta.p, ctx->betaSE.p, ctx->stat.p,
+    CD_LAUNCHN(ctx, p > 1 ? 3 : 2, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->dispersion.p, flags, ctx->wald_ws, ctx->beta.p, ctx->betaSE.p, ctx->stat.p,
                                    ctx->pvalue.p, ctx->deviance.p, want_cooks ? ctx->maxCooks.p : nullptr, ctx->betaIter.p,
                                    nullptr, st));
     ctx->tm_end();
@@ -755,6 +758,12 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->scal.ensure(128));
     CD_CUDA(ctx, ctx->counters.ensure(16));
     CD_CUDA(ctx, ctx->refit_count.ensure(1));
+    CD_CUDA(ctx, ctx->wald_c.ensure(sn));
+    CD_CUDA(ctx, ctx->wald_b0.ensure((size_t)CD_MAXP * (size_t)n));
+    CD_CUDA(ctx, ctx->wald_b.ensure((size_t)CD_MAXP * (size_t)n));
+    CD_CUDA(ctx, ctx->wald_iter.ensure((size_t)n));
+    ctx->wald_ws.cmat = ctx->wald_c.p; ctx->wald_ws.beta0 = ctx->wald_b0.p; ctx->wald_ws.beta_nat = ctx->wald_b.p;
+    ctx->wald_ws.iter = ctx->wald_iter.p; ctx->wald_ws.work_counter = ctx->counters.p + 15;
     {
         const int64_t cap = n / 4 + 4096;
         CD_CUDA(ctx, ctx->park_row.ensure((size_t)cap));

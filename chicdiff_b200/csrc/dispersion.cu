@@ -107,61 +107,34 @@ cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* n
 }
 
 // ---------------------------------------------------------------------------------------
-// Cox-Reid adjusted profile log-posterior of log(alpha) and its derivative
-// (DESeq2.cpp log_posterior / dlog_posterior).  ys / mus point at the region's replicates
-// in shared memory, element j at [j * stride].
+// Cox-Reid adjusted profile log-posterior of log(alpha) (DESeq2.cpp log_posterior) and its
+// derivative (dlog_posterior), evaluated together at one point.  The line search needs the
+// posterior at every proposal and the derivative at every accepted one; computed together they
+// share exp(a), w_j = 1/(1/mu_j + alpha), log(1 + mu_j alpha), log(y_j + r + 10) and the shifted
+// gamma-function rationals, so the pair costs ~1.3x the posterior alone, and the lanes of a warp
+// never split into "needs the derivative" and "does not".
+// ys / mus point at the region's replicates in shared memory, element j at [j * stride].
+// WANT_D = false (grid refit) skips the derivative.
 // ---------------------------------------------------------------------------------------
-template <int P>
-__device__ __forceinline__ double eval_lp(double a, const double* ys, const double* mus, int stride, int S,
-                                          double prior_mean, double prior_sigmasq, bool use_prior)
+template <int P, bool WANT_D>
+__device__ __forceinline__ void eval_post(double a, const double* ys, const double* mus, int stride, int S,
+                                          double prior_mean, double prior_sigmasq, bool use_prior,
+                                          double& lp_out, double& dlp_out)
 {
     const double alpha = exp(a);
-    const double r = 1.0 / alpha;
-    const double lgr = lgamma_c(r);
-    Sym<P> B;
-#pragma unroll
-    for (int k = 0; k < P * (P + 1) / 2; k++) B.v[k] = 0.0;
-    double ll = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < S; j++) {
-        const double yj = ys[j * stride], muj = mus[j * stride];
-        const double w = 1.0 / (1.0 / muj + alpha);
-#pragma unroll
-        for (int u = 0; u < P; u++)
-#pragma unroll
-            for (int v = 0; v <= u; v++)
-                B.v[u * (u + 1) / 2 + v] += w * c_des.X[j * P + u] * c_des.X[j * P + v];
-        // same instruction sequence for every lane; for a zero count the difference is exactly zero
-        double t = lgamma_c(yj + r) - lgr;
-        t = (t - yj * log(muj + r)) - r * log(1.0 + muj * alpha);
-        ll += t;
-    }
-    const double cr = -0.5 * chol_logdet<P>(B);
-    double pr = 0.0;
-    if (use_prior) {
-        const double d = a - prior_mean;
-        pr = -0.5 * d * d / prior_sigmasq;
-    }
-    return ll + pr + cr;
-}
-
-template <int P>
-__device__ __forceinline__ double eval_dlp(double a, const double* ys, const double* mus, int stride, int S,
-                                           double prior_mean, double prior_sigmasq, bool use_prior)
-{
-    const double alpha = exp(a);
-    const double r = 1.0 / alpha;
-    const double an2 = 1.0 / (alpha * alpha);
-    const double dgr = digamma_pos(r);
+    const double r = rcp_pos(alpha);
+    double lgr, dgr;
+    lgamma_digamma_pos(r, lgr, dgr);
     Sym<P> B, dB;
 #pragma unroll
     for (int k = 0; k < P * (P + 1) / 2; k++) { B.v[k] = 0.0; dB.v[k] = 0.0; }
-    double s = 0.0;
+    double ll = 0.0, ds = 0.0;
 #pragma unroll 1
     for (int j = 0; j < S; j++) {
         const double yj = ys[j * stride], muj = mus[j * stride];
-        const double t = 1.0 / muj + alpha;
-        const double w = 1.0 / t;
+        const double ma = muj * alpha;
+        const double ropm = rcp_pos(1.0 + ma);
+        const double w = muj * ropm;                    // = 1 / (1/mu + alpha)
         const double dw = -w * w;
 #pragma unroll
         for (int u = 0; u < P; u++)
@@ -169,27 +142,44 @@ __device__ __forceinline__ double eval_dlp(double a, const double* ys, const dou
             for (int v = 0; v <= u; v++) {
                 const double xx = c_des.X[j * P + u] * c_des.X[j * P + v];
                 B.v[u * (u + 1) / 2 + v] += w * xx;
-                dB.v[u * (u + 1) / 2 + v] += dw * xx;
+                if (WANT_D) dB.v[u * (u + 1) / 2 + v] += dw * xx;
             }
-        const double ma = muj * alpha;
-        // digamma(r) - digamma(y + r) first: it is exactly zero for a zero count and it keeps the
-        // small log / ratio terms from being absorbed by digamma(r) when 1/alpha is huge
-        const double term = ((dgr - digamma_pos(yj + r)) + (log(1.0 + ma) - ma / (1.0 + ma))) + yj / (muj + r);
-        s += term;
+        const double l1 = log_pos(1.0 + ma);
+        const double mr = muj + r;
+        double lg, dg;
+        lgamma_digamma_pos(yj + r, lg, dg);
+        // for a zero count lg - lgr and dgr - dg are exactly zero (same instruction sequence, same input)
+        ll += ((lg - lgr) - yj * log_pos(mr)) - r * l1;
+        if (WANT_D) ds += ((dgr - dg) + (l1 - ma * ropm)) + yj * rcp_pos(mr);
     }
-    const double ll = an2 * s;
-    chol_logdet<P>(B);
-    Sym<P> Bi;
-    chol_inverse<P>(B, Bi);
-    double tr = 0.0;
-#pragma unroll
-    for (int u = 0; u < P; u++)
-#pragma unroll
-        for (int v = 0; v < P; v++) tr += Bi.v[sidx<P>(u, v)] * dB.v[sidx<P>(v, u)];
-    const double cr = -0.5 * tr;
+    const double cr = -0.5 * chol_logdet<P>(B);
     double pr = 0.0;
-    if (use_prior) pr = -1.0 * (a - prior_mean) / prior_sigmasq;
-    return (ll + cr) * alpha + pr;
+    if (use_prior) {
+        const double d = a - prior_mean;
+        pr = -0.5 * d * d / prior_sigmasq;
+    }
+    lp_out = ll + pr + cr;
+    if (WANT_D) {
+        Sym<P> Bi;
+        chol_inverse<P>(B, Bi);
+        double tr = 0.0;
+#pragma unroll
+        for (int u = 0; u < P; u++)
+#pragma unroll
+            for (int v = 0; v < P; v++) tr += Bi.v[sidx<P>(u, v)] * dB.v[sidx<P>(v, u)];
+        const double dcr = -0.5 * tr;
+        const double dpr = use_prior ? -1.0 * (a - prior_mean) / prior_sigmasq : 0.0;
+        dlp_out = ((r * r) * ds + dcr) * alpha + dpr;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ double eval_lp(double a, const double* ys, const double* mus, int stride, int S,
+                                          double prior_mean, double prior_sigmasq, bool use_prior)
+{
+    double lp, unused;
+    eval_post<P, false>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior, lp, unused);
+    return lp;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -197,9 +187,9 @@ __device__ __forceinline__ double eval_dlp(double a, const double* ys, const dou
 // iteration counts are very uneven (most regions stop after 5-15 trips, ~2 % run all 100), so
 // a lane that finishes its region immediately pulls the next one from a global work counter
 // (one warp-aggregated atomic per refill) instead of idling until the slowest lane of its warp
-// is done.  Every trip of a lane has the same shape -- one posterior evaluation, then
-// optionally one derivative evaluation -- whether the lane is initialising a fresh region or
-// is inside the line search, so lanes in different states do not serialise each other.
+// is done.  Every trip of a lane has the same shape -- one fused posterior + derivative
+// evaluation -- whether the lane is initialising a fresh region or is inside the line search,
+// so lanes in different states do not serialise each other.
 // The region's replicates (y_j, mu_j) live in a conflict-free shared-memory column per lane.
 // ---------------------------------------------------------------------------------------
 constexpr int kFitDispThreads = 128;
@@ -290,10 +280,8 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
         }
-        // ---- phase 1: one posterior evaluation per active lane ----
-        // (the explicit __syncwarp()s make the lanes reconverge before each of the two heavy
-        //  evaluations; without them the branches above tail-merge into separate passes)
-        double x = a, lpx = 0.0;
+        // ---- one posterior + derivative evaluation per active lane ----
+        double x = a;
         if (active && !fresh) {
             iter++;
             const double a_propose = a + kappa * dlp;
@@ -301,18 +289,22 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
             if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
             x = a + kappa * dlp;
         }
+        // (explicit reconvergence: without it the branches above tail-merge into separate passes
+        //  over the evaluation, which was measured at 13 of 32 lanes per issued instruction)
         __syncwarp();
-        if (active) {
-            // fitDisp evaluates the posterior at the proposal twice (Armijo test, then "lpnew"); the
-            // two arguments are the same double, so one evaluation serves both
-            lpx = eval_lp<P>(x, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-        }
+        double lpx = 0.0, dlpx = 0.0;
+        // fitDisp evaluates the posterior at the proposal twice (Armijo test, then "lpnew") and, when
+        // the proposal is accepted, the derivative at the same point; the arguments are the same
+        // double, so one fused evaluation serves all three
+        if (active) eval_post<P, true>(x, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior, lpx, dlpx);
+        __syncwarp();
         // ---- decision ----
-        bool need_dlp = false, finished = false;
+        bool finished = false;
         if (active) {
             if (fresh) {
                 lp = lp0 = lpx;
-                need_dlp = true;
+                dlp = dlpx;
+                fresh = false;
             } else {
                 const double theta_kappa = -1.0 * lpx;
                 const double theta_hat_kappa = -1.0 * lp - kappa * epsilon * (dlp * dlp);
@@ -322,23 +314,17 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
                     const double change = lpx - lp;
                     if (change < tol) { lp = lpx; finished = true; }
                     else if (a < min_log_alpha) { finished = true; }
-                    else { lp = lpx; need_dlp = true; }
+                    else {
+                        lp = lpx;
+                        dlp = dlpx;
+                        kappa = fmin(kappa * 1.1, kappa_0);
+                        if (iter_accept % 5 == 0) kappa = kappa / 2.0;
+                    }
                 } else {
                     kappa = kappa / 2.0;
                 }
-                if (iter >= maxit) { finished = true; need_dlp = false; }
+                if (iter >= maxit) finished = true;
             }
-        }
-        // ---- phase 2: derivative where the search continues from a new point ----
-        __syncwarp();
-        if (need_dlp) dlp = eval_dlp<P>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior);
-        __syncwarp();
-        if (need_dlp) {
-            if (!fresh) {
-                kappa = fmin(kappa * 1.1, kappa_0);
-                if (iter_accept % 5 == 0) kappa = kappa / 2.0;
-            }
-            fresh = false;
         }
         if (finished) {
             log_alpha_out[i] = a;

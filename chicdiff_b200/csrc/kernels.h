@@ -83,9 +83,17 @@ cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* 
                                cudaStream_t st);
 
 // ---- stages 3 + 5: NB GLM, Cook's, Wald --------------------------------------------------
-// also used for the IRLS-mu variant of the gene-wise step (mu_out != null => only mu is written)
+struct WaldScratch {
+    double* cmat;        // S x n: mu-independent part of the NB log density
+    double* beta0;       // p x n: least-squares start
+    double* beta_nat;    // p x n: IRLS coefficients, natural-log scale
+    int32_t* iter;       // n
+    unsigned long long* work_counter;
+};
+// prep + persistent IRLS (p >= 2) + finalisation.  Also used for the IRLS-mu variant of the gene-wise
+// step (mu_out != null => only mu is written).  maxCooks == null skips Cook's distances.
 cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double* nf,
-                        const double* dispersion, uint8_t* flags,
+                        const double* dispersion, uint8_t* flags, const WaldScratch& ws,
                         double* beta /*p x n, log2*/, double* betaSE, double* stat, double* pvalue,
                         double* deviance, double* maxCooks, int32_t* betaIter, double* mu_out,
                         cudaStream_t st);

@@ -7,10 +7,23 @@
 // shortcut for design ~ 1 (the theta grid), calculateCooksDistance / recordMaxCooks, and
 // p = 2 * pnorm(-|beta / SE|).
 //
-// Mapping: one thread per region; y_j, nf_j and the mu-independent part of the NB log density
-// are staged per thread in conflict-free shared-memory columns.  The ridge normal equations
-// (X'WX + lambda I) beta = X'Wz are solved by an unrolled Cholesky (p <= 4); DESeq2 solves the
-// same system by QR of the row-augmented matrix.
+// Three kernels, one region per lane:
+//   wald_prep_kernel   the part of the NB log density that does not depend on mu
+//                      (lgamma(y + 1/alpha) - lgamma(1/alpha) - lgamma(y + 1)) and the least-squares
+//                      start of the IRLS; uniform work, plain grid
+//   wald_irls_kernel   the IRLS itself, persistent with work pulling like the dispersion line
+//                      search (iteration counts range from 2 to 100): one trip = solve the ridge
+//                      normal equations by an unrolled Cholesky (p <= 4; DESeq2 solves the same system
+//                      by QR of the row-augmented matrix), then one sweep over the replicates for
+//                      X'WX, X'Wz and the deviance at the new coefficients
+//   wald_final_kernel  covariance sandwich, hat diagonals, log likelihood at the unfloored mu,
+//                      Cook's distances, Wald statistic, p-value; uniform work, plain grid
+//
+// NB log density: log f(y; size, mu) = c(y, size) - size log(1 + mu/size) + y log(mu / (size + mu)),
+// one instruction sequence for every count including zero.  R's dnbinom_mu() evaluates the same
+// quantity through Loader's saddle-point expansion; the two agree to ~1e-14 relative except when
+// size = 1/alpha is huge, where the lgamma difference cancels: rows with 1/alpha > 1e6 take the
+// saddle-point path (dnbinom_mu_log in common.cuh).
 #include "kernels.h"
 
 namespace cd {
@@ -23,7 +36,191 @@ cudaError_t set_design_wald(const CdDesign& d, cudaStream_t st)
 }
 
 constexpr int kWaldThreads = 128;
+constexpr double kHalfLn2Pi = 0.918938533204672741780329736406;
+constexpr double kHugeSize = 1e6;
 
+static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// mu-dependent part of the log density
+__device__ __forceinline__ double nb_logdens(double y, double size, double alpha, double mu, double c)
+{
+    if (size > kHugeSize) return dnbinom_mu_log(y, size, mu);
+    const double l1 = log_pos(1.0 + mu * alpha);
+    const double l2 = log_pos(mu * rcp_pos(size + mu));
+    return (c - size * l1) + y * l2;
+}
+
+// ---------------------------------------------------------------------------------------
+// prep
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wald_prep_kernel(int64_t n, int S, int P, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                 const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
+                 double* __restrict__ cmat, double* __restrict__ beta0)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] & CD_FLAG_ALLZERO) return;
+    const double alpha = dispersion[i];
+    const double size = rcp_pos(alpha);
+    const double lgs = lgamma_c_pos(size);
+    double b[CD_MAXP];
+    for (int u = 0; u < P; u++) b[u] = 0.0;
+    for (int j = 0; j < S; j++) {
+        const double y = (double)K[(int64_t)j * n + i];
+        cmat[(int64_t)j * n + i] = ((lgamma_c_pos(y + size) - lgs) - lgamma_c_pos(y + 1.0)) - kHalfLn2Pi;
+        if (beta0) {
+            const double l = log_pos(y * rcp_pos(nf[(int64_t)j * n + i]) + 0.1);
+            for (int u = 0; u < P; u++) b[u] += c_desw.ls[u * S + j] * l;
+        }
+    }
+    if (beta0) for (int u = 0; u < P; u++) beta0[(int64_t)u * n + i] = b[u];
+}
+
+// ---------------------------------------------------------------------------------------
+// IRLS
+// ---------------------------------------------------------------------------------------
+// one sweep over the samples at coefficients beta: X'WX (packed, no ridge), X'Wz and the deviance
+template <int P>
+__device__ __forceinline__ void irls_pass(const double* beta, double alpha, double size, int S, int stride,
+                                          const double* ys, const double* nfs, const double* cs,
+                                          Sym<P>& A, double* b, double& dev)
+{
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) A.v[k] = 0.0;
+#pragma unroll
+    for (int u = 0; u < P; u++) b[u] = 0.0;
+    double ll = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < S; j++) {
+        const double yj = ys[j * stride], nfj = nfs[j * stride];
+        double eta = 0.0;
+#pragma unroll
+        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+        double mu = nfj * exp(eta);
+        double lmn = eta;
+        if (!(mu >= kMinMu)) { mu = kMinMu; lmn = log_pos(kMinMu * rcp_pos(nfj)); }     // fmax(mu, minmu)
+        ll += nb_logdens(yj, size, alpha, mu, cs[j * stride]);
+        const double w = mu * rcp_pos(1.0 + alpha * mu);
+        const double z = lmn + (yj - mu) * rcp_pos(mu);
+#pragma unroll
+        for (int u = 0; u < P; u++) {
+            const double xu = c_desw.X[j * P + u];
+            b[u] += w * z * xu;
+#pragma unroll
+            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * xu * c_desw.X[j * P + v];
+        }
+    }
+    dev = -2.0 * ll;
+}
+
+template <int P>
+__global__ void __launch_bounds__(kWaldThreads)
+wald_irls_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                 const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
+                 const double* __restrict__ cmat, const double* __restrict__ beta0,
+                 double* __restrict__ beta_out /*P x n, natural log scale*/, int32_t* __restrict__ iter_out,
+                 unsigned long long* __restrict__ work_counter)
+{
+    extern __shared__ double smem[];
+    const int stride = kWaldThreads;
+    double* ys = smem + threadIdx.x;
+    double* nfs = smem + (size_t)S * stride + threadIdx.x;
+    double* cs = smem + (size_t)2 * S * stride + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const double lambda = 1e-6 / (kLn2 * kLn2);
+
+    bool active = false, exhausted = false, fresh = false;
+    int64_t i = 0;
+    double beta[P], rhs[P];
+    Sym<P> A;
+    double alpha = 1.0, size = 1.0, dev_old = 0.0;
+    int iter = 0;
+#pragma unroll
+    for (int u = 0; u < P; u++) { beta[u] = 0.0; rhs[u] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) A.v[k] = 0.0;
+
+    while (true) {
+        const bool want = !active && !exhausted;
+        const unsigned need = __ballot_sync(0xffffffffu, want);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                i = (int64_t)(base + __popc(need & ((1u << lane) - 1u)));
+                if (i >= n) {
+                    exhausted = true;
+                } else if (flags[i] & CD_FLAG_ALLZERO) {
+                    iter_out[i] = 0;
+#pragma unroll
+                    for (int u = 0; u < P; u++) beta_out[(int64_t)u * n + i] = NAN;
+                } else {
+                    for (int j = 0; j < S; j++) {
+                        ys[j * stride] = (double)K[(int64_t)j * n + i];
+                        nfs[j * stride] = nf[(int64_t)j * n + i];
+                        cs[j * stride] = cmat[(int64_t)j * n + i];
+                    }
+#pragma unroll
+                    for (int u = 0; u < P; u++) beta[u] = beta0[(int64_t)u * n + i];
+                    alpha = dispersion[i];
+                    size = rcp_pos(alpha);
+                    active = true; fresh = true;
+                    iter = 0; dev_old = 0.0;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, !active)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        // ---- solve the ridge normal equations from the previous sweep ----
+        bool finished = false;
+        if (active && !fresh) {
+            iter++;
+            Sym<P> Ar = A;
+#pragma unroll
+            for (int u = 0; u < P; u++) Ar.v[u * (u + 1) / 2 + u] += lambda;
+            chol_logdet<P>(Ar);
+            double bn[P];
+#pragma unroll
+            for (int u = 0; u < P; u++) bn[u] = rhs[u];
+            chol_solve<P>(Ar, bn);
+            bool big = false;
+#pragma unroll
+            for (int u = 0; u < P; u++) { beta[u] = bn[u]; big = big || (fabs(bn[u]) > 30.0); }
+            if (big) { iter = 100; finished = true; }
+        }
+        __syncwarp();
+        // ---- one sweep over the replicates at the current coefficients ----
+        double dev = 0.0;
+        if (active && !finished) irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, A, rhs, dev);
+        __syncwarp();
+        if (active && !finished) {
+            if (fresh) {
+                fresh = false;
+            } else {
+                const double conv_test = fabs(dev - dev_old) / (fabs(dev) + 0.1);
+                if (isnan(conv_test)) { iter = 100; finished = true; }
+                else if (iter > 1 && conv_test < 1e-8) finished = true;
+                else if (iter >= 100) finished = true;
+                dev_old = dev;
+            }
+        }
+        if (finished) {
+#pragma unroll
+            for (int u = 0; u < P; u++) beta_out[(int64_t)u * n + i] = beta[u];
+            iter_out[i] = iter;
+            active = false;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// finalisation
+// ---------------------------------------------------------------------------------------
 // R mean(x, trim): sort, drop floor(n * trim) from each end
 __device__ __forceinline__ double trimmed_mean_dev(double* v, int n, double trim)
 {
@@ -41,54 +238,16 @@ __device__ __forceinline__ double trimmed_mean_dev(double* v, int n, double trim
 
 __device__ __forceinline__ int trim_bin(int n) { return n <= 3 ? 0 : (n <= 23 ? 1 : 2); }
 
-// one sweep over the samples at coefficients beta: X'WX (packed, no ridge), X'Wz and the deviance
-template <int P>
-__device__ __forceinline__ void irls_pass(const double* beta, double alpha, double size, int S, int stride,
-                                          const double* ys, const double* nfs, const double* cs, const int* kinds,
-                                          Sym<P>& A, double* b, double& dev)
-{
-#pragma unroll
-    for (int k = 0; k < P * (P + 1) / 2; k++) A.v[k] = 0.0;
-#pragma unroll
-    for (int u = 0; u < P; u++) b[u] = 0.0;
-    dev = 0.0;
-#pragma unroll 1
-    for (int j = 0; j < S; j++) {
-        const double yj = ys[j * stride], nfj = nfs[j * stride];
-        double eta = 0.0;
-#pragma unroll
-        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
-        double mu = nfj * exp(eta);
-        double lmn = eta;
-        if (!(mu >= kMinMu)) { mu = kMinMu; lmn = log(kMinMu / nfj); }     // fmax(mu, minmu)
-        NbConst kc; kc.c = cs[j * stride]; kc.kind = kinds[j * stride];
-        dev += -2.0 * nb_var(yj, size, mu, kc);
-        const double w = mu / (1.0 + alpha * mu);
-        const double z = lmn + (yj - mu) / mu;
-#pragma unroll
-        for (int u = 0; u < P; u++) {
-            const double xu = c_desw.X[j * P + u];
-            b[u] += w * z * xu;
-#pragma unroll
-            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * xu * c_desw.X[j * P + v];
-        }
-    }
-}
-
 template <int P>
 __global__ void __launch_bounds__(kWaldThreads)
-wald_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
-            const double* __restrict__ dispersion, uint8_t* __restrict__ flags,
-            double* __restrict__ beta_out, double* __restrict__ se_out, double* __restrict__ stat_out,
-            double* __restrict__ pvalue_out, double* __restrict__ deviance_out, double* __restrict__ maxCooks_out,
-            int32_t* __restrict__ betaIter_out, double* __restrict__ mu_out)
+wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                  const double* __restrict__ dispersion, uint8_t* __restrict__ flags,
+                  const double* __restrict__ cmat, const double* __restrict__ beta_nat,
+                  const int32_t* __restrict__ iter_in,
+                  double* __restrict__ beta_out, double* __restrict__ se_out, double* __restrict__ stat_out,
+                  double* __restrict__ pvalue_out, double* __restrict__ deviance_out, double* __restrict__ maxCooks_out,
+                  int32_t* __restrict__ betaIter_out, double* __restrict__ mu_out)
 {
-    extern __shared__ double smem[];
-    const int stride = kWaldThreads;
-    double* ys = smem + threadIdx.x;
-    double* nfs = smem + (size_t)S * stride + threadIdx.x;
-    double* cs = smem + (size_t)2 * S * stride + threadIdx.x;
-    int* kinds = reinterpret_cast<int*>(smem + (size_t)3 * S * stride) + threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const bool mu_only = (mu_out != nullptr);
@@ -100,108 +259,70 @@ wald_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __res
         return;
     }
     const double alpha = dispersion[i];
-    const double size = 1.0 / alpha;
-    double qsum = 0.0;
-    for (int j = 0; j < S; j++) {
-        const double yj = (double)K[(int64_t)j * n + i];
-        const double nfj = nf[(int64_t)j * n + i];
-        ys[j * stride] = yj;
-        nfs[j * stride] = nfj;
-        const NbConst kc = nb_const(yj, size);
-        cs[j * stride] = kc.c;
-        kinds[j * stride] = kc.kind;
-        qsum += yj / nfj;
-    }
-    double beta[P], se[P];
-    Sym<P> A;
-    double rhs[P];
-    double dev = 0.0;
-    int iter = 0;
-    bool noconv = false;
+    const double size = rcp_pos(alpha);
     const double lambda = 1e-6 / (kLn2 * kLn2);
+    double beta[P], se[P];
+    int iter = 1;
+    double qsum = 0.0;
+    for (int j = 0; j < S; j++) qsum += (double)K[(int64_t)j * n + i] * rcp_pos(nf[(int64_t)j * n + i]);
     if (P == 1) {
-        // fitNbinomGLMs intercept-only shortcut: beta = log2(mean normalised count)
-        beta[0] = log(qsum / S);
-        iter = 1;
+        beta[0] = log_pos(qsum / S);          // fitNbinomGLMs intercept-only shortcut (natural log scale)
     } else {
-        // start: least squares of log(q + 0.1) on X
 #pragma unroll
-        for (int u = 0; u < P; u++) beta[u] = 0.0;
-        for (int j = 0; j < S; j++) {
-            const double l = log(ys[j * stride] / nfs[j * stride] + 0.1);
-#pragma unroll
-            for (int u = 0; u < P; u++) beta[u] += c_desw.ls[u * S + j] * l;
-        }
-        double dev_old = 0.0, dev_new;
-        irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, kinds, A, rhs, dev_new);
-        for (int t = 0; t < 100; t++) {
-            iter++;
-            Sym<P> Ar = A;
-#pragma unroll
-            for (int u = 0; u < P; u++) Ar.v[u * (u + 1) / 2 + u] += lambda;
-            chol_logdet<P>(Ar);
-            double bn[P];
-#pragma unroll
-            for (int u = 0; u < P; u++) bn[u] = rhs[u];
-            chol_solve<P>(Ar, bn);
-            bool big = false;
-#pragma unroll
-            for (int u = 0; u < P; u++) { beta[u] = bn[u]; big = big || (fabs(bn[u]) > 30.0); }
-            if (big) { iter = 100; break; }
-            irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, kinds, A, rhs, dev_new);
-            dev = dev_new;
-            const double conv_test = fabs(dev - dev_old) / (fabs(dev) + 0.1);
-            if (isnan(conv_test)) { iter = 100; break; }
-            if (t > 0 && conv_test < 1e-8) break;
-            dev_old = dev;
-        }
-        noconv = !(iter < 100);
+        for (int u = 0; u < P; u++) beta[u] = beta_nat[(int64_t)u * n + i];
+        iter = iter_in[i];
     }
     if (mu_only) {
         for (int j = 0; j < S; j++) {
             double eta = 0.0;
 #pragma unroll
             for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
-            mu_out[(int64_t)j * n + i] = fmax(nfs[j * stride] * exp(eta), kMinMu);
+            mu_out[(int64_t)j * n + i] = fmax(nf[(int64_t)j * n + i] * exp(eta), kMinMu);
         }
         return;
     }
-    // covariance, hat diagonals, log likelihood at the unclamped mu, Cook's distance
-    Sym<P> Ari;
-    if (P == 1) {
-        double sw = 0.0;
-        const double m0 = exp(beta[0]);                  // = 2^log2(mean q)
-        for (int j = 0; j < S; j++) sw += 1.0 / (1.0 / (nfs[j * stride] * m0) + alpha);
-        A.v[0] = sw;
-        Ari.v[0] = 1.0 / sw;
-        se[0] = kLog2e * sqrt(1.0 / sw);
-    } else {
-        Sym<P> Ar = A;
+    // X'WX at the final coefficients (weights at the floored mu; at mu itself for the p = 1 shortcut)
+    Sym<P> A;
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) A.v[k] = 0.0;
+    double loglike = 0.0;
+    for (int j = 0; j < S; j++) {
+        const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
+        double eta = 0.0;
+#pragma unroll
+        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+        const double muw = nfj * exp(eta);                   // unfloored, as stored by nbinomWaldTest
+        loglike += nb_logdens(yj, size, alpha, muw, cmat[(int64_t)j * n + i]);
+        const double muc = (P == 1) ? muw : fmax(muw, kMinMu);
+        const double w = muc * rcp_pos(1.0 + alpha * muc);
+#pragma unroll
+        for (int u = 0; u < P; u++)
+#pragma unroll
+            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * c_desw.X[j * P + u] * c_desw.X[j * P + v];
+    }
+    Sym<P> Ar = A, Ari;
+    if (P > 1) {
 #pragma unroll
         for (int u = 0; u < P; u++) Ar.v[u * (u + 1) / 2 + u] += lambda;
-        chol_logdet<P>(Ar);
-        chol_inverse<P>(Ar, Ari);
-        bool bad = false;
-#pragma unroll
-        for (int u = 0; u < P; u++) {
-            // sigma_uu = sum_kl Ari[u][k] A[k][l] Ari[l][u]
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < P; k++)
-#pragma unroll
-                for (int l = 0; l < P; l++) s += Ari.v[sidx<P>(u, k)] * A.v[sidx<P>(k, l)] * Ari.v[sidx<P>(l, u)];
-            se[u] = kLog2e * sqrt(fmax(s, 0.0));
-            bad = bad || !(s > 0.0) || isnan(beta[u]);
-        }
-        noconv = noconv || bad;
     }
-    double loglike = 0.0;
-    // robust method-of-moments dispersion for Cook's distance
-    const bool want_cooks = (maxCooks_out != nullptr);
-    double ar = 0.0;
-    if (want_cooks) {
-        double v;
-        double tmp[CD_MAXS];
+    chol_logdet<P>(Ar);
+    chol_inverse<P>(Ar, Ari);
+    bool noconv = (P > 1) && !(iter < 100);
+#pragma unroll
+    for (int u = 0; u < P; u++) {
+        double s = 0.0;               // sigma_uu = sum_kl Ari[u][k] A[k][l] Ari[l][u]
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+            for (int l = 0; l < P; l++) s += Ari.v[sidx<P>(u, k)] * A.v[sidx<P>(k, l)] * Ari.v[sidx<P>(l, u)];
+        se[u] = kLog2e * sqrt(fmax(s, 0.0));
+        noconv = noconv || !(s > 0.0) || isnan(beta[u]);
+    }
+    uint8_t f = flags[i];
+    if (noconv) f |= CD_FLAG_BETA_NOCONV;
+    if (maxCooks_out) {
+        // robust method-of-moments dispersion for Cook's distance
+        double v, tmp[CD_MAXS];
         if (c_desw.any3) {
             v = -INFINITY;
             for (int c = 0; c < c_desw.ncell; c++) {
@@ -210,39 +331,33 @@ wald_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __res
                 const double trimr = (trim_bin(nc) == 0) ? 1.0 / 3.0 : (trim_bin(nc) == 1 ? 1.0 / 4.0 : 1.0 / 8.0);
                 const double scalec = (trim_bin(nc) == 0) ? 2.04 : (trim_bin(nc) == 1 ? 1.86 : 1.51);
                 int k = 0;
-                for (int j = 0; j < S; j++) if (c_desw.cell[j] == c) tmp[k++] = ys[j * stride] / nfs[j * stride];
+                for (int j = 0; j < S; j++) if (c_desw.cell[j] == c) tmp[k++] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
                 const double cm = trimmed_mean_dev(tmp, nc, trimr);
                 k = 0;
                 for (int j = 0; j < S; j++) if (c_desw.cell[j] == c) {
-                    const double d = ys[j * stride] / nfs[j * stride] - cm;
+                    const double d = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i] - cm;
                     tmp[k++] = d * d;
                 }
                 const double ve = scalec * trimmed_mean_dev(tmp, nc, trimr);
                 if (ve > v) v = ve;
             }
         } else {
-            for (int j = 0; j < S; j++) tmp[j] = ys[j * stride] / nfs[j * stride];
+            for (int j = 0; j < S; j++) tmp[j] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
             const double rm = trimmed_mean_dev(tmp, S, 1.0 / 8.0);
-            for (int j = 0; j < S; j++) { const double d = ys[j * stride] / nfs[j * stride] - rm; tmp[j] = d * d; }
+            for (int j = 0; j < S; j++) { const double d = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i] - rm; tmp[j] = d * d; }
             v = 1.51 * trimmed_mean_dev(tmp, S, 1.0 / 8.0);
         }
         const double mq = qsum / S;
-        ar = fmax((v - mq) / (mq * mq), 0.04);
-    }
-    double mc = -INFINITY, ck_best = -INFINITY;
-    double y_best = 0.0;
-    for (int j = 0; j < S; j++) {
-        const double yj = ys[j * stride], nfj = nfs[j * stride];
-        double eta = 0.0;
+        const double ar = fmax((v - mq) / (mq * mq), 0.04);
+        double mc = -INFINITY, ck_best = -INFINITY, y_best = 0.0;
+        for (int j = 0; j < S; j++) {
+            const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
+            double eta = 0.0;
 #pragma unroll
-        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
-        const double muw = nfj * exp(eta);                      // unclamped, as stored by nbinomWaldTest
-        NbConst kc; kc.c = cs[j * stride]; kc.kind = kinds[j * stride];
-        loglike += nb_var(yj, size, muw, kc);
-        if (want_cooks) {
-            // hat diagonal from the weights at the floored mu (fitBeta), or at mu itself (p = 1 shortcut)
+            for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+            const double muw = nfj * exp(eta);
             const double muc = (P == 1) ? muw : fmax(muw, kMinMu);
-            const double w = (P == 1) ? 1.0 / (1.0 / muc + alpha) : muc / (1.0 + alpha * muc);
+            const double w = muc / (1.0 + alpha * muc);
             double h = 0.0;
 #pragma unroll
             for (int u = 0; u < P; u++)
@@ -255,12 +370,8 @@ wald_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __res
             if (c_desw.cell_size[c_desw.cell[j]] >= 3 && ck > mc) mc = ck;
             if (ck > ck_best) { ck_best = ck; y_best = yj; }        // which.max: first maximum
         }
-    }
-    uint8_t f = flags[i];
-    if (noconv) f |= CD_FLAG_BETA_NOCONV;
-    if (want_cooks) {
         int greater = 0;
-        for (int j = 0; j < S; j++) greater += (ys[j * stride] > y_best);
+        for (int j = 0; j < S; j++) greater += ((double)K[(int64_t)j * n + i] > y_best);
         if (greater >= 3) f |= CD_FLAG_COOKS_KEEP;
         maxCooks_out[i] = (S > P && c_desw.any3) ? mc : NAN;
     }
@@ -278,27 +389,44 @@ wald_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __res
 }
 
 cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double* nf, const double* dispersion,
-                        uint8_t* flags, double* beta, double* betaSE, double* stat, double* pvalue, double* deviance,
-                        double* maxCooks, int32_t* betaIter, double* mu_out, cudaStream_t st)
+                        uint8_t* flags, const WaldScratch& ws, double* beta, double* betaSE, double* stat,
+                        double* pvalue, double* deviance, double* maxCooks, int32_t* betaIter, double* mu_out,
+                        cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    const int threads = kWaldThreads;
-    const int blocks = (int)((n + threads - 1) / threads);
-    const size_t smem = (size_t)S * threads * (3 * sizeof(double) + sizeof(int));
     cudaError_t e;
-#define CD_LAUNCH(P_)                                                                                               \
-    e = cudaFuncSetAttribute(wald_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-    if (e != cudaSuccess) return e;                                                                                 \
-    wald_kernel<P_><<<blocks, threads, smem, st>>>(n, S, K, nf, dispersion, flags, beta, betaSE, stat, pvalue,      \
-                                                   deviance, maxCooks, betaIter, mu_out)
+    wald_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, p, K, nf, dispersion, flags, ws.cmat, p > 1 ? ws.beta0 : nullptr);
+    const int threads = kWaldThreads;
+    const size_t smem = (size_t)3 * S * threads * sizeof(double);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + threads - 1) / threads;
+#define CD_IRLS(P_)                                                                                              \
+    {                                                                                                            \
+        e = cudaMemsetAsync(ws.work_counter, 0, sizeof(unsigned long long), st);                                 \
+        if (e != cudaSuccess) return e;                                                                          \
+        e = cudaFuncSetAttribute(wald_irls_kernel<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e != cudaSuccess) return e;                                                                          \
+        int per_sm = 1;                                                                                          \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wald_irls_kernel<P_>, threads, smem);         \
+        if (e != cudaSuccess) return e;                                                                          \
+        const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                       \
+        wald_irls_kernel<P_><<<(int)(want < resident ? want : resident), threads, smem, st>>>(                   \
+            n, S, K, nf, dispersion, flags, ws.cmat, ws.beta0, ws.beta_nat, ws.iter, ws.work_counter);        \
+    }
+#define CD_FINAL(P_)                                                                                             \
+    wald_final_kernel<P_><<<blocks_for(n, threads), threads, 0, st>>>(n, S, K, nf, dispersion, flags, ws.cmat,   \
+        ws.beta_nat, ws.iter, beta, betaSE, stat, pvalue, deviance, maxCooks, betaIter, mu_out)
     switch (p) {
-        case 1: CD_LAUNCH(1); break;
-        case 2: CD_LAUNCH(2); break;
-        case 3: CD_LAUNCH(3); break;
-        case 4: CD_LAUNCH(4); break;
+        case 1: CD_FINAL(1); break;
+        case 2: CD_IRLS(2); CD_FINAL(2); break;
+        case 3: CD_IRLS(3); CD_FINAL(3); break;
+        case 4: CD_IRLS(4); CD_FINAL(4); break;
         default: return cudaErrorInvalidValue;
     }
-#undef CD_LAUNCH
+#undef CD_IRLS
+#undef CD_FINAL
     return cudaGetLastError();
 }
 
