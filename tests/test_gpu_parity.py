@@ -246,3 +246,19 @@ def test_error_paths():
         e.region_test()                                                  # S - p = 2 without a prior variance
     assert "prior" in str(ei.value)
     e.close()
+
+
+def test_two_gpu_sharded_run_matches_single_gpu():
+    """Regions sharded by bait over 2 ranks (NCCL all-gathers / all-reduces inside cd_region_test) must give
+    the single-GPU answer.  Skipped on a 1-GPU box."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "scripts", "multi_gpu_check.py"), "c3", "60000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
