@@ -1,0 +1,78 @@
+## chicdiff_b200.R -- R adapter: DESeq2Wrap() on the CUDA backend.
+##
+## Drop-in for Chicdiff::DESeq2Wrap (Chicdiff/R/chicdiff.R:1494-1777) when chicdiff.settings$backend == "cuda".
+## Same arguments, same messages, same output table (column order of chicdiff.R:1752-1762, rows ordered by
+## regionID, attr(out, "theta") only for norm == "combined").  It only marshals columns; every number comes
+## from libchicdiff_b200.so through R/r_glue.c.  Could not be executed in the build image (no R there);
+## chicdiff_b200/api.py is the same adapter in Python and is what the tests run.
+##
+## Not produced under this backend: the `_DESeqObj<suffix>.Rds` DESeqDataSet of saveAuxData = TRUE.
+
+DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", theta = NULL) {
+  Grid <- chicdiff.settings[["theta_grid"]]
+  rmapfile <- chicdiff.settings[["rmapfile"]]
+  if (is.null(theta) & !is.null(chicdiff.settings[["theta"]])) theta <- chicdiff.settings[["theta"]]
+  norm <- chicdiff.settings[["norm"]]
+  if (!norm %in% c("standard", "fullmean", "combined")) stop("DESeq2Wrap error: Unknown normalisation method.")
+  if (!is.null(theta)) {
+    if (theta == 1 & norm != "standard") {
+      warning("Mixing parameter theta set to 1, equivalent to norm = \"standard\". The norm method has been reset accordingly.")
+      norm <- "standard"
+    }
+    if (!theta & norm != "fullmean") {
+      warning("Mixing parameter theta set to 0, equivalent to norm = \"fullmean\". The norm method has been reset accordingly.")
+      norm <- "fullmean"
+    }
+  }
+  ## region-contiguous rows per sample: (regionID, otherEndID) order = the order data.table sums them in
+  fragData <- copy(FullRegionData)
+  samples <- unique(fragData$sample)
+  setkey(fragData, regionID, otherEndID)
+  conditions <- sapply(samples, function(s) fragData[sample == s, condition[1]])
+  X <- model.matrix(~ condition, data.frame(condition = factor(conditions)))
+  one <- fragData[sample == samples[1]]
+  row_off <- c(0, cumsum(as.numeric(one[, .N, by = regionID]$N)))
+  n <- length(row_off) - 1L; S <- length(samples); p <- ncol(X)
+
+  ctx <- .Call("cdR_create", as.integer(if (is.null(chicdiff.settings[["gpu"]])) 0L else chicdiff.settings[["gpu"]]))
+  .Call("cdR_set_design", ctx, X)
+  .Call("cdR_set_regions", ctx, row_off)
+  for (i in seq_along(samples)) {
+    x <- fragData[sample == samples[i]]
+    .Call("cdR_set_sample_rows", ctx, i, as.integer(x$N), as.numeric(x$FullMean))
+  }
+  .Call("cdR_aggregate", ctx, n, S)
+  if (norm == "combined" && is.null(theta)) message("Optimising scaling factors...")
+  na <- NA_real_
+  pv <- chicdiff.settings[["dispPriorVar"]]; pvg <- chicdiff.settings[["dispPriorVarGrid"]]
+  fit <- .Call("cdR_region_test", ctx, n, S, p, match(norm, c("standard", "fullmean", "combined")) - 1L,
+               if (is.null(theta) || norm != "combined") na else as.numeric(theta), as.numeric(Grid),
+               if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg)
+  if (length(fit$deviances)) {
+    message("Total deviances by theta (Fullmean --> Standard):")
+    cat(sprintf("%f", fit$deviances), "\n", file = stderr())
+  }
+  if (norm == "combined") message("Theta=", fit$theta)
+  message("Processing model output")
+  adj <- .Call("cdR_results_adjust", S, p, fit$baseMean, fit$maxCooks, fit$flags, fit$pvalue)
+
+  ## annotation, unchanged from chicdiff.R:1700-1717
+  rmap <- fread(rmapfile)
+  colnames(rmap) <- c("OEchr", "OEstart", "OEend", "otherEndID")
+  RUsummary <- RU[, list(baitID = baitID[1], minOE = min(otherEndID), maxOE = max(otherEndID)), by = "regionID"]
+  annoData <- merge(RUsummary, rmap[, c("otherEndID", "OEchr", "OEstart"), with = FALSE], by.x = "minOE", by.y = "otherEndID")
+  annoData <- merge(annoData, rmap[, c("otherEndID", "OEend"), with = FALSE], by.x = "maxOE", by.y = "otherEndID")
+  colnames(rmap) <- c("baitchr", "baitstart", "baitend", "baitID")
+  annoData <- merge(annoData, rmap, by.x = "baitID", by.y = "baitID")
+  setkey(annoData, regionID)
+  stopifnot(identical(1:nrow(annoData), annoData$regionID))
+
+  label <- c(standard = "Standard DESeq2 normalisation", fullmean = "Chicago full mean-based normalisation",
+             combined = "combined normalisation")[[norm]]
+  message(label, ": # unweighted interactions with padj<0.05: ", sum(adj$padj < 0.05, na.rm = TRUE))
+  results <- data.table(baseMean = fit$baseMean, log2FoldChange = fit$log2FoldChange, lfcSE = fit$lfcSE,
+                        stat = fit$stat, pvalue = adj$pvalue, padj = adj$padj)
+  out <- cbind(results, annoData)
+  if (norm == "combined") attributes(out)$theta <- fit$theta
+  out
+}

@@ -231,3 +231,24 @@ def generate(name="tiny", n_regions=None, reps=None, ru_expand=5, ensure_nonzero
                      row_off=row_off, row_oe=row_oe.astype(np.int32), row_bait=row_bait.astype(np.int32),
                      N_rows=N_rows, FM_rows=FM_rows, true_lfc=true_lfc,
                      extra=dict(alpha=alpha, pair_index=pinv, n_pairs=U))
+
+
+def to_reference_tables(d):
+    """The same data in the shape of the reference's R objects: RU (chicdiff.R:392-397), the long
+    FullRegionData table after melt (chicdiff.R:912-925, sample-major blocks) and the rmap columns."""
+    n, R, S = d.n, d.R, d.S
+    region_of_row = np.repeat(np.arange(1, n + 1), np.diff(d.row_off))
+    RU = {"baitID": d.row_bait.astype(np.int64), "regionID": region_of_row.astype(np.int64), "otherEndID": d.row_oe.astype(np.int64)}
+    names = []
+    counts = {}
+    for c in d.conditions:
+        counts[c] = counts.get(c, 0) + 1
+        names.append("%s.rep%d" % (c, counts[c]))
+    frd = {
+        "baitID": np.tile(RU["baitID"], S), "otherEndID": np.tile(RU["otherEndID"], S), "regionID": np.tile(RU["regionID"], S),
+        "sample": np.repeat(np.asarray(names), R), "N": d.N_rows.reshape(-1), "FullMean": d.FM_rows.reshape(-1),
+        "condition": np.repeat(np.asarray(d.conditions), R),
+    }
+    F = len(d.frag_chr)
+    rmap = {"chr": d.frag_chr.astype(str), "start": d.frag_start, "end": d.frag_end, "ID": np.arange(1, F + 1)}
+    return RU, frd, rmap

@@ -262,3 +262,38 @@ def test_two_gpu_sharded_run_matches_single_gpu():
            "--master-port", "29517", os.path.join(root, "scripts", "multi_gpu_check.py"), "c3", "60000"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "MULTI_GPU_CHECK OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_DESeq2Wrap_mirror_table_matches_oracle():
+    """The host mirror of DESeq2Wrap (chicdiff.R:1494-1777): column set and order, regionID ordering, annotation
+    lookups, theta attribute, padj -- against the oracle on the reference-shaped tables."""
+    from chicdiff_b200 import api
+    d = synth.generate("tiny", seed_offset=11)
+    RU, frd, rmap = synth.to_reference_tables(d)
+    # shuffle the rows inside every sample block: the adapter must restore (regionID, otherEndID) order itself
+    rng = np.random.default_rng(0)
+    perm = np.concatenate([s * d.R + rng.permutation(d.R) for s in range(d.S)])
+    frd = {k: v[perm] for k, v in frd.items()}
+    st = api.defaultChicdiffSettings()
+    out = api.DESeq2Wrap(st, RU, frd, rmap=rmap)
+    assert list(out)[:16] == ["baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "padj", "baitID", "maxOE", "minOE",
+                              "regionID", "OEchr", "OEstart", "OEend", "baitchr", "baitstart", "baitend"]
+    Ko, FMo = O.aggregate(d.row_off, d.N_rows, d.FM_rows)
+    ro = O.region_test(Ko, FMo, d.X)
+    res_o = O.results(ro, Ko, d.X)
+    assert out["attr_theta"] == ro["theta"]
+    assert np.array_equal(out["regionID"], np.arange(1, d.n + 1))
+    assert np.array_equal(out["baitID"], d.region_bait)
+    lo = np.minimum.reduceat(d.row_oe, d.row_off[:-1]); hi = np.maximum.reduceat(d.row_oe, d.row_off[:-1])
+    assert np.array_equal(out["minOE"], lo) and np.array_equal(out["maxOE"], hi)
+    assert np.array_equal(out["OEstart"], d.frag_start[lo - 1]) and np.array_equal(out["OEend"], d.frag_end[hi - 1])
+    assert np.array_equal(out["baitstart"], d.frag_start[d.region_bait - 1])
+    for k in ("baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "padj"):
+        f, _ = frac_ok(out[k], res_o[k], ro["betaSE"][1] if k == "log2FoldChange" else None)
+        assert f == 1.0, k
+    # theta = 1 silently becomes "standard" and then carries no theta attribute (chicdiff.R:1511-1515, 1759)
+    out1 = api.DESeq2Wrap(st, RU, frd, theta=1, rmap=rmap)
+    assert "attr_theta" not in out1
+    st_bad = dict(st, norm="nonsense")
+    with pytest.raises(ValueError):
+        api.DESeq2Wrap(st_bad, RU, frd, rmap=rmap)
