@@ -545,60 +545,6 @@ int size_factors(cd_ctx* ctx, double* sf_host)
     return CD_OK;
 }
 
-// parametricDispersionFit on the global arrays; coefs out.  Mirrors glm.fit's IRLS with step halving.
-int trend_fit(cd_ctx* ctx, double coefs[2])
-{
-    const int64_t nt = ctx->n_tot;
-    double c0 = 0.1, c1 = 1.0;
-    int iter = 0;
-    auto pass = [&](double oc0, double oc1, double b0, double b1, double* v) -> int {
-        CD_LAUNCHN(ctx, 2, launch_trend_pass(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, oc0, oc1, b0, b1,
-                                             ctx->partial.p, ctx->scal.p + 40, ctx->st));
-        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 40, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
-        for (int k = 0; k < 8; k++) v[k] = ctx->h_pinned[k];
-        return CD_OK;
-    };
-    while (true) {
-        double v[8];
-        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
-        int rc = pass(c0, c1, b0, b1, v);
-        if (rc != CD_OK) return rc;
-        if (v[7] < 2.0) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (fewer than 2 usable regions); the reference would switch to a local fit, which is not implemented");
-        if (v[6] > 0.0) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (invalid starting values); the reference would switch to a local fit, which is not implemented");
-        double devold = v[5];
-        bool conv = false;
-        for (int it = 0; it < 25; it++) {
-            const double det = v[0] * v[2] - v[1] * v[1];
-            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
-            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
-            double w[8];
-            int halv = 0;
-            while (true) {
-                rc = pass(c0, c1, nb0, nb1, w);
-                if (rc != CD_OK) return rc;
-                if (w[6] == 0.0 && std::isfinite(w[5])) break;
-                if (++halv > 25) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (no valid step); local fit not implemented");
-                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
-            }
-            b0 = nb0; b1 = nb1;
-            for (int k = 0; k < 8; k++) v[k] = w[k];
-            const double dev = w[5];
-            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
-            devold = dev; ob0 = b0; ob1 = b1;
-        }
-        const double oc0 = c0, oc1 = c1;
-        c0 = b0; c1 = b1;
-        if (!(c0 > 0.0 && c1 > 0.0)) return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (non-positive coefficients); local fit not implemented");
-        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
-        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
-        iter++;
-        if (iter > 10) return ctx->fail(CD_ENUMERIC, "dispersion fit did not converge; local fit not implemented");
-    }
-    coefs[0] = c0; coefs[1] = c1;
-    return CD_OK;
-}
-
 struct PipeOut { double a0, a1, varLogDispEsts, dispPriorVar, sum_deviance; };
 
 // estimateDispersions + nbinomWaldTest for one normalisation (mode / theta) and one design
@@ -650,15 +596,15 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
         CD_COMM(ctx, ctx->comm.allgatherv(dispGeneEst, ctx->g_dispGeneEst.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
         CD_COMM(ctx, ctx->comm.allgatherv(flags, ctx->g_flags.p, ctx->shard_n, ctx->shard_off, sizeof(uint8_t), st));
     }
-    // trend + MAD on the global arrays (every rank computes the same numbers)
-    double coefs[2];
+    // trend + MAD on the global arrays (every rank computes the same numbers); one host sync for both
     ctx->tm_begin(5);
-    int rc = trend_fit(ctx, coefs);
-    if (rc != CD_OK) return rc;
-    CD_LAUNCHN(ctx, 1, launch_trend_apply(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, coefs[0], coefs[1],
+    double* trend_dev = ctx->scal.p + 110;         // coefs[2], status, outer iterations, passes
+    CD_LAUNCHN(ctx, 1, launch_trend_fit(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->partial.p,
+                                        reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, st));
+    CD_LAUNCHN(ctx, 1, launch_trend_apply(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
                                           ctx->g_dispFit.p, ctx->g_resid.p, st));
     double* med_dev = ctx->scal.p + 44;
-    rc = median_finite(ctx, ctx->g_resid.p, nt, med_dev, 0, 1.0);
+    int rc = median_finite(ctx, ctx->g_resid.p, nt, med_dev, 0, 1.0);
     if (rc != CD_OK) return rc;
     CD_CUDA(ctx, ctx->g_sortbuf2.ensure((size_t)nt));
     if (nt > 0) {
@@ -668,9 +614,18 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     rc = median_finite(ctx, ctx->g_sortbuf2.p, nt, ctx->scal.p + 45, 0, 1.4826);
     if (rc != CD_OK) return rc;
     ctx->tm_end();
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, trend_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaStreamSynchronize(st));
-    const double mad = ctx->h_pinned[0];
+    const double coefs[2] = {ctx->h_pinned[0], ctx->h_pinned[1]};
+    const int tstatus = (int)ctx->h_pinned[2];
+    if (tstatus != 0) {
+        static const char* why[] = {"", "fewer than 2 usable regions", "invalid starting values", "no valid step",
+                                    "non-positive coefficients", "did not converge"};
+        return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (%s); the reference would switch to a local "
+                                      "regression fit (locfit), which is not implemented", why[tstatus < 6 ? tstatus : 0]);
+    }
+    const double mad = ctx->h_pinned[8];
     if (std::isnan(mad))
         return ctx->fail(CD_ENUMERIC, "all gene-wise dispersion estimates are within 2 orders of magnitude of the minimum");
     const double varLogDispEsts = mad * mad;

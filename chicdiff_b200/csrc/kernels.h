@@ -78,8 +78,12 @@ cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* d
                               const uint8_t* flags, double c0, double c1, double b0, double b1,
                               double* partial, double* out, cudaStream_t st);
 // dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded
+// the whole parametricDispersionFit in one cooperative kernel; out[0..1] coefs, out[2] status, out[3] outer
+// iterations, out[4] passes; partial >= 8 * #SMs doubles, bar = one zero-initialised word
+cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+                             double* partial, unsigned int* bar, double* out, cudaStream_t st);
 cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst,
-                               const uint8_t* flags, double a0, double a1, double* dispFit, double* resid,
+                               const uint8_t* flags, const double* coefs_dev, double* dispFit, double* resid,
                                cudaStream_t st);
 
 // ---- stages 3 + 5: NB GLM, Cook's, Wald --------------------------------------------------

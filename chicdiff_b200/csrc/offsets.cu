@@ -197,25 +197,173 @@ cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* d
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------
+// The whole parametricDispersionFit on the device: one cooperative kernel, one CTA per SM.
+// Every pass (sums + deviance at coefficients b over the rows kept by the outer coefficients c)
+// is a chunked block reduction, a grid barrier, and a fixed-order sum of the per-CTA partials
+// that every CTA repeats for itself, so all CTAs take the same branch of glm.fit's control flow
+// (start validity, IRLS <= 25, step halving, outer loop <= 11) without a host round trip.
+// out[0..1] = coefficients, out[2] = status (0 ok; >0 = reason the reference would fall back to
+// a local fit), out[3] = outer iterations, out[4] = passes.
+// ---------------------------------------------------------------------------------------
+constexpr int kTrendThreads = 512;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& phase)
+{
+    __syncthreads();
+    phase++;                                   // every thread keeps the same phase count
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (atomicAdd(bar, 0u) < phase * nblocks) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void trend_pass_device(int64_t n, const double* __restrict__ baseMean,
+                                                  const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
+                                                  double c0, double c1, double b0, double b1, double* partial_base,
+                                                  unsigned int* bar, unsigned int& phase, double* sh_tot /*8, shared*/)
+{
+    // partials are double-buffered by pass parity: a CTA can be at most one pass ahead of the slowest
+    // one (there is a barrier in every pass), so one barrier per pass is enough
+    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (flags[i] & CD_FLAG_ALLZERO) continue;
+        const double d = dispGeneEst[i];
+        if (!(d > 100.0 * kMinDisp)) continue;
+        const double x = 1.0 / baseMean[i];
+        const double r = d / (c0 + c1 * x);
+        if (!((r > 1e-4) && (r < 15.0))) continue;
+        const double mu = b0 + b1 * x;
+        v[7] += 1.0;
+        if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; continue; }
+        const double w = 1.0 / (mu * mu);
+        v[0] += w; v[1] += w * x; v[2] += w * x * x;
+        v[3] += w * d; v[4] += w * x * d;
+        v[5] += -2.0 * (log(d / mu) - (d - mu) / mu);
+    }
+    // block reduction (fixed order)
+    __shared__ double sh[8][kTrendThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) sh[k][wid] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double x = 0.0;
+        for (int w = 0; w < kTrendThreads / 32; w++) x += sh[threadIdx.x][w];
+        __stcg(partial + (size_t)blockIdx.x * 8 + threadIdx.x, x);
+    }
+    grid_barrier(bar, gridDim.x, phase);
+    // fixed-order sum of the per-CTA partials, one warp per value; every CTA repeats it for itself
+    if (wid < 8) {
+        double x = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) x += __ldcg(partial + (size_t)b * 8 + wid);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) sh_tot[wid] = x;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTrendThreads)
+trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
+                 const uint8_t* __restrict__ flags, double* partial, unsigned int* bar, double* out)
+{
+    __shared__ double tot[8];
+    unsigned int phase = 0;
+    double c0 = 0.1, c1 = 1.0;
+    int iter = 0, status = 0, passes = 0;
+    while (true) {
+        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
+        trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial, bar, phase, tot); passes++;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = tot[k];
+        if (v[7] < 2.0) { status = 1; break; }
+        if (v[6] > 0.0) { status = 2; break; }
+        double devold = v[5];
+        bool conv = false;
+        for (int it = 0; it < 25 && status == 0; it++) {
+            const double det = v[0] * v[2] - v[1] * v[1];
+            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
+            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
+            double w[8];
+            int halv = 0;
+            while (true) {
+                trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, nb0, nb1, partial, bar, phase, tot); passes++;
+#pragma unroll
+                for (int k = 0; k < 8; k++) w[k] = tot[k];
+                if (w[6] == 0.0 && isfinite(w[5])) break;
+                if (++halv > 25) { status = 3; break; }
+                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
+            }
+            if (status) break;
+            b0 = nb0; b1 = nb1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = w[k];
+            const double dev = w[5];
+            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
+            devold = dev; ob0 = b0; ob1 = b1;
+        }
+        if (status) break;
+        const double oc0 = c0, oc1 = c1;
+        c0 = b0; c1 = b1;
+        if (!(c0 > 0.0 && c1 > 0.0)) { status = 4; break; }
+        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
+        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
+        iter++;
+        if (iter > 10) { status = 5; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out[0] = c0; out[1] = c1; out[2] = (double)status; out[3] = (double)(iter + 1); out[4] = (double)passes;
+    }
+}
+
+cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+                             double* partial, unsigned int* bar, double* out, cudaStream_t st)
+{
+    int dev = 0, sms = 148, coop = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (!coop) return cudaErrorNotSupported;
+    cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&partial, (void*)&bar, (void*)&out};
+    return cudaLaunchCooperativeKernel((const void*)trend_fit_kernel, dim3((unsigned)sms), dim3(kTrendThreads), args, 0, st);
+}
+
+// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded ; coefficients on device
 __global__ void __launch_bounds__(256)
 trend_apply_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
-                   const uint8_t* __restrict__ flags, double a0, double a1, double* __restrict__ dispFit,
+                   const uint8_t* __restrict__ flags, const double* __restrict__ coefs, double* __restrict__ dispFit,
                    double* __restrict__ resid)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) { dispFit[i] = NAN; resid[i] = INFINITY; return; }
-    const double f = a0 + a1 / baseMean[i];
+    const double f = coefs[0] + coefs[1] / baseMean[i];
     const double d = dispGeneEst[i];
     dispFit[i] = f;
     resid[i] = (d >= 100.0 * kMinDisp) ? log(d) - log(f) : INFINITY;
 }
 
 cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                               double a0, double a1, double* dispFit, double* resid, cudaStream_t st)
+                               const double* coefs_dev, double* dispFit, double* resid, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, baseMean, dispGeneEst, flags, a0, a1, dispFit, resid);
+    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, baseMean, dispGeneEst, flags, coefs_dev, dispFit, resid);
     return cudaGetLastError();
 }
 
