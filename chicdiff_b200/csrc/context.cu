@@ -220,6 +220,16 @@ struct cd_ctx {
     DevBuf<double> park_d;           // 5 x capacity
     DevBuf<int32_t> park_i;          // 2 x capacity
     FitDispPark park{};
+    // assembly inputs
+    int64_t F = 0;
+    int32_t frag_id0 = 0;
+    bool have_rmap = false, have_region_rows = false;
+    DevBuf<int32_t> frag_chr, frag_start, frag_end, row_bait, row_oe, asm_status;
+    std::vector<DevBuf<unsigned char>> tab_blob;
+    std::vector<AssembleTables> tabs_host;
+    std::vector<uint8_t> tab_set;
+    DevBuf<unsigned char> tabs_dev;
+    DevBuf<double> avDist;
     DevBuf<double> wald_c, wald_b0, wald_b;
     DevBuf<int32_t> wald_iter;
     WaldScratch wald_ws{};
@@ -403,6 +413,7 @@ int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off)
     ctx->n = n;
     ctx->R = row_off[n];
     ctx->have_regions = true;
+    ctx->have_region_rows = false;
     ctx->have_agg = false;
     ctx->rows_borrowed = false;
     ctx->N_rows_p = nullptr; ctx->FM_rows_p = nullptr;
@@ -455,6 +466,134 @@ int cd_set_aggregated(cd_ctx* ctx, int64_t n, const int32_t* K, const double* fu
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     ctx->n = n;
     ctx->have_agg = true;
+    return CD_OK;
+}
+
+int cd_set_rmap(cd_ctx* ctx, int64_t F, int32_t frag_id0, const int32_t* chr, const int32_t* start, const int32_t* end)
+{
+    if (!ctx) return CD_EINVAL;
+    if (F < 1 || !chr || !start || !end) return ctx->fail(CD_EINVAL, "cd_set_rmap: bad arguments");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->frag_chr.ensure((size_t)F)); CD_CUDA(ctx, ctx->frag_start.ensure((size_t)F)); CD_CUDA(ctx, ctx->frag_end.ensure((size_t)F));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->frag_chr.p, chr, sizeof(int32_t) * (size_t)F, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->frag_start.p, start, sizeof(int32_t) * (size_t)F, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->frag_end.p, end, sizeof(int32_t) * (size_t)F, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->F = F; ctx->frag_id0 = frag_id0; ctx->have_rmap = true;
+    return CD_OK;
+}
+
+int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions) return ctx->fail(CD_EINVAL, "cd_set_region_rows: call cd_set_regions first");
+    if (R != ctx->R || (R > 0 && (!row_bait || !row_oe))) return ctx->fail(CD_EINVAL, "cd_set_region_rows: row count does not match the regions");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->row_bait.ensure((size_t)R)); CD_CUDA(ctx, ctx->row_oe.ensure((size_t)R));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->row_bait.p, row_bait, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->row_oe.p, row_oe, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
+    ctx->have_region_rows = true;
+    ctx->have_agg = false;
+    return CD_OK;
+}
+
+int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* t)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_design || !ctx->have_rmap) return ctx->fail(CD_EINVAL, "cd_set_sample_tables: call cd_set_design and cd_set_rmap first");
+    const int S = ctx->des.S;
+    if (s < 0 || s >= S || !t || !t->s_j || !t->tblb || !t->s_i || !t->tlb || !t->tmean || !t->cnt_off || t->n_tblb < 1 || t->n_tlb < 1)
+        return ctx->fail(CD_EINVAL, "cd_set_sample_tables: bad arguments");
+    const int64_t F = ctx->F;
+    const int64_t ncnt = t->cnt_off[F];
+    if (t->cnt_off[0] != 0 || ncnt < 0 || (ncnt > 0 && (!t->cnt_oe || !t->cnt_N))) return ctx->fail(CD_EINVAL, "cd_set_sample_tables: bad count table");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((int)ctx->tab_blob.size() != S) { ctx->tab_blob.clear(); ctx->tab_blob.resize((size_t)S); ctx->tabs_host.assign((size_t)S, AssembleTables{}); ctx->tab_set.assign((size_t)S, 0); }
+    // one device allocation per replicate, 256-byte aligned sections
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nt = (size_t)t->n_tblb * (size_t)t->n_tlb;
+    size_t off[11], pos = 0;
+    const size_t sizes[10] = {sizeof(double) * (size_t)F, sizeof(int32_t) * (size_t)F, sizeof(double) * (size_t)F, sizeof(int32_t) * (size_t)F,
+                              sizeof(double) * nt, sizeof(double) * (size_t)t->n_tblb, sizeof(double) * 10, sizeof(int64_t) * ((size_t)F + 1),
+                              sizeof(int32_t) * (size_t)ncnt, sizeof(int32_t) * (size_t)ncnt};
+    for (int k = 0; k < 10; k++) { off[k] = pos; pos += al(sizes[k]); }
+    off[10] = pos;
+    DevBuf<unsigned char>& blob = ctx->tab_blob[(size_t)s];
+    CD_CUDA(ctx, blob.ensure(pos));
+    const void* src[10] = {t->s_j, t->tblb, t->s_i, t->tlb, t->tmean, nullptr, t->distfun, t->cnt_off, t->cnt_oe, t->cnt_N};
+    for (int k = 0; k < 10; k++)
+        if (src[k] && sizes[k]) CD_CUDA(ctx, cudaMemcpyAsync(blob.p + off[k], src[k], sizes[k], cudaMemcpyHostToDevice, ctx->st));
+    AssembleTables& a = ctx->tabs_host[(size_t)s];
+    a.s_j = (const double*)(blob.p + off[0]); a.tblb = (const int32_t*)(blob.p + off[1]);
+    a.s_i = (const double*)(blob.p + off[2]); a.tlb = (const int32_t*)(blob.p + off[3]);
+    a.tmean = (const double*)(blob.p + off[4]); a.tmin = (const double*)(blob.p + off[5]);
+    a.distfun = (const double*)(blob.p + off[6]); a.cnt_off = (const int64_t*)(blob.p + off[7]);
+    a.cnt_oe = (const int32_t*)(blob.p + off[8]); a.cnt_N = (const int32_t*)(blob.p + off[9]);
+    a.n_tblb = t->n_tblb; a.n_tlb = t->n_tlb;
+    CD_LAUNCHN(ctx, 1, launch_tmin(t->n_tblb, t->n_tlb, a.tmean, (double*)(blob.p + off[5]), ctx->st));
+    ctx->tab_set[(size_t)s] = 1;
+    ctx->have_agg = false;
+    return CD_OK;           // copies are ordered before cd_assemble on the context's stream
+}
+
+int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out, double* avDist_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions || !ctx->have_region_rows || !ctx->have_rmap)
+        return ctx->fail(CD_EINVAL, "cd_assemble: needs cd_set_rmap, cd_set_regions and cd_set_region_rows");
+    const int S = ctx->des.S;
+    if ((int)ctx->tab_set.size() != S) return ctx->fail(CD_EINVAL, "cd_assemble: no replicate tables set");
+    for (int s = 0; s < S; s++)
+        if (!ctx->tab_set[(size_t)s]) return ctx->fail(CD_EINVAL, "cd_assemble: tables of replicate %d were never set", s);
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n, R = ctx->R;
+    CD_CUDA(ctx, ctx->K.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, ctx->FM.ensure((size_t)S * (size_t)n));
+    CD_CUDA(ctx, ctx->avDist.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->asm_status.ensure(1));
+    CD_CUDA(ctx, ctx->tabs_dev.ensure(sizeof(AssembleTables) * (size_t)S));
+    if (keep_rows) {
+        if (ctx->rows_borrowed) return ctx->fail(CD_EINVAL, "cd_assemble: rows were set with cd_set_rows_device");
+        CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R));
+        CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R));
+        ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
+    }
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->tabs_dev.p, ctx->tabs_host.data(), sizeof(AssembleTables) * (size_t)S, cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->asm_status.p, 0, sizeof(int32_t), ctx->st));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->st));
+    CD_LAUNCHN(ctx, n > 0 ? 1 : 0, launch_assemble(n, S, ctx->row_off.p, R, ctx->row_bait.p, ctx->row_oe.p, ctx->F, ctx->frag_id0,
+                                                  ctx->frag_chr.p, ctx->frag_start.p, ctx->frag_end.p,
+                                                  (const AssembleTables*)ctx->tabs_dev.p, ctx->K.p, ctx->FM.p, ctx->avDist.p,
+                                                  keep_rows ? ctx->N_rows.p : nullptr, keep_rows ? ctx->FM_rows.p : nullptr,
+                                                  ctx->asm_status.p, ctx->st));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->st));
+    int32_t status = 0;
+    CD_CUDA(ctx, cudaMemcpyAsync(&status, ctx->asm_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
+    if (K_out) CD_CUDA(ctx, cudaMemcpyAsync(K_out, ctx->K.p, sizeof(int32_t) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM.p, sizeof(double) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    if (avDist_out) CD_CUDA(ctx, cudaMemcpyAsync(avDist_out, ctx->avDist.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    if (status & 1) return ctx->fail(CD_EINVAL, "cd_assemble: a region row names a fragment outside the rmap");
+    if (status & 2) return ctx->fail(CD_EINVAL, "cd_assemble: a region's rows do not share one baitID");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timings[0] = ms;
+    if (keep_rows) std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 1);
+    ctx->have_agg = true;
+    return CD_OK;
+}
+
+int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out)
+{
+    if (!ctx) return CD_EINVAL;
+    const int S = ctx->des.S;
+    if (s < 0 || s >= S || !ctx->have_regions || !ctx->N_rows_p || ctx->rows_borrowed || !ctx->sample_set[(size_t)s])
+        return ctx->fail(CD_EINVAL, "cd_get_sample_rows: no per-row columns on the device (cd_assemble with keep_rows, or cd_set_sample_rows)");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t R = (size_t)ctx->R;
+    if (N_out) CD_CUDA(ctx, cudaMemcpyAsync(N_out, ctx->N_rows_p + (size_t)s * R, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, ctx->st));
+    if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM_rows_p + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     return CD_OK;
 }
 

@@ -15,6 +15,20 @@ cudaError_t launch_aggregate(int64_t n, int S, const int64_t* row_off, int64_t R
                              const int32_t* N_rows, const double* FM_rows,
                              int32_t* K, double* FM, cudaStream_t st);
 
+// ---- per-replicate assembly fused with stage 1 (chicdiff.R:609-702, 820-910, 1540-1547) ----
+struct AssembleTables {          // device pointers of one replicate, tables indexed by fragID - frag_id0
+    const double* s_j; const int32_t* tblb; const double* s_i; const int32_t* tlb;
+    const double* tmean; const double* tmin; const double* distfun;
+    const int64_t* cnt_off; const int32_t* cnt_oe; const int32_t* cnt_N;
+    int n_tblb, n_tlb;
+};
+cudaError_t launch_tmin(int n_tblb, int n_tlb, const double* tmean, double* tmin, cudaStream_t st);
+cudaError_t launch_assemble(int64_t n, int S, const int64_t* row_off, int64_t R, const int32_t* row_bait,
+                            const int32_t* row_oe, int64_t F, int32_t frag_id0, const int32_t* frag_chr,
+                            const int32_t* frag_start, const int32_t* frag_end, const AssembleTables* tabs_dev,
+                            int32_t* K, double* FM, double* avDist, int32_t* N_rows /*S x R or null*/,
+                            double* FM_rows /*S x R or null*/, int32_t* status, cudaStream_t st);
+
 // ---- size factors + stage 2: offsets (chicdiff.R:1561-1562, 1583-1589, 1635-1638) ------
 cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR /*S x n, +inf = excluded*/,
                               cudaStream_t st);

@@ -19,7 +19,8 @@ FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLA
 EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
-            "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak"]
+            "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows"]
 
 
 class ChicdiffError(RuntimeError):
@@ -32,6 +33,12 @@ class CdOptions(C.Structure):
     _fields_ = [("norm", C.c_int), ("theta", C.c_double), ("theta_grid", C.POINTER(C.c_double)),
                 ("n_theta_grid", C.c_int), ("disp_prior_var", C.c_double), ("disp_prior_var_grid", C.c_double),
                 ("disp_grid_len", C.c_int)]
+
+
+class CdSampleTables(C.Structure):
+    _fields_ = [("s_j", C.c_void_p), ("tblb", C.c_void_p), ("s_i", C.c_void_p), ("tlb", C.c_void_p),
+                ("n_tblb", C.c_int), ("n_tlb", C.c_int), ("tmean", C.c_void_p), ("distfun", C.c_double * 10),
+                ("cnt_off", C.c_void_p), ("cnt_oe", C.c_void_p), ("cnt_N", C.c_void_p)]
 
 
 _RES_PTRS = ["baseMean", "baseVar", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "log2FoldChange", "lfcSE",
@@ -78,6 +85,11 @@ def load_library():
     L.cd_launch_count.restype = C.c_int64
     L.cd_device_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.cd_last_timings.argtypes = [C.c_void_p, C.c_void_p]
+    L.cd_set_rmap.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_set_region_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_set_sample_tables.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdSampleTables)]
+    L.cd_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_get_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cd_timer_start.argtypes = [C.c_void_p]
     L.cd_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cd_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -187,6 +199,56 @@ class Engine:
         fullmean = np.ascontiguousarray(fullmean, dtype=np.float64)
         self.n = K.shape[1]
         self._check(self._L.cd_set_aggregated(self._h, self.n, _ptr(K), _ptr(fullmean)))
+
+    # -- per-replicate assembly fused with stage 1 ------------------------------------------------
+    def set_rmap(self, chr_codes, start, end, frag_id0=1):
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (chr_codes, start, end)]
+        self._check(self._L.cd_set_rmap(self._h, len(a[0]), frag_id0, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])))
+
+    def set_region_rows(self, row_bait, row_oe):
+        rb = np.ascontiguousarray(row_bait, dtype=np.int32)
+        ro = np.ascontiguousarray(row_oe, dtype=np.int32)
+        self._keep_rows = [rb, ro]
+        self._check(self._L.cd_set_region_rows(self._h, len(rb), _ptr(rb), _ptr(ro)))
+
+    @staticmethod
+    def pack_sample_tables(tab, pin=None):
+        """dict (s_j, tblb, s_i, tlb, tmean, distfun, cnt_off, cnt_oe, cnt_N) -> (CdSampleTables, keep-alive list)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        keep = [f64(tab["s_j"]), i32(tab["tblb"]), f64(tab["s_i"]), i32(tab["tlb"]), f64(tab["tmean"]),
+                np.ascontiguousarray(tab["cnt_off"], dtype=np.int64), i32(tab["cnt_oe"]), i32(tab["cnt_N"])]
+        if pin is not None:
+            keep = [pin(k) for k in keep]
+        t = CdSampleTables()
+        ptr = (lambda a: a.data_ptr()) if pin is not None else (lambda a: a.ctypes.data)
+        t.s_j, t.tblb, t.s_i, t.tlb, t.tmean, t.cnt_off, t.cnt_oe, t.cnt_N = [ptr(k) for k in keep]
+        t.n_tblb, t.n_tlb = np.asarray(tab["tmean"]).shape
+        for k, v in enumerate(np.asarray(tab["distfun"], dtype=np.float64)):
+            t.distfun[k] = float(v)
+        return t, keep
+
+    def set_sample_tables(self, s, tab):
+        t, keep = tab if isinstance(tab, tuple) else self.pack_sample_tables(tab)
+        self._keep_tabs = getattr(self, "_keep_tabs", {})
+        self._keep_tabs[s] = keep
+        self._check(self._L.cd_set_sample_tables(self._h, s, C.byref(t)))
+
+    def assemble(self, keep_rows=False, fetch=True):
+        if fetch:
+            K = np.empty((self.S, self.n), np.int32)
+            FM = np.empty((self.S, self.n), np.float64)
+            av = np.empty(self.n, np.float64)
+            self._check(self._L.cd_assemble(self._h, int(keep_rows), _ptr(K), _ptr(FM), _ptr(av)))
+            return K, FM, av
+        self._check(self._L.cd_assemble(self._h, int(keep_rows), None, None, None))
+        return None
+
+    def get_sample_rows(self, s, R):
+        N = np.empty(R, np.int32)
+        FM = np.empty(R, np.float64)
+        self._check(self._L.cd_get_sample_rows(self._h, s, _ptr(N), _ptr(FM)))
+        return N, FM
 
     # -- stages -----------------------------------------------------------------------------
     def aggregate(self, fetch=True):

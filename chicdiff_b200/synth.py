@@ -92,6 +92,18 @@ def dist_fun(d, cubic=(-3.0, 2.6, -0.33, 0.009), obs=(np.log(1e4), np.log(1.5e6)
     return np.exp(out)
 
 
+def dist_fun_params(cubic, obs):
+    """The 10 numbers .chicEstimateDistFun returns (chicdiff.R:559-569): cubicFit[4], obs.min, obs.max,
+    head.coef[2], tail.coef[2] with the C1 continuation beta = f'(l), alpha = f(l) - beta l."""
+    c0, c1, c2, c3 = cubic
+    out = list(cubic) + [obs[0], obs[1]]
+    for l in obs:
+        beta = c1 + 2 * c2 * l + 3 * c3 * l * l
+        alpha = c0 + (c1 - beta) * l + c2 * l * l + c3 * l ** 3
+        out += [alpha, beta]
+    return np.asarray(out, dtype=np.float64)
+
+
 def r_round_half_even(x):
     return np.rint(x)
 
@@ -190,6 +202,10 @@ def generate(name="tiny", n_regions=None, reps=None, ru_expand=5, ensure_nonzero
     batch_eff = np.exp2(rng.normal(0, 0.3, (n, 2))) if n_batch > 1 else None
     fm_u_mean = np.zeros(U)
     fm_u_all = []
+    cubic = (-3.0, 2.6, -0.33, 0.009)
+    obs = (np.log(1e4), np.log(1.5e6))
+    distfun = dist_fun_params(cubic, obs)
+    tables = []
     for s in range(S):
         libsize = np.exp(rng.normal(0, 0.25))
         s_j = np.exp(rng.normal(0, 0.5, B))
@@ -198,8 +214,23 @@ def generate(name="tiny", n_regions=None, reps=None, ru_expand=5, ensure_nonzero
         tblb = np.minimum((np.argsort(np.argsort(s_j)) * 5) // B, 4)
         tlb = np.minimum((np.argsort(np.argsort(s_i)) * 5) // F, 4)
         tmean = np.exp(rng.uniform(np.log(1e-3), np.log(1e-1), (5, 5)))
-        bmean = s_j[bait_index] * s_i[p_oe - 1] * dist_fun(np.abs(p_dist))
-        fm = bmean + tmean[tblb[bait_index], tlb[p_oe - 1]]
+        # other ends CHiCAGO never saw in this replicate: s_i = NA (-> 1, chicdiff.R:672) and tlb = NA
+        # (-> lowest Tmean of the bait's tblb, chicdiff.R:689-692)
+        oe_unseen = rng.random(F) < 0.01
+        # per-fragment lookup tables in the form the C ABI takes (cd_sample_tables)
+        sj_frag = np.full(F, np.nan)
+        sj_frag[bait_ids - 1] = np.where(s_j_na, np.nan, s_j)
+        tblb_frag = np.full(F, -1, np.int32)
+        tblb_frag[bait_ids - 1] = tblb
+        si_frag = np.where(oe_unseen, np.nan, s_i)
+        tlb_frag = np.where(oe_unseen, -1, tlb).astype(np.int32)
+        tables.append(dict(s_j=sj_frag, tblb=tblb_frag, s_i=si_frag, tlb=tlb_frag, tmean=tmean, distfun=distfun, libsize=libsize))
+        # FullMean by the reference's rules (NumPy restatement, independent of the C oracle and the kernel)
+        si_eff = np.where(oe_unseen, 1.0, s_i)[p_oe - 1]
+        bmean = s_j[bait_index] * si_eff * dist_fun(np.abs(p_dist), cubic, obs)
+        tb = tblb[bait_index]
+        tm = np.where(oe_unseen[p_oe - 1], tmean.min(axis=1)[tb], tmean[tb, tlb[p_oe - 1]])
+        fm = bmean + tm
         fm_u_all.append((fm, s_j_na[bait_index], libsize))
         fm_u_mean += np.log(fm)
     fm_u_mean = np.exp(fm_u_mean / S)
@@ -225,12 +256,30 @@ def generate(name="tiny", n_regions=None, reps=None, ru_expand=5, ensure_nonzero
         cnt_u[0, pinv[row_off[zero]]] += 1
     for s in range(S):
         N_rows[s] = cnt_u[s][pinv]
+    # sparse per-replicate count tables (the .chinput / CHiCAGO rows): N > 0 pairs of the region universe
+    # plus a halo of pairs outside it, sorted by (baitID, otherEndID), CSR by bait fragment ID
+    n_halo = int(0.3 * U)
+    hb = bait_ids[rng.integers(0, B, n_halo)]
+    ho = hb + np.rint(rng.normal(0, 40, n_halo)).astype(np.int64)
+    okh = (ho >= 1) & (ho <= F) & (np.abs(ho - hb) > 1)
+    hkey = np.unique(hb[okh] * (F + 2) + ho[okh])
+    hkey = hkey[~np.isin(hkey, upair)]
+    for s in range(S):
+        nz = cnt_u[s] > 0
+        keep_h = rng.random(len(hkey)) < 0.5
+        keys = np.concatenate([upair[nz], hkey[keep_h]])
+        vals = np.concatenate([cnt_u[s][nz], 1 + rng.poisson(1.0, int(keep_h.sum()))]).astype(np.int32)
+        o = np.argsort(keys, kind="stable")
+        keys, vals = keys[o], vals[o]
+        tables[s]["cnt_off"] = np.searchsorted(keys, np.arange(1, F + 2) * (F + 2)).astype(np.int64)
+        tables[s]["cnt_oe"] = (keys % (F + 2)).astype(np.int32)
+        tables[s]["cnt_N"] = vals
     return SynthData(name=name, S=S, conditions=conditions, batch=batch, X=X,
                      frag_chr=frag_chr, frag_start=frag_start, frag_end=frag_end,
                      bait_ids=bait_ids, region_bait=bait_rep.astype(np.int32), region_seed=oe.astype(np.int32),
                      row_off=row_off, row_oe=row_oe.astype(np.int32), row_bait=row_bait.astype(np.int32),
                      N_rows=N_rows, FM_rows=FM_rows, true_lfc=true_lfc,
-                     extra=dict(alpha=alpha, pair_index=pinv, n_pairs=U))
+                     extra=dict(alpha=alpha, pair_index=pinv, n_pairs=U, tables=tables))
 
 
 def to_reference_tables(d):

@@ -102,6 +102,39 @@ int cd_set_aggregated(cd_ctx* ctx, int64_t n, const int32_t* K, const double* fu
 /* K_out / fullmean_out: host S x n sample-major, either may be NULL (results stay on the device) */
 int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out);
 
+/* ---- per-replicate assembly fused with stage 1 ---------------------------------------------------- */
+/* Instead of handing over the long table, hand over what getFullRegionData1() builds it from
+ * (chicdiff.R:609-702, 820-910) and let the device do the joins, Chicago's Bmean = s_j s_i f(d),
+ * FullMean = Bmean + Tmean, the count merge with zero fill AND the region sums in one pass.
+ * Call order: cd_set_design, cd_set_rmap, cd_set_regions, cd_set_region_rows, cd_set_sample_tables for every
+ * replicate, cd_assemble; then cd_region_test as usual. */
+typedef struct {
+    /* per-fragment tables of one replicate, index = fragID - frag_id0, length F (host pointers) */
+    const double* s_j;        /* first s_j per baitID (chicdiff.R:659); NaN = NA or bait absent -> Bmean NA (:702) */
+    const int32_t* tblb;      /* bait's tblb bin as an index into tmean rows; -1 = NA */
+    const double* s_i;        /* first s_i per otherEndID (:668); NaN = NA -> 1 (:672) */
+    const int32_t* tlb;       /* other end's tlb bin (tmean column); -1 = NA -> lowest Tmean of the tblb (:689-692) */
+    int n_tblb, n_tlb;
+    const double* tmean;      /* n_tblb x n_tlb row-major, first Tmean per (tblb, tlb) (:680); NaN = combination absent */
+    double distfun[10];       /* .chicEstimateDistFun (:538-573): cubicFit[4], obs.min, obs.max, head.coef[2], tail.coef[2] */
+    /* counts (.chinput, :820-860): CSR by bait fragment over (otherEndID, N) rows sorted by otherEndID */
+    const int64_t* cnt_off;   /* F + 1 */
+    const int32_t* cnt_oe;
+    const int32_t* cnt_N;
+} cd_sample_tables;
+
+/* restriction map: F fragments with contiguous IDs frag_id0 .. frag_id0 + F - 1 (chr as integer codes) */
+int cd_set_rmap(cd_ctx* ctx, int64_t F, int32_t frag_id0, const int32_t* chr, const int32_t* start, const int32_t* end);
+/* the region universe's rows (RU: baitID, otherEndID), region-contiguous, R = row_off[n] */
+int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe);
+int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);
+/* assembly + aggregation.  keep_rows != 0 also materialises the per-row N / FullMean columns on the device
+ * (cd_get_sample_rows).  Outputs are host pointers and may be NULL: K, FullMean (S x n sample-major) and
+ * avDist[n] = mean over the region's rows of the signed distance of chicdiff.R:878-881 (what
+ * IHWcorrection() needs from FullRegionData, :1965). */
+int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out, double* avDist_out);
+int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out);
+
 /* ---- stages 2-5 -------------------------------------------------------------------------- */
 typedef struct {
     int norm;                    /* CD_NORM_*; reference default "combined" */

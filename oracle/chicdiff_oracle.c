@@ -1097,3 +1097,79 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------ */
+/* per-replicate assembly (getFullRegionData1, chicdiff.R:609-702,      */
+/* 820-910): N and FullMean = Bmean + Tmean for every region-universe   */
+/* row from one replicate's CHiCAGO tables                              */
+/* ------------------------------------------------------------------ */
+
+/* Chicago:::.distFun with the parameters of .chicEstimateDistFun (chicdiff.R:559-569):
+ * p = cubicFit[4], obs.min, obs.max, head.coef[2], tail.coef[2] */
+double orc_dist_fun(double d, const double* p)
+{
+    double l = log(d), out;
+    if (l > p[5]) out = p[8] + l * p[9];
+    else if (l < p[4]) out = p[6] + l * p[7];
+    else out = p[0] + p[1] * l + p[2] * (l * l) + p[3] * (l * l * l);
+    return exp(out);
+}
+
+/*
+ * Tables are indexed by fragID - frag_id0 (length F).  s_j NaN = NA / bait absent from this replicate
+ * (chicdiff.R:659-662, Bmean := NA :702); tblb/tlb -1 = NA; s_i NaN -> 1 (:672); tmean[n_tblb][n_tlb]
+ * NaN = combination never seen (:680-683); tlb NA with tblb known -> min Tmean of that tblb (:689-692).
+ * distSign is recomputed for every row (:640-654): round(((oe.start+oe.end)-(bait.start+bait.end))/2),
+ * half to even, NA across chromosomes (then Bmean = 0, Chicago:::.estimateBMean).
+ * Counts: CSR by bait over (otherEndID, N) rows sorted by otherEndID; missing -> 0 (:853).
+ * Outputs (any may be NULL): N, FullMean, distSign (NaN = NA), Bmean, Tmean -- one value per row.
+ */
+int orc_assemble_sample(int64_t R, const int32_t* row_bait, const int32_t* row_oe,
+                        int64_t F, int32_t frag_id0, const int32_t* frag_chr, const int32_t* frag_start,
+                        const int32_t* frag_end, const double* s_j, const int32_t* tblb, const double* s_i,
+                        const int32_t* tlb, int n_tblb, int n_tlb, const double* tmean, const double* distfun,
+                        const int64_t* cnt_off, const int32_t* cnt_oe, const int32_t* cnt_N,
+                        int32_t* N_out, double* FM_out, double* dist_out, double* Bmean_out, double* Tmean_out)
+{
+    double* tmin = (double*)malloc(sizeof(double) * (size_t)(n_tblb > 0 ? n_tblb : 1));
+    for (int a = 0; a < n_tblb; a++) {
+        double m = NAN;
+        for (int b = 0; b < n_tlb; b++) {
+            double v = tmean[a * n_tlb + b];
+            if (!isnan(v) && (isnan(m) || v < m)) m = v;
+        }
+        tmin[a] = m;
+    }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t r = 0; r < R; r++) {
+        int64_t b = (int64_t)row_bait[r] - frag_id0, o = (int64_t)row_oe[r] - frag_id0;
+        if (b < 0 || b >= F || o < 0 || o >= F) { bad |= 1; continue; }
+        double d = NAN;
+        if (frag_chr[b] == frag_chr[o])
+            d = rint((((double)frag_start[o] + (double)frag_end[o]) - ((double)frag_start[b] + (double)frag_end[b])) / 2.0);
+        double sj = s_j[b];
+        double si = isnan(s_i[o]) ? 1.0 : s_i[o];
+        int tb = tblb[b], tl = tlb[o];
+        double tm = NAN;
+        if (tb >= 0) tm = (tl >= 0) ? tmean[tb * n_tlb + tl] : tmin[tb];
+        double bm;
+        if (isnan(d)) bm = 0.0; else bm = sj * si * orc_dist_fun(fabs(d), distfun);
+        if (isnan(sj)) bm = NAN;
+        /* count lookup */
+        int64_t lo = cnt_off[b], hi = cnt_off[b + 1];
+        int32_t key = row_oe[r], cnt = 0;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) / 2;
+            if (cnt_oe[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo < cnt_off[b + 1] && cnt_oe[lo] == key) cnt = cnt_N[lo];
+        if (N_out) N_out[r] = cnt;
+        if (FM_out) FM_out[r] = bm + tm;
+        if (dist_out) dist_out[r] = d;
+        if (Bmean_out) Bmean_out[r] = bm;
+        if (Tmean_out) Tmean_out[r] = tm;
+    }
+    free(tmin);
+    return bad ? -1 : 0;
+}

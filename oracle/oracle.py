@@ -330,3 +330,27 @@ def results(res, K, X, alpha=0.1):
     return dict(baseMean=res["baseMean"], log2FoldChange=res["beta"][p - 1], lfcSE=res["betaSE"][p - 1],
                 stat=res["stat"], pvalue=pvalue, padj=f["padj"], cooksCutoff=cutoff, cooksOutlier=outlier,
                 filterThreshold=f["cutoff"], filterTheta=f["theta"], filterIndex=f["j"])
+
+
+def assemble_sample(row_bait, row_oe, frag_chr, frag_start, frag_end, tab, frag_id0=1, want_all=False):
+    """getFullRegionData1's per-replicate step (chicdiff.R:609-702, 820-910) for one replicate's tables
+    (dict with s_j, tblb, s_i, tlb, tmean, distfun, cnt_off, cnt_oe, cnt_N).  Returns N, FullMean per row
+    (and distSign, Bmean, Tmean when want_all)."""
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    row_bait, row_oe = i32(row_bait), i32(row_oe)
+    R, F = len(row_bait), len(frag_chr)
+    tm = f64(tab["tmean"])
+    N = np.empty(R, np.int32)
+    FM = np.empty(R, np.float64)
+    extra = [np.empty(R, np.float64) for _ in range(3)] if want_all else [None, None, None]
+    keep = [row_bait, row_oe, i32(frag_chr), i32(frag_start), i32(frag_end), f64(tab["s_j"]), i32(tab["tblb"]), f64(tab["s_i"]),
+            i32(tab["tlb"]), tm, f64(tab["distfun"]), np.ascontiguousarray(tab["cnt_off"], dtype=np.int64), i32(tab["cnt_oe"]),
+            i32(tab["cnt_N"])]
+    rc = lib().orc_assemble_sample(C.c_int64(R), _p(keep[0]), _p(keep[1]), C.c_int64(F), C.c_int32(frag_id0), _p(keep[2]), _p(keep[3]),
+                                   _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(keep[7]), _p(keep[8]), C.c_int(tm.shape[0]),
+                                   C.c_int(tm.shape[1]), _p(keep[9]), _p(keep[10]), _p(keep[11]), _p(keep[12]), _p(keep[13]),
+                                   _p(N), _p(FM), *[None if e is None else _p(e) for e in extra])
+    if rc != 0:
+        raise ValueError("fragment ID outside the rmap")
+    return (N, FM) + tuple(extra) if want_all else (N, FM)
