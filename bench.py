@@ -232,6 +232,39 @@ def main():
         step_e2e()
     e2e_dev_ms, e2e_wall_ms, _ = timed(step_e2e, max(2, args.steps // 2))
 
+    # the same step started one stage earlier: per-replicate CHiCAGO tables -> fused assembly + aggregation
+    # (cd_assemble) -> region test.  Reported beside the main line, not instead of it.
+    asm = None
+    if "tables" in d.extra:
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        packed = [engine.Engine.pack_sample_tables(t, pin=pin) for t in d.extra["tables"]]
+        asm_h2d = sum(int(k.numel() * k.element_size()) for _, keep in packed for k in keep)
+        e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+        e.set_regions(d.row_off)
+        e.set_region_rows(d.row_bait, d.row_oe)
+        for si in range(S):
+            e.set_sample_tables(si, packed[si])
+
+        def step_asm_resident():
+            e.assemble(fetch=False)
+            return e.region_test(fetch="none")
+
+        def step_asm_e2e():
+            for si in range(S):
+                e.set_sample_tables(si, packed[si])
+            e.assemble(fetch=False)
+            return e.region_test(fetch="table")
+
+        for _ in range(2):
+            step_asm_resident()
+        a_dev_ms, _, a_tm = timed(step_asm_resident, max(2, args.steps // 2))
+        for _ in range(2):
+            step_asm_e2e()
+        a_e2e_ms, _, _ = timed(step_asm_e2e, max(2, args.steps // 2))
+        asm = {"what": "per-replicate CHiCAGO tables (s_j, s_i, tblb/tlb, Tmean table, distance function, sparse counts) -> cd_assemble "
+                       "(joins + Bmean/Tmean + count merge + region sums in one kernel) -> cd_region_test",
+               "ms_per_step": a_dev_ms, "assemble_kernel_ms": a_tm[0], "e2e_ms_per_step": a_e2e_ms, "h2d_bytes_per_step": asm_h2d}
+
     n_tot = torch.tensor([n], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(n_tot)
@@ -263,6 +296,10 @@ def main():
                         "h2d_bytes_per_step": int(N_host.numel() * 4 + FM_host.numel() * 8),
                         "d2h_bytes_per_step": int(n * (6 * 8 + 1))},
                 "gpu_launches": int(launches), "clocks": clocks}
+        if asm is not None:
+            asm["value"] = n_tot / (asm["ms_per_step"] * 1e-3)
+            asm["e2e_value"] = n_tot / (asm["e2e_ms_per_step"] * 1e-3)
+            line["assembly_path"] = asm
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             rate, dt, m = cpu_reference_rate(d, args.cpu_sample, threads)

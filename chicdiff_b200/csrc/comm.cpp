@@ -5,7 +5,7 @@
 
 namespace cd {
 
-static const int kNcclInt8 = 0, kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0;
+static const int kNcclInt8 = 0, kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMin = 3;
 
 std::string Comm::load()
 {
@@ -77,6 +77,13 @@ std::string Comm::allreduce_sum(double* buf, size_t count, cudaStream_t st)
 {
     if (!active()) return "";
     CD_NCCL(AllReduce_(buf, buf, count, kNcclFloat64, kNcclSum, comm_, st));
+    return "";
+}
+
+std::string Comm::allreduce_u64(unsigned long long* buf, size_t count, bool min_op, cudaStream_t st)
+{
+    if (!active()) return "";
+    CD_NCCL(AllReduce_(buf, buf, count, kNcclUint64, min_op ? kNcclMin : kNcclSum, comm_, st));
     return "";
 }
 

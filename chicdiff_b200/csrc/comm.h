@@ -23,6 +23,7 @@ public:
     std::string unique_id(char id[128]);
     std::string init(int nranks, int rank, const char id[128]);
     std::string allreduce_sum(double* buf, size_t count, cudaStream_t st);
+    std::string allreduce_u64(unsigned long long* buf, size_t count, bool min_op, cudaStream_t st);
     // every rank contributes counts[rank] elements of elem_size bytes; recv is laid out by displs
     std::string allgatherv(const void* send, void* recv, const std::vector<int64_t>& counts,
                            const std::vector<int64_t>& displs, size_t elem_size, cudaStream_t st);

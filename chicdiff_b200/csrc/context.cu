@@ -5,7 +5,6 @@
 #include "../../include/chicdiff_b200.h"
 #include "kernels.h"
 #include "comm.h"
-#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -133,36 +132,6 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double m, dou
     if (r == 123.456) *sink = r;
 }
 
-__global__ void count_finite_kernel(int64_t n, const double* __restrict__ v, unsigned long long* __restrict__ cnt)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool f = (i < n) && isfinite(v[i]);
-    const unsigned m = __ballot_sync(0xffffffffu, f);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(cnt, (unsigned long long)__popc(m));
-}
-
-// R median of the finite prefix of an ascending-sorted array; out = exp(median) if do_exp
-__global__ void median_sorted_kernel(const double* __restrict__ sorted, const unsigned long long* __restrict__ cnt,
-                                     double* __restrict__ out, int do_exp, double scale)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const unsigned long long m = *cnt;
-        double med = NAN;
-        if (m > 0) med = (m & 1ull) ? sorted[m / 2] : 0.5 * (sorted[m / 2 - 1] + sorted[m / 2]);
-        med *= scale;
-        *out = do_exp ? exp(med) : med;
-    }
-}
-
-__global__ void abs_dev_dev_kernel(int64_t n, const double* __restrict__ v, const double* __restrict__ center,
-                                   double* __restrict__ out)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double x = v[i];
-    out[i] = isinf(x) ? INFINITY : fabs(x - *center);
-}
-
 __global__ void count_flags_kernel(int64_t n, const uint8_t* __restrict__ flags, unsigned long long* __restrict__ out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -207,12 +176,11 @@ struct cd_ctx {
     DevBuf<double> nf, mu, baseVar, rough, alpha_init, log_alpha, initial_lp, last_lp, dispMAP, dispersion,
         beta, betaSE, stat, pvalue, deviance, maxCooks;
     DevBuf<int32_t> dispGeneIter, dispIter, betaIter, refit_list;
-    // global (all ranks) buffers: baseMean, dispGeneEst, flags, dispFit, resid ; local slice at g_off
-    DevBuf<double> g_baseMean, g_dispGeneEst, g_dispFit, g_resid, g_sortbuf, g_sortbuf2;
+    // inputs / outputs of the global steps (trend, MAD): local regions only, nothing is gathered
+    DevBuf<double> g_baseMean, g_dispGeneEst, g_dispFit, g_resid;
     DevBuf<uint8_t> g_flags;
-    DevBuf<int32_t> g_K;             // gathered counts for the size factors (sharded run only)
     DevBuf<double> g_LR;
-    DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned long long> sel_state, sel_hist, sel_aux;
     DevBuf<double> partial, scal;    // reduction scratch ; device scalars
     DevBuf<unsigned long long> counters;
     DevBuf<int32_t> refit_count;
@@ -628,52 +596,43 @@ int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-// ascending sort of n doubles (src -> dst) with CUB; +inf entries end up last
-int sort_doubles(cd_ctx* ctx, const double* src, double* dst, int64_t n)
+// R median() of the finite entries of B columns (column c at base + c*stride, n local values each, optionally
+// transformed to |x - center[c]|) over ALL ranks -> out_dev[c] = scale * median (exp'ed if do_exp).
+// Radix selection: six histogram passes; in a sharded run only the 2048-bin counters are all-reduced.
+int medians(cd_ctx* ctx, const double* base, int64_t stride, int64_t n, int B, const double* center_dev,
+            double* out_dev, int do_exp, double scale)
 {
-    size_t bytes = 0;
-    CD_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, bytes, src, dst, (int)n, 0, 64, ctx->st));
-    CD_CUDA(ctx, ctx->cub_tmp.ensure(bytes));
-    CD_LAUNCHN(ctx, 0, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, bytes, src, dst, (int)n, 0, 64, ctx->st));
-    return CD_OK;
-}
-
-// median of the finite entries of v (length n) -> device scalar out (exp / scale applied)
-int median_finite(cd_ctx* ctx, const double* v, int64_t n, double* out_dev, int do_exp, double scale)
-{
-    CD_CUDA(ctx, ctx->g_sortbuf.ensure((size_t)n));
-    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 8, 0, sizeof(unsigned long long), ctx->st));
-    if (n > 0) {
-        count_finite_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->st>>>(n, v, ctx->counters.p + 8);
-        ctx->launches++;
-        int rc = sort_doubles(ctx, v, ctx->g_sortbuf.p, n);
-        if (rc != CD_OK) return rc;
+    cudaStream_t st = ctx->st;
+    CD_CUDA(ctx, ctx->sel_state.ensure((size_t)B * kSelStateHost));
+    CD_CUDA(ctx, ctx->sel_hist.ensure((size_t)B * kSelBinsHost));
+    CD_CUDA(ctx, ctx->sel_aux.ensure((size_t)B * 3));
+    unsigned long long* counts = ctx->sel_aux.p;
+    unsigned long long* le = ctx->sel_aux.p + B;
+    unsigned long long* mg = ctx->sel_aux.p + 2 * B;
+    CD_LAUNCHN(ctx, 1, sel_launch_count(n, B, base, stride, center_dev, counts, st));
+    CD_COMM(ctx, ctx->comm.allreduce_u64(counts, (size_t)B, false, st));
+    CD_LAUNCHN(ctx, 1, sel_launch_init(B, counts, ctx->sel_state.p, ctx->sel_hist.p, le, mg, st));
+    for (int pass = 0; pass < 6; pass++) {
+        CD_LAUNCHN(ctx, 1, sel_launch_hist(n, B, base, stride, center_dev, ctx->sel_state.p, pass, ctx->sel_hist.p, st));
+        CD_COMM(ctx, ctx->comm.allreduce_u64(ctx->sel_hist.p, (size_t)B * kSelBinsHost, false, st));
+        CD_LAUNCHN(ctx, 1, sel_launch_scan(B, pass, ctx->sel_state.p, ctx->sel_hist.p, st));
     }
-    median_sorted_kernel<<<1, 32, 0, ctx->st>>>(ctx->g_sortbuf.p, ctx->counters.p + 8, out_dev, do_exp, scale);
-    ctx->launches++;
-    CD_CUDA(ctx, cudaGetLastError());
+    CD_LAUNCHN(ctx, 1, sel_launch_next(n, B, base, stride, center_dev, ctx->sel_state.p, le, mg, st));
+    CD_COMM(ctx, ctx->comm.allreduce_u64(le, (size_t)B, false, st));
+    CD_COMM(ctx, ctx->comm.allreduce_u64(mg, (size_t)B, true, st));
+    CD_LAUNCHN(ctx, 1, sel_launch_finish(B, ctx->sel_state.p, le, mg, out_dev, do_exp, scale, st));
     return CD_OK;
 }
 
-// estimateSizeFactors over ALL regions (gathers the counts in a sharded run) -> scal[0..S)
+// estimateSizeFactors over ALL regions of all ranks -> scal[0..S)
 int size_factors(cd_ctx* ctx, double* sf_host)
 {
     const int S = ctx->des.S;
-    const int64_t n = ctx->n, nt = ctx->n_tot;
-    const int32_t* Kall = ctx->K.p;
-    if (ctx->comm.active()) {
-        CD_CUDA(ctx, ctx->g_K.ensure((size_t)S * (size_t)nt));
-        for (int s = 0; s < S; s++)
-            CD_COMM(ctx, ctx->comm.allgatherv(ctx->K.p + (size_t)s * n, ctx->g_K.p + (size_t)s * nt, ctx->shard_n,
-                                              ctx->shard_off, sizeof(int32_t), ctx->st));
-        Kall = ctx->g_K.p;
-    }
-    CD_CUDA(ctx, ctx->g_LR.ensure((size_t)S * (size_t)nt));
-    CD_LAUNCHN(ctx, 1, launch_log_ratios(nt, S, Kall, ctx->g_LR.p, ctx->st));
-    for (int s = 0; s < S; s++) {
-        int rc = median_finite(ctx, ctx->g_LR.p + (size_t)s * nt, nt, ctx->scal.p + s, 1, 1.0);
-        if (rc != CD_OK) return rc;
-    }
+    const int64_t n = ctx->n;
+    CD_CUDA(ctx, ctx->g_LR.ensure((size_t)S * (size_t)n));
+    CD_LAUNCHN(ctx, 1, launch_log_ratios(n, S, ctx->K.p, ctx->g_LR.p, ctx->st));
+    int rc = medians(ctx, ctx->g_LR.p, n, n, S, nullptr, ctx->scal.p, 1, 1.0);
+    if (rc != CD_OK) return rc;
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     for (int s = 0; s < S; s++) {
@@ -684,6 +643,67 @@ int size_factors(cd_ctx* ctx, double* sf_host)
     return CD_OK;
 }
 
+// parametricDispersionFit in a sharded run: every pass sums over the local regions, the 8 sums are all-reduced,
+// and the host runs glm.fit's control flow (same sequence as trend_fit_kernel).  out_dev gets the same 5 numbers.
+int trend_fit_sharded(cd_ctx* ctx, double* out_dev)
+{
+    const int64_t n = ctx->n;
+    double c0 = 0.1, c1 = 1.0;
+    int iter = 0, status = 0, passes = 0;
+    auto pass = [&](double oc0, double oc1, double b0, double b1, double* v) -> int {
+        CD_LAUNCHN(ctx, 2, launch_trend_pass(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, oc0, oc1, b0, b1,
+                                             ctx->partial.p, ctx->scal.p + 40, ctx->st));
+        CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + 40, 8, ctx->st));
+        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 40, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+        for (int k = 0; k < 8; k++) v[k] = ctx->h_pinned[k];
+        passes++;
+        return CD_OK;
+    };
+    while (true) {
+        double v[8];
+        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
+        int rc = pass(c0, c1, b0, b1, v);
+        if (rc != CD_OK) return rc;
+        if (v[7] < 2.0) { status = 1; break; }
+        if (v[6] > 0.0) { status = 2; break; }
+        double devold = v[5];
+        bool conv = false;
+        for (int it = 0; it < 25 && status == 0; it++) {
+            const double det = v[0] * v[2] - v[1] * v[1];
+            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
+            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
+            double w[8];
+            int halv = 0;
+            while (true) {
+                rc = pass(c0, c1, nb0, nb1, w);
+                if (rc != CD_OK) return rc;
+                if (w[6] == 0.0 && std::isfinite(w[5])) break;
+                if (++halv > 25) { status = 3; break; }
+                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
+            }
+            if (status) break;
+            b0 = nb0; b1 = nb1;
+            for (int k = 0; k < 8; k++) v[k] = w[k];
+            const double dev = w[5];
+            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
+            devold = dev; ob0 = b0; ob1 = b1;
+        }
+        if (status) break;
+        const double oc0 = c0, oc1 = c1;
+        c0 = b0; c1 = b1;
+        if (!(c0 > 0.0 && c1 > 0.0)) { status = 4; break; }
+        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
+        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
+        iter++;
+        if (iter > 10) { status = 5; break; }
+    }
+    double* h = ctx->h_pinned + 16;
+    h[0] = c0; h[1] = c1; h[2] = (double)status; h[3] = (double)(iter + 1); h[4] = (double)passes;
+    CD_CUDA(ctx, cudaMemcpyAsync(out_dev, h, 5 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    return CD_OK;
+}
+
 struct PipeOut { double a0, a1, varLogDispEsts, dispPriorVar, sum_deviance; };
 
 // estimateDispersions + nbinomWaldTest for one normalisation (mode / theta) and one design
@@ -691,7 +711,7 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
                  bool want_cooks, PipeOut& po)
 {
     const int S = des.S, p = des.p;
-    const int64_t n = ctx->n, nt = ctx->n_tot, off = ctx->g_off;
+    const int64_t n = ctx->n, off = ctx->g_off;
     cudaStream_t st = ctx->st;
     const int df = S - p;
     if (std::isnan(prior_var_override) && df <= 3)
@@ -730,27 +750,24 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, nullptr, 1.0,
                                             grid_len, dispGeneEst, nullptr, flags, dispGeneEst, st));
     ctx->tm_end();
-    if (ctx->comm.active()) {
-        CD_COMM(ctx, ctx->comm.allgatherv(baseMean, ctx->g_baseMean.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
-        CD_COMM(ctx, ctx->comm.allgatherv(dispGeneEst, ctx->g_dispGeneEst.p, ctx->shard_n, ctx->shard_off, sizeof(double), st));
-        CD_COMM(ctx, ctx->comm.allgatherv(flags, ctx->g_flags.p, ctx->shard_n, ctx->shard_off, sizeof(uint8_t), st));
-    }
-    // trend + MAD on the global arrays (every rank computes the same numbers); one host sync for both
+    // trend + MAD over the regions of all ranks.  Nothing is gathered: the trend passes all-reduce 8 sums, the
+    // medians all-reduce histogram counters.  One host sync for both on a single GPU.
     ctx->tm_begin(5);
-    double* trend_dev = ctx->scal.p + 110;         // coefs[2], status, outer iterations, passes
-    CD_LAUNCHN(ctx, 1, launch_trend_fit(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->partial.p,
-                                        reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, st));
-    CD_LAUNCHN(ctx, 1, launch_trend_apply(nt, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
+    double* trend_dev = ctx->scal.p + 110;        // coefs[2], status, outer iterations, passes
+    int rc;
+    if (ctx->comm.active()) {
+        rc = trend_fit_sharded(ctx, trend_dev);
+        if (rc != CD_OK) return rc;
+    } else {
+        CD_LAUNCHN(ctx, 1, launch_trend_fit(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->partial.p,
+                                            reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, st));
+    }
+    CD_LAUNCHN(ctx, 1, launch_trend_apply(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
                                           ctx->g_dispFit.p, ctx->g_resid.p, st));
     double* med_dev = ctx->scal.p + 44;
-    int rc = median_finite(ctx, ctx->g_resid.p, nt, med_dev, 0, 1.0);
+    rc = medians(ctx, ctx->g_resid.p, n, n, 1, nullptr, med_dev, 0, 1.0);
     if (rc != CD_OK) return rc;
-    CD_CUDA(ctx, ctx->g_sortbuf2.ensure((size_t)nt));
-    if (nt > 0) {
-        abs_dev_dev_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(nt, ctx->g_resid.p, med_dev, ctx->g_sortbuf2.p);
-        ctx->launches++;
-    }
-    rc = median_finite(ctx, ctx->g_sortbuf2.p, nt, ctx->scal.p + 45, 0, 1.4826);
+    rc = medians(ctx, ctx->g_resid.p, n, n, 1, med_dev, ctx->scal.p + 45, 0, 1.4826);
     if (rc != CD_OK) return rc;
     ctx->tm_end();
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, trend_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -828,8 +845,8 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     ctx->shard_off.assign(ctx->shard_n.size(), 0);
     int64_t tot = 0;
     for (size_t r = 0; r < ctx->shard_n.size(); r++) { ctx->shard_off[r] = tot; tot += ctx->shard_n[r]; }
-    ctx->n_tot = tot;
-    ctx->g_off = ctx->shard_off[(size_t)ctx->comm.rank];
+    ctx->n_tot = tot;                  // regions over all ranks (for reporting; nothing is gathered)
+    ctx->g_off = 0;
     if (tot > 2147483647LL) return ctx->fail(CD_EINVAL, "more than 2^31-1 regions in total");
     if (tot < 1) return ctx->fail(CD_EINVAL, "cd_region_test: no regions");
 
@@ -845,9 +862,9 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->deviance.ensure((size_t)n)); CD_CUDA(ctx, ctx->maxCooks.ensure((size_t)n));
     CD_CUDA(ctx, ctx->dispGeneIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->dispIter.ensure((size_t)n));
     CD_CUDA(ctx, ctx->betaIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->refit_list.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->g_baseMean.ensure((size_t)tot)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure((size_t)tot));
-    CD_CUDA(ctx, ctx->g_dispFit.ensure((size_t)tot)); CD_CUDA(ctx, ctx->g_resid.ensure((size_t)tot));
-    CD_CUDA(ctx, ctx->g_flags.ensure((size_t)tot));
+    CD_CUDA(ctx, ctx->g_baseMean.ensure((size_t)n)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->g_dispFit.ensure((size_t)n)); CD_CUDA(ctx, ctx->g_resid.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->g_flags.ensure((size_t)n));
     CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * (CD_MAXS + 8)));
     CD_CUDA(ctx, ctx->scal.ensure(128));
     CD_CUDA(ctx, ctx->counters.ensure(16));

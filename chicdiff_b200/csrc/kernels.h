@@ -44,6 +44,24 @@ cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* 
                            cudaStream_t st);
 constexpr int kReduceBlocks = 592;      // 148 SMs x 4
 
+// ---- exact medians by radix selection (select.cu); B columns at base + c*stride, length n each ----
+// state: B x 8 words, hist: B x 2048 words, counts / le / mg: B words each (device).  In a sharded run the caller
+// all-reduces `counts` (sum) after sel_launch_count, `hist` (sum) after every sel_launch_hist, and `le` (sum) /
+// `mg` (min) after sel_launch_next.
+constexpr int kSelBinsHost = 2048;
+constexpr int kSelStateHost = 8;
+cudaError_t sel_launch_count(int64_t n, int B, const double* base, int64_t stride, const double* center,
+                             unsigned long long* counts, cudaStream_t st);
+cudaError_t sel_launch_init(int B, const unsigned long long* counts, unsigned long long* state, unsigned long long* hist,
+                            unsigned long long* le, unsigned long long* mg, cudaStream_t st);
+cudaError_t sel_launch_hist(int64_t n, int B, const double* base, int64_t stride, const double* center,
+                            const unsigned long long* state, int pass, unsigned long long* hist, cudaStream_t st);
+cudaError_t sel_launch_scan(int B, int pass, unsigned long long* state, unsigned long long* hist, cudaStream_t st);
+cudaError_t sel_launch_next(int64_t n, int B, const double* base, int64_t stride, const double* center,
+                            const unsigned long long* state, unsigned long long* le, unsigned long long* mg, cudaStream_t st);
+cudaError_t sel_launch_finish(int B, const unsigned long long* state, const unsigned long long* le, const unsigned long long* mg,
+                              double* out, int do_exp, double scale, cudaStream_t st);
+
 // ---- stage 4a: gene-wise dispersion -----------------------------------------------------
 cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf,
                               double* baseMean, double* baseVar, double* rough, uint8_t* flags,
