@@ -27,6 +27,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout when the first communicator comes up; stdout must carry only
+    the one JSON line, so file descriptor 1 points at stderr while the communicators are created."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
 METRIC = "regions tested/sec (agg+NB GLM+dispersion+Wald)"
 UNIT = "regions/s"
 
@@ -162,17 +177,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; chicdiff_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    e = engine.Engine(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            uid = [e.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            e.comm_init(world, rank, uid[0])
+            dist.barrier()
+            torch.cuda.synchronize()
 
     d = make_data(args.workload, args.regions, rank)
     S, p, n, R = d.S, int(d.X.shape[1]), d.n, d.R
-
-    e = engine.Engine(local_rank)
-    if world > 1:
-        uid = [e.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        e.comm_init(world, rank, uid[0])
     e.set_design(d.X)
     e.set_regions(d.row_off)
 
