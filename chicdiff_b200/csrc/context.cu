@@ -451,6 +451,60 @@ int cd_set_rmap(cd_ctx* ctx, int64_t F, int32_t frag_id0, const int32_t* chr, co
     return CD_OK;
 }
 
+int cd_region_universe(cd_ctx* ctx, int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int ru_expand, int64_t* R_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_design || !ctx->have_rmap) return ctx->fail(CD_EINVAL, "cd_region_universe: call cd_set_design and cd_set_rmap first");
+    if (m < 0 || m > 2000000000LL || ru_expand < 1 || (m > 0 && (!peak_bait || !peak_oe)))
+        return ctx->fail(CD_EINVAL, "cd_region_universe: bad arguments (RUexpand must be >= 1)");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    DevBuf<int32_t> pb, po;
+    DevBuf<int64_t> counts;
+    DevBuf<unsigned char> tmp;
+    CD_CUDA(ctx, pb.ensure((size_t)m)); CD_CUDA(ctx, po.ensure((size_t)m)); CD_CUDA(ctx, counts.ensure((size_t)m + 1));
+    CD_CUDA(ctx, ctx->row_off.ensure((size_t)m + 1));
+    CD_CUDA(ctx, ctx->asm_status.ensure(1));
+    CD_CUDA(ctx, cudaMemcpyAsync(pb.p, peak_bait, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(po.p, peak_oe, sizeof(int32_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    CD_CUDA(ctx, cudaMemsetAsync(counts.p, 0, sizeof(int64_t) * ((size_t)m + 1), st));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->asm_status.p, 0, sizeof(int32_t), st));
+    CD_LAUNCHN(ctx, 1, ru_launch_count(m, pb.p, po.p, ru_expand, ctx->F, ctx->frag_id0, ctx->frag_chr.p, counts.p, ctx->asm_status.p, st));
+    size_t bytes = 0;
+    CD_CUDA(ctx, ru_launch_scan(m, counts.p, ctx->row_off.p, nullptr, bytes, st));
+    CD_CUDA(ctx, tmp.ensure(bytes));
+    CD_CUDA(ctx, ru_launch_scan(m, counts.p, ctx->row_off.p, tmp.p, bytes, st));
+    int64_t R = 0;
+    int32_t status = 0;
+    CD_CUDA(ctx, cudaMemcpyAsync(&R, ctx->row_off.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(&status, ctx->asm_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    if (status & 1) return ctx->fail(CD_EINVAL, "Invalid parameters: a peak has oeID == baitID (.expandAvoidBait stops here too)");
+    if (status & 2) return ctx->fail(CD_EINVAL, "cd_region_universe: a baitID is not in the rmap");
+    CD_CUDA(ctx, ctx->row_bait.ensure((size_t)R)); CD_CUDA(ctx, ctx->row_oe.ensure((size_t)R));
+    CD_LAUNCHN(ctx, 1, ru_launch_fill(m, pb.p, po.p, ru_expand, ctx->F, ctx->frag_id0, ctx->frag_chr.p, ctx->row_off.p,
+                                      ctx->row_bait.p, ctx->row_oe.p, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->n = m; ctx->R = R;
+    ctx->have_regions = true; ctx->have_region_rows = true; ctx->have_agg = false; ctx->rows_borrowed = false;
+    ctx->N_rows_p = nullptr; ctx->FM_rows_p = nullptr;
+    std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 0);
+    if (R_out) *R_out = R;
+    return CD_OK;
+}
+
+int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_out, int32_t* row_oe_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_regions || !ctx->have_region_rows) return ctx->fail(CD_EINVAL, "cd_get_region_universe: no region universe on the device");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (row_off_out) CD_CUDA(ctx, cudaMemcpyAsync(row_off_out, ctx->row_off.p, sizeof(int64_t) * ((size_t)ctx->n + 1), cudaMemcpyDeviceToHost, ctx->st));
+    if (row_bait_out) CD_CUDA(ctx, cudaMemcpyAsync(row_bait_out, ctx->row_bait.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
+    if (row_oe_out) CD_CUDA(ctx, cudaMemcpyAsync(row_oe_out, ctx->row_oe.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    return CD_OK;
+}
+
 int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe)
 {
     if (!ctx) return CD_EINVAL;

@@ -15,6 +15,13 @@ cudaError_t launch_aggregate(int64_t n, int S, const int64_t* row_off, int64_t R
                              const int32_t* N_rows, const double* FM_rows,
                              int32_t* K, double* FM, cudaStream_t st);
 
+// ---- region universe (getRegionUniverse, chicdiff.R:353-426) ----
+cudaError_t ru_launch_count(int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int s, int64_t F, int32_t id0,
+                            const int32_t* chr, int64_t* counts /*m + 1*/, int32_t* status, cudaStream_t st);
+cudaError_t ru_launch_scan(int64_t m, const int64_t* counts, int64_t* row_off, void* tmp, size_t& tmp_bytes, cudaStream_t st);
+cudaError_t ru_launch_fill(int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int s, int64_t F, int32_t id0,
+                           const int32_t* chr, const int64_t* row_off, int32_t* row_bait, int32_t* row_oe, cudaStream_t st);
+
 // ---- per-replicate assembly fused with stage 1 (chicdiff.R:609-702, 820-910, 1540-1547) ----
 struct AssembleTables {          // device pointers of one replicate, tables indexed by fragID - frag_id0
     const double* s_j; const int32_t* tblb; const double* s_i; const int32_t* tlb;

@@ -20,7 +20,7 @@ EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_u
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
-            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows"]
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_region_universe", "cd_get_region_universe"]
 
 
 class ChicdiffError(RuntimeError):
@@ -90,6 +90,8 @@ def load_library():
     L.cd_set_sample_tables.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdSampleTables)]
     L.cd_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_get_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.cd_region_universe.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    L.cd_get_region_universe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_timer_start.argtypes = [C.c_void_p]
     L.cd_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cd_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -204,6 +206,21 @@ class Engine:
     def set_rmap(self, chr_codes, start, end, frag_id0=1):
         a = [np.ascontiguousarray(x, dtype=np.int32) for x in (chr_codes, start, end)]
         self._check(self._L.cd_set_rmap(self._h, len(a[0]), frag_id0, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])))
+
+    def region_universe(self, peak_bait, peak_oe, ru_expand=5, fetch=True):
+        """getRegionUniverse on the device; returns (row_off, row_bait, row_oe) when fetch."""
+        pb = np.ascontiguousarray(peak_bait, dtype=np.int32)
+        po = np.ascontiguousarray(peak_oe, dtype=np.int32)
+        R = C.c_int64()
+        self._check(self._L.cd_region_universe(self._h, len(pb), _ptr(pb), _ptr(po), int(ru_expand), C.byref(R)))
+        self.n = len(pb)
+        if not fetch:
+            return R.value
+        off = np.empty(self.n + 1, np.int64)
+        rb = np.empty(R.value, np.int32)
+        ro = np.empty(R.value, np.int32)
+        self._check(self._L.cd_get_region_universe(self._h, _ptr(off), _ptr(rb), _ptr(ro)))
+        return off, rb, ro
 
     def set_region_rows(self, row_bait, row_oe):
         rb = np.ascontiguousarray(row_bait, dtype=np.int32)

@@ -125,6 +125,13 @@ typedef struct {
 
 /* restriction map: F fragments with contiguous IDs frag_id0 .. frag_id0 + F - 1 (chr as integer codes) */
 int cd_set_rmap(cd_ctx* ctx, int64_t F, int32_t frag_id0, const int32_t* chr, const int32_t* start, const int32_t* end);
+/* getRegionUniverse() on the device (chicdiff.R:369-426): every filtered peak (baitID, oeID) -> the window
+ * .expandAvoidBait(bait, oe, RUexpand) (:353-367), trimmed to the genome (:402) and to the bait's chromosome
+ * (:404-419); regionID = 1-based index of the peak.  Needs cd_set_design and cd_set_rmap; replaces
+ * cd_set_regions + cd_set_region_rows.  R_out receives the number of rows. */
+int cd_region_universe(cd_ctx* ctx, int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int ru_expand, int64_t* R_out);
+/* host copies of the universe built by cd_region_universe: row_off[m+1], row_bait[R], row_oe[R] (any may be NULL) */
+int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_out, int32_t* row_oe_out);
 /* the region universe's rows (RU: baitID, otherEndID), region-contiguous, R = row_off[n] */
 int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe);
 int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);

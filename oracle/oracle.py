@@ -354,3 +354,33 @@ def assemble_sample(row_bait, row_oe, frag_chr, frag_start, frag_end, tab, frag_
     if rc != 0:
         raise ValueError("fragment ID outside the rmap")
     return (N, FM) + tuple(extra) if want_all else (N, FM)
+
+
+def region_universe(peak_bait, peak_oe, ru_expand, frag_chr, frag_id0=1):
+    """getRegionUniverse (chicdiff.R:369-426) restated with NumPy: windows by .expandAvoidBait (:353-367), rows
+    with otherEndID beyond the last fragment dropped (:402), rows not on the bait's chromosome dropped (:404-419;
+    IDs below the first fragment are NA after the rmap join and drop out with them).
+    Returns row_off[m+1], row_bait[R], row_oe[R]; regionID = 1-based peak index."""
+    bait = np.asarray(peak_bait, dtype=np.int64)
+    oe = np.asarray(peak_oe, dtype=np.int64)
+    s = int(ru_expand)
+    if np.any(bait == oe):
+        raise ValueError("Invalid parameters bait == oe")
+    F = len(frag_chr)
+    far = np.abs(bait - oe) > s + 1
+    lo = np.where(far | (oe < bait), oe - s, bait + 2)
+    hi = np.where(far | (oe > bait), oe + s, bait - 2)
+    width = hi - lo + 1
+    reg = np.repeat(np.arange(len(bait)), width)
+    start = np.concatenate([[0], np.cumsum(width)])[:-1]
+    f = np.arange(int(width.sum())) - np.repeat(start, width) + np.repeat(lo, width)
+    b = np.repeat(bait, width)
+    k = f - frag_id0
+    ok = (k >= 0) & (k < F)
+    chr_ = np.asarray(frag_chr)
+    same = np.zeros(len(f), bool)
+    same[ok] = chr_[k[ok]] == chr_[(b - frag_id0)[ok]]
+    keep = ok & same
+    counts = np.bincount(reg[keep], minlength=len(bait))
+    row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return row_off, b[keep].astype(np.int32), f[keep].astype(np.int32)

@@ -85,3 +85,27 @@ def test_product_results_adjust_matches_golden(golden, built):
     assert np.array_equal(np.isnan(gp), np.isnan(adj["padj"]))
     ok = ~np.isnan(gp)
     assert np.max(np.abs(adj["padj"][ok] - gp[ok]) / gp[ok]) < 1e-14
+
+
+def test_region_universe_restatement_reproduces_golden_windows(golden):
+    """getRegionUniverse (chicdiff.R:369-426): the oracle restatement must give back every (minOE, maxOE) of the
+    golden table from the seeds it implies, including the windows cut short next to the bait and at the
+    chromosome end."""
+    s = int(golden["settings_RUexpand"][0])
+    bait = golden["baitID"].astype(np.int64)
+    lo, hi = golden["minOE"].astype(np.int64), golden["maxOE"].astype(np.int64)
+    first, last = int(golden["rmap_id"].min()), int(golden["rmap_id"].max())
+    right = lo > bait
+    # seed implied by the window: s fragments inside the far edge, unless that edge was cut at the chromosome end
+    seed = np.where(right, np.where(hi == last, np.maximum(lo + s, bait + 2), hi - s),
+                    np.where(lo == first, np.minimum(hi - s, bait - 2), lo + s))
+    seed = np.where(right & (lo == bait + 2), hi - s, seed)
+    seed = np.where(~right & (hi == bait - 2), lo + s, seed)
+    chr_ = np.ones(len(golden["rmap_id"]), np.int32)
+    row_off, row_bait, row_oe = O.region_universe(bait, seed, s, chr_, frag_id0=first)
+    got_lo = np.minimum.reduceat(row_oe, row_off[:-1])
+    got_hi = np.maximum.reduceat(row_oe, row_off[:-1])
+    ok = (got_lo == lo) & (got_hi == hi)
+    assert ok.mean() > 0.999, ok.mean()          # a window cut on both sides leaves its seed ambiguous
+    assert np.array_equal(np.diff(row_off)[ok], (hi - lo + 1)[ok])
+    assert np.array_equal(row_bait, np.repeat(bait, np.diff(row_off)))

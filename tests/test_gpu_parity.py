@@ -404,3 +404,33 @@ def test_assembly_edge_cases():
         e.set_region_rows(np.array([5, 5, 5, 12, 12, 30, 30, 99], np.int32), row_oe)   # accepted here ...
         e.assemble()                                                                     # ... rejected by the kernel
     e.close()
+
+
+def test_region_universe_on_device():
+    """getRegionUniverse (chicdiff.R:369-426) on the device against the oracle restatement, then straight into
+    the fused assembly without a host round trip of the rows."""
+    d = synth.generate("c3", n_regions=50000)
+    e = engine.Engine(0)
+    e.set_design(d.X)
+    e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+    off, rb, ro = e.region_universe(d.region_bait, d.region_seed, 5)
+    off_o, rb_o, ro_o = O.region_universe(d.region_bait, d.region_seed, 5, d.frag_chr)
+    assert np.array_equal(off, off_o) and np.array_equal(rb, rb_o) and np.array_equal(ro, ro_o)
+    assert np.array_equal(off, d.row_off) and np.array_equal(ro, d.row_oe)
+    for s in range(d.S):
+        e.set_sample_tables(s, d.extra["tables"][s])
+    K, FM, av = e.assemble()
+    Ko, FMo = O.aggregate(d.row_off, d.N_rows, d.FM_rows)
+    assert np.array_equal(K, Ko)
+    # peaks at the genome edge and next to the bait, other RUexpand values
+    F = len(d.frag_chr)
+    pb = np.array([5, 5, 5, F - 1, 2, 100, 100], np.int32)
+    po = np.array([7, 3, 11, F, 1, 98, 102], np.int32)
+    for s_ in (1, 3, 5):
+        got = e.region_universe(pb, po, s_)
+        ref = O.region_universe(pb, po, s_, d.frag_chr)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+    with pytest.raises(engine.ChicdiffError):
+        e.region_universe(np.array([9], np.int32), np.array([9], np.int32), 5)
+    e.close()

@@ -243,3 +243,15 @@ def test_results_cooks_and_filtering(tiny, tiny_fit):
     ok = ~np.isnan(res["padj"])
     assert ok.sum() > 0 and np.all(res["padj"][ok] >= res["pvalue"][ok] - 1e-15)
     assert np.all(res["baseMean"][~ok & ~np.isnan(res["pvalue"])] < res["filterThreshold"])
+
+
+def test_region_universe_against_generator(tiny):
+    """two independent restatements of getRegionUniverse (the generator's and oracle.region_universe) agree"""
+    d, K, FM = tiny
+    row_off, row_bait, row_oe = O.region_universe(d.region_bait, d.region_seed, 5, d.frag_chr)
+    assert np.array_equal(row_off, d.row_off) and np.array_equal(row_bait, d.row_bait) and np.array_equal(row_oe, d.row_oe)
+    d23 = synth.generate("c3", n_regions=30000)            # 23 chromosomes: exercises the same-chromosome trimming
+    row_off, row_bait, row_oe = O.region_universe(d23.region_bait, d23.region_seed, 5, d23.frag_chr)
+    assert np.array_equal(row_off, d23.row_off) and np.array_equal(row_oe, d23.row_oe)
+    with pytest.raises(ValueError):
+        O.region_universe([10], [10], 5, d.frag_chr)
