@@ -198,6 +198,10 @@ struct cd_ctx {
     std::vector<uint8_t> tab_set;
     DevBuf<unsigned char> tabs_dev;
     DevBuf<double> avDist;
+    // countput output of the last cd_countput
+    int64_t cp_pairs = 0;
+    DevBuf<int32_t> cp_bait, cp_oe;
+    DevBuf<double> cp_nav, cp_bav, cp_score, cp_mid;
     DevBuf<double> wald_c, wald_b0, wald_b;
     DevBuf<int32_t> wald_iter;
     WaldScratch wald_ws{};
@@ -502,6 +506,94 @@ int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_
     if (row_bait_out) CD_CUDA(ctx, cudaMemcpyAsync(row_bait_out, ctx->row_bait.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
     if (row_oe_out) CD_CUDA(ctx, cudaMemcpyAsync(row_oe_out, ctx->row_oe.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    return CD_OK;
+}
+
+int cd_countput(cd_ctx* ctx, int n_reps, const cd_chicago_rows* reps, int64_t* n_pairs_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_rmap) return ctx->fail(CD_EINVAL, "cd_countput: call cd_set_rmap first");
+    if (n_reps < 1 || !reps) return ctx->fail(CD_EINVAL, "cd_countput: bad arguments");
+    int64_t T = 0;
+    for (int r = 0; r < n_reps; r++) {
+        if (reps[r].rows < 0 || (reps[r].rows > 0 && (!reps[r].baitID || !reps[r].otherEndID || !reps[r].N || !reps[r].Bmean || !reps[r].score)))
+            return ctx->fail(CD_EINVAL, "cd_countput: replicate %d has null columns", r);
+        T += reps[r].rows;
+    }
+    if (T > 4000000000LL) return ctx->fail(CD_EINVAL, "cd_countput: more than 4e9 rows in one condition");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    DevBuf<int32_t> bait, oe, N;
+    DevBuf<double> Bm, sc, g_nav, g_bav, g_score;
+    DevBuf<unsigned long long> k0, k1, g_key;
+    DevBuf<unsigned int> i0, i1, g_first, g_first_sorted, ord0, ord1;
+    DevBuf<int64_t> head, slot;
+    DevBuf<unsigned char> tmp;
+    const size_t Ts = (size_t)T;
+    CD_CUDA(ctx, bait.ensure(Ts)); CD_CUDA(ctx, oe.ensure(Ts)); CD_CUDA(ctx, N.ensure(Ts)); CD_CUDA(ctx, Bm.ensure(Ts)); CD_CUDA(ctx, sc.ensure(Ts));
+    CD_CUDA(ctx, k0.ensure(Ts)); CD_CUDA(ctx, k1.ensure(Ts)); CD_CUDA(ctx, i0.ensure(Ts)); CD_CUDA(ctx, i1.ensure(Ts));
+    CD_CUDA(ctx, head.ensure(Ts + 1)); CD_CUDA(ctx, slot.ensure(Ts + 1));
+    int64_t base = 0;
+    for (int r = 0; r < n_reps; r++) {
+        const size_t m = (size_t)reps[r].rows;
+        if (!m) continue;
+        CD_CUDA(ctx, cudaMemcpyAsync(bait.p + base, reps[r].baitID, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(oe.p + base, reps[r].otherEndID, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(N.p + base, reps[r].N, sizeof(int32_t) * m, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(Bm.p + base, reps[r].Bmean, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(sc.p + base, reps[r].score, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+        CD_LAUNCHN(ctx, 1, cp_launch_keys(reps[r].rows, base, bait.p + base, oe.p + base, k0.p, i0.p, st));
+        base += reps[r].rows;
+    }
+    int64_t G = 0;
+    if (T > 0) {
+        size_t bytes = 0;
+        CD_CUDA(ctx, cp_sort_pairs_u64(nullptr, bytes, k0.p, k1.p, i0.p, i1.p, T, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        CD_CUDA(ctx, cp_sort_pairs_u64(tmp.p, bytes, k0.p, k1.p, i0.p, i1.p, T, st));
+        CD_LAUNCHN(ctx, 1, cp_launch_heads(T, k1.p, head.p, st));
+        CD_CUDA(ctx, cudaMemsetAsync(head.p + T, 0, sizeof(int64_t), st));
+        bytes = 0;
+        CD_CUDA(ctx, cp_scan_i64(nullptr, bytes, head.p, slot.p, T + 1, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        CD_CUDA(ctx, cp_scan_i64(tmp.p, bytes, head.p, slot.p, T + 1, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(&G, slot.p + T, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+        const size_t Gs = (size_t)G;
+        CD_CUDA(ctx, g_key.ensure(Gs)); CD_CUDA(ctx, g_nav.ensure(Gs)); CD_CUDA(ctx, g_bav.ensure(Gs)); CD_CUDA(ctx, g_score.ensure(Gs));
+        CD_CUDA(ctx, g_first.ensure(Gs)); CD_CUDA(ctx, g_first_sorted.ensure(Gs)); CD_CUDA(ctx, ord0.ensure(Gs)); CD_CUDA(ctx, ord1.ensure(Gs));
+        CD_LAUNCHN(ctx, 1, cp_launch_reduce(T, k1.p, i1.p, head.p, slot.p, N.p, Bm.p, sc.p, g_key.p, g_nav.p, g_bav.p, g_score.p, g_first.p, st));
+        CD_LAUNCHN(ctx, 1, cp_launch_iota(G, ord0.p, st));
+        bytes = 0;
+        CD_CUDA(ctx, cp_sort_pairs_u32(nullptr, bytes, g_first.p, g_first_sorted.p, ord0.p, ord1.p, G, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        CD_CUDA(ctx, cp_sort_pairs_u32(tmp.p, bytes, g_first.p, g_first_sorted.p, ord0.p, ord1.p, G, st));
+        CD_CUDA(ctx, ctx->cp_bait.ensure(Gs)); CD_CUDA(ctx, ctx->cp_oe.ensure(Gs)); CD_CUDA(ctx, ctx->cp_nav.ensure(Gs));
+        CD_CUDA(ctx, ctx->cp_bav.ensure(Gs)); CD_CUDA(ctx, ctx->cp_score.ensure(Gs)); CD_CUDA(ctx, ctx->cp_mid.ensure(Gs));
+        CD_LAUNCHN(ctx, 1, cp_launch_gather(G, ord1.p, g_key.p, g_nav.p, g_bav.p, g_score.p, ctx->F, ctx->frag_id0, ctx->frag_start.p,
+                                            ctx->frag_end.p, ctx->cp_bait.p, ctx->cp_oe.p, ctx->cp_nav.p, ctx->cp_bav.p, ctx->cp_score.p,
+                                            ctx->cp_mid.p, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    ctx->cp_pairs = G;
+    if (n_pairs_out) *n_pairs_out = G;
+    return CD_OK;
+}
+
+int cd_get_countput(cd_ctx* ctx, int32_t* baitID, int32_t* otherEndID, double* Nav, double* Bav, double* score, double* oeID_mid)
+{
+    if (!ctx) return CD_EINVAL;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t G = (size_t)ctx->cp_pairs;
+    if (G == 0) return CD_OK;
+    cudaStream_t st = ctx->st;
+    if (baitID) CD_CUDA(ctx, cudaMemcpyAsync(baitID, ctx->cp_bait.p, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, st));
+    if (otherEndID) CD_CUDA(ctx, cudaMemcpyAsync(otherEndID, ctx->cp_oe.p, sizeof(int32_t) * G, cudaMemcpyDeviceToHost, st));
+    if (Nav) CD_CUDA(ctx, cudaMemcpyAsync(Nav, ctx->cp_nav.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    if (Bav) CD_CUDA(ctx, cudaMemcpyAsync(Bav, ctx->cp_bav.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    if (score) CD_CUDA(ctx, cudaMemcpyAsync(score, ctx->cp_score.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    if (oeID_mid) CD_CUDA(ctx, cudaMemcpyAsync(oeID_mid, ctx->cp_mid.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
     return CD_OK;
 }
 

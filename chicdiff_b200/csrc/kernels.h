@@ -22,6 +22,25 @@ cudaError_t ru_launch_scan(int64_t m, const int64_t* counts, int64_t* row_off, v
 cudaError_t ru_launch_fill(int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int s, int64_t F, int32_t id0,
                            const int32_t* chr, const int64_t* row_off, int32_t* row_bait, int32_t* row_oe, cudaStream_t st);
 
+// ---- countput (chicdiff.R:708-735, 755-770) ----
+cudaError_t cp_launch_keys(int64_t rows, int64_t base, const int32_t* bait, const int32_t* oe, unsigned long long* keys,
+                           unsigned int* idx, cudaStream_t st);
+cudaError_t cp_sort_pairs_u64(void* tmp, size_t& bytes, const unsigned long long* kin, unsigned long long* kout,
+                              const unsigned int* vin, unsigned int* vout, int64_t n, cudaStream_t st);
+cudaError_t cp_sort_pairs_u32(void* tmp, size_t& bytes, const unsigned int* kin, unsigned int* kout,
+                              const unsigned int* vin, unsigned int* vout, int64_t n, cudaStream_t st);
+cudaError_t cp_scan_i64(void* tmp, size_t& bytes, const int64_t* in, int64_t* out, int64_t n, cudaStream_t st);
+cudaError_t cp_launch_heads(int64_t T, const unsigned long long* keys, int64_t* head, cudaStream_t st);
+cudaError_t cp_launch_reduce(int64_t T, const unsigned long long* keys, const unsigned int* idx, const int64_t* head,
+                             const int64_t* slot, const int32_t* N, const double* Bmean, const double* score,
+                             unsigned long long* g_key, double* g_nav, double* g_bav, double* g_score,
+                             unsigned int* g_first, cudaStream_t st);
+cudaError_t cp_launch_iota(int64_t G, unsigned int* v, cudaStream_t st);
+cudaError_t cp_launch_gather(int64_t G, const unsigned int* order, const unsigned long long* g_key, const double* g_nav,
+                             const double* g_bav, const double* g_score, int64_t F, int32_t id0, const int32_t* frag_start,
+                             const int32_t* frag_end, int32_t* o_bait, int32_t* o_oe, double* o_nav, double* o_bav,
+                             double* o_score, double* o_mid, cudaStream_t st);
+
 // ---- per-replicate assembly fused with stage 1 (chicdiff.R:609-702, 820-910, 1540-1547) ----
 struct AssembleTables {          // device pointers of one replicate, tables indexed by fragID - frag_id0
     const double* s_j; const int32_t* tblb; const double* s_i; const int32_t* tlb;

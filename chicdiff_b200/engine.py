@@ -20,7 +20,7 @@ EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_u
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
-            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_region_universe", "cd_get_region_universe"]
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput"]
 
 
 class ChicdiffError(RuntimeError):
@@ -39,6 +39,11 @@ class CdSampleTables(C.Structure):
     _fields_ = [("s_j", C.c_void_p), ("tblb", C.c_void_p), ("s_i", C.c_void_p), ("tlb", C.c_void_p),
                 ("n_tblb", C.c_int), ("n_tlb", C.c_int), ("tmean", C.c_void_p), ("distfun", C.c_double * 10),
                 ("cnt_off", C.c_void_p), ("cnt_oe", C.c_void_p), ("cnt_N", C.c_void_p)]
+
+
+class CdChicagoRows(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("baitID", C.c_void_p), ("otherEndID", C.c_void_p), ("N", C.c_void_p),
+                ("Bmean", C.c_void_p), ("score", C.c_void_p)]
 
 
 _RES_PTRS = ["baseMean", "baseVar", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "log2FoldChange", "lfcSE",
@@ -92,6 +97,8 @@ def load_library():
     L.cd_get_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cd_region_universe.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.cd_get_region_universe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_countput.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdChicagoRows), C.POINTER(C.c_int64)]
+    L.cd_get_countput.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.cd_timer_start.argtypes = [C.c_void_p]
     L.cd_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cd_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -221,6 +228,26 @@ class Engine:
         ro = np.empty(R.value, np.int32)
         self._check(self._L.cd_get_region_universe(self._h, _ptr(off), _ptr(rb), _ptr(ro)))
         return off, rb, ro
+
+    def countput(self, reps):
+        """reps: list of dicts (baitID, otherEndID, N, Bmean, score) of ONE condition's replicates ->
+        dict(baitID, otherEndID, Nav, Bav, score, oeID_mid) in first-appearance order (cd_countput)."""
+        arr = (CdChicagoRows * len(reps))()
+        keep = []
+        for k, r in enumerate(reps):
+            cols = [np.ascontiguousarray(r["baitID"], dtype=np.int32), np.ascontiguousarray(r["otherEndID"], dtype=np.int32),
+                    np.ascontiguousarray(r["N"], dtype=np.int32), np.ascontiguousarray(r["Bmean"], dtype=np.float64),
+                    np.ascontiguousarray(r["score"], dtype=np.float64)]
+            keep.append(cols)
+            arr[k].rows = len(cols[0])
+            arr[k].baitID, arr[k].otherEndID, arr[k].N, arr[k].Bmean, arr[k].score = [c.ctypes.data for c in cols]
+        G = C.c_int64()
+        self._check(self._L.cd_countput(self._h, len(reps), arr, C.byref(G)))
+        g = G.value
+        out = dict(baitID=np.empty(g, np.int32), otherEndID=np.empty(g, np.int32), Nav=np.empty(g), Bav=np.empty(g),
+                   score=np.empty(g), oeID_mid=np.empty(g))
+        self._check(self._L.cd_get_countput(self._h, *[_ptr(out[k]) for k in ("baitID", "otherEndID", "Nav", "Bav", "score", "oeID_mid")]))
+        return out
 
     def set_region_rows(self, row_bait, row_oe):
         rb = np.ascontiguousarray(row_bait, dtype=np.int32)

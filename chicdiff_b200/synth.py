@@ -301,3 +301,18 @@ def to_reference_tables(d):
     F = len(d.frag_chr)
     rmap = {"chr": d.frag_chr.astype(str), "start": d.frag_start, "end": d.frag_end, "ID": np.arange(1, F + 1)}
     return RU, frd, rmap
+
+
+def chicago_rows(d, s, seed=0):
+    """The rows of replicate s's CHiCAGO table that countput uses (chicdiff.R:715-721): (baitID, otherEndID, N,
+    Bmean, score) for every observed pair, sorted by (baitID, otherEndID) like the keyed table."""
+    t = d.extra["tables"][s]
+    F = len(d.frag_chr)
+    per_bait = np.diff(t["cnt_off"])
+    bait = np.repeat(np.arange(1, F + 1), per_bait).astype(np.int32)
+    rng = np.random.Generator(np.random.PCG64(777 + 31 * s + seed))
+    m = len(bait)
+    bmean = np.exp(rng.normal(-2.0, 1.0, m))
+    score = np.maximum(0.0, rng.normal(2.0, 3.0, m))
+    score[rng.random(m) < 0.001] = np.nan
+    return dict(baitID=bait, otherEndID=t["cnt_oe"].copy(), N=t["cnt_N"].copy(), Bmean=bmean, score=score)

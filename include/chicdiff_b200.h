@@ -142,6 +142,20 @@ int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);
 int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out, double* avDist_out);
 int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out);
 
+/* ---- countput ------------------------------------------------------------------------------------- */
+/* The per-condition (baitID, otherEndID) table getFullRegionData() saves as <outprefix>_countput.Rds
+ * (chicdiff.R:708-735, 755-770): Nav = mean(N), Bav = mean(Bmean), score = max(score), oeID_mid = (start+end)/2
+ * over the replicates of ONE condition in which the pair occurs; rows in order of first appearance.
+ * Each replicate: the CHiCAGO rows that have a distance (chicdiff.R:715), host pointers.  Needs cd_set_rmap. */
+typedef struct {
+    int64_t rows;
+    const int32_t* baitID; const int32_t* otherEndID; const int32_t* N;
+    const double* Bmean; const double* score;
+} cd_chicago_rows;
+int cd_countput(cd_ctx* ctx, int n_reps, const cd_chicago_rows* reps, int64_t* n_pairs_out);
+/* fetch the table built by the last cd_countput (n_pairs rows; any pointer may be NULL) */
+int cd_get_countput(cd_ctx* ctx, int32_t* baitID, int32_t* otherEndID, double* Nav, double* Bav, double* score, double* oeID_mid);
+
 /* ---- stages 2-5 -------------------------------------------------------------------------- */
 typedef struct {
     int norm;                    /* CD_NORM_*; reference default "combined" */

@@ -384,3 +384,29 @@ def region_universe(peak_bait, peak_oe, ru_expand, frag_chr, frag_id0=1):
     counts = np.bincount(reg[keep], minlength=len(bait))
     row_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return row_off, b[keep].astype(np.int32), f[keep].astype(np.int32)
+
+
+def countput(reps, frag_start, frag_end, frag_id0=1):
+    """chicdiff.R:755-770 for ONE condition: rbind the replicates' CHiCAGO rows, then by (baitID, otherEndID) in
+    first-appearance order: Nav = mean(N), Bav = mean(Bmean), score = max(score) (NA if any NA),
+    oeID_mid = (start + end) / 2 (unrounded, :711)."""
+    bait = np.concatenate([np.asarray(r["baitID"], dtype=np.int64) for r in reps])
+    oe = np.concatenate([np.asarray(r["otherEndID"], dtype=np.int64) for r in reps])
+    N = np.concatenate([np.asarray(r["N"], dtype=np.float64) for r in reps])
+    B = np.concatenate([np.asarray(r["Bmean"], dtype=np.float64) for r in reps])
+    sc = np.concatenate([np.asarray(r["score"], dtype=np.float64) for r in reps])
+    key = bait * (1 << 32) + oe
+    _, first, inv, cnt = np.unique(key, return_index=True, return_inverse=True, return_counts=True)
+    order = np.argsort(first, kind="stable")                 # groups in order of first appearance
+    rank = np.empty_like(order); rank[order] = np.arange(len(order))
+    g = rank[inv]
+    G = len(first)
+    sumN = np.bincount(g, weights=N, minlength=G)
+    sumB = np.zeros(G); np.add.at(sumB, g, B)
+    mx = np.full(G, -np.inf); np.maximum.at(mx, g, np.where(np.isnan(sc), -np.inf, sc))
+    anyna = np.bincount(g, weights=np.isnan(sc), minlength=G) > 0
+    c = cnt[order]
+    f0 = first[order]
+    return dict(baitID=bait[f0].astype(np.int32), otherEndID=oe[f0].astype(np.int32), Nav=sumN / c, Bav=sumB / c,
+                score=np.where(anyna, np.nan, mx),
+                oeID_mid=(np.asarray(frag_start, float)[oe[f0] - frag_id0] + np.asarray(frag_end, float)[oe[f0] - frag_id0]) / 2.0)

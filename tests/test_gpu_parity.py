@@ -434,3 +434,30 @@ def test_region_universe_on_device():
     with pytest.raises(engine.ChicdiffError):
         e.region_universe(np.array([9], np.int32), np.array([9], np.int32), 5)
     e.close()
+
+
+def test_countput_on_device():
+    """countput (chicdiff.R:755-770): per-condition means / max over the replicates in which a pair occurs,
+    first-appearance row order."""
+    d = synth.generate("c1")
+    e = engine.Engine(0)
+    e.set_design(d.X)
+    e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+    for cond in sorted(set(d.conditions)):
+        reps = [synth.chicago_rows(d, s) for s in range(d.S) if d.conditions[s] == cond]
+        got = e.countput(reps)
+        ref = O.countput(reps, d.frag_start, d.frag_end)
+        assert len(got["baitID"]) == len(ref["baitID"]) > 0
+        assert np.array_equal(got["baitID"], ref["baitID"]) and np.array_equal(got["otherEndID"], ref["otherEndID"])
+        assert np.array_equal(got["oeID_mid"], ref["oeID_mid"])
+        assert np.max(np.abs(got["Nav"] - ref["Nav"])) < 1e-12
+        assert np.max(np.abs(got["Bav"] - ref["Bav"]) / ref["Bav"]) < 1e-14
+        assert np.array_equal(np.isnan(got["score"]), np.isnan(ref["score"])) and np.isnan(ref["score"]).any()
+        okm = ~np.isnan(ref["score"])
+        assert np.array_equal(got["score"][okm], ref["score"][okm])
+    # one replicate, and an empty replicate in the middle
+    r0 = synth.chicago_rows(d, 0)
+    empty = {k: v[:0] for k, v in r0.items()}
+    got = e.countput([r0, empty])
+    assert np.array_equal(got["baitID"], r0["baitID"]) and np.array_equal(got["Nav"], r0["N"].astype(float))
+    e.close()
