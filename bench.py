@@ -305,7 +305,10 @@ def main():
                 "stage_ms": {"aggregate": tm[0], "region_test": tm[1], "fit_disp_kernels": tm[2], "wald_kernels": tm[3],
                              "grid_refits": tm[4], "trend_and_mad": tm[5], "size_factors": tm[6]},
                 "roofline": {"bound": "hbm", "kernel": "aggregate_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                             # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the
+                             # committed ncu --set full capture (profiles/r01_final_kernels_aggregate_assemble_irls.txt)
+                             "traffic": 1841515000.0 if (n == 2135814 and S == 6) else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": agg_bytes},
                 "fp64": {"peak_tflops_measured_dfma": fp64_peak, "fit_disp_ms": tm[2], "wald_ms": tm[3]},
                 "e2e": {"value": n_tot / (e2e_dev_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_dev_ms,

@@ -461,3 +461,19 @@ def test_countput_on_device():
     got = e.countput([r0, empty])
     assert np.array_equal(got["baitID"], r0["baitID"]) and np.array_equal(got["Nav"], r0["N"].astype(float))
     e.close()
+
+
+@pytest.mark.parametrize("reps,extra_cols", [((6, 6), 0), ((5, 7), 0), ((16, 16), 0), ((8, 8), 2)])
+def test_other_designs(reps, extra_cols):
+    """more replicates (register/shared-memory paths with S = 12, 32), unbalanced groups, and a 4-column design
+    (intercept + two nuisance covariates + condition: the IRLS-mu variant of the gene-wise step with p = 4)."""
+    d = synth.generate("tiny", reps=reps, seed_offset=17 + reps[0])
+    X = d.X
+    if extra_cols:
+        S = X.shape[0]
+        c1 = (np.arange(S) % 2).astype(float)
+        c2 = ((np.arange(S) // 2) % 2).astype(float)
+        X = np.column_stack([X[:, 0], c1, c2, X[:, 1]])
+        d.X = X
+    K, FM, Ko, FMo, r, ro, _ = run_both(d)
+    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.998)
