@@ -370,6 +370,12 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
 #define CD_LAUNCH(P_)                                                                                          \
     {                                                                                                          \
         int per_sm = 1;                                                                                        \
+        if (smem > 48 * 1024) {                                                                                \
+            e = cudaFuncSetAttribute(fit_disp_kernel<P_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                    \
+            e = cudaFuncSetAttribute(fit_disp_kernel<P_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+            if (e != cudaSuccess) return e;                                                                    \
+        }                                                                                                      \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_disp_kernel<P_, false>, threads, smem); \
         if (e != cudaSuccess) return e;                                                                        \
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                     \
