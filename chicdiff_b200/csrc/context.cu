@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -198,6 +199,12 @@ struct cd_ctx {
     std::vector<uint8_t> tab_set;
     DevBuf<unsigned char> tabs_dev;
     DevBuf<double> avDist;
+    // peer-memory all-reduce of the sharded trend fit (set up in cd_comm_init; NCCL path is the fallback)
+    bool p2p_ok = false;
+    DevBuf<double> p2p_mail, p2p_gtot;
+    DevBuf<double*> p2p_peers_dev;
+    std::vector<void*> p2p_opened;
+    unsigned long long p2p_epoch = 0;
     // countput output of the last cd_countput
     int64_t cp_pairs = 0;
     DevBuf<int32_t> cp_bait, cp_oe;
@@ -309,6 +316,7 @@ void cd_destroy(cd_ctx* ctx)
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->ev_user[k]) cudaEventDestroy(ctx->ev_user[k]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (void* p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     cudaStream_t st = ctx->st;
     delete ctx;
@@ -322,11 +330,66 @@ int cd_comm_unique_id(cd_ctx* ctx, char id[128])
     return CD_OK;
 }
 
+// Exchange cudaIpc handles of one small mailbox per rank so that the trend-fit kernel can all-reduce its 8 sums
+// over NVLink itself.  Any failure leaves p2p_ok false and the NCCL host-driven path in use.
+static void setup_p2p(cd_ctx* ctx)
+{
+    ctx->p2p_ok = false;
+    const int nr = ctx->comm.nranks, rk = ctx->comm.rank;
+    if (nr < 2 || nr > 64) return;
+    const char* off = getenv("CHICDIFF_B200_NO_P2P");
+    if (off && off[0] == '1') return;
+    if (ctx->p2p_mail.ensure((size_t)2 * nr * 16) != cudaSuccess || ctx->p2p_gtot.ensure(16) != cudaSuccess ||
+        ctx->p2p_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
+    cudaMemset(ctx->p2p_mail.p, 0, sizeof(double) * 2 * nr * 16);
+    cudaIpcMemHandle_t mine;
+    if (cudaIpcGetMemHandle(&mine, ctx->p2p_mail.p) != cudaSuccess) { cudaGetLastError(); return; }
+    DevBuf<unsigned char> hb;
+    if (hb.ensure((size_t)nr * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) return;
+    cudaMemcpy(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    std::vector<int64_t> counts((size_t)nr, 1), displs((size_t)nr);
+    for (int r = 0; r < nr; r++) displs[(size_t)r] = r;
+    if (!ctx->comm.allgatherv(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), hb.p, counts, displs, sizeof(cudaIpcMemHandle_t), ctx->st).empty()) return;
+    std::vector<cudaIpcMemHandle_t> all((size_t)nr);
+    if (cudaMemcpyAsync(all.data(), hb.p, sizeof(cudaIpcMemHandle_t) * (size_t)nr, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return;
+    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) return;
+    std::vector<double*> peers((size_t)nr, nullptr);
+    bool ok = true;
+    for (int r = 0; r < nr; r++) {
+        if (r == rk) { peers[(size_t)r] = ctx->p2p_mail.p; continue; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        ctx->p2p_opened.push_back(ptr);
+        peers[(size_t)r] = (double*)ptr;
+    }
+    // every rank must agree, otherwise one would wait in the kernel for a peer that uses NCCL
+    double flag = ok ? 0.0 : 1.0;
+    DevBuf<double> fb;
+    if (fb.ensure(1) != cudaSuccess) return;
+    cudaMemcpy(fb.p, &flag, sizeof(double), cudaMemcpyHostToDevice);
+    if (!ctx->comm.allreduce_sum(fb.p, 1, ctx->st).empty()) return;
+    cudaMemcpyAsync(&flag, fb.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->st);
+    cudaStreamSynchronize(ctx->st);
+    if (flag != 0.0) return;
+    cudaMemcpy(ctx->p2p_peers_dev.p, peers.data(), sizeof(double*) * (size_t)nr, cudaMemcpyHostToDevice);
+    ctx->p2p_ok = true;
+}
+
 int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128])
 {
     if (!ctx || !id) return CD_EINVAL;
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
     CD_COMM(ctx, ctx->comm.init(nranks, rank, id));
+    setup_p2p(ctx);
+    return CD_OK;
+}
+
+int cd_comm_info(const cd_ctx* ctx, int* nranks, int* rank, int* peer_memory_allreduce)
+{
+    if (!ctx) return CD_EINVAL;
+    if (nranks) *nranks = ctx->comm.nranks;
+    if (rank) *rank = ctx->comm.rank;
+    if (peer_memory_allreduce) *peer_memory_allreduce = ctx->p2p_ok ? 1 : 0;
     return CD_OK;
 }
 
@@ -901,12 +964,18 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     ctx->tm_begin(5);
     double* trend_dev = ctx->scal.p + 110;        // coefs[2], status, outer iterations, passes
     int rc;
-    if (ctx->comm.active()) {
-        rc = trend_fit_sharded(ctx, trend_dev);
+    if (ctx->comm.active() && !ctx->p2p_ok) {
+        rc = trend_fit_sharded(ctx, trend_dev);                 // NCCL all-reduce per pass, host-driven
         if (rc != CD_OK) return rc;
     } else {
+        // one cooperative kernel; in a sharded run it all-reduces the 8 sums of every pass through peer memory
+        TrendP2P pp{};
+        pp.nranks = ctx->comm.active() ? ctx->comm.nranks : 1;
+        pp.rank = ctx->comm.rank;
+        pp.peers = ctx->p2p_peers_dev.p; pp.mymail = ctx->p2p_mail.p; pp.gtot = ctx->p2p_gtot.p;
+        pp.epoch = ++ctx->p2p_epoch;
         CD_LAUNCHN(ctx, 1, launch_trend_fit(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->partial.p,
-                                            reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, st));
+                                            reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, pp, st));
     }
     CD_LAUNCHN(ctx, 1, launch_trend_apply(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
                                           ctx->g_dispFit.p, ctx->g_resid.p, st));

@@ -136,10 +136,18 @@ cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* d
                               const uint8_t* flags, double c0, double c1, double b0, double b1,
                               double* partial, double* out, cudaStream_t st);
 // dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded
+// peer-memory description for the in-kernel all-reduce of the sharded trend fit (nranks == 1: unused)
+struct TrendP2P {
+    int nranks, rank;
+    double* const* peers;       // device array of nranks pointers: every rank's mailbox (own one included)
+    double* mymail;             // this rank's mailbox: 2 x nranks slots of 16 doubles (8 sums, sequence word, pad)
+    double* gtot;               // 16 doubles of local scratch
+    unsigned long long epoch;   // distinct per launch, identical on all ranks
+};
 // the whole parametricDispersionFit in one cooperative kernel; out[0..1] coefs, out[2] status, out[3] outer
-// iterations, out[4] passes; partial >= 8 * #SMs doubles, bar = one zero-initialised word
+// iterations, out[4] passes; partial >= 16 * #SMs doubles, bar = one zero-initialised word
 cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                             double* partial, unsigned int* bar, double* out, cudaStream_t st);
+                             double* partial, unsigned int* bar, double* out, const TrendP2P& pp, cudaStream_t st);
 cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst,
                                const uint8_t* flags, const double* coefs_dev, double* dispFit, double* resid,
                                cudaStream_t st);

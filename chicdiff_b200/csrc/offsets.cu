@@ -221,14 +221,56 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
     __syncthreads();
 }
 
+// Cross-GPU part of a pass (sharded runs): CTA 0 stores this rank's 8 sums straight into every peer's
+// mailbox over NVLink (peer pointers from cudaIpcOpenMemHandle), then a sequence word; it waits until all
+// ranks' slots of its own mailbox carry this pass's sequence and adds them in rank order, so every rank
+// obtains bit-identical totals and follows the same control flow.  Slots are double-buffered by pass parity:
+// a peer can only be one pass ahead, because finishing a pass needs everybody's contribution to it.
+__device__ __forceinline__ bool p2p_allreduce8(const TrendP2P& pp, unsigned long long seq, unsigned int parity,
+                                               const double* sh_tot, double* gtot_out)
+{
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < pp.nranks) {
+        double* dst = pp.peers[threadIdx.x] + ((size_t)parity * pp.nranks + pp.rank) * 16;
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[k] = sh_tot[k];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(dst + 8) = seq;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pp.nranks) {
+        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
+            pp.mymail + ((size_t)parity * pp.nranks + threadIdx.x) * 16 + 8);
+        const long long t0 = clock64();
+        while (*f != seq) {
+            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }      // ~10 s: a peer died; give up
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double x = 0.0;
+        for (int r = 0; r < pp.nranks; r++)
+            x += *reinterpret_cast<volatile double*>(pp.mymail + ((size_t)parity * pp.nranks + r) * 16 + threadIdx.x);
+        if (timed_out) x = (threadIdx.x == 6) ? 1.0 : NAN;          // reads as "invalid" in the control flow below
+        __stcg(gtot_out + threadIdx.x, x);
+    }
+    __syncthreads();
+    return timed_out == 0;
+}
+
 __device__ __forceinline__ void trend_pass_device(int64_t n, const double* __restrict__ baseMean,
                                                   const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
                                                   double c0, double c1, double b0, double b1, double* partial_base,
-                                                  unsigned int* bar, unsigned int& phase, double* sh_tot /*8, shared*/)
+                                                  unsigned int* bar, unsigned int& phase, double* sh_tot /*8, shared*/,
+                                                  const TrendP2P& pp, unsigned long long& pass_no)
 {
     // partials are double-buffered by pass parity: a CTA can be at most one pass ahead of the slowest
     // one (there is a barrier in every pass), so one barrier per pass is enough
-    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;
+    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;      // phase advances by 1 or 2 per pass; with
+    // 2 barriers per pass (sharded) a single buffer would do, the parity then simply stays constant
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
@@ -274,19 +316,28 @@ __device__ __forceinline__ void trend_pass_device(int64_t n, const double* __res
         if (lane == 0) sh_tot[wid] = x;
     }
     __syncthreads();
+    if (pp.nranks > 1) {
+        pass_no++;
+        double* gtot = pp.gtot + (size_t)(pass_no & 1ull) * 8;
+        if (blockIdx.x == 0) p2p_allreduce8(pp, (pp.epoch << 32) | pass_no, (unsigned int)(pass_no & 1ull), sh_tot, gtot);
+        grid_barrier(bar, gridDim.x, phase);
+        if (threadIdx.x < 8) sh_tot[threadIdx.x] = __ldcg(gtot + threadIdx.x);
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(kTrendThreads)
 trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
-                 const uint8_t* __restrict__ flags, double* partial, unsigned int* bar, double* out)
+                 const uint8_t* __restrict__ flags, double* partial, unsigned int* bar, double* out, TrendP2P pp)
 {
     __shared__ double tot[8];
     unsigned int phase = 0;
+    unsigned long long pass_no = 0;
     double c0 = 0.1, c1 = 1.0;
     int iter = 0, status = 0, passes = 0;
     while (true) {
         double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
-        trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial, bar, phase, tot); passes++;
+        trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial, bar, phase, tot, pp, pass_no); passes++;
         double v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = tot[k];
@@ -301,7 +352,7 @@ trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* _
             double w[8];
             int halv = 0;
             while (true) {
-                trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, nb0, nb1, partial, bar, phase, tot); passes++;
+                trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, nb0, nb1, partial, bar, phase, tot, pp, pass_no); passes++;
 #pragma unroll
                 for (int k = 0; k < 8; k++) w[k] = tot[k];
                 if (w[6] == 0.0 && isfinite(w[5])) break;
@@ -331,8 +382,9 @@ trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* _
 }
 
 cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                             double* partial, unsigned int* bar, double* out, cudaStream_t st)
+                             double* partial, unsigned int* bar, double* out, const TrendP2P& pp_in, cudaStream_t st)
 {
+    TrendP2P pp = pp_in;
     int dev = 0, sms = 148, coop = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -340,7 +392,7 @@ cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* di
     if (!coop) return cudaErrorNotSupported;
     cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&partial, (void*)&bar, (void*)&out};
+    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&partial, (void*)&bar, (void*)&out, (void*)&pp};
     return cudaLaunchCooperativeKernel((const void*)trend_fit_kernel, dim3((unsigned)sms), dim3(kTrendThreads), args, 0, st);
 }
 
