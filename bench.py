@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--regions", type=int, default=None, help="override the number of regions per rank")
-    ap.add_argument("--cpu-sample", type=int, default=300000, help="regions in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=600000, help="regions in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

@@ -477,3 +477,53 @@ def test_other_designs(reps, extra_cols):
         d.X = X
     K, FM, Ko, FMo, r, ro, _ = run_both(d)
     check(d, K, FM, Ko, FMo, r, ro, min_frac=0.998)
+
+
+def test_full_size_c3_properties():
+    """BASELINE configs[2] at full size (2.1 M regions, 23 M rows, 3-vs-3), where the oracle would take minutes:
+    size-independent properties instead.  Checksum of checksums for the aggregation (exact), idempotence of the
+    whole region test (bitwise), output identities (stat = LFC / SE, p = 2 Phi(-|stat|)), value ranges, and the
+    fused-assembly route giving the same counts."""
+    from scipy import special
+    d = synth.generate("c3")
+    assert d.n > 2_000_000
+    e = engine.Engine(0)
+    e.set_design(d.X)
+    e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    K, FM = e.aggregate()
+    assert np.array_equal(K.astype(np.int64).sum(axis=1), d.N_rows.astype(np.int64).sum(axis=1))      # nothing lost, nothing double counted
+    # spot-check 1000 random regions against a direct sum
+    rng = np.random.default_rng(5)
+    for i in rng.integers(0, d.n, 1000):
+        lo, hi = d.row_off[i], d.row_off[i + 1]
+        assert np.array_equal(K[:, i], d.N_rows[:, lo:hi].sum(axis=1))
+    r1 = e.region_test()
+    r2 = e.region_test()
+    for k in ("dispGeneEst", "dispersion", "log2FoldChange", "lfcSE", "stat", "pvalue", "deviance"):
+        assert np.array_equal(r1[k], r2[k], equal_nan=True), k                                         # deterministic reductions, no fp atomics
+    assert r1["theta"] == r2["theta"] and np.array_equal(r1["deviances"], r2["deviances"])
+    ok = ~np.isnan(r1["pvalue"])
+    assert ok.all()                                                                                    # generator leaves no all-zero region
+    assert np.max(np.abs(r1["stat"] - r1["log2FoldChange"] / r1["lfcSE"])) == 0.0
+    p_ref = special.erfc(np.abs(r1["stat"]) / np.sqrt(2.0))
+    assert np.max(np.abs(r1["pvalue"] - p_ref) / np.maximum(p_ref, 1e-300)) < 1e-12
+    assert np.all((r1["dispersion"] >= 1e-8) & (r1["dispersion"] <= 10.0))
+    assert np.all((r1["dispGeneIter"] >= 1) & (r1["dispGeneIter"] <= 100)) and np.all(r1["betaIter"] < 100)
+    assert r1["n_nonzero"] == d.n
+    # true effects are found: planted regions dominate the top of the ranking
+    top = np.argsort(r1["pvalue"])[:2000]
+    assert (d.true_lfc[top] != 0).mean() > 0.9
+    # the fused assembly route reproduces the same aggregated counts from the per-replicate tables
+    e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+    e.set_regions(d.row_off)
+    e.set_region_rows(d.row_bait, d.row_oe)
+    for s in range(d.S):
+        e.set_sample_tables(s, d.extra["tables"][s])
+    K2, FM2, av = e.assemble()
+    assert np.array_equal(K2, K)
+    assert np.array_equal(np.isnan(FM2), np.isnan(FM))
+    okm = ~np.isnan(FM)
+    assert np.max(np.abs(FM2[okm] - FM[okm]) / FM[okm]) < 1e-12
+    e.close()
