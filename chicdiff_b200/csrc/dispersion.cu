@@ -10,6 +10,7 @@
 // sample-major matrices and the region's replicates (y_j, mu_j) are staged per thread in a
 // conflict-free shared-memory column.
 #include "kernels.h"
+#include <cuda_pipeline.h>
 
 namespace cd {
 
@@ -203,7 +204,7 @@ constexpr int kFitDispTripCap = 24;     // first pass: a region still searching 
 // kFitDispTripCap trips (its scalar search state goes to the FitDispPark arrays); pass 2 resumes
 // all parked regions at once, one per lane, so the long searches overlap each other.
 #ifndef CD_FITDISP_MINBLOCKS
-#define CD_FITDISP_MINBLOCKS 1      /* measured: 6 (80 registers) is not faster -- the kernel is FP64-pipe bound */
+#define CD_FITDISP_MINBLOCKS 4      /* <= 128 registers; measured: 6 blocks (80 registers) is not faster */
 #endif
 template <int P, bool RESUME>
 __global__ void __launch_bounds__(kFitDispThreads, CD_FITDISP_MINBLOCKS)
@@ -234,11 +235,84 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
     double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0;
     int iter = 0, iter_accept = 0;
 
+    // First pass: the refill is software-pipelined per lane.  ncu showed a quarter of all stall samples in
+    // the old refill (global atomic -> shuffle -> scattered loads -> convert, executed by ~3 lanes while the
+    // other 29 wait).  Now every lane always owns `pending` (a region whose replicates are already on their
+    // way into its prefetch column by cp.async) and `queued` (a region index claimed by an atomic whose
+    // result is not needed before the lane's next refill), so becoming idle costs one shared-memory copy.
+    // pf layout per lane: S int32 counts, S double means, start value, prior mean.
+    int* pf_k = reinterpret_cast<int*>(smem + (size_t)2 * S * stride) + threadIdx.x;
+    double* pf_mu = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + threadIdx.x;
+    double* pf_init = pf_mu + (size_t)S * stride;
+    double* pf_prior = pf_init + stride;
+    int64_t pending = 0, queued = 0;
+    auto prefetch = [&](int64_t r) {
+        if (r < n) {
+            for (int j = 0; j < S; j++) {
+                __pipeline_memcpy_async(pf_k + j * stride, K + (int64_t)j * n + r, sizeof(int32_t));
+                __pipeline_memcpy_async(pf_mu + j * stride, mu_g + (int64_t)j * n + r, sizeof(double));
+            }
+            __pipeline_memcpy_async(pf_init, disp_init + r, sizeof(double));
+            if (use_prior) __pipeline_memcpy_async(pf_prior, prior_mean_disp + r, sizeof(double));
+        }
+        __pipeline_commit();
+    };
+    if (!RESUME) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 64ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        pending = (int64_t)base + lane;
+        queued = (int64_t)base + 32 + lane;
+        prefetch(pending);
+    }
+
     while (true) {
         // ---- refill idle lanes ----
         const bool want = !active && !exhausted;
         const unsigned need = __ballot_sync(0xffffffffu, want);
-        if (need) {
+        if (!RESUME) {
+            bool consumed = false;
+            if (want) {
+                if (pending >= n) {
+                    exhausted = true;
+                } else {
+                    __pipeline_wait_prior(0);
+                    i = pending;
+                    const double d0 = *pf_init;
+                    if (isnan(d0)) {
+                        // all-zero region: every estimate is NA (its start value was written as NaN upstream)
+                        log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
+                    } else {
+                        for (int j = 0; j < S; j++) {
+                            ys[j * stride] = (double)pf_k[j * stride];
+                            mus[j * stride] = pf_mu[j * stride];
+                        }
+                        if (use_prior) {
+                            // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more
+                            // than an order of magnitude below the trend
+                            const double ft = *pf_prior;
+                            a = log((d0 > 0.1 * ft) ? d0 : ft);
+                            prior_mean = log(ft);
+                        } else {
+                            a = log(d0);
+                        }
+                        active = true; fresh = true;
+                        iter = 0; iter_accept = 0; kappa = kappa_0;
+                    }
+                    pending = queued;
+                    prefetch(pending);
+                    consumed = true;
+                }
+            }
+            const unsigned took = __ballot_sync(0xffffffffu, consumed);
+            if (took) {
+                unsigned long long base = 0;
+                const int leader = __ffs(took) - 1;
+                if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(took));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (consumed) queued = (int64_t)(base + __popc(took & ((1u << lane) - 1u)));
+            }
+        } else if (need) {
             unsigned long long base = 0;
             const int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(need));
@@ -247,7 +321,7 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
                 const int64_t w = (int64_t)(base + __popc(need & ((1u << lane) - 1u)));
                 if (w >= n_work) {
                     exhausted = true;
-                } else if (RESUME) {
+                } else {
                     i = park.row[w];
                     a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
                     iter = park.iter[w]; iter_accept = park.iter_accept[w];
@@ -257,27 +331,6 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
                         mus[j * stride] = mu_g[(int64_t)j * n + i];
                     }
                     active = true; fresh = false;
-                } else {
-                    i = w;
-                    if (flags[i] & CD_FLAG_ALLZERO) {
-                        log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
-                    } else {
-                        for (int j = 0; j < S; j++) {
-                            ys[j * stride] = (double)K[(int64_t)j * n + i];
-                            mus[j * stride] = mu_g[(int64_t)j * n + i];
-                        }
-                        if (use_prior) {
-                            // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more
-                            // than an order of magnitude below the trend
-                            const double ft = prior_mean_disp[i], ge = disp_init[i];
-                            a = log((ge > 0.1 * ft) ? ge : ft);
-                            prior_mean = log(ft);
-                        } else {
-                            a = log(disp_init[i]);
-                        }
-                        active = true; fresh = true;
-                        iter = 0; iter_accept = 0; kappa = kappa_0;
-                    }
                 }
             }
         }
@@ -362,7 +415,7 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
     if (e != cudaSuccess) return e;
     const int threads = kFitDispThreads;
     const int64_t want = (n + threads - 1) / threads;
-    const size_t smem = (size_t)2 * S * threads * sizeof(double);
+    const size_t smem = ((size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads) * sizeof(double);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
