@@ -76,3 +76,43 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
   if (norm == "combined") attributes(out)$theta <- fit$theta
   out
 }
+
+
+## getFullRegionData1() on the CUDA backend (chicdiff.R:577-948) -- marshalling only.
+## Per replicate it builds the same small intermediate tables the reference builds (first s_j/tblb per bait :659,
+## first s_i/tlb per other end :668, first Tmean per (tblb, tlb) :680, .chicEstimateDistFun :696) as dense
+## per-fragment vectors, hands them and the .chinput counts to cd_set_sample_tables, and lets cd_assemble do the
+## joins, Bmean/Tmean reconstruction, count merge and region sums.  The .Call stubs cdR_set_rmap,
+## cdR_set_region_rows, cdR_set_sample_tables, cdR_assemble, cdR_get_sample_rows follow the pattern of r_glue.c.
+getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, ctx) {
+  rmap <- Chicago:::.readRmap(list(rmapfile = chicdiff.settings[["rmapfile"]]))
+  colnames(rmap) <- c("chr", "start", "end", "ID"); setkey(rmap, ID)
+  id0 <- rmap$ID[1]; nF <- nrow(rmap)
+  stopifnot(identical(rmap$ID, seq.int(id0, length.out = nF)))
+  .Call("cdR_set_rmap", ctx, as.integer(factor(rmap$chr)), as.integer(rmap$start), as.integer(rmap$end), as.integer(id0))
+  setkey(RU, regionID, otherEndID)
+  .Call("cdR_set_regions", ctx, c(0, cumsum(as.numeric(RU[, .N, by = regionID]$N))))
+  .Call("cdR_set_region_rows", ctx, as.integer(RU$baitID), as.integer(RU$otherEndID))
+  files <- unlist(chicdiff.settings[["chicagoData"]]); counts <- unlist(chicdiff.settings[["countData"]])
+  for (i in seq_along(files)) {
+    x <- readRDSorRDA(files[i]); x <- if ("chicagoData" %in% class(x)) as.data.table(x@x) else setDT(x)
+    setkey(x, baitID, otherEndID)
+    bait <- x[, list(s_j = s_j[1], tblb = tblb[1]), by = "baitID"]
+    oe <- x[, list(s_i = s_i[1], tlb = tlb[1]), by = "otherEndID"]
+    tb.lv <- sort(unique(na.omit(x$tblb))); tl.lv <- sort(unique(na.omit(x$tlb)))
+    tm <- x[!is.na(tblb) & !is.na(tlb), list(Tmean = Tmean[1]), by = c("tblb", "tlb")]
+    tmean <- matrix(NA_real_, length(tb.lv), length(tl.lv)); tmean[cbind(match(tm$tblb, tb.lv), match(tm$tlb, tl.lv))] <- tm$Tmean
+    s_j <- rep(NA_real_, nF); s_j[bait$baitID - id0 + 1L] <- bait$s_j
+    tblb <- rep(-1L, nF); tblb[bait$baitID - id0 + 1L] <- ifelse(is.na(bait$tblb), -1L, match(bait$tblb, tb.lv) - 1L)
+    s_i <- rep(NA_real_, nF); s_i[oe$otherEndID - id0 + 1L] <- oe$s_i
+    tlb <- rep(-1L, nF); tlb[oe$otherEndID - id0 + 1L] <- ifelse(is.na(oe$tlb), -1L, match(oe$tlb, tl.lv) - 1L)
+    dfp <- .chicEstimateDistFun(x)
+    cnt <- if (is.null(counts)) x[, .(baitID, otherEndID, N)] else fread(counts[i])[, .(baitID, otherEndID, N)]
+    setkey(cnt, baitID, otherEndID)
+    cnt_off <- c(0, cumsum(tabulate(cnt$baitID - id0 + 1L, nbins = nF)))
+    .Call("cdR_set_sample_tables", ctx, i, s_j, tblb, s_i, tlb, t(tmean),
+          c(dfp$cubicFit, dfp$obs.min, dfp$obs.max, dfp$head.coef, dfp$tail.coef),
+          as.numeric(cnt_off), as.integer(cnt$otherEndID), as.integer(cnt$N))
+  }
+  .Call("cdR_assemble", ctx, TRUE)      # -> list(K, FullMean, avDist); per-row columns via cdR_get_sample_rows
+}

@@ -3,8 +3,10 @@
 The reference is R (Chicdiff/R/chicdiff.R); no R interpreter exists in this image, so the host side above
 the C ABI is written in Python with the reference's names, argument meaning and error behaviour:
 
-    defaultChicdiffSettings()                          chicdiff.R:3-24
-    DESeq2Wrap(chicdiff_settings, RU, FullRegionData, suffix="", theta=None)      chicdiff.R:1494-1777
+    defaultChicdiffSettings()                                                      chicdiff.R:3-24
+    getFullRegionData(chicdiff_settings, RU, RUcontrol, ...) / getFullRegionData1   chicdiff.R:1460-1478, 577-948
+    .chicEstimateDistFun -> chicEstimateDistFun(distbin, refBinMean)               chicdiff.R:538-573
+    DESeq2Wrap(chicdiff_settings, RU, FullRegionData, suffix="", theta=None)       chicdiff.R:1494-1777
 
 Tables are dicts of equally long NumPy columns (the stand-in for data.table).  `R/chicdiff_b200.R` is the
 same adapter written in R for a real drop-in (it can not be executed here); both only marshal columns and
@@ -185,3 +187,194 @@ def read_rmap(path):
             start.append(int(f[1])); end.append(int(f[2])); fid.append(int(f[3]))
     o = np.argsort(np.asarray(fid), kind="stable")
     return {"chr": np.asarray(chr_)[o], "start": np.asarray(start)[o], "end": np.asarray(end)[o], "ID": np.asarray(fid)[o]}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# getFullRegionData (chicdiff.R:1460-1478 -> getFullRegionData1, :577-948)
+# ---------------------------------------------------------------------------------------------------------
+
+def chicEstimateDistFun(distbin, refBinMean, binsize=20000):
+    """.chicEstimateDistFun (chicdiff.R:538-573): unique non-NA (distbin, refBinMean) pairs ordered by decreasing
+    refBinMean get the midpoints round(binsize/2) + k*binsize; cubic least squares of log(refBinMean) on
+    log(midpoint); C1 linear head and tail.  Returns the 10 numbers cubicFit[4], obs.min, obs.max, head.coef[2],
+    tail.coef[2].  (Host side: ~75 points per replicate; binsize = Chicago::defaultSettings()$binsize.)"""
+    db = np.asarray(distbin)
+    rb = np.asarray(refBinMean, dtype=np.float64)
+    ok = ~np.isnan(rb)
+    pairs = sorted(set(zip(db[ok].tolist(), rb[ok].tolist())))
+    ref = np.array(sorted((v for _, v in pairs), reverse=True))
+    mid = np.rint(binsize / 2.0) + binsize * np.arange(len(ref))
+    l = np.log(mid)
+    A = np.stack([np.ones_like(l), l, l * l, l ** 3], axis=1)
+    fit, *_ = np.linalg.lstsq(A, np.log(ref), rcond=None)
+    obs = (np.log(mid.min()), np.log(mid.max()))
+    out = list(fit) + [obs[0], obs[1]]
+    for x in obs:
+        beta = fit[1] + 2 * fit[2] * x + 3 * fit[3] * x * x
+        alpha = fit[0] + (fit[1] - beta) * x + fit[2] * x * x + fit[3] * x ** 3
+        out += [alpha, beta]
+    return np.asarray(out, dtype=np.float64)
+
+
+def _first_by(keys, *cols):
+    """data.table's x[, list(v = v[1]), by = key] on a table sorted by (baitID, otherEndID): first row per key."""
+    u, first = np.unique(keys, return_index=True)
+    return (u,) + tuple(np.asarray(c)[first] for c in cols)
+
+
+def replicate_tables(x, rmap_ids, counts=None, binsize=20000):
+    """One replicate's CHiCAGO table (dict of columns: baitID, otherEndID, N, s_j, s_i, tblb, tlb, Tmean, distbin,
+    refBinMean) -> the per-fragment look-up tables of cd_sample_tables, exactly the intermediate tables of
+    getFullRegionData1: per-bait first (s_j, tblb) (:659), per-other-end first (s_i, tlb) (:668), first Tmean per
+    (tblb, tlb) (:680), .chicEstimateDistFun (:696), and the count rows (the .chinput, :828-853, or x's own N)."""
+    ids = np.asarray(rmap_ids, dtype=np.int64)
+    id0, F = int(ids[0]), len(ids)
+    if not np.array_equal(ids, np.arange(id0, id0 + F)):
+        raise ValueError("the rmap fragment IDs must be contiguous")
+    bait = np.asarray(x["baitID"], dtype=np.int64)
+    oe = np.asarray(x["otherEndID"], dtype=np.int64)
+    order = np.lexsort((oe, bait))                                   # setkey(x, baitID, otherEndID) (:632)
+    bait, oe = bait[order], oe[order]
+    col = lambda k: np.asarray(x[k])[order]
+    tb_lab, tl_lab = col("tblb"), col("tlb")
+
+    def codes(lab):
+        lab = np.asarray(lab, dtype=object)
+        na = np.array([v is None or (isinstance(v, float) and np.isnan(v)) for v in lab])
+        levels = sorted(set(lab[~na].tolist()))
+        lut = {v: k for k, v in enumerate(levels)}
+        return np.array([-1 if m else lut[v] for v, m in zip(lab, na)], dtype=np.int32), levels
+    tb_code, tb_levels = codes(tb_lab)
+    tl_code, tl_levels = codes(tl_lab)
+    s_j = np.full(F, np.nan); tblb = np.full(F, -1, np.int32)
+    ub, sj1, tb1 = _first_by(bait, col("s_j").astype(np.float64), tb_code)
+    s_j[ub - id0] = sj1; tblb[ub - id0] = tb1
+    s_i = np.full(F, np.nan); tlb = np.full(F, -1, np.int32)
+    o2 = np.lexsort((bait, oe))                                      # first row per otherEndID in (baitID, otherEndID) order
+    uo, first = np.unique(oe[o2], return_index=True)
+    s_i[uo - id0] = col("s_i").astype(np.float64)[o2][first]
+    tlb[uo - id0] = tl_code[o2][first]
+    tmean = np.full((max(1, len(tb_levels)), max(1, len(tl_levels))), np.nan)
+    tm = col("Tmean").astype(np.float64)
+    okc = (tb_code >= 0) & (tl_code >= 0)
+    key = tb_code[okc].astype(np.int64) * max(1, len(tl_levels)) + tl_code[okc]
+    uk, firstk = np.unique(key, return_index=True)
+    tmean.reshape(-1)[uk] = tm[okc][firstk]
+    distfun = chicEstimateDistFun(col("distbin"), col("refBinMean"), binsize)
+    if counts is None:
+        cb, co, cn = bait, oe, np.asarray(x["N"])[order]
+    else:
+        cb = np.asarray(counts["baitID"], dtype=np.int64); co = np.asarray(counts["otherEndID"], dtype=np.int64)
+        o3 = np.lexsort((co, cb))
+        cb, co, cn = cb[o3], co[o3], np.asarray(counts["N"])[o3]
+    inside = (cb >= id0) & (cb < id0 + F)
+    cb, co, cn = cb[inside], co[inside], cn[inside]
+    cnt_off = np.searchsorted(cb, np.arange(id0, id0 + F + 1)).astype(np.int64)
+    return dict(s_j=s_j, tblb=tblb, s_i=s_i, tlb=tlb, tmean=tmean, distfun=distfun, cnt_off=cnt_off,
+                cnt_oe=co.astype(np.int32), cnt_N=cn.astype(np.int32), tblb_levels=tb_levels, tlb_levels=tl_levels)
+
+
+def getFullRegionData1(chicdiff_settings, RU, rmap, chicago_tables, count_tables=None, is_control=False, engine_obj=None):
+    """getFullRegionData1 (chicdiff.R:577-948) on the CUDA backend for ONE region universe.
+
+    chicago_tables: {condition: [replicate table, ...]} in the order of settings$chicagoData; count_tables: same
+    shape with (baitID, otherEndID, N) chinput tables, or None to take N from the CHiCAGO tables.
+    Returns the long table (dict of columns baitID, otherEndID, regionID, distSign, sample, N, s_j, Bmean, Tmean,
+    score, FullMean, condition; sample-major blocks, then stable-sorted by regionID like setkey(recast, regionID))
+    and, for the test set, countput."""
+    ids = np.asarray(rmap["ID"], dtype=np.int64)
+    id0, F = int(ids[0]), len(ids)
+    chr_labels = np.asarray(rmap["chr"])
+    _, chr_codes = np.unique(chr_labels, return_inverse=True)
+    start = np.asarray(rmap["start"], dtype=np.int64); end = np.asarray(rmap["end"], dtype=np.int64)
+    ru_region = np.asarray(RU["regionID"], dtype=np.int64)
+    ru_bait = np.asarray(RU["baitID"], dtype=np.int64)
+    ru_oe = np.asarray(RU["otherEndID"], dtype=np.int64)
+    o = np.lexsort((ru_oe, ru_region))
+    ru_region, ru_bait, ru_oe = ru_region[o], ru_bait[o], ru_oe[o]
+    region_ids, first = np.unique(ru_region, return_index=True)
+    row_off = np.concatenate([first, [len(ru_region)]]).astype(np.int64)
+    names, conditions, reps, cnts = [], [], [], []
+    for cond, tabs in chicago_tables.items():
+        for k, t in enumerate(tabs):
+            names.append("%s.%s" % (cond, t.get("name", "rep%d" % (k + 1))))
+            conditions.append(cond)
+            reps.append(t)
+            cnts.append(None if count_tables is None else count_tables[cond][k])
+    S = len(reps)
+    eng = engine_obj or _get_engine(chicdiff_settings.get("gpu", 0) or 0)
+    X, _ = model_matrix(conditions, chicdiff_settings.get("batch"))
+    eng.set_design(X)
+    eng.set_rmap(chr_codes, start, end, id0)
+    eng.set_regions(row_off)
+    eng.set_region_rows(ru_bait, ru_oe)
+    tabs = []
+    for s in range(S):
+        message("\nReading Chicago dataset %d of %d : %s" % (s + 1, S, names[s]))
+        tabs.append(replicate_tables(reps[s], ids, cnts[s]))
+        eng.set_sample_tables(s, tabs[-1])
+    message("Processing count data")
+    eng.assemble(keep_rows=True, fetch=False)
+    R = len(ru_oe)
+    mid = np.rint(0.5 * (start + end))                                     # chicdiff.R:871 (R rounds half to even)
+    same = chr_codes[ru_oe - id0] == chr_codes[ru_bait - id0]
+    dist = np.where(same, mid[ru_oe - id0] - mid[ru_bait - id0], np.nan)  # :878-881
+    out = {k: [] for k in ("baitID", "otherEndID", "regionID", "distSign", "sample", "N", "s_j", "Bmean", "Tmean", "score",
+                           "FullMean", "condition")}
+    for s in range(S):
+        N, FM = eng.get_sample_rows(s, R)
+        Bm = eng.get_sample_bmean(s, R)
+        t = tabs[s]
+        x = reps[s]
+        # score of the pair in this replicate's CHiCAGO table, NA where the pair is absent (:634)
+        xb = np.asarray(x["baitID"], dtype=np.int64); xo = np.asarray(x["otherEndID"], dtype=np.int64)
+        xkey = xb * (1 << 32) + xo
+        xo_ = np.argsort(xkey, kind="stable")
+        pos = np.searchsorted(xkey[xo_], ru_bait * (1 << 32) + ru_oe)
+        pos = np.minimum(pos, len(xkey) - 1)
+        hit = xkey[xo_][pos] == ru_bait * (1 << 32) + ru_oe
+        score = np.where(hit, np.asarray(x["score"], dtype=np.float64)[xo_][pos], np.nan)
+        out["baitID"].append(ru_bait); out["otherEndID"].append(ru_oe); out["regionID"].append(ru_region)
+        out["distSign"].append(dist); out["sample"].append(np.repeat(names[s], R)); out["N"].append(N)
+        tb, tl = t["tblb"][ru_bait - id0], t["tlb"][ru_oe - id0]
+        with np.errstate(invalid="ignore"):
+            tmin = np.array([np.nan if np.isnan(r).all() else np.nanmin(r) for r in t["tmean"]])
+        Tm = np.where(tb >= 0, np.where(tl >= 0, t["tmean"][np.maximum(tb, 0), np.maximum(tl, 0)], tmin[np.maximum(tb, 0)]), np.nan)
+        out["s_j"].append(t["s_j"][ru_bait - id0]); out["Bmean"].append(Bm); out["Tmean"].append(Tm)
+        out["score"].append(score); out["FullMean"].append(FM); out["condition"].append(np.repeat(conditions[s], R))
+    long = {k: np.concatenate(v) for k, v in out.items()}
+    key = np.argsort(long["regionID"], kind="stable")                     # setkey(recast, regionID) (:925)
+    long = {k: v[key] for k, v in long.items()}
+    if is_control:
+        return long
+    message("Saving counts\n")
+    countput = {k: [] for k in ("baitID", "otherEndID", "Nav", "Bav", "score", "oeID_mid", "condition")}
+    for cond in dict.fromkeys(conditions):
+        rows = []
+        for s in range(S):
+            if conditions[s] != cond:
+                continue
+            x = reps[s]
+            keep = ~np.isnan(np.asarray(x["distSign"], dtype=np.float64))                  # :715
+            inr = (np.asarray(x["otherEndID"], dtype=np.int64) >= id0) & (np.asarray(x["otherEndID"], dtype=np.int64) < id0 + F)
+            keep &= inr                                                                    # inner merge with the rmap (:724)
+            xb = np.asarray(x["baitID"], dtype=np.int64)[keep]; xo = np.asarray(x["otherEndID"], dtype=np.int64)[keep]
+            oo = np.lexsort((xo, xb))
+            rows.append(dict(baitID=xb[oo], otherEndID=xo[oo], N=np.asarray(x["N"])[keep][oo],
+                             Bmean=np.asarray(x["Bmean"], dtype=np.float64)[keep][oo],
+                             score=np.asarray(x["score"], dtype=np.float64)[keep][oo]))
+        cp = eng.countput(rows)
+        for k in ("baitID", "otherEndID", "Nav", "Bav", "score", "oeID_mid"):
+            countput[k].append(cp[k])
+        countput["condition"].append(np.repeat(cond, len(cp["baitID"])))
+    countput = {k: np.concatenate(v) for k, v in countput.items()}
+    return [long, None, countput]
+
+
+def getFullRegionData(chicdiff_settings, RU, RUcontrol, rmap, chicago_tables, count_tables=None):
+    """chicdiff.R:1460-1478: list(FullRegionData, FullControlRegionData, countput)."""
+    message("Reading data for significant interactions")
+    res = getFullRegionData1(chicdiff_settings, RU, rmap, chicago_tables, count_tables, is_control=False)
+    message("\nReading data for control interactions")
+    res[1] = getFullRegionData1(chicdiff_settings, RUcontrol, rmap, chicago_tables, count_tables, is_control=True)
+    return res

@@ -30,7 +30,8 @@ assemble_kernel(int64_t n, int S, const int64_t* __restrict__ row_off, int64_t R
                 const int32_t* __restrict__ frag_start, const int32_t* __restrict__ frag_end,
                 const AssembleTables* __restrict__ tabs,
                 int32_t* __restrict__ K, double* __restrict__ FM, double* __restrict__ avDist,
-                int32_t* __restrict__ N_rows, double* __restrict__ FM_rows, int32_t* __restrict__ status)
+                int32_t* __restrict__ N_rows, double* __restrict__ FM_rows, double* __restrict__ BM_rows,
+                int32_t* __restrict__ status)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y;
@@ -80,7 +81,7 @@ assemble_kernel(int64_t n, int S, const int64_t* __restrict__ row_off, int64_t R
             acc += cnt;
             facc += fm;
             dsum += cis ? rint(0.5 * mido2) - midb : NAN;              // chicdiff.R:878-881
-            if (N_rows) { N_rows[(int64_t)s * R + r] = cnt; FM_rows[(int64_t)s * R + r] = fm; }
+            if (N_rows) { N_rows[(int64_t)s * R + r] = cnt; FM_rows[(int64_t)s * R + r] = fm; BM_rows[(int64_t)s * R + r] = bm; }
         }
     }
     K[(int64_t)s * n + i] = (acc > 2147483647LL) ? INT32_MIN : (int32_t)acc;
@@ -112,12 +113,12 @@ cudaError_t launch_assemble(int64_t n, int S, const int64_t* row_off, int64_t R,
                             const int32_t* row_oe, int64_t F, int32_t frag_id0, const int32_t* frag_chr,
                             const int32_t* frag_start, const int32_t* frag_end, const AssembleTables* tabs_dev,
                             int32_t* K, double* FM, double* avDist, int32_t* N_rows, double* FM_rows,
-                            int32_t* status, cudaStream_t st)
+                            double* BM_rows, int32_t* status, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     dim3 grid((unsigned)((n + 127) / 128), (unsigned)S);
     assemble_kernel<<<grid, 128, 0, st>>>(n, S, row_off, R, row_bait, row_oe, F, frag_id0, frag_chr, frag_start, frag_end,
-                                          tabs_dev, K, FM, avDist, N_rows, FM_rows, status);
+                                          tabs_dev, K, FM, avDist, N_rows, FM_rows, BM_rows, status);
     return cudaGetLastError();
 }
 

@@ -169,6 +169,8 @@ struct cd_ctx {
     DevBuf<int64_t> row_off;
     DevBuf<int32_t> N_rows;
     DevBuf<double> FM_rows;
+    DevBuf<double> BM_rows;          // per-row Bmean, only after cd_assemble(keep_rows)
+    bool have_bm_rows = false;
     const int32_t* N_rows_p = nullptr;
     const double* FM_rows_p = nullptr;
     DevBuf<int32_t> K;               // S x n
@@ -448,6 +450,7 @@ int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off)
     ctx->n = n;
     ctx->R = row_off[n];
     ctx->have_regions = true;
+    ctx->have_bm_rows = false;
     ctx->have_region_rows = false;
     ctx->have_agg = false;
     ctx->rows_borrowed = false;
@@ -733,8 +736,10 @@ int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out
         if (ctx->rows_borrowed) return ctx->fail(CD_EINVAL, "cd_assemble: rows were set with cd_set_rows_device");
         CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R));
         CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R));
+        CD_CUDA(ctx, ctx->BM_rows.ensure((size_t)S * (size_t)R));
         ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
     }
+    ctx->have_bm_rows = keep_rows != 0;
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->tabs_dev.p, ctx->tabs_host.data(), sizeof(AssembleTables) * (size_t)S, cudaMemcpyHostToDevice, ctx->st));
     CD_CUDA(ctx, cudaMemsetAsync(ctx->asm_status.p, 0, sizeof(int32_t), ctx->st));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->st));
@@ -742,7 +747,7 @@ int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out
                                                   ctx->frag_chr.p, ctx->frag_start.p, ctx->frag_end.p,
                                                   (const AssembleTables*)ctx->tabs_dev.p, ctx->K.p, ctx->FM.p, ctx->avDist.p,
                                                   keep_rows ? ctx->N_rows.p : nullptr, keep_rows ? ctx->FM_rows.p : nullptr,
-                                                  ctx->asm_status.p, ctx->st));
+                                                  keep_rows ? ctx->BM_rows.p : nullptr, ctx->asm_status.p, ctx->st));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->st));
     int32_t status = 0;
     CD_CUDA(ctx, cudaMemcpyAsync(&status, ctx->asm_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->st));
@@ -770,6 +775,18 @@ int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out)
     const size_t R = (size_t)ctx->R;
     if (N_out) CD_CUDA(ctx, cudaMemcpyAsync(N_out, ctx->N_rows_p + (size_t)s * R, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, ctx->st));
     if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM_rows_p + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    return CD_OK;
+}
+
+int cd_get_sample_bmean(cd_ctx* ctx, int s, double* bmean_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (s < 0 || s >= ctx->des.S || !ctx->have_bm_rows || !bmean_out)
+        return ctx->fail(CD_EINVAL, "cd_get_sample_bmean: needs cd_assemble with keep_rows");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t R = (size_t)ctx->R;
+    CD_CUDA(ctx, cudaMemcpyAsync(bmean_out, ctx->BM_rows.p + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     return CD_OK;
 }

@@ -53,7 +53,8 @@ cudaError_t launch_assemble(int64_t n, int S, const int64_t* row_off, int64_t R,
                             const int32_t* row_oe, int64_t F, int32_t frag_id0, const int32_t* frag_chr,
                             const int32_t* frag_start, const int32_t* frag_end, const AssembleTables* tabs_dev,
                             int32_t* K, double* FM, double* avDist, int32_t* N_rows /*S x R or null*/,
-                            double* FM_rows /*S x R or null*/, int32_t* status, cudaStream_t st);
+                            double* FM_rows /*S x R or null*/, double* BM_rows /*S x R or null*/, int32_t* status,
+                            cudaStream_t st);
 
 // ---- size factors + stage 2: offsets (chicdiff.R:1561-1562, 1583-1589, 1635-1638) ------
 cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR /*S x n, +inf = excluded*/,

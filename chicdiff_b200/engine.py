@@ -20,7 +20,7 @@ EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_u
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
-            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput"]
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput"]
 
 
 class ChicdiffError(RuntimeError):
@@ -96,6 +96,7 @@ def load_library():
     L.cd_set_sample_tables.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdSampleTables)]
     L.cd_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_get_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.cd_get_sample_bmean.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.cd_region_universe.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.cd_get_region_universe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_countput.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdChicagoRows), C.POINTER(C.c_int64)]
@@ -299,6 +300,11 @@ class Engine:
         FM = np.empty(R, np.float64)
         self._check(self._L.cd_get_sample_rows(self._h, s, _ptr(N), _ptr(FM)))
         return N, FM
+
+    def get_sample_bmean(self, s, R):
+        B = np.empty(R, np.float64)
+        self._check(self._L.cd_get_sample_bmean(self._h, s, _ptr(B)))
+        return B
 
     # -- stages -----------------------------------------------------------------------------
     def aggregate(self, fetch=True):

@@ -316,3 +316,42 @@ def chicago_rows(d, s, seed=0):
     score = np.maximum(0.0, rng.normal(2.0, 3.0, m))
     score[rng.random(m) < 0.001] = np.nan
     return dict(baitID=bait, otherEndID=t["cnt_oe"].copy(), N=t["cnt_N"].copy(), Bmean=bmean, score=score)
+
+
+def chicago_table(d, s, seed=0, binsize=20000, nbins=75):
+    """Replicate s as a reference-shaped CHiCAGO table (the columns getFullRegionData1 reads, chicdiff.R:614-696):
+    one row per observed pair whose other end CHiCAGO has seen, with s_j / tblb per bait, s_i / tlb per other end,
+    Tmean per (tblb, tlb), distSign, distbin / refBinMean (the distance function sampled at the bin midpoints),
+    plus the replicate's own Bmean and score.  The matching .chinput is `chinput_table`."""
+    t = d.extra["tables"][s]
+    F = len(d.frag_chr)
+    per_bait = np.diff(t["cnt_off"])
+    bait = np.repeat(np.arange(1, F + 1), per_bait).astype(np.int64)
+    oe = t["cnt_oe"].astype(np.int64)
+    seen = ~np.isnan(t["s_i"][oe - 1])                       # other ends without s_i were never seen by CHiCAGO
+    bait, oe, N = bait[seen], oe[seen], t["cnt_N"][seen]
+    mid2 = d.frag_start + d.frag_end
+    same = d.frag_chr[oe - 1] == d.frag_chr[bait - 1]
+    dist = np.where(same, np.rint((mid2[oe - 1] - mid2[bait - 1]) / 2.0), np.nan)
+    tb = t["tblb"][bait - 1]; tl = t["tlb"][oe - 1]
+    mids = np.rint(binsize / 2.0) + binsize * np.arange(nbins)
+    k = np.minimum(np.floor(np.abs(np.nan_to_num(dist)) / binsize).astype(np.int64), nbins)
+    cubic = t["distfun"][:4]
+    ref_at = np.exp(cubic[0] + cubic[1] * np.log(mids) + cubic[2] * np.log(mids) ** 2 + cubic[3] * np.log(mids) ** 3)
+    inb = (k < nbins) & same
+    refbin = np.where(inb, ref_at[np.minimum(k, nbins - 1)], np.nan)
+    distbin = np.array(["(%d,%d]" % (binsize * kk, binsize * (kk + 1)) if ok else None for kk, ok in zip(k, inb)], dtype=object)
+    rng = np.random.Generator(np.random.PCG64(4242 + 17 * s + seed))
+    m = len(bait)
+    return dict(baitID=bait, otherEndID=oe, N=N, distSign=dist, s_j=t["s_j"][bait - 1], s_i=t["s_i"][oe - 1],
+                tblb=np.array(["tb%d" % v for v in tb], dtype=object), tlb=np.array(["tl%d" % v for v in tl], dtype=object),
+                Tmean=t["tmean"][tb, tl], Bmean=np.exp(rng.normal(-2, 1, m)), score=np.maximum(0.0, rng.normal(2, 3, m)),
+                distbin=distbin, refBinMean=refbin, name="rep%d" % (s + 1))
+
+
+def chinput_table(d, s):
+    """The replicate's .chinput (chicdiff.R:828): every pair with N >= 1, seen by CHiCAGO or not."""
+    t = d.extra["tables"][s]
+    F = len(d.frag_chr)
+    bait = np.repeat(np.arange(1, F + 1), np.diff(t["cnt_off"])).astype(np.int64)
+    return dict(baitID=bait, otherEndID=t["cnt_oe"].astype(np.int64), N=t["cnt_N"])

@@ -144,6 +144,8 @@ int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);
  * IHWcorrection() needs from FullRegionData, :1965). */
 int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out, double* avDist_out);
 int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out);
+/* per-row Bmean of replicate s (chicdiff.R:701-702); only after cd_assemble(keep_rows != 0) */
+int cd_get_sample_bmean(cd_ctx* ctx, int s, double* bmean_out);
 
 /* ---- countput ------------------------------------------------------------------------------------- */
 /* The per-condition (baitID, otherEndID) table getFullRegionData() saves as <outprefix>_countput.Rds

@@ -527,3 +527,49 @@ def test_full_size_c3_properties():
     okm = ~np.isnan(FM)
     assert np.max(np.abs(FM2[okm] - FM[okm]) / FM[okm]) < 1e-12
     e.close()
+
+
+def test_getFullRegionData_mirror_and_pipeline():
+    """The second boundary function (chicdiff.R:1460-1478): getFullRegionData on reference-shaped inputs (CHiCAGO
+    tables + .chinput tables per condition, RU, RUcontrol, rmap) -> long tables + countput, then DESeq2Wrap on the
+    result, i.e. the body of chicdiffPipeline between the region universes and IHW (chicdiff.R:315-332)."""
+    from chicdiff_b200 import api
+    d = synth.generate("tiny", seed_offset=23)
+    RU, _, rmap = synth.to_reference_tables(d)
+    conds = list(dict.fromkeys(d.conditions))
+    chicago = {c: [synth.chicago_table(d, s) for s in range(d.S) if d.conditions[s] == c] for c in conds}
+    chinput = {c: [synth.chinput_table(d, s) for s in range(d.S) if d.conditions[s] == c] for c in conds}
+    # a control universe: same baits, windows shifted by 40 fragments (stays on the single chromosome)
+    F = len(d.frag_chr)
+    seeds = np.clip(d.region_seed.astype(np.int64) + 40, 1, F)
+    okc = np.abs(seeds - d.region_bait) > 1
+    off_c, rb_c, ro_c = O.region_universe(d.region_bait[okc], seeds[okc], 5, d.frag_chr)
+    RUc = {"baitID": rb_c.astype(np.int64), "otherEndID": ro_c.astype(np.int64),
+           "regionID": np.repeat(np.arange(1, len(off_c)), np.diff(off_c)).astype(np.int64)}
+    st = api.defaultChicdiffSettings()
+    frd, frd_control, countput = api.getFullRegionData(st, RU, RUc, rmap, chicago, chinput)
+    assert list(frd) == ["baitID", "otherEndID", "regionID", "distSign", "sample", "N", "s_j", "Bmean", "Tmean", "score",
+                         "FullMean", "condition"]
+    assert len(frd["N"]) == d.R * d.S and np.all(np.diff(frd["regionID"]) >= 0)
+    ids = np.arange(1, F + 1)
+    for uni, table in ((RU, frd), (RUc, frd_control)):
+        o = np.lexsort((uni["otherEndID"], uni["regionID"]))
+        rb, ro = uni["baitID"][o], uni["otherEndID"][o]
+        for s in range(d.S):
+            name = "%s.rep%d" % (d.conditions[s], s + 1)
+            sel = np.flatnonzero(table["sample"] == name)
+            oo = sel[np.lexsort((table["otherEndID"][sel], table["regionID"][sel]))]
+            tabs = api.replicate_tables(synth.chicago_table(d, s), ids, synth.chinput_table(d, s))
+            N_o, FM_o, dist_o, bm_o, tm_o = O.assemble_sample(rb, ro, d.frag_chr, d.frag_start, d.frag_end, tabs, want_all=True)
+            assert np.array_equal(table["N"][oo], N_o)
+            for col, ref in (("FullMean", FM_o), ("Bmean", bm_o), ("Tmean", tm_o)):
+                assert np.array_equal(np.isnan(table[col][oo]), np.isnan(ref)), col
+                okm = ~np.isnan(ref)
+                assert np.allclose(table[col][oo][okm], ref[okm], rtol=1e-12, atol=0), col
+    assert set(countput) == {"baitID", "otherEndID", "Nav", "Bav", "score", "oeID_mid", "condition"}
+    assert set(countput["condition"]) == set(conds)
+    # downstream: the region test on the assembled long table (the test set has no all-zero region here? use theta)
+    out = api.DESeq2Wrap(st, RU, frd, rmap=rmap, theta=0.5)
+    assert len(out["pvalue"]) == d.n and out["attr_theta"] == 0.5
+    out_c = api.DESeq2Wrap(st, RUc, frd_control, rmap=rmap, theta=out["attr_theta"])       # chicdiff.R:331
+    assert len(out_c["pvalue"]) == len(off_c) - 1

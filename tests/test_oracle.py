@@ -255,3 +255,33 @@ def test_region_universe_against_generator(tiny):
     assert np.array_equal(row_off, d23.row_off) and np.array_equal(row_oe, d23.row_oe)
     with pytest.raises(ValueError):
         O.region_universe([10], [10], 5, d.frag_chr)
+
+
+def test_replicate_tables_from_chicago_table(tiny):
+    """Host adapter: the look-up tables built from a reference-shaped CHiCAGO table (per-bait / per-other-end
+    first values, Tmean table, .chicEstimateDistFun) equal the generator's own tables wherever the table says
+    anything, and the distance function is recovered from its binned samples."""
+    from chicdiff_b200 import api
+    d, K, FM = tiny
+    ids = np.arange(1, len(d.frag_chr) + 1)
+    for s in (0, 3):
+        x = synth.chicago_table(d, s)
+        t = api.replicate_tables(x, ids, synth.chinput_table(d, s))
+        g = d.extra["tables"][s]
+        baits = np.unique(x["baitID"]); oes = np.unique(x["otherEndID"])
+        assert np.array_equal(np.isnan(t["s_j"][baits - 1]), np.isnan(g["s_j"][baits - 1]))
+        okb = ~np.isnan(g["s_j"][baits - 1])
+        assert np.array_equal(t["s_j"][baits - 1][okb], g["s_j"][baits - 1][okb])
+        assert np.array_equal(t["s_i"][oes - 1], g["s_i"][oes - 1])
+        assert np.isnan(t["s_i"][np.setdiff1d(ids, oes) - 1]).all()
+        assert np.array_equal(t["tblb"][baits - 1], g["tblb"][baits - 1]) and np.array_equal(t["tlb"][oes - 1], g["tlb"][oes - 1])
+        seen = ~np.isnan(t["tmean"])
+        assert seen.sum() >= 20 and np.array_equal(t["tmean"][seen], g["tmean"][seen])
+        assert np.array_equal(t["cnt_off"], g["cnt_off"]) and np.array_equal(t["cnt_N"], g["cnt_N"])
+        assert np.max(np.abs(t["distfun"][:4] - g["distfun"][:4])) < 1e-7           # cubic recovered from 75 bin means
+        assert abs(t["distfun"][4] - np.log(10000)) < 1e-12
+    # .chicEstimateDistFun on its own: C1 continuation at both ends
+    p = api.chicEstimateDistFun(x["distbin"], x["refBinMean"])
+    f = lambda l: p[0] + p[1] * l + p[2] * l * l + p[3] * l ** 3
+    for l, (a0, b0) in ((p[4], p[6:8]), (p[5], p[8:10])):
+        assert abs(f(l) - (a0 + b0 * l)) < 1e-9
