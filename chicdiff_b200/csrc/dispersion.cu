@@ -402,6 +402,135 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Second pass over the parked regions, sample-parallel.  The ~2-3 % of regions that are still searching after
+// kFitDispTripCap trips run up to 100 trips each: a latency problem (the chain of trips is sequential), not a
+// throughput problem.  Here G lanes share one region, lane l evaluating replicate l's likelihood terms, and
+// the per-replicate contributions (log-likelihood, derivative sum, X'WX, X'dWX) are joined by an xor-butterfly
+// inside the group, so a trip costs one replicate's worth of special functions instead of S.  Every lane of a
+// group carries the same search state and takes the same decisions.
+// ---------------------------------------------------------------------------------------
+template <int P, int G>
+__global__ void __launch_bounds__(128)
+fit_disp_resume_tile_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
+                            const double* __restrict__ prior_mean_disp, double prior_sigmasq,
+                            double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
+                            double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out, FitDispPark park)
+{
+    constexpr int NS = P * (P + 1) / 2;
+    const int lane_g = threadIdx.x & (G - 1);                     // replicate handled by this lane
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
+    const bool use_prior = (prior_mean_disp != nullptr);
+    const unsigned long long parked = *park.count;
+    const int64_t n_work = (int64_t)(parked < (unsigned long long)park.capacity ? parked : (unsigned long long)park.capacity);
+    const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
+    const double min_log_alpha = log(kMinDisp / 10.0);
+    const int maxit = 100;
+    const bool has_sample = lane_g < S;
+    double xrow[P];
+#pragma unroll
+    for (int u = 0; u < P; u++) xrow[u] = has_sample ? c_des.X[lane_g * P + u] : 0.0;
+
+    for (int64_t w0 = 0; w0 < n_work; w0 += n_groups) {
+        const int64_t w = w0 + group;
+        bool active = w < n_work;
+        int64_t i = 0;
+        double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 1.0, kappa = kappa_0, prior_mean = 0.0, y = 0.0, mu = 1.0;
+        int iter = 0, iter_accept = 0;
+        if (active) {
+            i = park.row[w];
+            a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
+            iter = park.iter[w]; iter_accept = park.iter_accept[w];
+            if (use_prior) prior_mean = log(prior_mean_disp[i]);
+            if (has_sample) { y = (double)K[(int64_t)lane_g * n + i]; mu = mu_g[(int64_t)lane_g * n + i]; }
+        }
+        while (__any_sync(0xffffffffu, active)) {
+            double x = a;
+            if (active) {
+                iter++;
+                const double a_propose = a + kappa * dlp;
+                if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
+                if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
+                x = a + kappa * dlp;
+            }
+            // ---- this lane's replicate ----
+            const double alpha = exp(x);
+            const double r = rcp_pos(alpha);
+            const double log_r = -x;
+            double lgr, dgr;
+            lgamma_digamma_pos(r, lgr, dgr);
+            double red[2 * NS + 2];
+            {
+                const double ma = mu * alpha;
+                const double ropm = rcp_pos(1.0 + ma);
+                const double wj = mu * ropm, dwj = -wj * wj;
+                const double l1 = log_pos(1.0 + ma);
+                double lg, dg;
+                lgamma_digamma_pos(y + r, lg, dg);
+                const double on = has_sample ? 1.0 : 0.0;
+                int k = 0;
+#pragma unroll
+                for (int u = 0; u < P; u++)
+#pragma unroll
+                    for (int v = 0; v <= u; v++) {
+                        const double xx = xrow[u] * xrow[v];
+                        red[k] = wj * xx; red[NS + k] = dwj * xx; k++;
+                    }
+                red[2 * NS] = on * (((lg - lgr) - y * (log_r + l1)) - r * l1);
+                red[2 * NS + 1] = on * (((dgr - dg) + (l1 - ma * ropm)) + y * (alpha * ropm));
+            }
+#pragma unroll
+            for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+                for (int k = 0; k < 2 * NS + 2; k++) red[k] += __shfl_xor_sync(0xffffffffu, red[k], off);
+            Sym<P> B, dB, Bi;
+#pragma unroll
+            for (int k = 0; k < NS; k++) { B.v[k] = red[k]; dB.v[k] = red[NS + k]; }
+            const double cr = -0.5 * chol_logdet<P>(B);
+            chol_inverse<P>(B, Bi);
+            double tr = 0.0;
+#pragma unroll
+            for (int u = 0; u < P; u++)
+#pragma unroll
+                for (int v = 0; v < P; v++) tr += Bi.v[sidx<P>(u, v)] * dB.v[sidx<P>(v, u)];
+            double lpx = red[2 * NS] + cr;
+            double dlpx = ((r * r) * red[2 * NS + 1] - 0.5 * tr) * alpha;
+            if (use_prior) {
+                const double d = x - prior_mean;
+                lpx += -0.5 * d * d / prior_sigmasq;
+                dlpx += -1.0 * d / prior_sigmasq;
+            }
+            // ---- decision (identical in all lanes of the group) ----
+            if (active) {
+                bool finished = false;
+                const double theta_kappa = -1.0 * lpx;
+                const double theta_hat_kappa = -1.0 * lp - kappa * epsilon * (dlp * dlp);
+                if (theta_kappa <= theta_hat_kappa) {
+                    iter_accept++;
+                    a = x;
+                    const double change = lpx - lp;
+                    if (change < tol) { lp = lpx; finished = true; }
+                    else if (a < min_log_alpha) { finished = true; }
+                    else {
+                        lp = lpx;
+                        dlp = dlpx;
+                        kappa = fmin(kappa * 1.1, kappa_0);
+                        if (iter_accept % 5 == 0) kappa = kappa / 2.0;
+                    }
+                } else {
+                    kappa = kappa / 2.0;
+                }
+                if (iter >= maxit) finished = true;
+                if (finished) {
+                    if (lane_g == 0) { log_alpha_out[i] = a; iter_out[i] = iter; initial_lp_out[i] = lp0; last_lp_out[i] = lp; }
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
 cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu, const uint8_t* flags,
                             const double* disp_init, const double* prior_mean_disp, double prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
@@ -419,14 +548,16 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // Second pass: with few parked regions (small shards) the chain of up to 76 remaining trips is a latency
+    // problem -> sample-parallel tile kernel; with many it is a throughput problem -> one region per lane again.
+    const int G = S <= 8 ? 8 : (S <= 16 ? 16 : 32);
+    const bool tile = (double)n * 0.04 * G <= (double)sms * 1024.0;
     // persistent grids: exactly the number of CTAs that are resident at once
 #define CD_LAUNCH(P_)                                                                                          \
     {                                                                                                          \
         int per_sm = 1;                                                                                        \
         if (smem > 48 * 1024) {                                                                                \
             e = cudaFuncSetAttribute(fit_disp_kernel<P_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                    \
-            e = cudaFuncSetAttribute(fit_disp_kernel<P_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
             if (e != cudaSuccess) return e;                                                                    \
         }                                                                                                      \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_disp_kernel<P_, false>, threads, smem); \
@@ -435,11 +566,28 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
         const int blocks = (int)(want < resident ? want : resident);                                           \
         fit_disp_kernel<P_, false><<<blocks, threads, smem, st>>>(n, S, K, mu, flags, disp_init,               \
             prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);         \
-        const int64_t want2 = (park.capacity + threads - 1) / threads;                                         \
-        const int blocks2 = (int)(want2 < resident ? want2 : resident);                                        \
-        fit_disp_kernel<P_, true><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, S, K, mu, flags,        \
-            disp_init, prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter + 1, \
-            park);                                                                                             \
+        if (tile) {                                                                                            \
+            const int blocks2 = sms * 8;                                                                       \
+            if (S <= 8)                                                                                        \
+                fit_disp_resume_tile_kernel<P_, 8><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,      \
+                    prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
+            else if (S <= 16)                                                                                  \
+                fit_disp_resume_tile_kernel<P_, 16><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,     \
+                    prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
+            else                                                                                               \
+                fit_disp_resume_tile_kernel<P_, 32><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,     \
+                    prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
+        } else {                                                                                               \
+            if (smem > 48 * 1024) {                                                                            \
+                e = cudaFuncSetAttribute(fit_disp_kernel<P_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                if (e != cudaSuccess) return e;                                                                \
+            }                                                                                                  \
+            const int64_t want2 = (park.capacity + threads - 1) / threads;                                     \
+            const int blocks2 = (int)(want2 < resident ? want2 : resident);                                    \
+            fit_disp_kernel<P_, true><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, S, K, mu, flags,    \
+                disp_init, prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp,               \
+                work_counter + 1, park);                                                                       \
+        }                                                                                                      \
     }
     switch (p) {
         case 1: CD_LAUNCH(1); break;
