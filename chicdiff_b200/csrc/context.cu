@@ -207,6 +207,10 @@ struct cd_ctx {
     DevBuf<double*> p2p_peers_dev;
     std::vector<void*> p2p_opened;
     unsigned long long p2p_epoch = 0;
+    // columns of the last cd_parse_chinput
+    int64_t ch_rows = 0;
+    DevBuf<int32_t> ch_bait, ch_oe, ch_N, ch_len;
+    DevBuf<double> ch_dist;
     // countput output of the last cd_countput
     int64_t cp_pairs = 0;
     DevBuf<int32_t> cp_bait, cp_oe;
@@ -572,6 +576,74 @@ int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_
     if (row_bait_out) CD_CUDA(ctx, cudaMemcpyAsync(row_bait_out, ctx->row_bait.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
     if (row_oe_out) CD_CUDA(ctx, cudaMemcpyAsync(row_oe_out, ctx->row_oe.p, sizeof(int32_t) * (size_t)ctx->R, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    return CD_OK;
+}
+
+int cd_parse_chinput(cd_ctx* ctx, const char* text, int64_t nbytes, int64_t* n_rows_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (nbytes < 0 || nbytes > 2147483647LL || (nbytes > 0 && !text)) return ctx->fail(CD_EINVAL, "cd_parse_chinput: bad arguments (at most 2^31-1 bytes per call)");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    ctx->ch_rows = 0;
+    if (n_rows_out) *n_rows_out = 0;
+    if (nbytes == 0) return CD_OK;
+    DevBuf<char> d_text;
+    DevBuf<uint8_t> flag, valid;
+    DevBuf<int64_t> starts, d_count;
+    DevBuf<unsigned char> tmp;
+    DevBuf<int32_t> t_bait, t_oe, t_N, t_len;
+    DevBuf<double> t_dist;
+    CD_CUDA(ctx, d_text.ensure((size_t)nbytes)); CD_CUDA(ctx, flag.ensure((size_t)nbytes)); CD_CUDA(ctx, d_count.ensure(1));
+    CD_CUDA(ctx, cudaMemcpyAsync(d_text.p, text, (size_t)nbytes, cudaMemcpyHostToDevice, st));
+    CD_LAUNCHN(ctx, 1, ch_launch_line_flags(nbytes, d_text.p, flag.p, st));
+    // every byte could start a line (runs of blank lines), so the offset array is sized for that
+    size_t bytes = 0;
+    CD_CUDA(ctx, starts.ensure((size_t)nbytes));
+    {
+        int64_t nl = 0;
+        CD_CUDA(ctx, ch_line_starts(nullptr, bytes, flag.p, starts.p, d_count.p, nbytes, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        CD_CUDA(ctx, ch_line_starts(tmp.p, bytes, flag.p, starts.p, d_count.p, nbytes, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(&nl, d_count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+        const size_t L = (size_t)nl;
+        CD_CUDA(ctx, t_bait.ensure(L)); CD_CUDA(ctx, t_oe.ensure(L)); CD_CUDA(ctx, t_N.ensure(L)); CD_CUDA(ctx, t_len.ensure(L));
+        CD_CUDA(ctx, t_dist.ensure(L)); CD_CUDA(ctx, valid.ensure(L));
+        CD_LAUNCHN(ctx, 1, ch_launch_parse(nl, nbytes, d_text.p, starts.p, t_bait.p, t_oe.p, t_N.p, t_len.p, t_dist.p, valid.p, st));
+        CD_CUDA(ctx, ctx->ch_bait.ensure(L)); CD_CUDA(ctx, ctx->ch_oe.ensure(L)); CD_CUDA(ctx, ctx->ch_N.ensure(L));
+        CD_CUDA(ctx, ctx->ch_len.ensure(L)); CD_CUDA(ctx, ctx->ch_dist.ensure(L));
+        bytes = 0;
+        CD_CUDA(ctx, ch_compact_f64(nullptr, bytes, t_dist.p, valid.p, ctx->ch_dist.p, d_count.p, nl, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        size_t b2 = bytes;
+        CD_CUDA(ctx, ch_compact_f64(tmp.p, b2, t_dist.p, valid.p, ctx->ch_dist.p, d_count.p, nl, st));
+        b2 = bytes; CD_CUDA(ctx, ch_compact_i32(tmp.p, b2, t_bait.p, valid.p, ctx->ch_bait.p, d_count.p, nl, st));
+        b2 = bytes; CD_CUDA(ctx, ch_compact_i32(tmp.p, b2, t_oe.p, valid.p, ctx->ch_oe.p, d_count.p, nl, st));
+        b2 = bytes; CD_CUDA(ctx, ch_compact_i32(tmp.p, b2, t_N.p, valid.p, ctx->ch_N.p, d_count.p, nl, st));
+        b2 = bytes; CD_CUDA(ctx, ch_compact_i32(tmp.p, b2, t_len.p, valid.p, ctx->ch_len.p, d_count.p, nl, st));
+        int64_t rows = 0;
+        CD_CUDA(ctx, cudaMemcpyAsync(&rows, d_count.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->ch_rows = rows;
+        if (n_rows_out) *n_rows_out = rows;
+    }
+    return CD_OK;
+}
+
+int cd_get_chinput(cd_ctx* ctx, int32_t* baitID, int32_t* otherEndID, int32_t* N, int32_t* otherEndLen, double* distSign)
+{
+    if (!ctx) return CD_EINVAL;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t m = (size_t)ctx->ch_rows;
+    if (!m) return CD_OK;
+    cudaStream_t st = ctx->st;
+    if (baitID) CD_CUDA(ctx, cudaMemcpyAsync(baitID, ctx->ch_bait.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+    if (otherEndID) CD_CUDA(ctx, cudaMemcpyAsync(otherEndID, ctx->ch_oe.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+    if (N) CD_CUDA(ctx, cudaMemcpyAsync(N, ctx->ch_N.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+    if (otherEndLen) CD_CUDA(ctx, cudaMemcpyAsync(otherEndLen, ctx->ch_len.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+    if (distSign) CD_CUDA(ctx, cudaMemcpyAsync(distSign, ctx->ch_dist.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
     return CD_OK;
 }
 

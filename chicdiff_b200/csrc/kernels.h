@@ -22,6 +22,17 @@ cudaError_t ru_launch_scan(int64_t m, const int64_t* counts, int64_t* row_off, v
 cudaError_t ru_launch_fill(int64_t m, const int32_t* peak_bait, const int32_t* peak_oe, int s, int64_t F, int32_t id0,
                            const int32_t* chr, const int64_t* row_off, int32_t* row_bait, int32_t* row_oe, cudaStream_t st);
 
+// ---- .chinput text codec (fread of chicdiff.R:828) ----
+cudaError_t ch_launch_line_flags(int64_t nbytes, const char* text, uint8_t* flag, cudaStream_t st);
+cudaError_t ch_line_starts(void* tmp, size_t& bytes, const uint8_t* flag, int64_t* starts, int64_t* n_out, int64_t nbytes,
+                           cudaStream_t st);
+cudaError_t ch_launch_parse(int64_t nlines, int64_t nbytes, const char* text, const int64_t* line_start, int32_t* bait,
+                            int32_t* oe, int32_t* N, int32_t* oelen, double* dist, uint8_t* valid, cudaStream_t st);
+cudaError_t ch_compact_i32(void* tmp, size_t& bytes, const int32_t* in, const uint8_t* flags, int32_t* out, int64_t* n_out,
+                           int64_t n, cudaStream_t st);
+cudaError_t ch_compact_f64(void* tmp, size_t& bytes, const double* in, const uint8_t* flags, double* out, int64_t* n_out,
+                           int64_t n, cudaStream_t st);
+
 // ---- countput (chicdiff.R:708-735, 755-770) ----
 cudaError_t cp_launch_keys(int64_t rows, int64_t base, const int32_t* bait, const int32_t* oe, unsigned long long* keys,
                            unsigned int* idx, cudaStream_t st);

@@ -20,7 +20,7 @@ EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_u
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
-            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput"]
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]
 
 
 class ChicdiffError(RuntimeError):
@@ -99,6 +99,8 @@ def load_library():
     L.cd_get_sample_bmean.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.cd_region_universe.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.cd_get_region_universe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_parse_chinput.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.cd_get_chinput.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.cd_countput.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdChicagoRows), C.POINTER(C.c_int64)]
     L.cd_get_countput.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     L.cd_timer_start.argtypes = [C.c_void_p]
@@ -235,6 +237,16 @@ class Engine:
         ro = np.empty(R.value, np.int32)
         self._check(self._L.cd_get_region_universe(self._h, _ptr(off), _ptr(rb), _ptr(ro)))
         return off, rb, ro
+
+    def parse_chinput(self, data):
+        """bytes of a .chinput file -> dict(baitID, otherEndID, N, otherEndLen, distSign) (cd_parse_chinput)."""
+        m = C.c_int64()
+        self._check(self._L.cd_parse_chinput(self._h, data, len(data), C.byref(m)))
+        g = m.value
+        out = dict(baitID=np.empty(g, np.int32), otherEndID=np.empty(g, np.int32), N=np.empty(g, np.int32),
+                   otherEndLen=np.empty(g, np.int32), distSign=np.empty(g, np.float64))
+        self._check(self._L.cd_get_chinput(self._h, *[_ptr(out[k]) for k in ("baitID", "otherEndID", "N", "otherEndLen", "distSign")]))
+        return out
 
     def countput(self, reps):
         """reps: list of dicts (baitID, otherEndID, N, Bmean, score) of ONE condition's replicates ->

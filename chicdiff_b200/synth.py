@@ -355,3 +355,21 @@ def chinput_table(d, s):
     F = len(d.frag_chr)
     bait = np.repeat(np.arange(1, F + 1), np.diff(t["cnt_off"])).astype(np.int64)
     return dict(baitID=bait, otherEndID=t["cnt_oe"].astype(np.int64), N=t["cnt_N"])
+
+
+def chinput_text(d, s, max_rows=None):
+    """The replicate's .chinput as text: '#' comment line, header, then baitID otherEndID N otherEndLen distSign
+    (tab separated; distSign NA across chromosomes), as written by CHiCAGO's bam2chicago."""
+    t = chinput_table(d, s)
+    bait, oe, N = t["baitID"], t["otherEndID"], t["N"]
+    if max_rows is not None:
+        bait, oe, N = bait[:max_rows], oe[:max_rows], N[:max_rows]
+    ln = (d.frag_end - d.frag_start + 1)[oe - 1]
+    mid2 = d.frag_start + d.frag_end
+    same = d.frag_chr[oe - 1] == d.frag_chr[bait - 1]
+    dist = np.rint((mid2[oe - 1] - mid2[bait - 1]) / 2.0).astype(np.int64)
+    lines = ["##\tsamplename=rep%d\tbamname=synthetic.bam\tbaitmapfile=x.baitmap\tdigestfile=x.rmap" % (s + 1),
+             "baitID\totherEndID\tN\totherEndLen\tdistSign"]
+    for b, o, n, l, sm, dd in zip(bait.tolist(), oe.tolist(), N.tolist(), ln.tolist(), same.tolist(), dist.tolist()):
+        lines.append("%d\t%d\t%d\t%d\t%s" % (b, o, n, l, dd if sm else "NA"))
+    return ("\n".join(lines) + "\n").encode()

@@ -147,6 +147,15 @@ int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out)
 /* per-row Bmean of replicate s (chicdiff.R:701-702); only after cd_assemble(keep_rows != 0) */
 int cd_get_sample_bmean(cd_ctx* ctx, int s, double* bmean_out);
 
+/* ---- .chinput codec -------------------------------------------------------------------------------- */
+/* Parses the text of a .chinput file (what the reference reads with fread, chicdiff.R:828, 1272): an optional
+ * '#' comment line, a header line, then rows `baitID otherEndID N otherEndLen distSign` (tab / space separated,
+ * distSign may be NA).  text: host pointer to the file's bytes (nbytes < 2^31).  n_rows_out: parsed rows. */
+int cd_parse_chinput(cd_ctx* ctx, const char* text, int64_t nbytes, int64_t* n_rows_out);
+/* columns of the last cd_parse_chinput in file order (any pointer may be NULL); otherEndLen NA = INT32_MIN,
+ * distSign NA = NaN */
+int cd_get_chinput(cd_ctx* ctx, int32_t* baitID, int32_t* otherEndID, int32_t* N, int32_t* otherEndLen, double* distSign);
+
 /* ---- countput ------------------------------------------------------------------------------------- */
 /* The per-condition (baitID, otherEndID) table getFullRegionData() saves as <outprefix>_countput.Rds
  * (chicdiff.R:708-735, 755-770): Nav = mean(N), Bav = mean(Bmean), score = max(score), oeID_mid = (start+end)/2

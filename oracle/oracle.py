@@ -410,3 +410,16 @@ def countput(reps, frag_start, frag_end, frag_id0=1):
     return dict(baitID=bait[f0].astype(np.int32), otherEndID=oe[f0].astype(np.int32), Nav=sumN / c, Bav=sumB / c,
                 score=np.where(anyna, np.nan, mx),
                 oeID_mid=(np.asarray(frag_start, float)[oe[f0] - frag_id0] + np.asarray(frag_end, float)[oe[f0] - frag_id0]) / 2.0)
+
+
+def parse_chinput(data):
+    """fread() of a .chinput (chicdiff.R:828): skip the '#' comment line and the header, five columns, NA -> NaN."""
+    rows = []
+    for line in data.decode().splitlines():
+        f = line.replace(",", "\t").split()
+        if not f or not f[0][0].isdigit():
+            continue
+        rows.append(f)
+    col = lambda k, na: np.array([na if (len(r) <= k or r[k].upper().startswith("N")) else float(r[k]) for r in rows])
+    return dict(baitID=col(0, np.nan).astype(np.int32), otherEndID=col(1, np.nan).astype(np.int32), N=col(2, np.nan).astype(np.int32),
+                otherEndLen=np.where(np.isnan(col(3, np.nan)), -2147483648, col(3, 0)).astype(np.int32), distSign=col(4, np.nan))

