@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--regions", type=int, default=None, help="override the number of regions per rank")
     ap.add_argument("--cpu-sample", type=int, default=600000, help="regions in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank owns a genome-wide set of its own; strong: ONE set, regions partitioned by "
+                         "bait across the ranks (cd_plan_shards)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -187,7 +190,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    d = make_data(args.workload, args.regions, rank)
+    d = make_data(args.workload, args.regions, rank if args.scaling == "weak" else 0)
+    if args.scaling == "strong" and world > 1:
+        # one genome-wide set, regions partitioned by bait (every rank generates the same set and keeps its shard)
+        from chicdiff_b200 import parallel
+        bounds = parallel.shard_slices(d.region_bait, d.row_off, world)
+        off, (Nl, FMl, rb, ro), (lo, hi) = parallel.take_shard(d.row_off, [d.N_rows, d.FM_rows, d.row_bait, d.row_oe], bounds, rank)
+        d.row_off, d.N_rows, d.FM_rows, d.row_bait, d.row_oe = off, Nl, FMl, rb, ro
+        d.region_bait, d.region_seed, d.true_lfc = d.region_bait[lo:hi], d.region_seed[lo:hi], d.true_lfc[lo:hi]
     S, p, n, R = d.S, int(d.X.shape[1]), d.n, d.R
     e.set_design(d.X)
     e.set_regions(d.row_off)
@@ -294,7 +304,7 @@ def main():
         achieved = agg_bytes / (agg_ms * 1e-3) / 1e9
         value = n_tot / (dev_ms * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "synthetic genome-wide 3-vs-3 PCHi-C (BASELINE configs[2]): %d regions, %d region rows, "
                                        "%d samples per GPU" % (n, R, S),
