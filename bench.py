@@ -311,8 +311,9 @@ def main():
                            "regions_total": n_tot, "design_columns": p, "norm": "combined", "theta_grid": 5,
                            "fits_per_step": 6, "l2": "inputs (%.2f GB per GPU) larger than L2; no flush" % ((N_host.numel() * 4 + FM_host.numel() * 8) / 1e9),
                            "parallelism": "regions sharded by bait, %d rank(s); global steps by all-reduce only (trend sums: %s; median "
-                                          "histograms, offsets sums, deviance: NCCL); nothing is gathered"
-                                          % (world, "in-kernel over NVLink peer memory" if e.comm_info()["peer_memory_allreduce"] else "NCCL")},
+                                          "histograms: %s; offsets sums, deviance: NCCL); nothing is gathered"
+                                          % (world, "in-kernel over NVLink peer memory" if e.comm_info()["peer_memory_allreduce"] else "NCCL",
+                                             "in-kernel over NVLink peer memory" if e.comm_info()["peer_memory_medians"] else "NCCL")},
                 "wall_ms_per_step": wall_ms,
                 "stage_ms": {"aggregate": tm[0], "region_test": tm[1], "fit_disp_kernels": tm[2], "wald_kernels": tm[3],
                              "grid_refits": tm[4], "trend_and_mad": tm[5], "size_factors": tm[6]},

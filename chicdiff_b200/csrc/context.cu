@@ -203,10 +203,14 @@ struct cd_ctx {
     DevBuf<double> avDist;
     // peer-memory all-reduce of the sharded trend fit (set up in cd_comm_init; NCCL path is the fallback)
     bool p2p_ok = false;
-    DevBuf<double> p2p_mail, p2p_gtot;
+    DevBuf<double> p2p_mail;
     DevBuf<double*> p2p_peers_dev;
     std::vector<void*> p2p_opened;
     unsigned long long p2p_epoch = 0;
+    bool sel_p2p_ok = false;                      // medians exchange their counters through peer memory too
+    DevBuf<unsigned long long> sel_mail;
+    DevBuf<unsigned long long*> sel_peers_dev;
+    unsigned long long sel_seq = 0;
     // columns of the last cd_parse_chinput
     int64_t ch_rows = 0;
     DevBuf<int32_t> ch_bait, ch_oe, ch_N, ch_len;
@@ -336,49 +340,68 @@ int cd_comm_unique_id(cd_ctx* ctx, char id[128])
     return CD_OK;
 }
 
-// Exchange cudaIpc handles of one small mailbox per rank so that the trend-fit kernel can all-reduce its 8 sums
-// over NVLink itself.  Any failure leaves p2p_ok false and the NCCL host-driven path in use.
-static void setup_p2p(cd_ctx* ctx)
+// Exchange cudaIpc handles of two mailboxes per rank so that the trend-fit kernel can all-reduce its 8 sums and the
+// median kernels their counters over NVLink themselves.  Any failure leaves the flags false and the NCCL
+// host-driven path in use.
+static bool open_peer_mailboxes(cd_ctx* ctx, void* mine_ptr, std::vector<void*>& peers)
 {
-    ctx->p2p_ok = false;
     const int nr = ctx->comm.nranks, rk = ctx->comm.rank;
-    if (nr < 2 || nr > 64) return;
-    const char* off = getenv("CHICDIFF_B200_NO_P2P");
-    if (off && off[0] == '1') return;
-    if (ctx->p2p_mail.ensure((size_t)2 * nr * 16) != cudaSuccess || ctx->p2p_gtot.ensure(16) != cudaSuccess ||
-        ctx->p2p_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
-    cudaMemset(ctx->p2p_mail.p, 0, sizeof(double) * 2 * nr * 16);
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, ctx->p2p_mail.p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaIpcGetMemHandle(&mine, mine_ptr) != cudaSuccess) { cudaGetLastError(); return false; }
     DevBuf<unsigned char> hb;
-    if (hb.ensure((size_t)nr * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) return;
+    if (hb.ensure((size_t)nr * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) return false;
     cudaMemcpy(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), &mine, sizeof(mine), cudaMemcpyHostToDevice);
     std::vector<int64_t> counts((size_t)nr, 1), displs((size_t)nr);
     for (int r = 0; r < nr; r++) displs[(size_t)r] = r;
-    if (!ctx->comm.allgatherv(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), hb.p, counts, displs, sizeof(cudaIpcMemHandle_t), ctx->st).empty()) return;
+    if (!ctx->comm.allgatherv(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), hb.p, counts, displs, sizeof(cudaIpcMemHandle_t), ctx->st).empty()) return false;
     std::vector<cudaIpcMemHandle_t> all((size_t)nr);
-    if (cudaMemcpyAsync(all.data(), hb.p, sizeof(cudaIpcMemHandle_t) * (size_t)nr, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return;
-    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) return;
-    std::vector<double*> peers((size_t)nr, nullptr);
+    if (cudaMemcpyAsync(all.data(), hb.p, sizeof(cudaIpcMemHandle_t) * (size_t)nr, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) return false;
+    peers.assign((size_t)nr, nullptr);
     bool ok = true;
     for (int r = 0; r < nr; r++) {
-        if (r == rk) { peers[(size_t)r] = ctx->p2p_mail.p; continue; }
+        if (r == rk) { peers[(size_t)r] = mine_ptr; continue; }
         void* ptr = nullptr;
         if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         ctx->p2p_opened.push_back(ptr);
-        peers[(size_t)r] = (double*)ptr;
+        peers[(size_t)r] = ptr;
     }
-    // every rank must agree, otherwise one would wait in the kernel for a peer that uses NCCL
-    double flag = ok ? 0.0 : 1.0;
+    return ok;
+}
+
+static void setup_p2p(cd_ctx* ctx)
+{
+    ctx->p2p_ok = false;
+    ctx->sel_p2p_ok = false;
+    const int nr = ctx->comm.nranks;
+    if (nr < 2 || nr > 64) return;
+    const char* off = getenv("CHICDIFF_B200_NO_P2P");
+    if (off && off[0] == '1') return;
+    if (ctx->p2p_mail.ensure((size_t)2 * nr * 16) != cudaSuccess ||
+        ctx->p2p_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
+    cudaMemset(ctx->p2p_mail.p, 0, sizeof(double) * 2 * nr * 16);
+    const bool want_sel = nr <= 16;                // 2 x nr x 32 slots of 16 KiB: 8 MiB at 8 ranks
+    if (want_sel) {
+        if (ctx->sel_mail.ensure(sel_p2p_mail_words(nr)) != cudaSuccess || ctx->sel_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
+        cudaMemset(ctx->sel_mail.p, 0, sizeof(unsigned long long) * sel_p2p_mail_words(nr));
+    }
+    std::vector<void*> peers, sel_peers;
+    bool ok = open_peer_mailboxes(ctx, ctx->p2p_mail.p, peers);
+    bool sel_ok = ok && want_sel && open_peer_mailboxes(ctx, ctx->sel_mail.p, sel_peers);
+    // every rank must agree, otherwise one would wait in a kernel for a peer that uses NCCL
+    double flag[2] = {ok ? 0.0 : 1.0, sel_ok ? 0.0 : 1.0};
     DevBuf<double> fb;
-    if (fb.ensure(1) != cudaSuccess) return;
-    cudaMemcpy(fb.p, &flag, sizeof(double), cudaMemcpyHostToDevice);
-    if (!ctx->comm.allreduce_sum(fb.p, 1, ctx->st).empty()) return;
-    cudaMemcpyAsync(&flag, fb.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->st);
+    if (fb.ensure(2) != cudaSuccess) return;
+    cudaMemcpy(fb.p, flag, sizeof(flag), cudaMemcpyHostToDevice);
+    if (!ctx->comm.allreduce_sum(fb.p, 2, ctx->st).empty()) return;
+    cudaMemcpyAsync(flag, fb.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->st);
     cudaStreamSynchronize(ctx->st);
-    if (flag != 0.0) return;
+    if (flag[0] != 0.0) return;
     cudaMemcpy(ctx->p2p_peers_dev.p, peers.data(), sizeof(double*) * (size_t)nr, cudaMemcpyHostToDevice);
     ctx->p2p_ok = true;
+    if (flag[1] != 0.0) return;
+    cudaMemcpy(ctx->sel_peers_dev.p, sel_peers.data(), sizeof(void*) * (size_t)nr, cudaMemcpyHostToDevice);
+    ctx->sel_p2p_ok = true;
 }
 
 int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128])
@@ -395,7 +418,7 @@ int cd_comm_info(const cd_ctx* ctx, int* nranks, int* rank, int* peer_memory_all
     if (!ctx) return CD_EINVAL;
     if (nranks) *nranks = ctx->comm.nranks;
     if (rank) *rank = ctx->comm.rank;
-    if (peer_memory_allreduce) *peer_memory_allreduce = ctx->p2p_ok ? 1 : 0;
+    if (peer_memory_allreduce) *peer_memory_allreduce = (ctx->p2p_ok ? 1 : 0) | (ctx->sel_p2p_ok ? 2 : 0);
     return CD_OK;
 }
 
@@ -907,19 +930,42 @@ int medians(cd_ctx* ctx, const double* base, int64_t stride, int64_t n, int B, c
     unsigned long long* counts = ctx->sel_aux.p;
     unsigned long long* le = ctx->sel_aux.p + B;
     unsigned long long* mg = ctx->sel_aux.p + 2 * B;
+    // sharded: the consuming kernels exchange through peer memory, else NCCL all-reduces sit between the kernels
+    const bool peer = ctx->comm.active() && ctx->sel_p2p_ok && B <= kSelP2PMaxCols;
+    const bool nccl = ctx->comm.active() && !peer;
+    auto exch = [&]() {
+        SelP2P pp{};
+        pp.nranks = 1;
+        if (peer) {
+            pp.nranks = ctx->comm.nranks; pp.rank = ctx->comm.rank;
+            pp.peers = ctx->sel_peers_dev.p; pp.mymail = ctx->sel_mail.p;
+            pp.seq = ++ctx->sel_seq; pp.err = ctx->counters.p + 10;
+        }
+        return pp;
+    };
     CD_LAUNCHN(ctx, 1, sel_launch_count(n, B, base, stride, center_dev, counts, st));
-    CD_COMM(ctx, ctx->comm.allreduce_u64(counts, (size_t)B, false, st));
-    CD_LAUNCHN(ctx, 1, sel_launch_init(B, counts, ctx->sel_state.p, ctx->sel_hist.p, le, mg, st));
+    if (nccl) CD_COMM(ctx, ctx->comm.allreduce_u64(counts, (size_t)B, false, st));
+    CD_LAUNCHN(ctx, 1, sel_launch_init(B, counts, ctx->sel_state.p, ctx->sel_hist.p, le, mg, exch(), st));
     for (int pass = 0; pass < 6; pass++) {
         CD_LAUNCHN(ctx, 1, sel_launch_hist(n, B, base, stride, center_dev, ctx->sel_state.p, pass, ctx->sel_hist.p, st));
-        CD_COMM(ctx, ctx->comm.allreduce_u64(ctx->sel_hist.p, (size_t)B * kSelBinsHost, false, st));
-        CD_LAUNCHN(ctx, 1, sel_launch_scan(B, pass, ctx->sel_state.p, ctx->sel_hist.p, st));
+        if (nccl) CD_COMM(ctx, ctx->comm.allreduce_u64(ctx->sel_hist.p, (size_t)B * kSelBinsHost, false, st));
+        CD_LAUNCHN(ctx, 1, sel_launch_scan(B, pass, ctx->sel_state.p, ctx->sel_hist.p, exch(), st));
     }
     CD_LAUNCHN(ctx, 1, sel_launch_next(n, B, base, stride, center_dev, ctx->sel_state.p, le, mg, st));
-    CD_COMM(ctx, ctx->comm.allreduce_u64(le, (size_t)B, false, st));
-    CD_COMM(ctx, ctx->comm.allreduce_u64(mg, (size_t)B, true, st));
-    CD_LAUNCHN(ctx, 1, sel_launch_finish(B, ctx->sel_state.p, le, mg, out_dev, do_exp, scale, st));
+    if (nccl) {
+        CD_COMM(ctx, ctx->comm.allreduce_u64(le, (size_t)B, false, st));
+        CD_COMM(ctx, ctx->comm.allreduce_u64(mg, (size_t)B, true, st));
+    }
+    CD_LAUNCHN(ctx, 1, sel_launch_finish(B, ctx->sel_state.p, le, mg, out_dev, do_exp, scale, exch(), st));
     return CD_OK;
+}
+
+// after a host sync that follows medians(): did a peer-memory exchange give up?
+int check_peer_exchange(cd_ctx* ctx, unsigned long long err_word)
+{
+    if (err_word == 0ull) return CD_OK;
+    cudaMemsetAsync(ctx->counters.p + 10, 0, sizeof(unsigned long long), ctx->st);
+    return ctx->fail(CD_ECOMM, "peer-memory exchange timed out: another rank stopped before reaching the same step");
 }
 
 // estimateSizeFactors over ALL regions of all ranks -> scal[0..S)
@@ -932,7 +978,11 @@ int size_factors(cd_ctx* ctx, double* sf_host)
     int rc = medians(ctx, ctx->g_LR.p, n, n, S, nullptr, ctx->scal.p, 1, 1.0);
     if (rc != CD_OK) return rc;
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 40, ctx->counters.p + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    unsigned long long errw;
+    memcpy(&errw, ctx->h_pinned + 40, sizeof(errw));
+    if ((rc = check_peer_exchange(ctx, errw)) != CD_OK) return rc;
     for (int s = 0; s < S; s++) {
         sf_host[s] = ctx->h_pinned[s];
         if (std::isnan(sf_host[s]))
@@ -1061,9 +1111,9 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
         TrendP2P pp{};
         pp.nranks = ctx->comm.active() ? ctx->comm.nranks : 1;
         pp.rank = ctx->comm.rank;
-        pp.peers = ctx->p2p_peers_dev.p; pp.mymail = ctx->p2p_mail.p; pp.gtot = ctx->p2p_gtot.p;
+        pp.peers = ctx->p2p_peers_dev.p; pp.mymail = ctx->p2p_mail.p;
         pp.epoch = ++ctx->p2p_epoch;
-        CD_LAUNCHN(ctx, 1, launch_trend_fit(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->partial.p,
+        CD_LAUNCHN(ctx, 1, launch_trend_fit(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->g_resid.p, ctx->partial.p,
                                             reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, pp, st));
     }
     CD_LAUNCHN(ctx, 1, launch_trend_apply(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
@@ -1076,7 +1126,11 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     ctx->tm_end();
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, trend_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->counters.p + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaStreamSynchronize(st));
+    unsigned long long errw;
+    memcpy(&errw, ctx->h_pinned + 9, sizeof(errw));
+    if ((rc = check_peer_exchange(ctx, errw)) != CD_OK) return rc;
     const double coefs[2] = {ctx->h_pinned[0], ctx->h_pinned[1]};
     const int tstatus = (int)ctx->h_pinned[2];
     if (tstatus != 0) {
@@ -1171,7 +1225,10 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->g_flags.ensure((size_t)n));
     CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * (CD_MAXS + 8)));
     CD_CUDA(ctx, ctx->scal.ensure(128));
-    CD_CUDA(ctx, ctx->counters.ensure(16));
+    if (!ctx->counters.p) {
+        CD_CUDA(ctx, ctx->counters.ensure(16));
+        CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), st));
+    }
     CD_CUDA(ctx, ctx->refit_count.ensure(1));
     CD_CUDA(ctx, ctx->wald_c.ensure(sn));
     CD_CUDA(ctx, ctx->wald_b0.ensure((size_t)CD_MAXP * (size_t)n));

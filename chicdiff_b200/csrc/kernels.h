@@ -83,22 +83,34 @@ cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* 
 constexpr int kReduceBlocks = 592;      // 148 SMs x 4
 
 // ---- exact medians by radix selection (select.cu); B columns at base + c*stride, length n each ----
-// state: B x 8 words, hist: B x 2048 words, counts / le / mg: B words each (device).  In a sharded run the caller
-// all-reduces `counts` (sum) after sel_launch_count, `hist` (sum) after every sel_launch_hist, and `le` (sum) /
-// `mg` (min) after sel_launch_next.
+// state: B x 8 words, hist: B x 2048 words, counts / le / mg: B words each (device).  A sharded run needs
+// `counts` (sum) all-reduced between count and init, `hist` (sum) between every hist and scan, and `le` (sum) /
+// `mg` (min) between next and finish.  With a SelP2P of nranks > 1 the init / scan / finish kernels do that
+// exchange themselves through peer memory (one sequence number per kernel); with nranks == 1 they do not, and
+// the caller either runs alone or all-reduces the buffers on the stream (NCCL) before those kernels.
 constexpr int kSelBinsHost = 2048;
 constexpr int kSelStateHost = 8;
+constexpr int kSelP2PMaxCols = 32;
+struct SelP2P {
+    int nranks, rank;                       // nranks == 1: no exchange
+    unsigned long long* const* peers;       // device array of nranks mailbox pointers (own one included)
+    unsigned long long* mymail;             // 2 x nranks x kSelP2PMaxCols slots of 2048 words, then as many flag words
+    unsigned long long seq;                 // nonzero, +1 per exchanging kernel, identical on all ranks
+    unsigned long long* err;                // set to 1 when a peer never answered
+};
+inline size_t sel_p2p_mail_words(int nranks) { return (size_t)2 * nranks * kSelP2PMaxCols * (kSelBinsHost + 1); }
 cudaError_t sel_launch_count(int64_t n, int B, const double* base, int64_t stride, const double* center,
                              unsigned long long* counts, cudaStream_t st);
-cudaError_t sel_launch_init(int B, const unsigned long long* counts, unsigned long long* state, unsigned long long* hist,
-                            unsigned long long* le, unsigned long long* mg, cudaStream_t st);
+cudaError_t sel_launch_init(int B, unsigned long long* counts, unsigned long long* state, unsigned long long* hist,
+                            unsigned long long* le, unsigned long long* mg, const SelP2P& pp, cudaStream_t st);
 cudaError_t sel_launch_hist(int64_t n, int B, const double* base, int64_t stride, const double* center,
                             const unsigned long long* state, int pass, unsigned long long* hist, cudaStream_t st);
-cudaError_t sel_launch_scan(int B, int pass, unsigned long long* state, unsigned long long* hist, cudaStream_t st);
+cudaError_t sel_launch_scan(int B, int pass, unsigned long long* state, unsigned long long* hist, const SelP2P& pp,
+                            cudaStream_t st);
 cudaError_t sel_launch_next(int64_t n, int B, const double* base, int64_t stride, const double* center,
                             const unsigned long long* state, unsigned long long* le, unsigned long long* mg, cudaStream_t st);
 cudaError_t sel_launch_finish(int B, const unsigned long long* state, const unsigned long long* le, const unsigned long long* mg,
-                              double* out, int do_exp, double scale, cudaStream_t st);
+                              double* out, int do_exp, double scale, const SelP2P& pp, cudaStream_t st);
 
 // ---- stage 4a: gene-wise dispersion -----------------------------------------------------
 cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf,
@@ -153,13 +165,12 @@ struct TrendP2P {
     int nranks, rank;
     double* const* peers;       // device array of nranks pointers: every rank's mailbox (own one included)
     double* mymail;             // this rank's mailbox: 2 x nranks slots of 16 doubles (8 sums, sequence word, pad)
-    double* gtot;               // 16 doubles of local scratch
     unsigned long long epoch;   // distinct per launch, identical on all ranks
 };
 // the whole parametricDispersionFit in one cooperative kernel; out[0..1] coefs, out[2] status, out[3] outer
-// iterations, out[4] passes; partial >= 16 * #SMs doubles, bar = one zero-initialised word
+// iterations, out[4] passes; xs = n doubles of scratch, partial >= 16 * #SMs doubles, bar = one zero-initialised word
 cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                             double* partial, unsigned int* bar, double* out, const TrendP2P& pp, cudaStream_t st);
+                             double* xs, double* partial, unsigned int* bar, double* out, const TrendP2P& pp, cudaStream_t st);
 cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst,
                                const uint8_t* flags, const double* coefs_dev, double* dispFit, double* resid,
                                cudaStream_t st);

@@ -222,24 +222,25 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nbl
 }
 
 // Cross-GPU part of a pass (sharded runs): CTA 0 stores this rank's 8 sums straight into every peer's
-// mailbox over NVLink (peer pointers from cudaIpcOpenMemHandle), then a sequence word; it waits until all
-// ranks' slots of its own mailbox carry this pass's sequence and adds them in rank order, so every rank
-// obtains bit-identical totals and follows the same control flow.  Slots are double-buffered by pass parity:
-// a peer can only be one pass ahead, because finishing a pass needs everybody's contribution to it.
-__device__ __forceinline__ bool p2p_allreduce8(const TrendP2P& pp, unsigned long long seq, unsigned int parity,
-                                               const double* sh_tot, double* gtot_out)
+// mailbox over NVLink (peer pointers from cudaIpcOpenMemHandle), then a sequence word.  EVERY CTA then waits
+// until all ranks' slots of the local mailbox carry this pass's sequence and adds them in rank order, so all
+// CTAs of all ranks obtain bit-identical totals and follow the same control flow, without a second grid
+// barrier.  Slots are double-buffered by pass parity: a peer can only be one pass ahead, because finishing a
+// pass needs everybody's contribution to it, and CTA 0 contributes to pass k+1 only after the grid barrier of
+// pass k+1, i.e. after all local CTAs have read pass k.  (Between two launches the stream carries other
+// collectives -- the medians -- so a peer cannot start the next launch while this one still reads.)
+__device__ __forceinline__ void p2p_allreduce8(const TrendP2P& pp, unsigned long long seq, unsigned int parity, double* sh_tot)
 {
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
-    if ((int)threadIdx.x < pp.nranks) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < pp.nranks) {
         double* dst = pp.peers[threadIdx.x] + ((size_t)parity * pp.nranks + pp.rank) * 16;
 #pragma unroll
         for (int k = 0; k < 8; k++) dst[k] = sh_tot[k];
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(dst + 8) = seq;
     }
-    __syncthreads();
     if ((int)threadIdx.x < pp.nranks) {
         volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
             pp.mymail + ((size_t)parity * pp.nranks + threadIdx.x) * 16 + 8);
@@ -255,40 +256,60 @@ __device__ __forceinline__ bool p2p_allreduce8(const TrendP2P& pp, unsigned long
         for (int r = 0; r < pp.nranks; r++)
             x += *reinterpret_cast<volatile double*>(pp.mymail + ((size_t)parity * pp.nranks + r) * 16 + threadIdx.x);
         if (timed_out) x = (threadIdx.x == 6) ? 1.0 : NAN;          // reads as "invalid" in the control flow below
-        __stcg(gtot_out + threadIdx.x, x);
+        sh_tot[threadIdx.x] = x;
     }
     __syncthreads();
-    return timed_out == 0;
 }
 
+// One pass: the sums glm.fit needs at coefficients b over the rows kept by the outer coefficients c.
+// xs is n doubles of scratch that carries 1/baseMean between passes: NaN = row never used (all-zero region or
+// dispersion at the floor), negative = excluded by the current outer coefficients.  `refresh` = 2 on the first
+// pass of the launch (fill xs), 1 on the first pass of an outer iteration (re-decide the sign), 0 otherwise.
+// Every row is always handled by the same thread, so xs needs no synchronisation.
 __device__ __forceinline__ void trend_pass_device(int64_t n, const double* __restrict__ baseMean,
                                                   const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
+                                                  double* __restrict__ xs, int refresh,
                                                   double c0, double c1, double b0, double b1, double* partial_base,
                                                   unsigned int* bar, unsigned int& phase, double* sh_tot /*8, shared*/,
                                                   const TrendP2P& pp, unsigned long long& pass_no)
 {
     // partials are double-buffered by pass parity: a CTA can be at most one pass ahead of the slowest
     // one (there is a barrier in every pass), so one barrier per pass is enough
-    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;      // phase advances by 1 or 2 per pass; with
-    // 2 barriers per pass (sharded) a single buffer would do, the parity then simply stays constant
+    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        if (flags[i] & CD_FLAG_ALLZERO) continue;
+        double xv;
         const double d = dispGeneEst[i];
-        if (!(d > 100.0 * kMinDisp)) continue;
-        const double x = 1.0 / baseMean[i];
-        const double r = d / (c0 + c1 * x);
-        if (!((r > 1e-4) && (r < 15.0))) continue;
+        if (refresh == 2) {
+            xv = NAN;
+            if (!(flags[i] & CD_FLAG_ALLZERO) && (d > 100.0 * kMinDisp)) xv = 1.0 / baseMean[i];
+        } else {
+            xv = xs[i];
+        }
+        if (refresh) {
+            if (xv != xv) { if (refresh == 2) xs[i] = xv; continue; }
+            const double x = fabs(xv);
+            const double r = d / (c0 + c1 * x);
+            xv = ((r > 1e-4) && (r < 15.0)) ? x : -x;
+            xs[i] = xv;
+        }
+        if (!(xv > 0.0)) continue;
+        const double x = xv;
         const double mu = b0 + b1 * x;
         v[7] += 1.0;
         if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; continue; }
-        const double w = 1.0 / (mu * mu);
-        v[0] += w; v[1] += w * x; v[2] += w * x * x;
-        v[3] += w * d; v[4] += w * x * d;
-        v[5] += -2.0 * (log(d / mu) - (d - mu) / mu);
+        double w, t;
+        if (mu > 1e-100 && mu < 1e100) { const double inv = rcp_pos(mu); w = inv * inv; t = d * inv; }
+        else { w = 1.0 / (mu * mu); t = d / mu; }
+        const double wx = w * x;
+        v[0] += w; v[1] += wx; v[2] += wx * x;
+        v[3] += w * d; v[4] += wx * d;
+        // unit deviance of the Gamma family: -2 (log(d/mu) - (d - mu)/mu)
+        const double lt = (t > 1e-300 && t < 1e300) ? log_pos(t) : log(t);
+        v[5] += -2.0 * (lt - (t - 1.0));
     }
     // block reduction (fixed order)
     __shared__ double sh[8][kTrendThreads / 32];
@@ -318,17 +339,14 @@ __device__ __forceinline__ void trend_pass_device(int64_t n, const double* __res
     __syncthreads();
     if (pp.nranks > 1) {
         pass_no++;
-        double* gtot = pp.gtot + (size_t)(pass_no & 1ull) * 8;
-        if (blockIdx.x == 0) p2p_allreduce8(pp, (pp.epoch << 32) | pass_no, (unsigned int)(pass_no & 1ull), sh_tot, gtot);
-        grid_barrier(bar, gridDim.x, phase);
-        if (threadIdx.x < 8) sh_tot[threadIdx.x] = __ldcg(gtot + threadIdx.x);
-        __syncthreads();
+        p2p_allreduce8(pp, (pp.epoch << 32) | pass_no, (unsigned int)(pass_no & 1ull), sh_tot);
     }
 }
 
 __global__ void __launch_bounds__(kTrendThreads)
 trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
-                 const uint8_t* __restrict__ flags, double* partial, unsigned int* bar, double* out, TrendP2P pp)
+                 const uint8_t* __restrict__ flags, double* __restrict__ xs, double* partial, unsigned int* bar, double* out,
+                 TrendP2P pp)
 {
     __shared__ double tot[8];
     unsigned int phase = 0;
@@ -337,7 +355,9 @@ trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* _
     int iter = 0, status = 0, passes = 0;
     while (true) {
         double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
-        trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial, bar, phase, tot, pp, pass_no); passes++;
+        trend_pass_device(n, baseMean, dispGeneEst, flags, xs, passes == 0 ? 2 : 1, c0, c1, b0, b1, partial, bar, phase, tot, pp,
+                          pass_no);
+        passes++;
         double v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = tot[k];
@@ -352,7 +372,8 @@ trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* _
             double w[8];
             int halv = 0;
             while (true) {
-                trend_pass_device(n, baseMean, dispGeneEst, flags, c0, c1, nb0, nb1, partial, bar, phase, tot, pp, pass_no); passes++;
+                trend_pass_device(n, baseMean, dispGeneEst, flags, xs, 0, c0, c1, nb0, nb1, partial, bar, phase, tot, pp, pass_no);
+                passes++;
 #pragma unroll
                 for (int k = 0; k < 8; k++) w[k] = tot[k];
                 if (w[6] == 0.0 && isfinite(w[5])) break;
@@ -382,7 +403,7 @@ trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* _
 }
 
 cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                             double* partial, unsigned int* bar, double* out, const TrendP2P& pp_in, cudaStream_t st)
+                             double* xs, double* partial, unsigned int* bar, double* out, const TrendP2P& pp_in, cudaStream_t st)
 {
     TrendP2P pp = pp_in;
     int dev = 0, sms = 148, coop = 0;
@@ -392,7 +413,8 @@ cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* di
     if (!coop) return cudaErrorNotSupported;
     cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&partial, (void*)&bar, (void*)&out, (void*)&pp};
+    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&xs, (void*)&partial, (void*)&bar, (void*)&out,
+                    (void*)&pp};
     return cudaLaunchCooperativeKernel((const void*)trend_fit_kernel, dim3((unsigned)sms), dim3(kTrendThreads), args, 0, st);
 }
 

@@ -187,7 +187,7 @@ class Engine:
     def comm_info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         self._check(self._L.cd_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(nranks=a.value, rank=b.value, peer_memory_allreduce=bool(c.value))
+        return dict(nranks=a.value, rank=b.value, peer_memory_allreduce=bool(c.value & 1), peer_memory_medians=bool(c.value & 2))
 
     # -- setup ------------------------------------------------------------------------------
     def set_design(self, X):

@@ -78,8 +78,9 @@ const char* cd_last_error(const cd_ctx* ctx);      /* ctx may be NULL: last erro
  * (the Python host uses torch.distributed); every rank then calls cd_comm_init. */
 int cd_comm_unique_id(cd_ctx* ctx, char id[128]);
 int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128]);
-/* peer_memory_allreduce = 1 when the sharded trend fit all-reduces through NVLink peer memory inside its kernel
- * (cudaIpc mailboxes), 0 when it falls back to one NCCL all-reduce per pass */
+/* peer_memory_allreduce: bit 0 set when the sharded trend fit all-reduces its sums through NVLink peer memory inside
+ * its kernel (cudaIpc mailboxes), bit 1 set when the median kernels exchange their counters the same way; a clear
+ * bit means NCCL all-reduces enqueued by the host between the kernels */
 int cd_comm_info(const cd_ctx* ctx, int* nranks, int* rank, int* peer_memory_allreduce);
 /* contiguous bait-balanced partition of regions (region_bait must be non-decreasing):
  * shard k owns regions [bounds[k], bounds[k+1]); cuts fall only between baits and balance rows. */
