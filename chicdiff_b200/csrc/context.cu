@@ -5,6 +5,7 @@
 #include "../../include/chicdiff_b200.h"
 #include "kernels.h"
 #include "comm.h"
+#include "results_host.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -165,6 +166,7 @@ struct cd_ctx {
     // regions / rows
     int64_t n = 0, R = 0;
     bool have_regions = false, have_agg = false, rows_borrowed = false;
+    bool have_results = false;       // the arrays of a successful cd_region_test are in device memory
     std::vector<uint8_t> sample_set;
     DevBuf<int64_t> row_off;
     DevBuf<int32_t> N_rows;
@@ -211,6 +213,11 @@ struct cd_ctx {
     DevBuf<unsigned long long> sel_mail;
     DevBuf<unsigned long long*> sel_peers_dev;
     unsigned long long sel_seq = 0;
+    // work buffers of cd_results_resident
+    DevBuf<unsigned long long> res_key[4], res_small;
+    DevBuf<unsigned int> res_idx[2], res_cnt;
+    DevBuf<double> res_pv, res_padj, res_bms, res_ps, res_smalld, res_cmin, res_smin;
+    DevBuf<unsigned char> res_tmp;
     // columns of the last cd_parse_chinput
     int64_t ch_rows = 0;
     DevBuf<int32_t> ch_bait, ch_oe, ch_N, ch_len;
@@ -1190,6 +1197,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     if (!ctx) return CD_EINVAL;
     if (!opt || !out) return ctx->fail(CD_EINVAL, "cd_region_test: null options / results");
     if (!ctx->have_agg) return ctx->fail(CD_EINVAL, "cd_region_test: call cd_aggregate (or cd_set_aggregated) first");
+    ctx->have_results = false;
     if (opt->norm < 0 || opt->norm > 2) return ctx->fail(CD_EINVAL, "DESeq2Wrap error: Unknown normalisation method.");
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
     const int S = ctx->des.S, p = ctx->des.p;
@@ -1332,6 +1340,74 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
     ctx->timings[1] = ms;
     ctx->tm_collect();
+    ctx->have_results = true;
+    return CD_OK;
+}
+
+int cd_results_resident(cd_ctx* ctx, double* pvalue_out, double* padj_out, double* scalars_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_results) return ctx->fail(CD_EINVAL, "cd_results_resident: no successful cd_region_test on this context yet");
+    if (ctx->comm.active() && ctx->comm.nranks > 1)
+        return ctx->fail(CD_EINVAL, "cd_results_resident: results() is global over all regions; in a sharded run gather the "
+                                    "columns and call cd_results_adjust");
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const int64_t n = ctx->n;
+    const int S = ctx->des.S, p = ctx->des.p;
+    const double alpha = 0.1;
+    const double cutoff = res_qf(0.99, (double)p, (double)(S - p));
+    const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    const int C = res_chunks(n);
+    for (int k = 0; k < 4; k++) CD_CUDA(ctx, ctx->res_key[k].ensure(nn));
+    for (int k = 0; k < 2; k++) CD_CUDA(ctx, ctx->res_idx[k].ensure(nn));
+    CD_CUDA(ctx, ctx->res_pv.ensure(nn)); CD_CUDA(ctx, ctx->res_padj.ensure(nn));
+    CD_CUDA(ctx, ctx->res_bms.ensure(nn)); CD_CUDA(ctx, ctx->res_ps.ensure(nn));
+    CD_CUDA(ctx, ctx->res_cnt.ensure((size_t)50 * (size_t)std::max(C, 1)));
+    CD_CUDA(ctx, ctx->res_cmin.ensure((size_t)std::max(C, 1))); CD_CUDA(ctx, ctx->res_smin.ensure((size_t)std::max(C, 1)));
+    CD_CUDA(ctx, ctx->res_small.ensure(2 + 50 + 50));
+    CD_CUDA(ctx, ctx->res_smalld.ensure(100));
+    unsigned long long* counts = ctx->res_small.p;
+    unsigned long long* m_tot = ctx->res_small.p + 2;
+    unsigned long long* best = ctx->res_small.p + 52;
+    double* cut = ctx->res_smalld.p;
+    double* theta = ctx->res_smalld.p + 50;
+    unsigned long long *pkey0 = ctx->res_key[0].p, *pkey1 = ctx->res_key[1].p, *bmkey0 = ctx->res_key[2].p, *bmkey1 = ctx->res_key[3].p;
+    unsigned int *idx0 = ctx->res_idx[0].p, *idx1 = ctx->res_idx[1].p;
+    const double* baseMean = ctx->g_baseMean.p + ctx->g_off;
+    const uint8_t* flags = ctx->g_flags.p + ctx->g_off;
+
+    CD_LAUNCHN(ctx, 1, res_launch_keys(n, p, cutoff, baseMean, ctx->maxCooks.p, flags, ctx->pvalue.p, ctx->res_pv.p, ctx->res_padj.p,
+                                       pkey0, bmkey0, idx0, counts, st));
+    int j = 0;
+    double cut_h[50], theta_h[50];
+    for (int k = 0; k < 50; k++) { cut_h[k] = NAN; theta_h[k] = NAN; }
+    if (n > 0) {
+        size_t bytes = 0;
+        CD_CUDA(ctx, cp_sort_pairs_u64(nullptr, bytes, bmkey0, bmkey1, idx0, idx1, n, st));
+        CD_CUDA(ctx, ctx->res_tmp.ensure(bytes));
+        CD_LAUNCHN(ctx, 1, cp_sort_pairs_u64(ctx->res_tmp.p, bytes, bmkey0, bmkey1, idx0, idx1, n, st));
+        CD_LAUNCHN(ctx, 1, res_launch_cutoffs(n, bmkey1, counts, cut, theta, st));
+        CD_LAUNCHN(ctx, 1, cp_sort_pairs_u64(ctx->res_tmp.p, bytes, pkey0, pkey1, idx0, idx1, n, st));
+        CD_LAUNCHN(ctx, 1, res_launch_gather(n, idx1, baseMean, ctx->res_pv.p, ctx->res_bms.p, ctx->res_ps.p, st));
+        CD_LAUNCHN(ctx, 3, res_launch_num_rej(n, counts, ctx->res_bms.p, ctx->res_ps.p, cut, ctx->res_cnt.p, m_tot, alpha, best, st));
+        unsigned long long best_h[50];
+        CD_CUDA(ctx, cudaMemcpyAsync(best_h, best, sizeof(best_h), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(cut_h, cut, sizeof(cut_h), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(theta_h, theta, sizeof(theta_h), cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+        double numRej[50];
+        for (int k = 0; k < 50; k++) numRej[k] = (double)best_h[k];
+        j = res_pick_cutoff(theta_h, numRej, 50);
+        CD_LAUNCHN(ctx, 3, res_launch_bh(n, counts, ctx->res_bms.p, ctx->res_ps.p, idx1, cut, j, ctx->res_cnt.p, m_tot,
+                                         ctx->res_cmin.p, ctx->res_smin.p, ctx->res_padj.p, st));
+    }
+    if (pvalue_out && n > 0) CD_CUDA(ctx, cudaMemcpyAsync(pvalue_out, ctx->res_pv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (padj_out && n > 0) CD_CUDA(ctx, cudaMemcpyAsync(padj_out, ctx->res_padj.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    if (scalars_out) {
+        scalars_out[0] = cutoff; scalars_out[1] = cut_h[j]; scalars_out[2] = theta_h[j]; scalars_out[3] = (double)(j + 1);
+    }
     return CD_OK;
 }
 

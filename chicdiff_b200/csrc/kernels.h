@@ -112,6 +112,23 @@ cudaError_t sel_launch_next(int64_t n, int B, const double* base, int64_t stride
 cudaError_t sel_launch_finish(int B, const unsigned long long* state, const unsigned long long* le, const unsigned long long* mg,
                               double* out, int do_exp, double scale, const SelP2P& pp, cudaStream_t st);
 
+// ---- results() on resident arrays (results_resident.cu) ----
+// counts: [0] rows with a p-value after the Cook's filter, [1] rows with baseMean == 0
+cudaError_t res_launch_keys(int64_t n, int p, double cutoff, const double* baseMean, const double* maxCooks, const uint8_t* flags,
+                            const double* pvalue, double* pv_out, double* padj, unsigned long long* pkey,
+                            unsigned long long* bmkey, unsigned int* idx, unsigned long long* counts, cudaStream_t st);
+cudaError_t res_launch_cutoffs(int64_t n, const unsigned long long* bm_sorted_keys, const unsigned long long* counts, double* cut,
+                               double* theta, cudaStream_t st);
+cudaError_t res_launch_gather(int64_t n, const unsigned int* sorted_idx, const double* baseMean, const double* pv, double* bm_s,
+                              double* p_s, cudaStream_t st);
+int res_chunks(int64_t n);                       // chunks of sorted rows; cnt needs 50 x chunks words, cmin / smin chunks doubles
+cudaError_t res_launch_num_rej(int64_t n, const unsigned long long* counts, const double* bm_s, const double* p_s,
+                               const double* cut, unsigned int* cnt, unsigned long long* m_tot, double alpha,
+                               unsigned long long* best, cudaStream_t st);
+cudaError_t res_launch_bh(int64_t n, const unsigned long long* counts, const double* bm_s, const double* p_s,
+                          const unsigned int* sorted_idx, const double* cut, int j, const unsigned int* off,
+                          const unsigned long long* m_tot, double* cmin, double* smin, double* padj, cudaStream_t st);
+
 // ---- stage 4a: gene-wise dispersion -----------------------------------------------------
 cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf,
                               double* baseMean, double* baseVar, double* rough, uint8_t* flags,

@@ -4,6 +4,7 @@
 // threshold rule, alpha = 0.1) and the Benjamini-Hochberg adjusted p-values.
 // Global over all regions and O(n log n): host code, outside the five timed stages.
 #include "../../include/chicdiff_b200.h"
+#include "results_host.h"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -149,6 +150,30 @@ void lowess(const std::vector<double>& x, const std::vector<double>& y, double f
 
 }  // namespace
 
+namespace cd {
+
+double res_qf(double prob, double df1, double df2) { return qf(prob, df1, df2); }
+
+// genefilter's rule inside results(): lowess(theta, numRej, f = 1/5); the first cut-off whose rejection count
+// exceeds max(fit) - RMS residual over the cut-offs with rejections; cut-off 0 when no count exceeds 10
+int res_pick_cutoff(const double* theta_p, const double* numRej_p, int nt)
+{
+    const std::vector<double> theta(theta_p, theta_p + nt), numRej(numRej_p, numRej_p + nt);
+    std::vector<double> lo_fit;
+    lowess(theta, numRej, 1.0 / 5.0, 3, 0.01 * (theta[nt - 1] - theta[0]), lo_fit);
+    int j = 0;
+    const double maxRej = *std::max_element(numRej.begin(), numRej.end());
+    if (maxRej > 10.0) {
+        double ss = 0.0; int cnt = 0;
+        for (int k = 0; k < nt; k++) if (numRej[k] > 0) { const double r = numRej[k] - lo_fit[k]; ss += r * r; cnt++; }
+        const double thresh = *std::max_element(lo_fit.begin(), lo_fit.end()) - std::sqrt(ss / cnt);
+        for (int k = 0; k < nt; k++) if (numRej[k] > thresh) { j = k; break; }
+    }
+    return j;
+}
+
+}  // namespace cd
+
 extern "C" int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const double* maxCooks,
                                  const uint8_t* flags, double* pvalue, double* padj, double* scalars_out)
 {
@@ -184,45 +209,38 @@ extern "C" int cd_results_adjust(int64_t n, int S, int p, const double* baseMean
         }
         cut[k] = q;
     }
-    // rows with a p-value, ascending by p (stable, so ties keep row order like R's order())
-    std::vector<int64_t> ord;
+    // rows with a p-value, ascending by p (stable, so ties keep row order like R's order()); the sorted records
+    // carry baseMean so that the 50 counting passes below stream through memory
+    struct Rec { double p, bm; int64_t i; };
+    std::vector<Rec> ord;
     ord.reserve((size_t)n);
-    for (int64_t i = 0; i < n; i++) if (!std::isnan(pvalue[i])) ord.push_back(i);
-    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return pvalue[a] < pvalue[b]; });
+    for (int64_t i = 0; i < n; i++) if (!std::isnan(pvalue[i])) ord.push_back(Rec{pvalue[i], baseMean[i], i});
+    std::stable_sort(ord.begin(), ord.end(), [](const Rec& a, const Rec& b) { return a.p < b.p; });
     std::vector<double> numRej(NT, 0.0);
     for (int k = 0; k < NT; k++) {
+        const double ck = cut[k];
         int64_t m = 0;
-        for (int64_t i : ord) m += (baseMean[i] >= cut[k]);
+        for (const Rec& r : ord) m += (r.bm >= ck);
         int64_t rank = 0, best = 0;
-        for (int64_t i : ord) {
-            if (!(baseMean[i] >= cut[k])) continue;
+        for (const Rec& r : ord) {
+            if (!(r.bm >= ck)) continue;
             rank++;
-            if ((double)m / (double)rank * pvalue[i] < alpha) best = rank;
+            if ((double)m / (double)rank * r.p < alpha) best = rank;
         }
         numRej[k] = (double)best;
     }
-    std::vector<double> lo_fit;
-    lowess(theta, numRej, 1.0 / 5.0, 3, 0.01 * (theta[NT - 1] - theta[0]), lo_fit);
-    int j = 0;
-    const double maxRej = *std::max_element(numRej.begin(), numRej.end());
-    if (maxRej > 10.0) {
-        double ss = 0.0; int cnt = 0;
-        for (int k = 0; k < NT; k++) if (numRej[k] > 0) { const double r = numRej[k] - lo_fit[k]; ss += r * r; cnt++; }
-        const double thresh = *std::max_element(lo_fit.begin(), lo_fit.end()) - std::sqrt(ss / cnt);
-        for (int k = 0; k < NT; k++) if (numRej[k] > thresh) { j = k; break; }
-    }
+    const int j = cd::res_pick_cutoff(theta.data(), numRej.data(), NT);
     // BH at the chosen cut-off
     for (int64_t i = 0; i < n; i++) padj[i] = NAN;
     int64_t m = 0;
-    for (int64_t i : ord) m += (baseMean[i] >= cut[j]);
+    for (const Rec& r : ord) m += (r.bm >= cut[j]);
     double running = INFINITY;
     int64_t rank = m;
     for (auto it = ord.rbegin(); it != ord.rend(); ++it) {
-        const int64_t i = *it;
-        if (!(baseMean[i] >= cut[j])) continue;
-        const double v = (double)m / (double)rank * pvalue[i];
+        if (!(it->bm >= cut[j])) continue;
+        const double v = (double)m / (double)rank * it->p;
         running = std::min(running, v);
-        padj[i] = std::min(1.0, running);
+        padj[it->i] = std::min(1.0, running);
         rank--;
     }
     if (scalars_out) {

@@ -16,7 +16,7 @@ CD_NORM = {"standard": 0, "fullmean": 1, "combined": 2}
 FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLAG_GENE_NOINCREASE, FLAG_COOKS_KEEP = \
     1, 2, 4, 8, 16, 32, 64
 
-EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info",
+EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
@@ -76,6 +76,7 @@ def load_library():
     L.cd_destroy.restype = None
     L.cd_comm_unique_id.argtypes = [C.c_void_p, C.c_char_p]
     L.cd_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    L.cd_results_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.cd_plan_shards.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.cd_set_design.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -188,6 +189,14 @@ class Engine:
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         self._check(self._L.cd_comm_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(nranks=a.value, rank=b.value, peer_memory_allreduce=bool(c.value & 1), peer_memory_medians=bool(c.value & 2))
+
+    def results_resident(self):
+        """results() (Cook's cutoff, independent filtering, BH) on the arrays of the last region_test, on the device
+        (cd_results_resident); same keys as results_adjust()."""
+        n = self.n
+        pv, padj, sc = np.empty(n), np.empty(n), np.zeros(4)
+        self._check(self._L.cd_results_resident(self._h, pv.ctypes.data, padj.ctypes.data, sc.ctypes.data))
+        return dict(pvalue=pv, padj=padj, cooksCutoff=sc[0], filterThreshold=sc[1], filterTheta=sc[2], filterIndex=int(sc[3]))
 
     # -- setup ------------------------------------------------------------------------------
     def set_design(self, X):

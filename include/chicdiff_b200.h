@@ -15,7 +15,8 @@
  *     :1619-1662  theta grid: 5 intercept-only fits, argmin sum(deviance)   -> cd_region_test (theta = NaN)
  *     :1573-1574, estimateDispersions + nbinomWaldTest                      -> cd_region_test
  *      1602-1603, 1643-1644, 1673-1674
- *     :1721,1730,1739  results(): Cook's cutoff, independent filtering, BH  -> cd_results_adjust
+ *     :1721,1730,1739  results(): Cook's cutoff, independent filtering, BH  -> cd_results_adjust,
+ *                                                                              cd_results_resident
  *   getFullRegionData(chicdiff.settings, RU, RUcontrol, suffix)            chicdiff.R:1460-1478
  *     supplies the per-row N / FullMean columns                            -> cd_set_sample_rows
  *
@@ -212,6 +213,12 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out);
  * NULL) receives {cooksCutoff, filterThreshold, filterTheta, filterIndex(1-based)}. */
 int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const double* maxCooks,
                       const uint8_t* flags, double* pvalue, double* padj, double* scalars_out);
+
+/* The same results() step (chicdiff.R:1721,1730,1739) on the arrays the last successful cd_region_test of this
+ * context left in device memory: two radix sorts and prefix counts on the GPU, only the 50-point lowess of the
+ * filtering rule on the host.  pvalue_out / padj_out (n doubles each, host; either may be NULL) and scalars_out
+ * as in cd_results_adjust.  Not for sharded contexts (the step is global): gather and use cd_results_adjust. */
+int cd_results_resident(cd_ctx* ctx, double* pvalue_out, double* padj_out, double* scalars_out);
 
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernel launches issued by this context since creation */

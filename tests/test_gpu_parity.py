@@ -596,3 +596,56 @@ def test_chinput_codec_on_device():
     assert np.isnan(got["distSign"][0]) and got["distSign"][1:].tolist() == [-4500.0, 15000.0]
     assert e.parse_chinput(b"")["N"].size == 0 and e.parse_chinput(b"# only a comment\n")["N"].size == 0
     e.close()
+
+
+def _resident_vs_host(e, r, S, p):
+    dev = e.results_resident()
+    host = engine.results_adjust(r["baseMean"], r["maxCooks"], r["flags"], r["pvalue"], S, p)
+    assert np.array_equal(dev["pvalue"], host["pvalue"], equal_nan=True), "Cook's filter differs"
+    assert np.array_equal(dev["padj"], host["padj"], equal_nan=True), "adjusted p-values differ"
+    for k in ("cooksCutoff", "filterThreshold", "filterTheta", "filterIndex"):
+        assert dev[k] == host[k] or (np.isnan(dev[k]) and np.isnan(host[k])), k
+    return dev, host
+
+
+def test_results_on_resident_arrays_match_host_routine():
+    """cd_results_resident (radix sorts + prefix counts on the device) against cd_results_adjust (host) on the same
+    columns: same Cook's filter, same filtering cut-off, bit-identical BH values (chicdiff.R:1721,1730,1739)."""
+    # an all-zero region (baseMean 0, NA p-value) and a fixed theta
+    d = synth.generate("tiny", seed_offset=5)
+    lo, hi = d.row_off[11], d.row_off[12]
+    d.N_rows[:, lo:hi] = 0
+    e = engine.Engine(0)
+    with pytest.raises(engine.ChicdiffError):
+        e.results_resident()                                             # nothing tested yet
+    e.set_design(d.X); e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    e.aggregate()
+    r = e.region_test(theta=0.25)
+    dev, _ = _resident_vs_host(e, r, d.S, d.X.shape[1])
+    assert np.isnan(dev["padj"][11])
+    e.close()
+    # 100k regions (49 chunks of sorted rows), Cook's outliers present, and the oracle's results() as third opinion
+    d = synth.generate("c3", n_regions=100000)
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    K, _ = e.aggregate()
+    r = e.region_test()
+    dev, host = _resident_vs_host(e, r, d.S, d.X.shape[1])
+    assert np.isnan(dev["pvalue"]).sum() >= np.isnan(r["pvalue"]).sum()
+    with np.errstate(invalid="ignore"):
+        assert (dev["padj"] < 0.05).sum() > 100
+    # an 8-vs-8 design with a covariate (p = 3: no two-level heuristic)
+    d = synth.generate("c4", n_regions=20000)
+    e2 = engine.Engine(0)
+    e2.set_design(d.X); e2.set_regions(d.row_off)
+    for s in range(d.S):
+        e2.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    e2.aggregate()
+    r = e2.region_test()
+    _resident_vs_host(e2, r, d.S, d.X.shape[1])
+    e2.close()
+    e.close()
