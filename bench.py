@@ -291,6 +291,25 @@ def main():
                        "(joins + Bmean/Tmean + count merge + region sums in one kernel) -> cd_region_test",
                "ms_per_step": a_dev_ms, "assemble_kernel_ms": a_tm[0], "e2e_ms_per_step": a_e2e_ms, "h2d_bytes_per_step": asm_h2d}
 
+    # the "next" step after the Wald test, outside the metric: results() (Cook's cutoff, independent filtering, BH) on the
+    # arrays still in device memory, beside the host routine on the same columns
+    res_step = None
+    if world == 1:
+        r_tab = e.region_test(fetch="table")
+        e.results_resident()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            adj_dev = e.results_resident()
+        res_dev_ms = (time.perf_counter() - t0) / 3 * 1e3
+        t0 = time.perf_counter()
+        adj_host = engine.results_adjust(r_tab["baseMean"], r_tab["maxCooks"], r_tab["flags"], r_tab["pvalue"], S, p)
+        res_host_ms = (time.perf_counter() - t0) * 1e3
+        res_step = {"what": "results(): cd_results_resident (device sorts + prefix counts, padj and filtered p-values copied to the "
+                            "host) vs cd_results_adjust (host) on the same columns",
+                    "device_wall_ms": res_dev_ms, "host_wall_ms": res_host_ms,
+                    "identical": bool(np.array_equal(adj_dev["padj"], adj_host["padj"], equal_nan=True)),
+                    "d2h_bytes": int(n * 16)}
+
     n_tot = torch.tensor([n], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(n_tot)
@@ -332,6 +351,8 @@ def main():
             asm["value"] = n_tot / (asm["ms_per_step"] * 1e-3)
             asm["e2e_value"] = n_tot / (asm["e2e_ms_per_step"] * 1e-3)
             line["assembly_path"] = asm
+        if res_step is not None:
+            line["results_step"] = res_step
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             rate, dt, m = cpu_reference_rate(d, args.cpu_sample, threads)

@@ -137,7 +137,7 @@ def DESeq2Wrap(chicdiff_settings, RU, FullRegionData, suffix="", theta=None, rma
     if norm == "combined":
         message("Theta=%s" % res["theta"])
     message("Processing model output")
-    adj = engine.results_adjust(res["baseMean"], res["maxCooks"], res["flags"], res["pvalue"], S, p)
+    adj = eng.results_resident()            # results() on the arrays still in device memory (chicdiff.R:1721,1730,1739)
     label = {"standard": "Standard DESeq2 normalisation", "fullmean": "Chicago full mean-based normalisation",
              "combined": "combined normalisation"}[norm]
     with np.errstate(invalid="ignore"):
