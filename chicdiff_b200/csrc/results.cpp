@@ -6,7 +6,9 @@
 #include "../../include/chicdiff_b200.h"
 #include "results_host.h"
 #include <algorithm>
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <numeric>
 #include <vector>
 
@@ -245,6 +247,75 @@ extern "C" int cd_results_adjust(int64_t n, int S, int p, const double* baseMean
     }
     if (scalars_out) {
         scalars_out[0] = cutoff; scalars_out[1] = cut[j]; scalars_out[2] = theta[j]; scalars_out[3] = (double)(j + 1);
+    }
+    return CD_OK;
+}
+
+// IHWcorrection(), "apply to test data" (chicdiff.R:2038-2049): stratum of every region by cut(log|avDist|, breaks)
+// with breaks half-way between neighbouring strata of the lookup learned on the control set, weight =
+// avWeights[stratum] / mean(avWeights over the rows), weighted p-value, BH.
+extern "C" int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalue, int ngroups, const double* minLogDist,
+                            const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
+                            double* weighted_pvalue_out, double* weighted_padj_out)
+{
+    if (n < 0 || ngroups < 1 || !minLogDist || !maxLogDist || !avWeights || (n > 0 && (!avDist || !pvalue))) return CD_EINVAL;
+    // breaks <- (c(minLogDist, Inf) + c(0, maxLogDist)) / 2   (:2039); cut() sorts them and refuses duplicates
+    std::vector<double> breaks((size_t)ngroups + 1);
+    for (int k = 0; k <= ngroups; k++) {
+        const double a = k < ngroups ? minLogDist[k] : INFINITY;
+        const double b = k > 0 ? maxLogDist[k - 1] : 0.0;
+        breaks[(size_t)k] = (a + b) / 2;
+        if (std::isnan(breaks[(size_t)k])) return CD_EINVAL;
+    }
+    std::sort(breaks.begin(), breaks.end());
+    for (int k = 1; k <= ngroups; k++) if (breaks[(size_t)k] == breaks[(size_t)k - 1]) return CD_EINVAL;   // 'breaks' are not unique
+    std::vector<int32_t> group((size_t)n);
+    std::vector<int64_t> per_group((size_t)ngroups + 1, 0);               // [0] = NA
+    for (int64_t i = 0; i < n; i++) {
+        const double x = std::log(std::fabs(avDist[i]));
+        int32_t g = INT32_MIN;                                            // NA_integer_
+        if (!std::isnan(x) && x > breaks[0] && x <= breaks[(size_t)ngroups]) {
+            // right-closed intervals (breaks[g-1], breaks[g]]
+            const auto it = std::lower_bound(breaks.begin(), breaks.end(), x);
+            g = (int32_t)(it - breaks.begin());
+        }
+        group[(size_t)i] = g;
+        per_group[g == INT32_MIN ? 0 : (size_t)g]++;
+    }
+    // mean(out$avWeights) over the merged table (rows ordered by stratum; NA strata poison it), R's two-pass
+    // long-double mean
+    double meanw = NAN;
+    if (n > 0 && per_group[0] == 0) {
+        long double sum = 0.0L;
+        for (int g = 1; g <= ngroups; g++)
+            for (int64_t c = 0; c < per_group[(size_t)g]; c++) sum += (long double)avWeights[g - 1];
+        long double m = sum / (long double)n, t = 0.0L;
+        for (int g = 1; g <= ngroups; g++)
+            for (int64_t c = 0; c < per_group[(size_t)g]; c++) t += ((long double)avWeights[g - 1] - m);
+        meanw = (double)(m + t / (long double)n);
+    }
+    std::vector<double> wp((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t g = group[(size_t)i];
+        const double w = (g == INT32_MIN) ? NAN : avWeights[g - 1] / meanw;
+        wp[(size_t)i] = pvalue[i] / w;
+        if (group_out) group_out[i] = g;
+        if (weight_out) weight_out[i] = w;
+        if (weighted_pvalue_out) weighted_pvalue_out[i] = wp[(size_t)i];
+    }
+    if (weighted_padj_out) {
+        // p.adjust(method = "BH") over the non-NA entries
+        std::vector<int64_t> ord;
+        ord.reserve((size_t)n);
+        for (int64_t i = 0; i < n; i++) { weighted_padj_out[i] = NAN; if (!std::isnan(wp[(size_t)i])) ord.push_back(i); }
+        std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return wp[(size_t)a] < wp[(size_t)b]; });
+        const int64_t m = (int64_t)ord.size();
+        double running = INFINITY;
+        for (int64_t r = m; r >= 1; r--) {
+            const int64_t i = ord[(size_t)r - 1];
+            running = std::min(running, (double)m / (double)r * wp[(size_t)i]);
+            weighted_padj_out[i] = std::min(1.0, running);
+        }
     }
     return CD_OK;
 }

@@ -16,7 +16,7 @@ CD_NORM = {"standard": 0, "fullmean": 1, "combined": 2}
 FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLAG_GENE_NOINCREASE, FLAG_COOKS_KEEP = \
     1, 2, 4, 8, 16, 32, 64
 
-EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident",
+EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident", "cd_ihw_apply",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
@@ -129,6 +129,26 @@ def plan_shards(region_bait, row_off, nshards):
     if rc != 0:
         raise ChicdiffError(rc, "cd_plan_shards: bad arguments")
     return bounds
+
+
+def ihw_apply(avDist, pvalue, minLogDist, maxLogDist, avWeights):
+    """IHWcorrection()'s "apply to test data" block (cd_ihw_apply, chicdiff.R:2038-2049); rows stay in input order."""
+    L = load_library()
+    avDist = np.ascontiguousarray(avDist, dtype=np.float64)
+    pvalue = np.ascontiguousarray(pvalue, dtype=np.float64)
+    lo = np.ascontiguousarray(minLogDist, dtype=np.float64)
+    hi = np.ascontiguousarray(maxLogDist, dtype=np.float64)
+    w = np.ascontiguousarray(avWeights, dtype=np.float64)
+    n = len(avDist)
+    group = np.empty(n, np.int32)
+    weight, wp, wpadj = np.empty(n), np.empty(n), np.empty(n)
+    L.cd_ihw_apply.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.cd_ihw_apply(n, _ptr(avDist), _ptr(pvalue), len(w), _ptr(lo), _ptr(hi), _ptr(w), _ptr(group), _ptr(weight), _ptr(wp),
+                        _ptr(wpadj))
+    if rc != 0:
+        raise ChicdiffError(rc, "cd_ihw_apply: bad arguments or non-unique breaks")
+    return dict(group=group, weight=weight, weighted_pvalue=wp, weighted_padj=wpadj)
 
 
 def results_adjust(baseMean, maxCooks, flags, pvalue, S, p):

@@ -220,6 +220,16 @@ int cd_results_adjust(int64_t n, int S, int p, const double* baseMean, const dou
  * as in cd_results_adjust.  Not for sharded contexts (the step is global): gather and use cd_results_adjust. */
 int cd_results_resident(cd_ctx* ctx, double* pvalue_out, double* padj_out, double* scalars_out);
 
+/* IHWcorrection(), "apply to test data" block (chicdiff.R:2038-2049), after R's ihw() has been trained on the control
+ * set and the distance lookup learned (:1994-2033): minLogDist / maxLogDist / avWeights are the ngroups rows of
+ * distLookup as they stand at :2033 (first minimum set to 0, last maximum to Inf).  Per region, in input order:
+ * group = cut(log|avDist|, breaks) (1-based, INT32_MIN = NA), weight = avWeights[group] / mean(avWeights over the
+ * rows), weighted_pvalue = pvalue / weight, weighted_padj = BH.  The reference's merge() leaves the table sorted by
+ * group; callers that need that order sort by (group, input order).  Host routine; any output may be NULL. */
+int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalue, int ngroups, const double* minLogDist,
+                 const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
+                 double* weighted_pvalue_out, double* weighted_padj_out);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernel launches issued by this context since creation */
 int64_t cd_launch_count(const cd_ctx* ctx);

@@ -158,6 +158,31 @@ def region_test(K, FMagg, X, norm="combined", theta=None, theta_grid=(0, .25, .5
 # Pinned by tests/test_golden.py against the shipped golden table.
 # ---------------------------------------------------------------------------------------------
 
+def ihw_apply(avDist, pvalue, minLogDist, maxLogDist, avWeights):
+    """IHWcorrection(), "apply to test data" (chicdiff.R:2038-2049).  Lookup columns as they stand at :2033.
+    Rows stay in input order (the reference's merge() sorts by group afterwards)."""
+    avDist = np.asarray(avDist, dtype=np.float64)
+    lo, hi, w = (np.asarray(a, dtype=np.float64) for a in (minLogDist, maxLogDist, avWeights))
+    breaks = (np.concatenate([lo, [np.inf]]) + np.concatenate([[0.0], hi])) / 2          # :2039
+    breaks = np.sort(breaks)
+    if np.any(np.diff(breaks) == 0):
+        raise ValueError("'breaks' are not unique")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = np.log(np.abs(avDist))
+    # cut(x, breaks): right-closed (b[g-1], b[g]], NA outside
+    g = np.searchsorted(breaks, x, side="left")
+    na = np.isnan(x) | (g < 1) | (g > len(w))
+    group = np.where(na, -1, g)
+    avw = np.where(na, np.nan, w[np.clip(group, 1, len(w)) - 1])
+    # mean() over the merged table (ordered by group); R accumulates in long double and refines once
+    srt = avw[np.argsort(group, kind="stable")].astype(np.longdouble)
+    m = srt.sum() / len(srt) if len(srt) else np.longdouble(np.nan)
+    m = m + (srt - m).sum() / len(srt) if len(srt) else m
+    weight = avw / float(m)
+    wp = np.asarray(pvalue, dtype=np.float64) / weight
+    return dict(group=group, weight=weight, weighted_pvalue=wp, weighted_padj=p_adjust_bh(wp))
+
+
 def p_adjust_bh(p):
     p = np.asarray(p, dtype=np.float64)
     out = np.full(p.shape, np.nan)

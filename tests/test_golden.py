@@ -45,6 +45,57 @@ def test_ihw_weight_identities(golden):
     assert np.max(np.abs(golden["pvalue"] / golden["weight"] - golden["weighted_pvalue"])) < 1e-15
 
 
+def _lookup_from_golden(golden):
+    """A distLookup (chicdiff.R:2013-2033) consistent with the golden table: per stratum the range of log|avDist|
+    and the weight; first minimum 0, last maximum Inf as at :2030-2031."""
+    grp, x = golden["group"], golden["avgLogDist"]
+    G = int(grp.max())
+    lo = np.array([x[grp == g].min() for g in range(1, G + 1)])
+    hi = np.array([x[grp == g].max() for g in range(1, G + 1)])
+    w = np.array([golden["avWeights"][grp == g][0] for g in range(1, G + 1)])
+    for g in range(1, G + 1):
+        assert np.all(golden["avWeights"][grp == g] == w[g - 1])          # one weight per stratum
+    assert np.all(lo[1:] > hi[:-1])                                       # strata are distance bands
+    lo[0], hi[-1] = 0.0, np.inf
+    return lo, hi, w
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_ihw_weight_application_reproduces_golden_columns(golden, impl):
+    """chicdiff.R:2038-2049 from avDist + pvalue + the stratum lookup: group, weight, weighted p, weighted padj."""
+    lo, hi, w = _lookup_from_golden(golden)
+    if impl == "oracle":
+        r = O.ihw_apply(golden["avDist"], golden["pvalue"], lo, hi, w)
+    else:
+        from chicdiff_b200 import engine
+        r = engine.ihw_apply(golden["avDist"], golden["pvalue"], lo, hi, w)
+    assert np.array_equal(r["group"], golden["group"])
+    assert np.max(np.abs(np.log(np.abs(golden["avDist"])) - golden["avgLogDist"])) < 1e-12
+    assert np.max(np.abs(r["weight"] - golden["weight"]) / golden["weight"]) < 1e-15
+    assert np.max(np.abs(r["weighted_pvalue"] - golden["weighted_pvalue"]) / golden["weighted_pvalue"]) < 1e-15
+    assert np.max(np.abs(r["weighted_padj"] - golden["weighted_padj"]) / golden["weighted_padj"]) < 1e-14
+    assert (r["weighted_padj"] < 0.05).sum() == 2759
+
+
+def test_ihw_weight_application_na_rules():
+    """avDist == 0 or NA falls outside every stratum; mean(avWeights) without na.rm then poisons every weight."""
+    from chicdiff_b200 import engine
+    lo, hi, w = np.array([0.0, 10.0]), np.array([9.0, np.inf]), np.array([2.0, 0.5])
+    av = np.array([np.exp(5.0), -np.exp(12.0), np.exp(9.5), np.exp(9.6)])
+    p = np.array([0.01, 0.02, 0.5, np.nan])
+    for f in (O.ihw_apply, engine.ihw_apply):
+        r = f(av, p, lo, hi, w)
+        assert list(r["group"]) == [1, 2, 1, 2]                           # break at (10 + 9) / 2, right-closed
+        mean = (2.0 + 0.5 + 2.0 + 0.5) / 4
+        assert np.allclose(r["weight"], np.array([2.0, 0.5, 2.0, 0.5]) / mean, rtol=0, atol=1e-16)
+        assert np.isnan(r["weighted_padj"][3]) and not np.isnan(r["weighted_padj"][:3]).any()
+        r = f(np.array([0.0, np.exp(5.0)]), np.array([0.1, 0.2]), lo, hi, w)
+        assert r["group"][0] < 0 and np.isnan(r["weight"]).all() and np.isnan(r["weighted_padj"]).all()
+    for f in (O.ihw_apply, engine.ihw_apply):
+        with pytest.raises(Exception):                                    # cut(): 'breaks' are not unique
+            f(av, p, np.array([0.0, 0.0]), np.array([0.0, np.inf]), w)
+
+
 def test_annotation_lookups(golden):
     rid, rs, re_ = golden["rmap_id"], golden["rmap_start"], golden["rmap_end"]
     assert np.array_equal(np.diff(rid), np.ones(len(rid) - 1, dtype=rid.dtype))     # contiguous IDs
