@@ -116,3 +116,21 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
   }
   .Call("cdR_assemble", ctx, TRUE)      # -> list(K, FullMean, avDist); per-row columns via cdR_get_sample_rows
 }
+
+
+## IHWcorrection(), "apply to test data" block (chicdiff.R:2038-2049) -- marshalling only.  `out` is the DESeq2Wrap
+## table with avDist attached (:1965-1967), `distLookup` the table learned from the control set (:2013-2033).
+## Returns `out` with group, avWeights, weight, weighted_pvalue, weighted_padj, ordered by group like the
+## reference's merge() leaves it.
+ihwApply.cuda <- function(out, distLookup) {
+  r <- .Call("cdR_ihw_apply", as.numeric(out$avDist), as.numeric(out$pvalue), as.numeric(distLookup$minLogDist),
+             as.numeric(distLookup$maxLogDist), as.numeric(distLookup$avWeights))
+  out[, avgLogDist := log(abs(avDist))]
+  out$group <- r$group
+  out$avWeights <- distLookup$avWeights[r$group]
+  out$weight <- ifelse(is.nan(r$weight), NA_real_, r$weight)
+  out$weighted_pvalue <- ifelse(is.nan(r$weighted_pvalue) & !is.nan(out$pvalue), NA_real_, r$weighted_pvalue)
+  out$weighted_padj <- ifelse(is.nan(r$weighted_padj), NA_real_, r$weighted_padj)
+  setkey(out, group)
+  out
+}

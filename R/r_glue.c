@@ -148,3 +148,47 @@ SEXP cdR_results_adjust(SEXP S_, SEXP p_, SEXP baseMean, SEXP maxCooks, SEXP fla
     UNPROTECT(4);
     return out;
 }
+
+/* results() on the arrays the last cdR_region_test left on the device (no columns cross the bus except the two
+ * returned): list(pvalue, padj, filterThreshold) */
+SEXP cdR_results_resident(SEXP ptr, SEXP n_)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    R_xlen_t n = (R_xlen_t)asReal(n_);
+    SEXP pv = PROTECT(allocVector(REALSXP, n));
+    SEXP padj = PROTECT(allocVector(REALSXP, n));
+    SEXP thr = PROTECT(allocVector(REALSXP, 1));
+    double sc[4];
+    CD_CHECK(ctx, cd_results_resident(ctx, REAL(pv), REAL(padj), sc));
+    REAL(thr)[0] = sc[1];
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, pv); SET_VECTOR_ELT(out, 1, padj); SET_VECTOR_ELT(out, 2, thr);
+    SEXP nm = PROTECT(allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, mkChar("pvalue")); SET_STRING_ELT(nm, 1, mkChar("padj")); SET_STRING_ELT(nm, 2, mkChar("filterThreshold"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+
+/* IHWcorrection(), chicdiff.R:2038-2049: list(group, weight, weighted_pvalue, weighted_padj) in input row order.
+ * NaN outputs where R has NA_real_ are turned into NA by the adapter (is.nan -> NA), group INT32_MIN is NA_integer_. */
+SEXP cdR_ihw_apply(SEXP avDist, SEXP pvalue, SEXP minLogDist, SEXP maxLogDist, SEXP avWeights)
+{
+    R_xlen_t n = XLENGTH(avDist);
+    int G = (int)XLENGTH(avWeights);
+    SEXP group = PROTECT(allocVector(INTSXP, n));
+    SEXP weight = PROTECT(allocVector(REALSXP, n));
+    SEXP wp = PROTECT(allocVector(REALSXP, n));
+    SEXP wpadj = PROTECT(allocVector(REALSXP, n));
+    if (cd_ihw_apply((int64_t)n, REAL(avDist), REAL(pvalue), G, REAL(minLogDist), REAL(maxLogDist), REAL(avWeights),
+                     INTEGER(group), REAL(weight), REAL(wp), REAL(wpadj)) != CD_OK)
+        error("chicdiff_b200: cd_ihw_apply: bad arguments or 'breaks' are not unique");
+    SEXP out = PROTECT(allocVector(VECSXP, 4));
+    SET_VECTOR_ELT(out, 0, group); SET_VECTOR_ELT(out, 1, weight); SET_VECTOR_ELT(out, 2, wp); SET_VECTOR_ELT(out, 3, wpadj);
+    SEXP nm = PROTECT(allocVector(STRSXP, 4));
+    SET_STRING_ELT(nm, 0, mkChar("group")); SET_STRING_ELT(nm, 1, mkChar("weight"));
+    SET_STRING_ELT(nm, 2, mkChar("weighted_pvalue")); SET_STRING_ELT(nm, 3, mkChar("weighted_padj"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(6);
+    return out;
+}
