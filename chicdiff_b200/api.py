@@ -378,3 +378,22 @@ def getFullRegionData(chicdiff_settings, RU, RUcontrol, rmap, chicago_tables, co
     message("\nReading data for control interactions")
     res[1] = getFullRegionData1(chicdiff_settings, RUcontrol, rmap, chicago_tables, count_tables, is_control=True)
     return res
+
+
+def IHWapply(out, distLookup):
+    """The "apply to test data" block of IHWcorrection() (chicdiff.R:2038-2049).
+
+    out: dict of columns of the DESeq2Wrap table plus "avDist" (:1965-1967); distLookup: dict(minLogDist, maxLogDist,
+    avWeights) as learned on the control set (:2013-2033).  Returns a copy of `out` with avgLogDist, group, avWeights,
+    weight, weighted_pvalue, weighted_padj, rows ordered by group (NA first) like the reference's merge() leaves them."""
+    r = engine.ihw_apply(out["avDist"], out["pvalue"], distLookup["minLogDist"], distLookup["maxLogDist"], distLookup["avWeights"])
+    res = {k: np.asarray(v) for k, v in out.items() if not str(k).startswith("attr_")}
+    with np.errstate(divide="ignore", invalid="ignore"):
+        res["avgLogDist"] = np.log(np.abs(np.asarray(out["avDist"], dtype=np.float64)))
+    na = r["group"] < 0
+    w = np.asarray(distLookup["avWeights"], dtype=np.float64)
+    res["group"] = r["group"]
+    res["avWeights"] = np.where(na, np.nan, w[np.clip(r["group"], 1, len(w)) - 1])
+    res["weight"], res["weighted_pvalue"], res["weighted_padj"] = r["weight"], r["weighted_pvalue"], r["weighted_padj"]
+    order = np.argsort(np.where(na, 0, r["group"]), kind="stable")
+    return {k: v[order] for k, v in res.items()}

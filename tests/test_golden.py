@@ -77,6 +77,18 @@ def test_ihw_weight_application_reproduces_golden_columns(golden, impl):
     assert (r["weighted_padj"] < 0.05).sum() == 2759
 
 
+def test_IHWapply_mirror_restores_golden_row_order(golden):
+    """The reference's merge(by = "group") leaves the output sorted by stratum, regionID order inside (:2043-2046)."""
+    from chicdiff_b200 import api
+    lo, hi, w = _lookup_from_golden(golden)
+    by_region = np.argsort(golden["regionID"], kind="stable")             # the order DESeq2Wrap returns (:1752-1754)
+    table = {k: golden[k][by_region] for k in ("regionID", "pvalue", "avDist", "baitID")}
+    out = api.IHWapply(table, dict(minLogDist=lo, maxLogDist=hi, avWeights=w))
+    for k in ("regionID", "baitID", "group", "avWeights", "weight", "weighted_pvalue"):
+        assert np.allclose(out[k], golden[k], rtol=1e-15, atol=0), k
+    assert np.max(np.abs(out["weighted_padj"] - golden["weighted_padj"]) / golden["weighted_padj"]) < 1e-14
+
+
 def test_ihw_weight_application_na_rules():
     """avDist == 0 or NA falls outside every stratum; mean(avWeights) without na.rm then poisons every weight."""
     from chicdiff_b200 import engine
