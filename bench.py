@@ -359,6 +359,10 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "first %d of %d regions of the same synthetic set (%.1f s), full DESeq2Wrap numerics, "
                                               "OpenMP over regions on all host cores" % (m, n, dt)}
+            # the reference's DESeq2 loops are single-threaded and Chicdiff never enables BiocParallel: one core as well
+            rate1, dt1, m1 = cpu_reference_rate(d, max(2000, args.cpu_sample // 16), 1)
+            line["cpu_baseline_single_thread"] = {"value": rate1, "unit": UNIT, "cores": 1, "kind": "port",
+                                                  "sample": "first %d regions (%.1f s)" % (m1, dt1)}
         print(json.dumps(line), flush=True)
     e.close()
     if world > 1:
