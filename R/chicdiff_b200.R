@@ -54,7 +54,9 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
   }
   if (norm == "combined") message("Theta=", fit$theta)
   message("Processing model output")
-  adj <- .Call("cdR_results_adjust", S, p, fit$baseMean, fit$maxCooks, fit$flags, fit$pvalue)
+  ## results() on the arrays still in device memory (cdR_results_adjust is the host routine for gathered columns)
+  adj <- .Call("cdR_results_resident", ctx, n)
+  adj$pvalue[is.nan(adj$pvalue)] <- NA_real_; adj$padj[is.nan(adj$padj)] <- NA_real_
 
   ## annotation, unchanged from chicdiff.R:1700-1717
   rmap <- fread(rmapfile)

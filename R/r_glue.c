@@ -10,7 +10,9 @@
  *   :1540-1547  fragData[, list(N = sum(N), ..., FullMean = sum(FullMean)), by = ...]   -> cdR_aggregate
  *   :1551-1674  DESeqDataSetFromMatrix / estimateSizeFactors / theta grid /
  *               estimateDispersions / nbinomWaldTest                                    -> cdR_region_test
- *   :1721-1739  results()                                                              -> cdR_results_adjust
+ *   :1721-1739  results()                                                              -> cdR_results_resident,
+ *                                                                                         cdR_results_adjust
+ * and, inside IHWcorrection (:2038-2049), the weight application                         -> cdR_ihw_apply
  */
 #include <R.h>
 #include <Rinternals.h>
