@@ -84,8 +84,7 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
 ## Per replicate it builds the same small intermediate tables the reference builds (first s_j/tblb per bait :659,
 ## first s_i/tlb per other end :668, first Tmean per (tblb, tlb) :680, .chicEstimateDistFun :696) as dense
 ## per-fragment vectors, hands them and the .chinput counts to cd_set_sample_tables, and lets cd_assemble do the
-## joins, Bmean/Tmean reconstruction, count merge and region sums.  The .Call stubs cdR_set_rmap,
-## cdR_set_region_rows, cdR_set_sample_tables, cdR_assemble, cdR_get_sample_rows follow the pattern of r_glue.c.
+## joins, Bmean/Tmean reconstruction, count merge and region sums (stubs in r_glue.c).
 getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, ctx) {
   rmap <- Chicago:::.readRmap(list(rmapfile = chicdiff.settings[["rmapfile"]]))
   colnames(rmap) <- c("chr", "start", "end", "ID"); setkey(rmap, ID)
@@ -116,7 +115,8 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
           c(dfp$cubicFit, dfp$obs.min, dfp$obs.max, dfp$head.coef, dfp$tail.coef),
           as.numeric(cnt_off), as.integer(cnt$otherEndID), as.integer(cnt$N))
   }
-  .Call("cdR_assemble", ctx, TRUE)      # -> list(K, FullMean, avDist); per-row columns via cdR_get_sample_rows
+  n <- length(unique(RU$regionID))
+  .Call("cdR_assemble", ctx, n, length(files), TRUE)      # -> list(K, FullMean, avDist); per-row columns via cdR_get_sample_rows
 }
 
 

@@ -194,3 +194,158 @@ SEXP cdR_ihw_apply(SEXP avDist, SEXP pvalue, SEXP minLogDist, SEXP maxLogDist, S
     UNPROTECT(6);
     return out;
 }
+
+/* ---- per-replicate assembly (getFullRegionData1, chicdiff.R:609-702, 820-910) and its neighbours ---- */
+
+static int64_t* offsets_from_real(SEXP v)
+{
+    R_xlen_t m = XLENGTH(v);
+    int64_t* off = (int64_t*)R_alloc((size_t)m, sizeof(int64_t));
+    for (R_xlen_t i = 0; i < m; i++) off[i] = (int64_t)REAL(v)[i];
+    return off;
+}
+
+/* chr: integer codes of the rmap's chromosome column; start/end integer; id0 = first fragment ID (IDs contiguous) */
+SEXP cdR_set_rmap(SEXP ptr, SEXP chr, SEXP start, SEXP end, SEXP id0)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    CD_CHECK(ctx, cd_set_rmap(ctx, (int64_t)XLENGTH(chr), asInteger(id0), INTEGER(chr), INTEGER(start), INTEGER(end)));
+    return R_NilValue;
+}
+
+/* getRegionUniverse(): peaks (baitID, otherEndID) -> list(row_off (numeric, m + 1), baitID, otherEndID) */
+SEXP cdR_region_universe(SEXP ptr, SEXP peak_bait, SEXP peak_oe, SEXP ru_expand)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    R_xlen_t m = XLENGTH(peak_bait);
+    int64_t R = 0;
+    CD_CHECK(ctx, cd_region_universe(ctx, (int64_t)m, INTEGER(peak_bait), INTEGER(peak_oe), asInteger(ru_expand), &R));
+    int64_t* off = (int64_t*)R_alloc((size_t)m + 1, sizeof(int64_t));
+    SEXP rb = PROTECT(allocVector(INTSXP, (R_xlen_t)R));
+    SEXP ro = PROTECT(allocVector(INTSXP, (R_xlen_t)R));
+    CD_CHECK(ctx, cd_get_region_universe(ctx, off, INTEGER(rb), INTEGER(ro)));
+    SEXP roff = PROTECT(allocVector(REALSXP, m + 1));
+    for (R_xlen_t i = 0; i <= m; i++) REAL(roff)[i] = (double)off[i];
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, roff); SET_VECTOR_ELT(out, 1, rb); SET_VECTOR_ELT(out, 2, ro);
+    SEXP nm = PROTECT(allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, mkChar("row_off")); SET_STRING_ELT(nm, 1, mkChar("baitID")); SET_STRING_ELT(nm, 2, mkChar("otherEndID"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+
+SEXP cdR_set_region_rows(SEXP ptr, SEXP row_bait, SEXP row_oe)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    CD_CHECK(ctx, cd_set_region_rows(ctx, (int64_t)XLENGTH(row_bait), INTEGER(row_bait), INTEGER(row_oe)));
+    return R_NilValue;
+}
+
+/* s: 1-based replicate; s_j / s_i numeric (NA -> NaN is what REAL() already holds), tblb / tlb 0-based bin codes with
+ * -1 = NA; tmean: numeric matrix passed TRANSPOSED (t(tmean)) so that R's column-major storage is n_tblb x n_tlb
+ * row-major; distfun: the 10 numbers of .chicEstimateDistFun; cnt_off numeric (F + 1), cnt_oe / cnt_N integer */
+SEXP cdR_set_sample_tables(SEXP ptr, SEXP s, SEXP s_j, SEXP tblb, SEXP s_i, SEXP tlb, SEXP tmean_t, SEXP distfun,
+                           SEXP cnt_off, SEXP cnt_oe, SEXP cnt_N)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    cd_sample_tables t;
+    memset(&t, 0, sizeof(t));
+    t.s_j = REAL(s_j); t.tblb = INTEGER(tblb); t.s_i = REAL(s_i); t.tlb = INTEGER(tlb);
+    t.n_tlb = nrows(tmean_t); t.n_tblb = ncols(tmean_t);
+    t.tmean = REAL(tmean_t);
+    if (XLENGTH(distfun) != 10) error("chicdiff_b200: distfun must hold 10 numbers");
+    memcpy(t.distfun, REAL(distfun), sizeof(t.distfun));
+    t.cnt_off = offsets_from_real(cnt_off); t.cnt_oe = INTEGER(cnt_oe); t.cnt_N = INTEGER(cnt_N);
+    CD_CHECK(ctx, cd_set_sample_tables(ctx, asInteger(s) - 1, &t));
+    return R_NilValue;
+}
+
+/* list(K = n x S integer matrix, FullMean = n x S numeric matrix, avDist = numeric n) */
+SEXP cdR_assemble(SEXP ptr, SEXP n_, SEXP S_, SEXP keep_rows)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    R_xlen_t n = (R_xlen_t)asReal(n_);
+    int S = asInteger(S_);
+    SEXP K = PROTECT(allocMatrix(INTSXP, (int)n, S));
+    SEXP FM = PROTECT(allocMatrix(REALSXP, (int)n, S));
+    SEXP av = PROTECT(allocVector(REALSXP, n));
+    CD_CHECK(ctx, cd_assemble(ctx, asLogical(keep_rows) ? 1 : 0, INTEGER(K), REAL(FM), REAL(av)));
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, K); SET_VECTOR_ELT(out, 1, FM); SET_VECTOR_ELT(out, 2, av);
+    SEXP nm = PROTECT(allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, mkChar("K")); SET_STRING_ELT(nm, 1, mkChar("FullMean")); SET_STRING_ELT(nm, 2, mkChar("avDist"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+
+/* per-row columns of replicate s (1-based) after cdR_assemble(keep_rows = TRUE): list(N, FullMean, Bmean) */
+SEXP cdR_get_sample_rows(SEXP ptr, SEXP s, SEXP R_)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    R_xlen_t R = (R_xlen_t)asReal(R_);
+    SEXP N = PROTECT(allocVector(INTSXP, R));
+    SEXP FM = PROTECT(allocVector(REALSXP, R));
+    SEXP BM = PROTECT(allocVector(REALSXP, R));
+    CD_CHECK(ctx, cd_get_sample_rows(ctx, asInteger(s) - 1, INTEGER(N), REAL(FM)));
+    CD_CHECK(ctx, cd_get_sample_bmean(ctx, asInteger(s) - 1, REAL(BM)));
+    SEXP out = PROTECT(allocVector(VECSXP, 3));
+    SET_VECTOR_ELT(out, 0, N); SET_VECTOR_ELT(out, 1, FM); SET_VECTOR_ELT(out, 2, BM);
+    SEXP nm = PROTECT(allocVector(STRSXP, 3));
+    SET_STRING_ELT(nm, 0, mkChar("N")); SET_STRING_ELT(nm, 1, mkChar("FullMean")); SET_STRING_ELT(nm, 2, mkChar("Bmean"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(5);
+    return out;
+}
+
+/* countput of one condition (chicdiff.R:755-770).  reps: list of data.frames / lists with columns baitID, otherEndID, N
+ * (integer), Bmean, score (numeric) in that order -- the CHiCAGO rows that have a distance (:715).
+ * Returns list(baitID, otherEndID, Nav, Bav, score, oeID_mid). */
+SEXP cdR_countput(SEXP ptr, SEXP reps)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    int nr = (int)XLENGTH(reps);
+    cd_chicago_rows* rows = (cd_chicago_rows*)R_alloc((size_t)nr, sizeof(cd_chicago_rows));
+    for (int k = 0; k < nr; k++) {
+        SEXP t = VECTOR_ELT(reps, k);
+        rows[k].rows = (int64_t)XLENGTH(VECTOR_ELT(t, 0));
+        rows[k].baitID = INTEGER(VECTOR_ELT(t, 0)); rows[k].otherEndID = INTEGER(VECTOR_ELT(t, 1));
+        rows[k].N = INTEGER(VECTOR_ELT(t, 2));
+        rows[k].Bmean = REAL(VECTOR_ELT(t, 3)); rows[k].score = REAL(VECTOR_ELT(t, 4));
+    }
+    int64_t G = 0;
+    CD_CHECK(ctx, cd_countput(ctx, nr, rows, &G));
+    SEXP b = PROTECT(allocVector(INTSXP, (R_xlen_t)G)), o = PROTECT(allocVector(INTSXP, (R_xlen_t)G));
+    SEXP nav = PROTECT(allocVector(REALSXP, (R_xlen_t)G)), bav = PROTECT(allocVector(REALSXP, (R_xlen_t)G));
+    SEXP sc = PROTECT(allocVector(REALSXP, (R_xlen_t)G)), mid = PROTECT(allocVector(REALSXP, (R_xlen_t)G));
+    CD_CHECK(ctx, cd_get_countput(ctx, INTEGER(b), INTEGER(o), REAL(nav), REAL(bav), REAL(sc), REAL(mid)));
+    static const char* names[6] = {"baitID", "otherEndID", "Nav", "Bav", "score", "oeID_mid"};
+    SEXP cols[6] = {b, o, nav, bav, sc, mid};
+    SEXP out = PROTECT(allocVector(VECSXP, 6));
+    SEXP nm = PROTECT(allocVector(STRSXP, 6));
+    for (int k = 0; k < 6; k++) { SET_VECTOR_ELT(out, k, cols[k]); SET_STRING_ELT(nm, k, mkChar(names[k])); }
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(8);
+    return out;
+}
+
+/* fread() of a .chinput file that is already in memory as a raw vector -> list of its five columns */
+SEXP cdR_parse_chinput(SEXP ptr, SEXP raw)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    int64_t rows = 0;
+    CD_CHECK(ctx, cd_parse_chinput(ctx, (const char*)RAW(raw), (int64_t)XLENGTH(raw), &rows));
+    SEXP b = PROTECT(allocVector(INTSXP, (R_xlen_t)rows)), o = PROTECT(allocVector(INTSXP, (R_xlen_t)rows));
+    SEXP N = PROTECT(allocVector(INTSXP, (R_xlen_t)rows)), len = PROTECT(allocVector(INTSXP, (R_xlen_t)rows));
+    SEXP dist = PROTECT(allocVector(REALSXP, (R_xlen_t)rows));
+    CD_CHECK(ctx, cd_get_chinput(ctx, INTEGER(b), INTEGER(o), INTEGER(N), INTEGER(len), REAL(dist)));
+    static const char* names[5] = {"baitID", "otherEndID", "N", "otherEndLen", "distSign"};
+    SEXP cols[5] = {b, o, N, len, dist};
+    SEXP out = PROTECT(allocVector(VECSXP, 5));
+    SEXP nm = PROTECT(allocVector(STRSXP, 5));
+    for (int k = 0; k < 5; k++) { SET_VECTOR_ELT(out, k, cols[k]); SET_STRING_ELT(nm, k, mkChar(names[k])); }
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(7);
+    return out;
+}

@@ -87,3 +87,75 @@ def test_results_adjust_matches_oracle_restatement(built):
     assert np.array_equal(np.isnan(adj["padj"]), np.isnan(f["padj"]))
     ok = ~np.isnan(f["padj"])
     assert np.max(np.abs(adj["padj"][ok] - f["padj"][ok])) < 1e-15
+
+
+def _split_top_level(args):
+    out, depth, cur, quote = [], 0, "", None
+    for ch in args:
+        if quote:
+            cur += ch
+            if ch == quote:
+                quote = None
+            continue
+        if ch in "\"'":
+            quote = ch
+        if ch in "([{":
+            depth += 1
+        if ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _calls(text, opener):
+    """argument strings of every `opener(...)` occurrence, parentheses balanced"""
+    res, i = [], 0
+    while True:
+        i = text.find(opener + "(", i)
+        if i < 0:
+            return res
+        j, depth = i + len(opener), 0
+        while True:
+            depth += text[j] == "("
+            depth -= text[j] == ")"
+            j += 1
+            if depth == 0:
+                break
+        res.append(text[i + len(opener) + 1:j - 1])
+        i = j
+
+
+def test_r_glue_compiles_against_the_abi_header():
+    """R/r_glue.c cannot be built without R; against declarations-only stand-ins for R's headers (tests/r_mock) the
+    compiler still checks every cd_* call in it against include/chicdiff_b200.h."""
+    import subprocess
+    cmd = ["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-std=c11", "-I" + os.path.join(ROOT, "tests", "r_mock"),
+           os.path.join(ROOT, "R", "r_glue.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_r_adapter_calls_match_the_glue():
+    """every .Call("cdR_x", ...) of R/chicdiff_b200.R has a stub in R/r_glue.c with the same number of arguments, and
+    every stub only reaches entry points the header declares"""
+    glue = open(os.path.join(ROOT, "R", "r_glue.c")).read()
+    glue_nc = re.sub(r"/\*.*?\*/", "", glue, flags=re.S)
+    stubs = {m.group(1): len(_split_top_level(m.group(2))) for m in re.finditer(r"^SEXP (cdR_\w+)\(([^)]*)\)", glue_nc, flags=re.M)}
+    assert len(stubs) >= 16
+    rsrc = open(os.path.join(ROOT, "R", "chicdiff_b200.R")).read()
+    rsrc = "\n".join(l.split("##")[0] for l in rsrc.splitlines())
+    seen = set()
+    for args in _calls(rsrc, ".Call"):
+        parts = _split_top_level(args)
+        name = parts[0].strip("\"'")
+        assert name in stubs, name
+        assert len(parts) - 1 == stubs[name], (name, len(parts) - 1, stubs[name])
+        seen.add(name)
+    assert {"cdR_create", "cdR_region_test", "cdR_results_resident", "cdR_ihw_apply", "cdR_assemble"} <= seen
+    used = set(re.findall(r"\b(cd_[a-z_0-9]+)\s*\(", glue_nc))
+    assert used <= set(declared_symbols()), used - set(declared_symbols())
