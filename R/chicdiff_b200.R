@@ -58,16 +58,16 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
   adj <- .Call("cdR_results_resident", ctx, n)
   adj$pvalue[is.nan(adj$pvalue)] <- NA_real_; adj$padj[is.nan(adj$padj)] <- NA_real_
 
-  ## annotation, unchanged from chicdiff.R:1700-1717
-  rmap <- fread(rmapfile)
-  colnames(rmap) <- c("OEchr", "OEstart", "OEend", "otherEndID")
-  RUsummary <- RU[, list(baitID = baitID[1], minOE = min(otherEndID), maxOE = max(otherEndID)), by = "regionID"]
-  annoData <- merge(RUsummary, rmap[, c("otherEndID", "OEchr", "OEstart"), with = FALSE], by.x = "minOE", by.y = "otherEndID")
-  annoData <- merge(annoData, rmap[, c("otherEndID", "OEend"), with = FALSE], by.x = "maxOE", by.y = "otherEndID")
-  colnames(rmap) <- c("baitchr", "baitstart", "baitend", "baitID")
-  annoData <- merge(annoData, rmap, by.x = "baitID", by.y = "baitID")
-  setkey(annoData, regionID)
-  stopifnot(identical(1:nrow(annoData), annoData$regionID))
+  ## annotation columns of the output table (what chicdiff.R:1700-1717 derives by three merges): one row per region,
+  ## coordinates looked up in the restriction map by fragment ID.  Column order as in the reference's cbind (:1752).
+  frag <- fread(rmapfile, col.names = c("chr", "start", "end", "ID"))
+  ends <- RU[order(regionID), .(bait = baitID[1], lo = min(otherEndID), hi = max(otherEndID)), by = regionID]
+  stopifnot(identical(ends$regionID, seq_len(nrow(ends))))
+  at <- function(id) match(id, frag$ID)
+  annoData <- data.table(baitID = ends$bait, maxOE = ends$hi, minOE = ends$lo, regionID = ends$regionID,
+                         OEchr = frag$chr[at(ends$lo)], OEstart = frag$start[at(ends$lo)], OEend = frag$end[at(ends$hi)],
+                         baitchr = frag$chr[at(ends$bait)], baitstart = frag$start[at(ends$bait)],
+                         baitend = frag$end[at(ends$bait)], key = "regionID")
 
   label <- c(standard = "Standard DESeq2 normalisation", fullmean = "Chicago full mean-based normalisation",
              combined = "combined normalisation")[[norm]]
