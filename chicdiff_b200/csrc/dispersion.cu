@@ -204,7 +204,7 @@ constexpr int kFitDispTripCap = 24;     // first pass: a region still searching 
 // kFitDispTripCap trips (its scalar search state goes to the FitDispPark arrays); pass 2 resumes
 // all parked regions at once, one per lane, so the long searches overlap each other.
 #ifndef CD_FITDISP_MINBLOCKS
-#define CD_FITDISP_MINBLOCKS 4      /* <= 128 registers; measured: 6 blocks (80 registers) is not faster */
+#define CD_FITDISP_MINBLOCKS 4      /* <= 128 registers; measured: 5 blocks (<= 102) and 6 blocks (80) are not faster */
 #endif
 template <int P, bool RESUME>
 __global__ void __launch_bounds__(kFitDispThreads, CD_FITDISP_MINBLOCKS)
