@@ -426,7 +426,7 @@ static void design_init(design_t* d, int S, int p, const double* X)
 {
     d->S = S; d->p = p;
     memcpy(d->X, X, sizeof(double) * S * p);
-    double xtx[ORC_MAXP * ORC_MAXP], inv[ORC_MAXP * ORC_MAXP], ones[ORC_MAXS];
+    double xtx[ORC_MAXP * ORC_MAXP], inv[ORC_MAXP * ORC_MAXP], ones[ORC_MAXS] = {0};
     for (int j = 0; j < S; j++) ones[j] = 1;
     xtwx(X, ones, S, p, xtx);
     det_inv(xtx, p, inv);
@@ -638,7 +638,7 @@ static fitbeta_res fit_beta_row(const double* y, const double* nf, const design_
     r.dev = dev;
     for (int u = 0; u < p; u++) r.beta[u] = beta[u];
     for (int j = 0; j < S; j++) { w[j] = mu[j] / (1.0 + alpha * mu[j]); r.mu_clamped[j] = mu[j]; }
-    double B[ORC_MAXP * ORC_MAXP], Br[ORC_MAXP * ORC_MAXP], Bri[ORC_MAXP * ORC_MAXP];
+    double B[ORC_MAXP * ORC_MAXP], Br[ORC_MAXP * ORC_MAXP] = {0}, Bri[ORC_MAXP * ORC_MAXP];
     xtwx(d->X, w, S, p, B);
     for (int u = 0; u < p; u++) for (int v = 0; v < p; v++) Br[u * p + v] = B[u * p + v] + ((u == v) ? lambda[u] : 0.0);
     det_inv(Br, p, Bri);
