@@ -65,7 +65,11 @@ static __constant__ double kDigamC[7] = {-1.0 / 12.0, 1.0 / 120.0, -1.0 / 252.0,
 __device__ __forceinline__ double rcp_pos(double b)
 {
     double r;
+#ifdef __CUDA_ARCH__
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#else
+    r = (1.0 / b) * (1.0 + 0x1p-21);   // host build of the accuracy tests (tests/device_math): a seed of similar quality
+#endif
     double e = fma(-b, r, 1.0);
     r = fma(r, e, r);
     e = fma(-b, r, 1.0);

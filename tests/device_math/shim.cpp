@@ -1,0 +1,31 @@
+// extern "C" wrappers around the device math of chicdiff_b200/csrc/common.cuh, compiled for the host (see cuda_runtime.h here)
+#include "common.cuh"
+
+extern "C" {
+double dm_rcp_pos(double x) { return cd::rcp_pos(x); }
+double dm_log_pos(double x) { return cd::log_pos(x); }
+void dm_lgamma_digamma_pos(double x, double* lg, double* dg) { cd::lgamma_digamma_pos(x, *lg, *dg); }
+double dm_lgamma_c_pos(double x) { return cd::lgamma_c_pos(x); }
+double dm_trigamma_pos(double x) { return cd::trigamma_pos(x); }
+double dm_dnbinom_mu_log(double y, double size, double mu) { return cd::dnbinom_mu_log(y, size, mu); }
+double dm_chol_logdet2(double a00, double a10, double a11)
+{
+    cd::Sym<2> A;
+    A.v[0] = a00; A.v[1] = a10; A.v[2] = a11;
+    return cd::chol_logdet<2>(A);
+}
+void dm_vec(int what, long n, const double* x, double* out, double* out2)
+{
+    for (long i = 0; i < n; i++) {
+        if (what == 0) out[i] = cd::log_pos(x[i]);
+        else if (what == 1) out[i] = cd::rcp_pos(x[i]);
+        else if (what == 2) cd::lgamma_digamma_pos(x[i], out[i], out2[i]);
+        else if (what == 3) out[i] = cd::lgamma_c_pos(x[i]);
+        else if (what == 4) out[i] = cd::trigamma_pos(x[i]);
+    }
+}
+void dm_dnbinom_vec(long n, const double* y, const double* size, const double* mu, double* out)
+{
+    for (long i = 0; i < n; i++) out[i] = cd::dnbinom_mu_log(y[i], size[i], mu[i]);
+}
+}
