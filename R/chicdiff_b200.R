@@ -8,6 +8,32 @@
 ##
 ## Not produced under this backend: the `_DESeqObj<suffix>.Rds` DESeqDataSet of saveAuxData = TRUE.
 
+## Dispersion prior variance for designs with 1 <= S - p <= 3 (2-vs-2; the intercept-only theta-grid fits of a
+## 2-vs-2 run).  The library calls this once per dispersion fit with the residuals log(dispGeneEst) - log(dispFit) of
+## the regions whose gene-wise estimate is >= 1e-6.  It restates that branch of DESeq2's estimateDispersionsPriorVar
+## (SURVEY.md Appendix A.7) and runs on R's own RNG, hist() and loess(), which is what makes the value identical to
+## a DESeq2 run; the RNG state of the session is saved and restored as DESeq2 does.
+dispPriorVarSmallDf <- function(df, resid) {
+  saved <- if (exists(".Random.seed", envir = .GlobalEnv)) get(".Random.seed", envir = .GlobalEnv) else NULL
+  on.exit(if (is.null(saved)) suppressWarnings(rm(".Random.seed", envir = .GlobalEnv))
+          else assign(".Random.seed", saved, envir = .GlobalEnv))
+  set.seed(2)
+  brks <- -20:20 / 2
+  inside <- function(v) v[v > min(brks) & v < max(brks)]
+  obs <- hist(inside(resid), breaks = brks, plot = FALSE)$density
+  varGrid <- seq(from = 0, to = 8, length = 200)
+  kl <- sapply(varGrid, function(v) {
+    sim <- log(rchisq(1e4, df = df)) + rnorm(1e4, 0, sqrt(v)) - log(df)
+    dens <- hist(inside(sim), breaks = brks, plot = FALSE)$density
+    both <- c(obs, dens)
+    small <- min(both[both > 0])
+    sum(obs * (log(obs + small) - log(dens + small)))
+  })
+  fit <- loess(kl ~ varGrid, span = .2)
+  fine <- seq(from = 0, to = 8, length = 1000)
+  max(fine[which.min(predict(fit, fine))], 0.25)
+}
+
 DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", theta = NULL) {
   Grid <- chicdiff.settings[["theta_grid"]]
   rmapfile <- chicdiff.settings[["rmapfile"]]
@@ -47,7 +73,7 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
   pv <- chicdiff.settings[["dispPriorVar"]]; pvg <- chicdiff.settings[["dispPriorVarGrid"]]
   fit <- .Call("cdR_region_test", ctx, n, S, p, match(norm, c("standard", "fullmean", "combined")) - 1L,
                if (is.null(theta) || norm != "combined") na else as.numeric(theta), as.numeric(Grid),
-               if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg)
+               if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg, dispPriorVarSmallDf)
   if (length(fit$deviances)) {
     message("Total deviances by theta (Fullmean --> Standard):")
     cat(sprintf("%f", fit$deviances), "\n", file = stderr())

@@ -93,8 +93,26 @@ SEXP cdR_aggregate(SEXP ptr, SEXP n_, SEXP S_)
     return out;
 }
 
-/* norm: 0/1/2; theta, priorVar, priorVarGrid: NA_real_ = let the library decide; grid: numeric vector */
-SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta, SEXP grid, SEXP priorVar, SEXP priorVarGrid)
+/* cd_options.prior_var_fn -> an R closure function(df, resid): called on the R thread that is inside .Call, so
+ * evaluating R code here is allowed; an R error inside it longjmps out through cd_region_test, which holds no locks
+ * and whose device buffers belong to the context (the next call reuses them). */
+static double prior_var_trampoline(void* user, int df, int64_t n_resid, const double* resid)
+{
+    SEXP fn = (SEXP)user;
+    SEXP r = PROTECT(allocVector(REALSXP, (R_xlen_t)n_resid));
+    memcpy(REAL(r), resid, sizeof(double) * (size_t)n_resid);
+    SEXP d = PROTECT(ScalarInteger(df));
+    SEXP call = PROTECT(lang3(fn, d, r));
+    SEXP val = PROTECT(eval(call, R_GlobalEnv));
+    double v = asReal(val);
+    UNPROTECT(4);
+    return v;
+}
+
+/* norm: 0/1/2; theta, priorVar, priorVarGrid: NA_real_ = let the library decide; grid: numeric vector;
+ * priorVarFn: NULL or function(df, resid) returning dispPriorVar for designs with S - p <= 3 */
+SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta, SEXP grid, SEXP priorVar, SEXP priorVarGrid,
+                     SEXP priorVarFn)
 {
     cd_ctx* ctx = get_ctx(ptr);
     int n = asInteger(n_), S = asInteger(S_);
@@ -105,6 +123,7 @@ SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta,
     opt.theta = asReal(theta);                 /* NA_real_ is a NaN */
     opt.theta_grid = REAL(grid); opt.n_theta_grid = LENGTH(grid);
     opt.disp_prior_var = asReal(priorVar); opt.disp_prior_var_grid = asReal(priorVarGrid);
+    if (!isNull(priorVarFn)) { opt.prior_var_fn = prior_var_trampoline; opt.prior_var_user = (void*)priorVarFn; }
     cd_results res;
     memset(&res, 0, sizeof(res));
     const char* names[] = {"baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "maxCooks", "dispGeneEst", "dispFit",

@@ -130,7 +130,8 @@ def DESeq2Wrap(chicdiff_settings, RU, FullRegionData, suffix="", theta=None, rma
     if norm == "combined" and theta is None:
         message("Optimising scaling factors...")
     res = eng.region_test(norm=norm, theta=None if norm != "combined" else theta, theta_grid=Grid,
-                          disp_prior_var=st.get("dispPriorVar"), disp_prior_var_grid=st.get("dispPriorVarGrid"), fetch="table")
+                          disp_prior_var=st.get("dispPriorVar"), disp_prior_var_grid=st.get("dispPriorVarGrid"), fetch="table",
+                          prior_var_fn=st.get("dispPriorVarFn"))
     if res["deviances"] is not None:
         message("Total deviances by theta (Fullmean --> Standard):")
         message(" ".join("%f" % d for d in res["deviances"]))

@@ -1063,15 +1063,17 @@ struct PipeOut { double a0, a1, varLogDispEsts, dispPriorVar, sum_deviance; };
 
 // estimateDispersions + nbinomWaldTest for one normalisation (mode / theta) and one design
 int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, double prior_var_override, int grid_len,
-                 bool want_cooks, PipeOut& po)
+                 bool want_cooks, PipeOut& po, const cd_options* opt)
 {
     const int S = des.S, p = des.p;
     const int64_t n = ctx->n, off = ctx->g_off;
     cudaStream_t st = ctx->st;
     const int df = S - p;
-    if (std::isnan(prior_var_override) && df <= 3)
+    const bool ask_caller = std::isnan(prior_var_override) && df <= 3 && opt && opt->prior_var_fn;
+    if (std::isnan(prior_var_override) && df <= 3 && !ask_caller)
         return ctx->fail(CD_ENUMERIC, "S - p = %d <= 3: DESeq2 estimates the dispersion prior variance by a seeded Monte-Carlo "
-                                      "match here (set.seed(2), rchisq, loess), which is not implemented; pass disp_prior_var", df);
+                                      "match here (set.seed(2), rchisq, loess), which is not implemented; pass disp_prior_var "
+                                      "or a prior_var_fn callback", df);
     CD_CUDA(ctx, set_design_dispersion(des, st));
     CD_CUDA(ctx, set_design_wald(des, st));
     double* baseMean = ctx->g_baseMean.p + off;
@@ -1152,7 +1154,20 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
     const double varLogDispEsts = mad * mad;
     double dispPriorVar;
     if (!std::isnan(prior_var_override)) dispPriorVar = prior_var_override;
-    else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
+    else if (ask_caller) {
+        // the residuals are in g_resid (+inf where the region is excluded); the caller's rule sees the finite ones
+        if (ctx->comm.active() && ctx->comm.nranks > 1)
+            return ctx->fail(CD_EINVAL, "prior_var_fn needs the residuals of all regions: not available in a sharded run, pass "
+                                        "disp_prior_var");
+        std::vector<double> resid((size_t)n);
+        CD_CUDA(ctx, cudaMemcpyAsync(resid.data(), ctx->g_resid.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CD_CUDA(ctx, cudaStreamSynchronize(st));
+        size_t m = 0;
+        for (size_t i = 0; i < (size_t)n; i++) if (std::isfinite(resid[i])) resid[m++] = resid[i];
+        dispPriorVar = opt->prior_var_fn(opt->prior_var_user, df, (int64_t)m, resid.data());
+        if (!(dispPriorVar > 0.0) || !std::isfinite(dispPriorVar))
+            return ctx->fail(CD_ENUMERIC, "prior_var_fn returned %g for df = %d (%lld residuals)", dispPriorVar, df, (long long)m);
+    } else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
 
     // MAP
     ctx->tm_begin(2);
@@ -1281,7 +1296,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
         if (ng < 1 || ng > 16) return ctx->fail(CD_EINVAL, "theta grid must have 1..16 values");
         int best = -1, nbest = 0;
         for (int k = 0; k < ng; k++) {
-            rc = run_pipeline(ctx, ctx->des1, CD_NORM_COMBINED, grid[k], opt->disp_prior_var_grid, grid_len, false, po);
+            rc = run_pipeline(ctx, ctx->des1, CD_NORM_COMBINED, grid[k], opt->disp_prior_var_grid, grid_len, false, po, opt);
             if (rc != CD_OK) return rc;
             out->deviances[k] = po.sum_deviance;
             if (std::isnan(po.sum_deviance))
@@ -1296,7 +1311,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
         if (nbest != 1) return ctx->fail(CD_ENUMERIC, "theta grid: the minimum total deviance is tied");
         theta = grid[best];
     }
-    rc = run_pipeline(ctx, ctx->des, norm, std::isnan(theta) ? 0.0 : theta, opt->disp_prior_var, grid_len, true, po);
+    rc = run_pipeline(ctx, ctx->des, norm, std::isnan(theta) ? 0.0 : theta, opt->disp_prior_var, grid_len, true, po, opt);
     if (rc != CD_OK) return rc;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
 

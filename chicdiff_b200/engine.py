@@ -29,10 +29,13 @@ class ChicdiffError(RuntimeError):
         self.code = code
 
 
+PRIOR_VAR_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int64, C.POINTER(C.c_double))
+
+
 class CdOptions(C.Structure):
     _fields_ = [("norm", C.c_int), ("theta", C.c_double), ("theta_grid", C.POINTER(C.c_double)),
                 ("n_theta_grid", C.c_int), ("disp_prior_var", C.c_double), ("disp_prior_var_grid", C.c_double),
-                ("disp_grid_len", C.c_int)]
+                ("disp_grid_len", C.c_int), ("prior_var_fn", PRIOR_VAR_FN), ("prior_var_user", C.c_void_p)]
 
 
 class CdSampleTables(C.Structure):
@@ -358,8 +361,10 @@ class Engine:
         return None
 
     def region_test(self, norm="combined", theta=None, theta_grid=None, disp_prior_var=None,
-                    disp_prior_var_grid=None, disp_grid_len=20, fetch="all"):
-        """cd_region_test.  fetch: "all" | "table" (columns of the output table only) | "none"."""
+                    disp_prior_var_grid=None, disp_grid_len=20, fetch="all", prior_var_fn=None):
+        """cd_region_test.  fetch: "all" | "table" (columns of the output table only) | "none".
+        prior_var_fn(df, residuals) -> dispPriorVar is asked once per dispersion fit whose design has S - p <= 3 and no
+        disp_prior_var* given (the place where an R front end evaluates DESeq2's Monte-Carlo rule)."""
         n, S, p = self.n, self.S, self.p
         opt = CdOptions()
         opt.norm = CD_NORM[norm]
@@ -372,6 +377,16 @@ class Engine:
         opt.disp_prior_var = float("nan") if disp_prior_var is None else float(disp_prior_var)
         opt.disp_prior_var_grid = float("nan") if disp_prior_var_grid is None else float(disp_prior_var_grid)
         opt.disp_grid_len = disp_grid_len
+        cb_error = []
+        if prior_var_fn is not None:
+            def _cb(_user, df, m, ptr):
+                try:
+                    return float(prior_var_fn(int(df), np.ctypeslib.as_array(ptr, shape=(int(m),)).copy()))
+                except Exception as ex:              # never unwind through the C frames
+                    cb_error.append(ex)
+                    return float("nan")
+            cb = PRIOR_VAR_FN(_cb)                   # kept alive by this frame for the duration of the call
+            opt.prior_var_fn = cb
         res = CdResults()
         arrays = {}
         shapes = dict(beta=(p, n), betaSE=(p, n), normFactors=(S, n), mu=(S, n))
@@ -385,7 +400,10 @@ class Engine:
         for k in want:
             arrays[k] = np.empty(shapes.get(k, (n,)), dtypes.get(k, np.float64))
             setattr(res, k, arrays[k].ctypes.data)
-        self._check(self._L.cd_region_test(self._h, C.byref(opt), C.byref(res)))
+        rc = self._L.cd_region_test(self._h, C.byref(opt), C.byref(res))
+        if cb_error:
+            raise cb_error[0]
+        self._check(rc)
         out = dict(arrays)
         out["sizeFactors"] = np.array(res.sizeFactors[:S])
         out["theta"] = None if res.theta != res.theta else res.theta

@@ -181,6 +181,14 @@ typedef struct {
     double disp_prior_var;       /* NaN = estimate (closed form needs S - p > 3) */
     double disp_prior_var_grid;  /* same for the intercept-only theta-grid fits (needs S - 1 > 3) */
     int disp_grid_len;           /* fitDispGrid length; 0 = 20 */
+    /* Designs with S - p <= 3 (2-vs-2; the intercept-only theta-grid fits when S <= 4): DESeq2's
+     * estimateDispersionsPriorVar matches a seeded Monte-Carlo histogram with R's own RNG and loess.  When the
+     * corresponding disp_prior_var* is NaN and prior_var_fn is set, the library hands the dispersion residuals
+     * log(dispGeneEst) - log(dispFit) of the regions with dispGeneEst >= 1e-6 (host array, n_resid values, valid
+     * during the call) to the caller on the calling thread, once per dispersion fit, and uses the returned value as
+     * dispPriorVar; an R front end evaluates DESeq2's own rule there.  NaN return = failure. */
+    double (*prior_var_fn)(void* user, int df, int64_t n_resid, const double* resid);
+    void* prior_var_user;
 } cd_options;
 
 typedef struct {

@@ -44,6 +44,11 @@ SEXP Rf_mkChar(const char*);
 SEXP Rf_setAttrib(SEXP, SEXP, SEXP);
 SEXP Rf_duplicate(SEXP);
 SEXP Rf_ScalarReal(double);
+SEXP Rf_ScalarInteger(int);
+SEXP Rf_lang3(SEXP, SEXP, SEXP);
+SEXP Rf_eval(SEXP, SEXP);
+Rboolean Rf_isNull(SEXP);
+extern SEXP R_GlobalEnv;
 #define error Rf_error
 #define asInteger Rf_asInteger
 #define asReal Rf_asReal
@@ -58,4 +63,8 @@ SEXP Rf_ScalarReal(double);
 #define setAttrib Rf_setAttrib
 #define duplicate Rf_duplicate
 #define ScalarReal Rf_ScalarReal
+#define ScalarInteger Rf_ScalarInteger
+#define lang3 Rf_lang3
+#define eval Rf_eval
+#define isNull Rf_isNull
 #endif

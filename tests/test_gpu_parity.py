@@ -649,3 +649,61 @@ def test_results_on_resident_arrays_match_host_routine():
     _resident_vs_host(e2, r, d.S, d.X.shape[1])
     e2.close()
     e.close()
+
+
+def _rule(df, resid):
+    """a deterministic stand-in for DESeq2's Monte-Carlo rule: any function of (df, residuals) will do here"""
+    mad = 1.4826 * np.median(np.abs(resid - np.median(resid)))
+    return max(mad ** 2 - 0.05 * df, 0.25)
+
+
+def _oracle_residuals(ro):
+    ge, fit = ro["dispGeneEst"], ro["dispFit"]
+    with np.errstate(invalid="ignore"):
+        keep = ge >= 1e-6
+    return np.log(ge[keep]) - np.log(fit[keep])
+
+
+def test_prior_variance_callback_for_small_df():
+    """2-vs-2 (S - p = 2; theta-grid fits S - 1 = 3): DESeq2 estimates dispPriorVar with R's RNG.  The library asks the
+    caller instead (cd_options.prior_var_fn) and must hand over exactly the residuals DESeq2's rule sees."""
+    d = synth.generate("c1")
+    p = d.X.shape[1]
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    K, FM = e.aggregate()
+    # one fit at a fixed theta: the oracle runs twice (any prior first: gene-wise estimates and trend do not depend on it)
+    seen = []
+    def rule(df, resid):
+        seen.append((df, resid))
+        return _rule(df, resid)
+    r = e.region_test(theta=0.5, prior_var_fn=rule)
+    assert [c[0] for c in seen] == [d.S - p]
+    Ko, FMo = O.aggregate(d.row_off, d.N_rows, d.FM_rows)
+    ro = O.region_test(Ko, FMo, d.X, theta=0.5, prior_var=1.0)
+    res_o = _oracle_residuals(ro)
+    assert abs(len(seen[0][1]) - len(res_o)) <= 2                     # rows at the 1e-6 threshold may fall either side
+    v = _rule(d.S - p, res_o)
+    assert abs(r["dispPriorVar"] - v) <= 1e-4 * v
+    assert abs(r["dispPriorVar"] - _rule(d.S - p, seen[0][1])) == 0.0
+    ro = O.region_test(Ko, FMo, d.X, theta=0.5, prior_var=r["dispPriorVar"])
+    assert frac_ok(r["dispersion"], ro["dispersion"])[0] >= 0.999
+    # theta grid: five intercept-only fits (df = S - 1) and the final fit (df = S - p), in that order
+    seen.clear()
+    r = e.region_test(prior_var_fn=rule)
+    assert [c[0] for c in seen] == [d.S - 1] * 5 + [d.S - p]
+    assert r["dispPriorVar"] == _rule(d.S - p, seen[-1][1])
+    # a rule that fails: NaN is refused, an exception travels to the caller
+    with pytest.raises(engine.ChicdiffError):
+        e.region_test(theta=0.5, prior_var_fn=lambda df, resid: float("nan"))
+    def boom(df, resid):
+        raise KeyError("rule failed")
+    with pytest.raises(KeyError):
+        e.region_test(theta=0.5, prior_var_fn=boom)
+    # without a rule the old message stays
+    with pytest.raises(engine.ChicdiffError) as ei:
+        e.region_test(theta=0.5)
+    assert "prior" in str(ei.value)
+    e.close()
