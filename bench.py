@@ -342,7 +342,12 @@ def main():
                              # committed ncu --set full capture (profiles/r01_final_kernels_aggregate_assemble_irls.txt)
                              "traffic": 1841515000.0 if (n == 2135814 and S == 6) else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": agg_bytes},
-                "fp64": {"peak_tflops_measured_dfma": fp64_peak, "fit_disp_ms": tm[2], "wald_ms": tm[3]},
+                "fp64": {"peak_tflops_measured_dfma": fp64_peak, "fit_disp_ms": tm[2], "wald_ms": tm[3],
+                         # from the committed ncu capture of the line-search kernel on this workload (not re-measured here):
+                         # (2 DFMA + DMUL + DADD) per cycle x SM clock, and the FP64 pipe's busy cycles
+                         "line_search_tflops_ncu": 15.0, "line_search_frac_of_dfma_peak_ncu": 0.41,
+                         "line_search_fp64_pipe_busy_ncu": 0.59,
+                         "ncu_source": "profiles/r01_final_kernels_fit_disp_trend.txt"},
                 "e2e": {"value": n_tot / (e2e_dev_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_dev_ms,
                         "h2d_bytes_per_step": int(N_host.numel() * 4 + FM_host.numel() * 8),
                         "d2h_bytes_per_step": int(n * (6 * 8 + 1))},
