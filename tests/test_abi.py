@@ -159,3 +159,26 @@ def test_r_adapter_calls_match_the_glue():
     assert {"cdR_create", "cdR_region_test", "cdR_results_resident", "cdR_ihw_apply", "cdR_assemble"} <= seen
     used = set(re.findall(r"\b(cd_[a-z_0-9]+)\s*\(", glue_nc))
     assert used <= set(declared_symbols()), used - set(declared_symbols())
+
+
+def test_c_example_builds_against_the_abi_and_fails_loudly_without_a_device(built, tmp_path):
+    """examples/c_abi_example.c drives the boundary from plain C.  It must compile and link against the header and the
+    library; on a box without a GPU it has to stop with the library's message (status 3), never compute on the CPU."""
+    import subprocess
+    exe = str(tmp_path / "c_abi_example")
+    libdir = os.path.join(ROOT, "chicdiff_b200")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_example.c"), "-L" + libdir, "-lchicdiff_b200", "-Wl,-rpath," + libdir, "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    from chicdiff_b200 import engine
+    try:
+        engine.Engine(0).close()
+        have_gpu = True
+    except engine.ChicdiffError:
+        have_gpu = False
+    if have_gpu:
+        assert r.returncode == 0, (r.stdout, r.stderr)            # at least 25 of the 40 planted regions are called
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
