@@ -1,9 +1,10 @@
 // comm.h -- the collectives of the sharded run (one process per GPU): NCCL over NVLink, loaded
 // with dlopen so that libchicdiff_b200.so has no link-time dependency on NCCL (a single-GPU R
-// session never needs it).  The only exchanges on the path are
-//   * all-gather of the aggregated counts (size-factor medians need every region),
-//   * all-gather of (baseMean, dispGeneEst, flags) for the global dispersion trend,
-//   * all-reduce of S+1 offset sums and of one deviance per theta.
+// session never needs it).  Nothing on the path is gathered; the exchanges that go through NCCL are
+//   * all-reduce of S+1 offset sums (moments estimate) and of one total deviance per dispersion fit,
+//   * when peer memory is unavailable: all-reduce of the trend fit's 8 sums per pass and of the median kernels'
+//     histogram counters (otherwise those happen inside the kernels over NVLink, see offsets.cu / select.cu),
+//   * the one-off exchange of shard sizes and cudaIpc mailbox handles at cd_comm_init.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

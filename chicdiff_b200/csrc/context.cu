@@ -1,7 +1,8 @@
 // context.cu -- the C ABI (include/chicdiff_b200.h) and the orchestration of the hot path:
 // DESeq2Wrap's numeric core (chicdiff.R:1540-1674) as a sequence of sm_100a kernels on one
-// stream, with the few global steps (size-factor medians, dispersion trend, MAD, theta grid)
-// driven from the host and, in a sharded run, joined across ranks by NCCL.
+// stream, with the few global steps (size-factor medians, dispersion trend, MAD, theta grid) joined
+// across the ranks of a sharded run by all-reduces only: inside the kernels through NVLink peer memory
+// where a kernel consumes the sum, by NCCL otherwise.
 #include "../../include/chicdiff_b200.h"
 #include "kernels.h"
 #include "comm.h"
