@@ -182,3 +182,37 @@ def test_c_example_builds_against_the_abi_and_fails_loudly_without_a_device(buil
         assert r.returncode == 0, (r.stdout, r.stderr)            # at least 25 of the 40 planted regions are called
     else:
         assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+def test_every_context_entry_point_refuses_a_null_context(built):
+    """Nothing may crash across the ABI: a NULL context gives CD_EINVAL (or 0 / NULL for the two getters)."""
+    from chicdiff_b200 import engine
+    engine.load_library()
+    L = C.CDLL(engine._LIB_PATH)                                 # a private handle: the prototypes set below stay local
+    src = open(os.path.join(ROOT, "include", "chicdiff_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(int|int64_t|void|const char\*)\s+(cd_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", src)
+    checked = 0
+    for ret, name, args in protos:
+        params = _split_top_level(args)
+        if not params or "cd_ctx*" not in params[0].replace(" *", "*") or "**" in params[0]:
+            continue                                             # cd_create, cd_version and the context-free host routines
+        f = getattr(L, name)
+        f.argtypes = None
+        if name == "cd_destroy":
+            f.restype = None
+            f(C.c_void_p(None))
+            checked += 1
+            continue
+        f.restype = C.c_void_p if ret == "const char*" else (C.c_int64 if ret == "int64_t" else C.c_int)
+        # every remaining argument as a zero of pointer width: never dereferenced because the context check comes first
+        rc = f(C.c_void_p(None), *[C.c_void_p(None) if "*" in a or "[" in a else
+                                   (C.c_double(0.0) if a.strip().startswith("double") else C.c_int64(0)) for a in params[1:]])
+        if name == "cd_launch_count":
+            assert rc == 0
+        elif name == "cd_last_error":
+            pass                                                 # NULL context = message of the last cd_create
+        else:
+            assert rc == -1, (name, rc)
+        checked += 1
+    assert checked >= 30
