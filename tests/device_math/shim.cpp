@@ -1,6 +1,9 @@
 // extern "C" wrappers around the device math of chicdiff_b200/csrc/common.cuh, compiled for the host (see cuda_runtime.h here)
 #include "common.cuh"
 
+namespace cd { CdDesign c_des; }      // host stand-in for the constant-memory design of dispersion.cu
+#include "posterior.cuh"
+
 extern "C" {
 double dm_rcp_pos(double x) { return cd::rcp_pos(x); }
 double dm_log_pos(double x) { return cd::log_pos(x); }
@@ -23,6 +26,17 @@ void dm_vec(int what, long n, const double* x, double* out, double* out2)
         else if (what == 3) out[i] = cd::lgamma_c_pos(x[i]);
         else if (what == 4) out[i] = cd::trigamma_pos(x[i]);
     }
+}
+// the fused Cox-Reid posterior and derivative of the line search, at log(alpha) = a, for one region
+void dm_eval_post(int S, int p, const double* X, const double* y, const double* mu, double a, double prior_mean,
+                  double prior_sigmasq, int use_prior, double* lp, double* dlp)
+{
+    cd::c_des.S = S; cd::c_des.p = p;
+    for (int k = 0; k < S * p; k++) cd::c_des.X[k] = X[k];
+    if (p == 1) cd::eval_post<1, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
+    else if (p == 2) cd::eval_post<2, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
+    else if (p == 3) cd::eval_post<3, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
+    else cd::eval_post<4, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
 }
 void dm_dnbinom_vec(long n, const double* y, const double* size, const double* mu, double* out)
 {

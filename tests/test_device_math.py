@@ -112,3 +112,51 @@ def test_packed_cholesky_logdet(dm):
         got = dm.dm_chol_logdet2(A[0, 0], A[1, 0], A[1, 1])
         assert abs(got - np.linalg.slogdet(A)[1]) < 1e-10 * max(1.0, abs(got))
     assert np.isnan(dm.dm_chol_logdet2(1.0, 2.0, 1.0))   # not positive definite
+
+
+def test_fused_posterior_and_derivative_follow_the_oracle(dm):
+    """eval_post (posterior.cuh), the function every trip of the dispersion line search evaluates on the GPU, against
+    the oracle's log_posterior / dlog_posterior (DESeq2.cpp) and a central difference, over dispersions from the 1e-8
+    floor to 10, for the intercept-only, two-level and batch designs, with and without the MAP prior."""
+    from oracle import oracle as O
+    Lo = O.lib()
+    dm.dm_eval_post.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    designs = {
+        1: np.ones((6, 1)),
+        2: np.column_stack([np.ones(6), [0, 0, 0, 1, 1, 1]]).astype(float),
+        3: np.column_stack([np.ones(8), [0, 1, 0, 1, 0, 1, 0, 1], [0, 0, 0, 0, 1, 1, 1, 1]]).astype(float),
+    }
+    worst_lp = worst_dlp = 0.0
+    for p, X in designs.items():
+        S = X.shape[0]
+        X = np.ascontiguousarray(X)
+        for _ in range(400):
+            mu = np.maximum(np.exp(rng.uniform(np.log(0.5), np.log(3000.0), S)), 0.5)
+            alpha_true = np.exp(rng.uniform(np.log(1e-3), np.log(2.0)))
+            y = rng.negative_binomial(1.0 / alpha_true, 1.0 / (1.0 + mu * alpha_true)).astype(float)
+            a = rng.uniform(np.log(1e-8), np.log(10.0))
+            use_prior = int(rng.random() < 0.5)
+            pm, ps = rng.normal(-2.0, 1.0), rng.uniform(0.25, 2.0)
+            lp, dlp = C.c_double(), C.c_double()
+            dm.dm_eval_post(S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, pm, ps, use_prior, C.byref(lp), C.byref(dlp))
+            lo = Lo.orc_log_posterior(a, S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, pm, ps, use_prior, 1)
+            dlo = Lo.orc_dlog_posterior(a, S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, pm, ps, use_prior, 1)
+            # The posterior is a sum of terms of size ~ lgamma(y + 1/alpha): that size sets the attainable accuracy
+            scale = 1.0 + np.sum(np.abs(special.gammaln(y + np.exp(-a)))) * 1e-3
+            worst_lp = max(worst_lp, abs(lp.value - lo) / max(abs(lo), scale))
+            worst_dlp = max(worst_dlp, abs(dlp.value - dlo) / max(abs(dlo), 1e-3 * scale, 1.0))
+    assert worst_lp < 1e-11, worst_lp
+    assert worst_dlp < 1e-8, worst_dlp
+    # the derivative really is the derivative of the posterior (moderate dispersion, where differences are meaningful)
+    X = designs[2]
+    mu = np.array([20.0, 35.0, 18.0, 60.0, 44.0, 52.0]); y = np.array([25.0, 30.0, 11.0, 71.0, 38.0, 60.0])
+    def f(a):
+        lp, dlp = C.c_double(), C.c_double()
+        dm.dm_eval_post(6, 2, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, 0.0, 1.0, 0, C.byref(lp), C.byref(dlp))
+        return lp.value, dlp.value
+    for a in (-4.0, -2.5, -1.0, 0.5):
+        h = 1e-5
+        num = (f(a + h)[0] - f(a - h)[0]) / (2 * h)
+        assert abs(num - f(a)[1]) < 1e-6 * max(1.0, abs(num))
