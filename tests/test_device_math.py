@@ -160,3 +160,36 @@ def test_fused_posterior_and_derivative_follow_the_oracle(dm):
         h = 1e-5
         num = (f(a + h)[0] - f(a - h)[0]) / (2 * h)
         assert abs(num - f(a)[1]) < 1e-6 * max(1.0, abs(num))
+
+
+def test_experimental_posterior_is_the_same_function(dm):
+    """experiments/posterior_v2.cuh (one logarithm per pair of samples for the gamma rationals, closed-form 1x1 / 2x2
+    Cox-Reid term) against eval_post on the host: same value and derivative up to the rounding of the lgamma-sized terms."""
+    for f in (dm.dm_eval_post, dm.dm_eval_post_v2):
+        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                      C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    designs = [np.ones((6, 1)), np.ones((5, 1)), np.column_stack([np.ones(6), [0, 0, 0, 1, 1, 1]]).astype(float),
+               np.column_stack([np.ones(8), [0, 1, 0, 1, 0, 1, 0, 1], [0, 0, 0, 0, 1, 1, 1, 1]]).astype(float)]
+    for X in designs:
+        S, p = X.shape
+        X = np.ascontiguousarray(X)
+        worst_lp = worst_dlp = 0.0
+        for _ in range(1500):
+            mu = np.exp(rng.uniform(np.log(0.5), np.log(1e5), S))
+            alpha_true = np.exp(rng.uniform(np.log(1e-3), np.log(2.0)))
+            y = rng.negative_binomial(1.0 / alpha_true, 1.0 / (1.0 + mu * alpha_true)).astype(float)
+            if rng.random() < 0.2:
+                y[rng.integers(0, S)] = 0.0
+            a = rng.uniform(np.log(1e-8), np.log(10.0))
+            use_prior = int(rng.random() < 0.5)
+            out = []
+            for f in (dm.dm_eval_post, dm.dm_eval_post_v2):
+                lp, dlp = C.c_double(), C.c_double()
+                f(S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, -2.0, 0.7, use_prior, C.byref(lp), C.byref(dlp))
+                out.append((lp.value, dlp.value))
+            scale = 1.0 + np.sum(np.abs(special.gammaln(y + np.exp(-a))))
+            worst_lp = max(worst_lp, abs(out[0][0] - out[1][0]) / scale)
+            worst_dlp = max(worst_dlp, abs(out[0][1] - out[1][1]) / max(abs(out[0][1]), 1.0))
+        assert worst_lp < 5e-15, (S, p, worst_lp)
+        assert worst_dlp < 1e-12, (S, p, worst_dlp)
