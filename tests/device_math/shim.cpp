@@ -4,6 +4,7 @@
 namespace cd { CdDesign c_des; }      // host stand-in for the constant-memory design of dispersion.cu
 #include "posterior.cuh"
 #include "../../experiments/posterior_v2.cuh"
+#include "../../experiments/log_v2.cuh"
 
 extern "C" {
 double dm_rcp_pos(double x) { return cd::rcp_pos(x); }
@@ -21,6 +22,7 @@ double dm_chol_logdet2(double a00, double a10, double a11)
 void dm_vec(int what, long n, const double* x, double* out, double* out2)
 {
     for (long i = 0; i < n; i++) {
+        if (what == 10) { out[i] = cd::log_pos_v2(x[i], cd::kLogTab); continue; }      // experiments/log_v2.cuh
         if (what == 0) out[i] = cd::log_pos(x[i]);
         else if (what == 1) out[i] = cd::rcp_pos(x[i]);
         else if (what == 2) cd::lgamma_digamma_pos(x[i], out[i], out2[i]);

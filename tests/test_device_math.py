@@ -193,3 +193,22 @@ def test_experimental_posterior_is_the_same_function(dm):
             worst_dlp = max(worst_dlp, abs(out[0][1] - out[1][1]) / max(abs(out[0][1]), 1.0))
         assert worst_lp < 5e-15, (S, p, worst_lp)
         assert worst_dlp < 1e-12, (S, p, worst_dlp)
+
+
+def test_experimental_table_log(dm):
+    """experiments/log_v2.cuh: within 1.5 ulp for every argument >= 1 (all the kernel's logarithms except the determinant's)
+    and within 2e-16 absolute on [0.5, 1), where the table entry and k ln2 cancel."""
+    rng = np.random.default_rng(8)
+    for x in (np.exp(rng.uniform(0, np.log(1e300), 200000)), rng.uniform(1, 4, 200000),
+              1 + np.exp(rng.uniform(np.log(1e-16), np.log(1e-1), 200000)),
+              np.array([1.0, 2.0, 4.0, 1 + 2.0 ** -7, 2 - 2.0 ** -7, 2 - 2.0 ** -6, np.nextafter(2, 1), np.nextafter(1, 2)])):
+        a, _ = _vec(dm, 10, x)
+        ref = np.log(x.astype(np.longdouble))
+        err = np.abs(a.astype(np.longdouble) - ref)
+        assert float(np.max(err / np.spacing(np.abs(ref.astype(np.float64)) + 1e-300))) <= 1.5
+    below = np.concatenate([rng.uniform(0.5, 1, 200000), np.exp(rng.uniform(np.log(1e-300), np.log(0.5), 100000))])
+    a, _ = _vec(dm, 10, below)
+    ref = np.log(below.astype(np.longdouble))
+    err = np.abs(a.astype(np.longdouble) - ref)
+    assert float(np.max(err / np.maximum(np.abs(ref), 1.0))) < 2e-16
+    assert _vec(dm, 10, np.array([1.0]))[0][0] == 0.0
