@@ -1,5 +1,10 @@
-import os, sys
-sys.path.insert(0, "/root/repo")
+"""Development aid (needs a GPU): lists the regions of a 400 k-region C3 subset whose gene-wise dispersion differs between
+the CUDA path and the oracle, with the oracle's posterior at both estimates -- the tool behind the "decision flip"
+analysis in DESIGN.md section 5 (all such rows sit on noise-level Armijo / stop decisions)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from chicdiff_b200 import engine, synth
 from oracle import oracle as O
