@@ -127,9 +127,11 @@ def run_reference(args, rank, world):
     O.build()
     threads = os.cpu_count() or 1
     d = make_data(args.workload, args.regions, 0)
-    sample = args.cpu_sample
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_reference_rate(d, min(sample, 20000), threads)
+    # bounded sample: the whole --steps K run should end within a few minutes whatever K is.  A small probe gives the
+    # rate of this box; the per-step sample is what fits ~150 s / K, between 20 000 regions and --cpu-sample
+    probe_rate, _, _ = cpu_reference_rate(d, min(args.cpu_sample, 20000), threads)
+    sample = int(max(20000, min(args.cpu_sample, probe_rate * 150.0 / max(args.steps, 1))))
+    sample = min(sample, d.n)
     times = []
     m = 0
     for _ in range(args.steps):
