@@ -275,11 +275,33 @@ def replicate_tables(x, rmap_ids, counts=None, binsize=20000):
                 cnt_oe=co.astype(np.int32), cnt_N=cn.astype(np.int32), tblb_levels=tb_levels, tlb_levels=tl_levels)
 
 
+def reconstruct_count_tables(reps):
+    """The reference's branch for countData = NULL (chicdiff.R:738-746, 774-786): the (baitID, otherEndID, N) columns of
+    the replicates' CHiCAGO tables are merged with Reduce(merge, ...), an INNER join, before the counts are read back, so
+    a pair keeps its counts only if every replicate has a row for it; everywhere else the later left join fills 0 (:802).
+    Returns one count table per replicate, restricted to the pairs common to all of them."""
+    keys = []
+    for t in reps:
+        b = np.asarray(t["baitID"], dtype=np.int64)
+        o = np.asarray(t["otherEndID"], dtype=np.int64)
+        keys.append((b << 32) | o)
+    common = keys[0]
+    for k in keys[1:]:
+        common = np.intersect1d(common, k)
+    out = []
+    for t, k in zip(reps, keys):
+        keep = np.isin(k, common)
+        out.append({"baitID": np.asarray(t["baitID"])[keep], "otherEndID": np.asarray(t["otherEndID"])[keep],
+                    "N": np.asarray(t["N"])[keep]})
+    return out
+
+
 def getFullRegionData1(chicdiff_settings, RU, rmap, chicago_tables, count_tables=None, is_control=False, engine_obj=None):
     """getFullRegionData1 (chicdiff.R:577-948) on the CUDA backend for ONE region universe.
 
     chicago_tables: {condition: [replicate table, ...]} in the order of settings$chicagoData; count_tables: same
-    shape with (baitID, otherEndID, N) chinput tables, or None to take N from the CHiCAGO tables.
+    shape with (baitID, otherEndID, N) chinput tables, or None to take N from the CHiCAGO tables the way the reference
+    does for countData = NULL (pairs present in every replicate only, see reconstruct_count_tables).
     Returns the long table (dict of columns baitID, otherEndID, regionID, distSign, sample, N, s_j, Bmean, Tmean,
     score, FullMean, condition; sample-major blocks, then stable-sorted by regionID like setkey(recast, regionID))
     and, for the test set, countput."""
@@ -303,6 +325,9 @@ def getFullRegionData1(chicdiff_settings, RU, rmap, chicago_tables, count_tables
             reps.append(t)
             cnts.append(None if count_tables is None else count_tables[cond][k])
     S = len(reps)
+    if count_tables is None:
+        message("Reconstructing countData")
+        cnts = reconstruct_count_tables(reps)
     eng = engine_obj or _get_engine(chicdiff_settings.get("gpu", 0) or 0)
     X, _ = model_matrix(conditions, chicdiff_settings.get("batch"))
     eng.set_design(X)

@@ -68,3 +68,32 @@ def test_read_rmap_sorts_by_fragment_id_and_strips_quotes(tmp_path):
     r = api.read_rmap(str(f))
     assert list(r["ID"]) == [2, 3, 4] and list(r["chr"]) == ["chr1", "chr1", "chrX"]
     assert list(r["start"]) == [1, 100, 201] and list(r["end"]) == [99, 200, 300]
+
+
+def test_counts_reconstructed_from_chicago_tables_keep_only_pairs_seen_in_every_replicate():
+    """countData = NULL in the reference: Reduce(merge, ...) over the replicates' (baitID, otherEndID, N) columns is an
+    inner join (chicdiff.R:778), so a pair missing from one replicate loses its counts in all of them."""
+    reps = [
+        {"baitID": np.array([1, 1, 2, 3]), "otherEndID": np.array([10, 11, 20, 30]), "N": np.array([5, 6, 7, 8])},
+        {"baitID": np.array([1, 2, 2, 3]), "otherEndID": np.array([10, 20, 21, 30]), "N": np.array([1, 2, 3, 4])},
+        {"baitID": np.array([3, 1, 2]), "otherEndID": np.array([30, 10, 20]), "N": np.array([9, 9, 9])},
+    ]
+    out = api.reconstruct_count_tables(reps)
+    for t in out:
+        pairs = sorted(zip(t["baitID"].tolist(), t["otherEndID"].tolist()))
+        assert pairs == [(1, 10), (2, 20), (3, 30)]
+    assert out[0]["N"].tolist() == [5, 7, 8] and out[1]["N"].tolist() == [1, 2, 4] and sorted(out[2]["N"].tolist()) == [9, 9, 9]
+    # a random check against a dictionary-based inner join
+    rng = np.random.default_rng(1)
+    reps = []
+    for _ in range(4):
+        m = 500
+        b = rng.integers(1, 20, m); o = rng.integers(1, 60, m)
+        key = np.unique(b * 1000 + o)
+        reps.append({"baitID": key // 1000, "otherEndID": key % 1000, "N": rng.integers(1, 50, len(key))})
+    out = api.reconstruct_count_tables(reps)
+    common = set.intersection(*[set(zip(t["baitID"].tolist(), t["otherEndID"].tolist())) for t in reps])
+    for t_in, t_out in zip(reps, out):
+        want = {(b, o): n for b, o, n in zip(t_in["baitID"].tolist(), t_in["otherEndID"].tolist(), t_in["N"].tolist()) if (b, o) in common}
+        got = {(b, o): n for b, o, n in zip(t_out["baitID"].tolist(), t_out["otherEndID"].tolist(), t_out["N"].tolist())}
+        assert got == want
