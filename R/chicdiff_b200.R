@@ -121,6 +121,15 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
   .Call("cdR_set_regions", ctx, c(0, cumsum(as.numeric(RU[, .N, by = regionID]$N))))
   .Call("cdR_set_region_rows", ctx, as.integer(RU$baitID), as.integer(RU$otherEndID))
   files <- unlist(chicdiff.settings[["chicagoData"]]); counts <- unlist(chicdiff.settings[["countData"]])
+  ## countData = NULL: the reference reads the counts back from Reduce(merge, ...) over the replicates' CHiCAGO tables,
+  ## an inner join (chicdiff.R:778): only pairs with a row in every replicate keep their counts
+  common <- NULL
+  if (is.null(counts)) {
+    pairs <- lapply(files, function(f) { x <- readRDSorRDA(f); x <- if ("chicagoData" %in% class(x)) as.data.table(x@x) else setDT(x)
+                                         unique(x[, .(baitID, otherEndID)]) })
+    common <- Reduce(function(a, b) merge(a, b, by = c("baitID", "otherEndID")), pairs)
+    setkey(common, baitID, otherEndID)
+  }
   for (i in seq_along(files)) {
     x <- readRDSorRDA(files[i]); x <- if ("chicagoData" %in% class(x)) as.data.table(x@x) else setDT(x)
     setkey(x, baitID, otherEndID)
@@ -134,7 +143,7 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
     s_i <- rep(NA_real_, nF); s_i[oe$otherEndID - id0 + 1L] <- oe$s_i
     tlb <- rep(-1L, nF); tlb[oe$otherEndID - id0 + 1L] <- ifelse(is.na(oe$tlb), -1L, match(oe$tlb, tl.lv) - 1L)
     dfp <- .chicEstimateDistFun(x)
-    cnt <- if (is.null(counts)) x[, .(baitID, otherEndID, N)] else fread(counts[i])[, .(baitID, otherEndID, N)]
+    cnt <- if (is.null(counts)) x[common, .(baitID, otherEndID, N), nomatch = 0L] else fread(counts[i])[, .(baitID, otherEndID, N)]
     setkey(cnt, baitID, otherEndID)
     cnt_off <- c(0, cumsum(tabulate(cnt$baitID - id0 + 1L, nbins = nF)))
     .Call("cdR_set_sample_tables", ctx, i, s_j, tblb, s_i, tlb, t(tmean),
