@@ -381,6 +381,8 @@ static void setup_p2p(cd_ctx* ctx)
 {
     ctx->p2p_ok = false;
     ctx->sel_p2p_ok = false;
+    for (void* p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);          // a second cd_comm_init starts from scratch
+    ctx->p2p_opened.clear();
     const int nr = ctx->comm.nranks;
     if (nr < 2 || nr > 64) return;
     const char* off = getenv("CHICDIFF_B200_NO_P2P");
