@@ -5,6 +5,7 @@ namespace cd { CdDesign c_des; }      // host stand-in for the constant-memory d
 #include "posterior.cuh"
 #include "../../experiments/posterior_v2.cuh"
 #include "../../experiments/log_v2.cuh"
+#include "../../experiments/posterior_v3.cuh"
 
 extern "C" {
 double dm_rcp_pos(double x) { return cd::rcp_pos(x); }
@@ -51,6 +52,15 @@ void dm_eval_post_v2(int S, int p, const double* X, const double* y, const doubl
     else if (p == 2) cd::eval_post_v2<2, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
     else if (p == 3) cd::eval_post_v2<3, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
     else cd::eval_post_v2<4, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, *lp, *dlp);
+}
+// experiments/posterior_v3.cuh (p <= 2): v2 with the table-assisted logarithm
+void dm_eval_post_v3(int S, int p, const double* X, const double* y, const double* mu, double a, double prior_mean,
+                     double prior_sigmasq, int use_prior, double* lp, double* dlp)
+{
+    cd::c_des.S = S; cd::c_des.p = p;
+    for (int k = 0; k < S * p; k++) cd::c_des.X[k] = X[k];
+    if (p == 1) cd::eval_post_v3<1, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, cd::kLogTab, *lp, *dlp);
+    else cd::eval_post_v3<2, true>(a, y, mu, 1, S, prior_mean, prior_sigmasq, use_prior != 0, cd::kLogTab, *lp, *dlp);
 }
 void dm_dnbinom_vec(long n, const double* y, const double* size, const double* mu, double* out)
 {
