@@ -118,13 +118,11 @@ cudaError_t launch_aggregate(int64_t n, int S, const int64_t* row_off, int64_t R
                              const double* FM_rows, int32_t* K, double* FM, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    static bool configured = false;
     const size_t smem = sizeof(AggStage) * kAggStages;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // (the attribute is per device: set it on every launch, like the other launchers, so that contexts on several
+    //  devices of one process all get it)
+    cudaError_t e = cudaFuncSetAttribute(aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int64_t blocks = (n + kAggRegions - 1) / kAggRegions;
     aggregate_kernel<<<(unsigned)blocks, kAggThreads, smem, st>>>(n, S, row_off, R, N_rows, FM_rows, K, FM);
     return cudaGetLastError();

@@ -20,27 +20,58 @@ ch_line_flags_kernel(int64_t nbytes, const char* __restrict__ text, uint8_t* __r
 
 __device__ __forceinline__ bool ch_is_sep(char c) { return c == '\t' || c == ' ' || c == ',' || c == '\r'; }
 
-// parses one optionally signed integer or "NA" starting at p; returns false at end of line
-__device__ __forceinline__ bool ch_field(const char* __restrict__ text, int64_t& p, int64_t end, long long& val, bool& na)
+// parses one number ("12", "-4500", "12.0", "1e5", "1.25E+3") or "NA" starting at p; returns false at end of line.
+// The value comes back as a double (exact for every integer a .chinput file holds); malformed text reads as NA.
+__device__ __forceinline__ bool ch_field(const char* __restrict__ text, int64_t& p, int64_t end, double& val, bool& na)
 {
     while (p < end && ch_is_sep(text[p])) p++;
     if (p >= end || text[p] == '\n') return false;
     na = false;
+    val = 0.0;
     if (text[p] == 'N' || text[p] == 'n') {                       // NA / NaN
         na = true;
         while (p < end && !ch_is_sep(text[p]) && text[p] != '\n') p++;
-        val = 0;
         return true;
     }
     bool neg = false;
     if (text[p] == '-') { neg = true; p++; } else if (text[p] == '+') p++;
-    long long v = 0;
-    bool any = false;
-    while (p < end && text[p] >= '0' && text[p] <= '9') { v = v * 10 + (text[p] - '0'); p++; any = true; }
-    // tolerate a fractional part / exponent written by other tools ("12.0"): skip to the separator
-    while (p < end && !ch_is_sep(text[p]) && text[p] != '\n') p++;
-    if (!any) { na = true; v = 0; }
+    double v = 0.0;
+    int digits = 0, frac = 0;
+    while (p < end && text[p] >= '0' && text[p] <= '9') { v = v * 10.0 + (double)(text[p] - '0'); p++; digits++; }
+    if (p < end && text[p] == '.') {
+        p++;
+        while (p < end && text[p] >= '0' && text[p] <= '9') { v = v * 10.0 + (double)(text[p] - '0'); p++; digits++; frac++; }
+    }
+    int ex = 0;
+    bool bad = digits == 0;
+    if (p < end && (text[p] == 'e' || text[p] == 'E')) {
+        p++;
+        bool eneg = false;
+        if (p < end && (text[p] == '-' || text[p] == '+')) { eneg = text[p] == '-'; p++; }
+        int ed = 0;
+        while (p < end && text[p] >= '0' && text[p] <= '9') { if (ex < 1000) ex = ex * 10 + (text[p] - '0'); p++; ed++; }
+        if (ed == 0) bad = true;
+        if (eneg) ex = -ex;
+    }
+    // anything left before the separator is not a number
+    if (p < end && !ch_is_sep(text[p]) && text[p] != '\n') {
+        bad = true;
+        while (p < end && !ch_is_sep(text[p]) && text[p] != '\n') p++;
+    }
+    if (bad) { na = true; return true; }
+    int e10 = ex - frac;
+    double scale = 1.0, base = 10.0;
+    for (int k = e10 < 0 ? -e10 : e10; k > 0; k >>= 1) { if (k & 1) scale *= base; base *= base; }
+    v = (e10 < 0) ? v / scale : v * scale;
     val = neg ? -v : v;
+    return true;
+}
+
+// an integer column: the value must be a whole number that fits int32
+__device__ __forceinline__ bool ch_as_int(double v, bool na, int32_t& out)
+{
+    if (na || !(v >= -2147483647.0 && v <= 2147483647.0) || v != floor(v)) return false;
+    out = (int32_t)v;
     return true;
 }
 
@@ -55,18 +86,21 @@ ch_parse_kernel(int64_t nlines, int64_t nbytes, const char* __restrict__ text, c
     const int64_t end = (l + 1 < nlines) ? line_start[l + 1] : nbytes;
     const char c0 = (p < end) ? text[p] : '\n';
     bool ok = (c0 >= '0' && c0 <= '9');
-    long long v[5] = {0, 0, 0, 0, 0};
+    double v[5] = {0, 0, 0, 0, 0};
     bool na[5] = {true, true, true, true, true};
     if (ok) {
         for (int f = 0; f < 5; f++) {
             if (!ch_field(text, p, end, v[f], na[f])) { if (f < 3) ok = false; break; }
         }
-        ok = ok && !na[0] && !na[1] && !na[2];
     }
+    // a row whose baitID / otherEndID / N is not a whole number is not a .chinput row: dropped, never truncated
+    int32_t ib = 0, io = 0, iN = 0, il = INT32_MIN;
+    ok = ok && ch_as_int(v[0], na[0], ib) && ch_as_int(v[1], na[1], io) && ch_as_int(v[2], na[2], iN);
+    if (!ch_as_int(v[3], na[3], il)) il = INT32_MIN;
     valid[l] = ok ? 1 : 0;
-    bait[l] = (int32_t)v[0]; oe[l] = (int32_t)v[1]; N[l] = (int32_t)v[2];
-    oelen[l] = na[3] ? INT32_MIN : (int32_t)v[3];
-    dist[l] = na[4] ? NAN : (double)v[4];
+    bait[l] = ib; oe[l] = io; N[l] = iN;
+    oelen[l] = il;
+    dist[l] = na[4] ? NAN : v[4];
 }
 
 template <typename T>

@@ -62,7 +62,11 @@ std::string Comm::unique_id(char id[128])
 std::string Comm::init(int nr, int rk, const char id[128])
 {
     if (nr < 1 || rk < 0 || rk >= nr) return "bad nranks/rank";
-    if (nr == 1) { nranks = 1; rank = 0; return ""; }
+    // a second init replaces the first communicator
+    if (comm_ && CommDestroy_) { CommDestroy_(comm_); comm_ = nullptr; }
+    if (scratch_) { cudaFree(scratch_); scratch_ = nullptr; }
+    nranks = 1; rank = 0;
+    if (nr == 1) return "";
     std::string e = load();
     if (!e.empty()) return e;
     Uid u;

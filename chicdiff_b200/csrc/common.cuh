@@ -98,6 +98,44 @@ __device__ __forceinline__ double log_pos(double x)
     return dk * kLogC[0] - ((hfsq - fma(s, hfsq + R, dk * kLogC[1])) - f);
 }
 
+// Table-assisted natural logarithm for the line-search kernel, where the logarithm runs 2.5 times per replicate and
+// evaluation.  The mantissa is reduced multiplicatively with a 128-entry table instead of the division s = f / (2 + f):
+// x = 2^k m, m rc_i = 1 + r with |r| <= 2^-7, log x = k ln2 - log rc_i + log1p(r), log1p by a degree-8 Taylor
+// polynomial.  No reciprocal, 13 FP64 instructions (log_pos: ~25 + the MUFU seed).  rc_i has 20 significant bits, so
+// fma(m, rc_i, -1) is exact up to its single rounding.  The first interval uses rc = 1 (r = m - 1) and the last one is
+// moved to the next binade (r = m/2 - 1), so the result keeps full relative accuracy around x = 1, which
+// log(1 + mu alpha) at small alpha needs.  <= 1.5 ulp for x >= 1, <= 3e-16 max(1, |log x|) below
+// (tests/test_device_math.py).  tab = 128 x {rc, -log rc}: kLogTab copied to shared memory by the kernel (the lanes of
+// a warp index it with unrelated mantissas, which constant memory would serialise).
+static __constant__ double kLogTab[256] = {
+#include "log_table.inc"
+};
+
+__device__ __forceinline__ double log_pos_v2(double x, const double* tab)
+{
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int k = (hi >> 20) - 1023;
+    hi &= 0x000fffff;
+    const int idx = hi >> 13;                         // top 7 bits of the mantissa
+    const int up = (hi + 0x2000) & 0x100000;          // set iff idx == 127: treat [2 - 1/64, 2) as [1 - 1/128, 1) of the next binade
+    hi |= (up ^ 0x3ff00000);
+    k += (up >> 20);
+    const double m = __hiloint2double(hi, lo);
+    const double rc = tab[2 * idx], lc = tab[2 * idx + 1];
+    const double r = fma(m, rc, -1.0);
+    double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+    q = fma(r, q, -1.0 / 6.0);
+    q = fma(r, q, 1.0 / 5.0);
+    q = fma(r, q, -1.0 / 4.0);
+    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, -0.5);
+    const double dk = (double)k;
+    const double t = fma(dk, kLogC[0], lc);           // k ln2_hi is exact (ln2_hi has 32 trailing zero bits)
+    const double u = fma(r * r, q, dk * kLogC[1]);
+    return t + (r + u);
+}
+
 // log Gamma(x) - 0.5 log(2 pi) and digamma(x) for x > 0 in one go, same instruction sequence for every
 // argument (libdevice's lgamma picks an argument-range code path; with one region per lane the lanes of a
 // warp hold unrelated arguments y_j + 1/alpha, so those paths serialise).  Shift by 10 with the

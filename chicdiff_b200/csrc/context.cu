@@ -110,17 +110,6 @@ double trigamma_host(double x)
            f * (5.0 / 66.0 + f * (-691.0 / 2730.0 + f * (7.0 / 6.0)))))));
 }
 
-// xim = mean_s 1 / (colsum_s / count)   (momentsDispEstimate)
-__global__ void xim_kernel(int S, const double* __restrict__ sums, double* __restrict__ xim)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const double cnt = sums[S];
-        double acc = 0.0;
-        for (int s = 0; s < S; s++) acc += 1.0 / (sums[s] / cnt);
-        *xim = acc / S;
-    }
-}
-
 // FP64 peak probe: 8 independent DFMA chains per thread
 __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double m, double* __restrict__ sink)
 {
@@ -164,6 +153,7 @@ struct cd_ctx {
     // design
     bool have_design = false;
     CdDesign des{}, des1{};          // user design and the intercept-only design of the theta grid
+    DevBuf<CdDesign> des_dev;        // [0] = des, [1] = des1: this context's own device copies (no __constant__ globals)
     // regions / rows
     int64_t n = 0, R = 0;
     bool have_regions = false, have_agg = false, rows_borrowed = false;
@@ -178,6 +168,8 @@ struct cd_ctx {
     const double* FM_rows_p = nullptr;
     DevBuf<int32_t> K;               // S x n
     DevBuf<double> FM;               // S x n
+    DevBuf<int32_t> Kb;              // S x G*n: the counts replicated for the fits of a batch (theta grid)
+    int64_t batch_cap = 0;           // virtual regions the work buffers are sized for
     // work buffers (local shard)
     DevBuf<double> nf, mu, baseVar, rough, alpha_init, log_alpha, initial_lp, last_lp, dispMAP, dispersion,
         beta, betaSE, stat, pvalue, deviance, maxCooks;
@@ -187,6 +179,7 @@ struct cd_ctx {
     DevBuf<uint8_t> g_flags;
     DevBuf<double> g_LR;
     DevBuf<unsigned long long> sel_state, sel_hist, sel_aux;
+    DevBuf<double> trend_xs;         // scratch of the trend fit: one double per virtual region
     DevBuf<double> partial, scal;    // reduction scratch ; device scalars
     DevBuf<unsigned long long> counters;
     DevBuf<int32_t> refit_count;
@@ -230,7 +223,7 @@ struct cd_ctx {
     DevBuf<double> wald_c, wald_b0, wald_b;
     DevBuf<int32_t> wald_iter;
     WaldScratch wald_ws{};
-    double* h_pinned = nullptr;      // pinned host scratch (64 doubles)
+    double* h_pinned = nullptr;      // pinned host scratch (1024 doubles)
     std::vector<int64_t> shard_n, shard_off;
     int64_t n_tot = 0, g_off = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -315,7 +308,7 @@ int cd_create(cd_ctx** out, int device)
     if (!c) return CD_ENOMEM;
     c->device = device;
     if ((e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double))) != cudaSuccess) {
+        (e = cudaMallocHost((void**)&c->h_pinned, 1024 * sizeof(double))) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete c;
         return CD_ECUDA;
@@ -348,70 +341,89 @@ int cd_comm_unique_id(cd_ctx* ctx, char id[128])
     return CD_OK;
 }
 
-// Exchange cudaIpc handles of two mailboxes per rank so that the trend-fit kernel can all-reduce its 8 sums and the
-// median kernels their counters over NVLink themselves.  Any failure leaves the flags false and the NCCL
-// host-driven path in use.
-static bool open_peer_mailboxes(cd_ctx* ctx, void* mine_ptr, std::vector<void*>& peers)
+// Exchange cudaIpc handles of two mailboxes per rank so that the trend-fit kernel can all-reduce its sums and the
+// median kernel its counters over NVLink themselves.  Every rank runs the SAME sequence of collectives whatever
+// happens locally (a failed allocation or handle export is reported in the final agreement all-reduce, never by
+// skipping a collective), so no rank can be left waiting in a collective the others do not enter.
+static bool open_peer_mailboxes(cd_ctx* ctx, void* mine_ptr, bool local_ok, std::vector<void*>& peers)
 {
     const int nr = ctx->comm.nranks, rk = ctx->comm.rank;
+    bool ok = local_ok;
     cudaIpcMemHandle_t mine;
-    if (cudaIpcGetMemHandle(&mine, mine_ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, mine_ptr) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    // handle + a validity byte per rank
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
     DevBuf<unsigned char> hb;
-    if (hb.ensure((size_t)nr * sizeof(cudaIpcMemHandle_t)) != cudaSuccess) return false;
-    cudaMemcpy(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), &mine, sizeof(mine), cudaMemcpyHostToDevice);
+    std::vector<unsigned char> all((size_t)nr * rec, 0);
+    const bool have_buf = hb.ensure((size_t)nr * rec) == cudaSuccess;
+    if (have_buf) {
+        unsigned char mine_rec[sizeof(cudaIpcMemHandle_t) + 8] = {0};
+        memcpy(mine_rec, &mine, sizeof(mine));
+        mine_rec[sizeof(mine)] = ok ? 1 : 0;
+        cudaMemcpy(hb.p + (size_t)rk * rec, mine_rec, rec, cudaMemcpyHostToDevice);
+    }
     std::vector<int64_t> counts((size_t)nr, 1), displs((size_t)nr);
     for (int r = 0; r < nr; r++) displs[(size_t)r] = r;
-    if (!ctx->comm.allgatherv(hb.p + (size_t)rk * sizeof(cudaIpcMemHandle_t), hb.p, counts, displs, sizeof(cudaIpcMemHandle_t), ctx->st).empty()) return false;
-    std::vector<cudaIpcMemHandle_t> all((size_t)nr);
-    if (cudaMemcpyAsync(all.data(), hb.p, sizeof(cudaIpcMemHandle_t) * (size_t)nr, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) return false;
-    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) return false;
+    // (without a staging buffer this rank cannot take part: an allocation of a few hundred bytes failing means the
+    //  device is unusable anyway; the collective below would fail on every rank alike)
+    if (!have_buf) return false;
+    if (!ctx->comm.allgatherv(hb.p + (size_t)rk * rec, hb.p, counts, displs, rec, ctx->st).empty()) ok = false;
+    if (cudaMemcpyAsync(all.data(), hb.p, all.size(), cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) ok = false;
+    if (cudaStreamSynchronize(ctx->st) != cudaSuccess) ok = false;
     peers.assign((size_t)nr, nullptr);
-    bool ok = true;
-    for (int r = 0; r < nr; r++) {
+    for (int r = 0; r < nr && ok; r++) {
+        if (!all[(size_t)r * rec + sizeof(cudaIpcMemHandle_t)]) { ok = false; break; }        // that rank could not export
         if (r == rk) { peers[(size_t)r] = mine_ptr; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all.data() + (size_t)r * rec, sizeof(h));
         void* ptr = nullptr;
-        if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         ctx->p2p_opened.push_back(ptr);
         peers[(size_t)r] = ptr;
     }
     return ok;
 }
 
-static void setup_p2p(cd_ctx* ctx)
+// returns an empty string or the reason peer memory is unavailable (identical decision on every rank)
+static std::string setup_p2p(cd_ctx* ctx)
 {
     ctx->p2p_ok = false;
     ctx->sel_p2p_ok = false;
     for (void* p : ctx->p2p_opened) cudaIpcCloseMemHandle(p);          // a second cd_comm_init starts from scratch
     ctx->p2p_opened.clear();
     const int nr = ctx->comm.nranks;
-    if (nr < 2 || nr > 64) return;
+    if (nr < 2) return "";
+    bool local_ok = nr <= 16;                      // median mailbox: 2 x nr x 32 slots of 16 KiB (8 MiB at 8 ranks)
     const char* off = getenv("CHICDIFF_B200_NO_P2P");
-    if (off && off[0] == '1') return;
-    if (ctx->p2p_mail.ensure((size_t)2 * nr * 16) != cudaSuccess ||
-        ctx->p2p_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
-    cudaMemset(ctx->p2p_mail.p, 0, sizeof(double) * 2 * nr * 16);
-    const bool want_sel = nr <= 16;                // 2 x nr x 32 slots of 16 KiB: 8 MiB at 8 ranks
-    if (want_sel) {
-        if (ctx->sel_mail.ensure(sel_p2p_mail_words(nr)) != cudaSuccess || ctx->sel_peers_dev.ensure((size_t)nr) != cudaSuccess) return;
+    if (off && off[0] == '1') local_ok = false;
+    if (local_ok && (ctx->p2p_mail.ensure(trend_p2p_mail_doubles(nr)) != cudaSuccess || ctx->p2p_peers_dev.ensure((size_t)nr) != cudaSuccess ||
+                     ctx->sel_mail.ensure(sel_p2p_mail_words(nr)) != cudaSuccess || ctx->sel_peers_dev.ensure((size_t)nr) != cudaSuccess))
+        local_ok = false;
+    if (local_ok) {
+        cudaMemset(ctx->p2p_mail.p, 0, sizeof(double) * trend_p2p_mail_doubles(nr));
         cudaMemset(ctx->sel_mail.p, 0, sizeof(unsigned long long) * sel_p2p_mail_words(nr));
     }
     std::vector<void*> peers, sel_peers;
-    bool ok = open_peer_mailboxes(ctx, ctx->p2p_mail.p, peers);
-    bool sel_ok = ok && want_sel && open_peer_mailboxes(ctx, ctx->sel_mail.p, sel_peers);
-    // every rank must agree, otherwise one would wait in a kernel for a peer that uses NCCL
+    const bool ok = open_peer_mailboxes(ctx, ctx->p2p_mail.p, local_ok, peers);
+    const bool sel_ok = open_peer_mailboxes(ctx, ctx->sel_mail.p, local_ok, sel_peers);
+    // every rank must agree, otherwise one would wait in a kernel for a peer that never writes its mailbox
     double flag[2] = {ok ? 0.0 : 1.0, sel_ok ? 0.0 : 1.0};
     DevBuf<double> fb;
-    if (fb.ensure(2) != cudaSuccess) return;
+    if (fb.ensure(2) != cudaSuccess) return "cudaMalloc failed";
     cudaMemcpy(fb.p, flag, sizeof(flag), cudaMemcpyHostToDevice);
-    if (!ctx->comm.allreduce_sum(fb.p, 2, ctx->st).empty()) return;
+    const std::string e = ctx->comm.allreduce_sum(fb.p, 2, ctx->st);
+    if (!e.empty()) return e;
     cudaMemcpyAsync(flag, fb.p, sizeof(flag), cudaMemcpyDeviceToHost, ctx->st);
     cudaStreamSynchronize(ctx->st);
-    if (flag[0] != 0.0) return;
+    if (flag[0] != 0.0 || flag[1] != 0.0)
+        return "peer memory between the GPUs of this run is unavailable on at least one rank (cudaIpc / NVLink peer access; more "
+               "than 16 ranks; or CHICDIFF_B200_NO_P2P=1): the global steps of a sharded run exchange their sums inside the kernels";
     cudaMemcpy(ctx->p2p_peers_dev.p, peers.data(), sizeof(double*) * (size_t)nr, cudaMemcpyHostToDevice);
-    ctx->p2p_ok = true;
-    if (flag[1] != 0.0) return;
     cudaMemcpy(ctx->sel_peers_dev.p, sel_peers.data(), sizeof(void*) * (size_t)nr, cudaMemcpyHostToDevice);
+    ctx->p2p_ok = true;
     ctx->sel_p2p_ok = true;
+    return "";
 }
 
 int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128])
@@ -419,7 +431,16 @@ int cd_comm_init(cd_ctx* ctx, int nranks, int rank, const char id[128])
     if (!ctx || !id) return CD_EINVAL;
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
     CD_COMM(ctx, ctx->comm.init(nranks, rank, id));
-    setup_p2p(ctx);
+    if (!ctx->counters.p) {
+        CD_CUDA(ctx, ctx->counters.ensure(16));
+        CD_CUDA(ctx, cudaMemset(ctx->counters.p, 0, 16 * sizeof(unsigned long long)));
+    }
+    const std::string why = setup_p2p(ctx);
+    if (!why.empty()) {
+        // fall back to a single-rank context rather than leaving a communicator nobody can use
+        ctx->comm.init(1, 0, id);
+        return ctx->fail(CD_ECOMM, "cd_comm_init: %s", why.c_str());
+    }
     return CD_OK;
 }
 
@@ -466,6 +487,11 @@ int cd_set_design(cd_ctx* ctx, int S, int p, const double* X)
     double ones[CD_MAXS];
     for (int j = 0; j < S; j++) ones[j] = 1.0;
     build_design(S, 1, ones, ctx->des1);
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    CD_CUDA(ctx, ctx->des_dev.ensure(2));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->des_dev.p, &ctx->des, sizeof(CdDesign), cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->des_dev.p + 1, &ctx->des1, sizeof(CdDesign), cudaMemcpyHostToDevice, ctx->st));
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));          // the sources are members, but be explicit about lifetime
     ctx->have_design = true;
     ctx->have_regions = ctx->have_agg = false;
     ctx->sample_set.assign((size_t)S, 0);
@@ -927,50 +953,42 @@ int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// layout of the small device scalar buffer ctx->scal (doubles)
+constexpr int kScalSf = 0;            // S size factors
+constexpr int kScalXim = 64;          // per fit: moments offset
+constexpr int kScalMed = 96;          // per fit: median of the log residuals
+constexpr int kScalMad = 128;         // per fit: 1.4826 x median absolute deviation
+constexpr int kScalDev = 160;         // per fit: total deviance
+constexpr int kScalTrend = 192;       // per fit: 8 doubles (coefficients, status, outer iterations, passes)
+constexpr int kScalSums = 384;        // per fit: S + 1 masked column sums of the normalisation factors
+constexpr int kScalSize = 1024;
+// layout of the pinned host scratch ctx->h_pinned (doubles)
+constexpr int kPinTrend = 0, kPinMad = 128, kPinErr = 144, kPinDev = 160, kPinTrendIn = 200, kPinSf = 400;
+
 // R median() of the finite entries of B columns (column c at base + c*stride, n local values each, optionally
-// transformed to |x - center[c]|) over ALL ranks -> out_dev[c] = scale * median (exp'ed if do_exp).
-// Radix selection: six histogram passes; in a sharded run only the 2048-bin counters are all-reduced.
+// transformed to |x - center[c]|) over ALL ranks -> out_dev[c] = scale * median (exp'ed if do_exp): one cooperative
+// kernel; in a sharded run it all-reduces its 2048-bin counters through peer memory itself.
 int medians(cd_ctx* ctx, const double* base, int64_t stride, int64_t n, int B, const double* center_dev,
             double* out_dev, int do_exp, double scale)
 {
-    cudaStream_t st = ctx->st;
-    CD_CUDA(ctx, ctx->sel_state.ensure((size_t)B * kSelStateHost));
-    CD_CUDA(ctx, ctx->sel_hist.ensure((size_t)B * kSelBinsHost));
-    CD_CUDA(ctx, ctx->sel_aux.ensure((size_t)B * 3));
-    unsigned long long* counts = ctx->sel_aux.p;
-    unsigned long long* le = ctx->sel_aux.p + B;
-    unsigned long long* mg = ctx->sel_aux.p + 2 * B;
-    // sharded: the consuming kernels exchange through peer memory, else NCCL all-reduces sit between the kernels
-    const bool peer = ctx->comm.active() && ctx->sel_p2p_ok && B <= kSelP2PMaxCols;
-    const bool nccl = ctx->comm.active() && !peer;
-    auto exch = [&]() {
-        SelP2P pp{};
-        pp.nranks = 1;
-        if (peer) {
-            pp.nranks = ctx->comm.nranks; pp.rank = ctx->comm.rank;
-            pp.peers = ctx->sel_peers_dev.p; pp.mymail = ctx->sel_mail.p;
-            pp.seq = ++ctx->sel_seq; pp.err = ctx->counters.p + 10;
-        }
-        return pp;
-    };
-    CD_LAUNCHN(ctx, 1, sel_launch_count(n, B, base, stride, center_dev, counts, st));
-    if (nccl) CD_COMM(ctx, ctx->comm.allreduce_u64(counts, (size_t)B, false, st));
-    CD_LAUNCHN(ctx, 1, sel_launch_init(B, counts, ctx->sel_state.p, ctx->sel_hist.p, le, mg, exch(), st));
-    for (int pass = 0; pass < 6; pass++) {
-        CD_LAUNCHN(ctx, 1, sel_launch_hist(n, B, base, stride, center_dev, ctx->sel_state.p, pass, ctx->sel_hist.p, st));
-        if (nccl) CD_COMM(ctx, ctx->comm.allreduce_u64(ctx->sel_hist.p, (size_t)B * kSelBinsHost, false, st));
-        CD_LAUNCHN(ctx, 1, sel_launch_scan(B, pass, ctx->sel_state.p, ctx->sel_hist.p, exch(), st));
+    CD_CUDA(ctx, ctx->sel_state.ensure((size_t)kSelP2PMaxCols * kSelStateHost));
+    CD_CUDA(ctx, ctx->sel_hist.ensure((size_t)kSelP2PMaxCols * kSelBinsHost));
+    CD_CUDA(ctx, ctx->sel_aux.ensure((size_t)kSelP2PMaxCols * 3));
+    SelP2P pp{};
+    pp.nranks = 1;
+    pp.err = ctx->counters.p + 10;
+    if (ctx->comm.active()) {
+        pp.nranks = ctx->comm.nranks; pp.rank = ctx->comm.rank;
+        pp.peers = ctx->sel_peers_dev.p; pp.mymail = ctx->sel_mail.p;
+        pp.seq = ctx->sel_seq + 1;
+        ctx->sel_seq += kSelExchanges;
     }
-    CD_LAUNCHN(ctx, 1, sel_launch_next(n, B, base, stride, center_dev, ctx->sel_state.p, le, mg, st));
-    if (nccl) {
-        CD_COMM(ctx, ctx->comm.allreduce_u64(le, (size_t)B, false, st));
-        CD_COMM(ctx, ctx->comm.allreduce_u64(mg, (size_t)B, true, st));
-    }
-    CD_LAUNCHN(ctx, 1, sel_launch_finish(B, ctx->sel_state.p, le, mg, out_dev, do_exp, scale, exch(), st));
+    CD_LAUNCHN(ctx, 1, sel_launch_fused(n, B, base, stride, center_dev, out_dev, do_exp, scale, ctx->sel_state.p, ctx->sel_hist.p,
+                                        ctx->sel_aux.p, reinterpret_cast<unsigned int*>(ctx->counters.p + 8), pp, ctx->st));
     return CD_OK;
 }
 
-// after a host sync that follows medians(): did a peer-memory exchange give up?
+// after a host sync that follows a global step: did a peer-memory exchange give up?
 int check_peer_exchange(cd_ctx* ctx, unsigned long long err_word)
 {
     if (err_word == 0ull) return CD_OK;
@@ -985,91 +1003,32 @@ int size_factors(cd_ctx* ctx, double* sf_host)
     const int64_t n = ctx->n;
     CD_CUDA(ctx, ctx->g_LR.ensure((size_t)S * (size_t)n));
     CD_LAUNCHN(ctx, 1, launch_log_ratios(n, S, ctx->K.p, ctx->g_LR.p, ctx->st));
-    int rc = medians(ctx, ctx->g_LR.p, n, n, S, nullptr, ctx->scal.p, 1, 1.0);
+    int rc = medians(ctx, ctx->g_LR.p, n, n, S, nullptr, ctx->scal.p + kScalSf, 1, 1.0);
     if (rc != CD_OK) return rc;
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->st));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 40, ctx->counters.p + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinSf, ctx->scal.p + kScalSf, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinErr, ctx->counters.p + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     unsigned long long errw;
-    memcpy(&errw, ctx->h_pinned + 40, sizeof(errw));
+    memcpy(&errw, ctx->h_pinned + kPinErr, sizeof(errw));
     if ((rc = check_peer_exchange(ctx, errw)) != CD_OK) return rc;
     for (int s = 0; s < S; s++) {
-        sf_host[s] = ctx->h_pinned[s];
+        sf_host[s] = ctx->h_pinned[kPinSf + s];
         if (std::isnan(sf_host[s]))
             return ctx->fail(CD_ENUMERIC, "every gene contains at least one zero, cannot compute log geometric means");
     }
     return CD_OK;
 }
 
-// parametricDispersionFit in a sharded run: every pass sums over the local regions, the 8 sums are all-reduced,
-// and the host runs glm.fit's control flow (same sequence as trend_fit_kernel).  out_dev gets the same 5 numbers.
-int trend_fit_sharded(cd_ctx* ctx, double* out_dev)
-{
-    const int64_t n = ctx->n;
-    double c0 = 0.1, c1 = 1.0;
-    int iter = 0, status = 0, passes = 0;
-    auto pass = [&](double oc0, double oc1, double b0, double b1, double* v) -> int {
-        CD_LAUNCHN(ctx, 2, launch_trend_pass(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, oc0, oc1, b0, b1,
-                                             ctx->partial.p, ctx->scal.p + 40, ctx->st));
-        CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + 40, 8, ctx->st));
-        CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 40, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
-        for (int k = 0; k < 8; k++) v[k] = ctx->h_pinned[k];
-        passes++;
-        return CD_OK;
-    };
-    while (true) {
-        double v[8];
-        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
-        int rc = pass(c0, c1, b0, b1, v);
-        if (rc != CD_OK) return rc;
-        if (v[7] < 2.0) { status = 1; break; }
-        if (v[6] > 0.0) { status = 2; break; }
-        double devold = v[5];
-        bool conv = false;
-        for (int it = 0; it < 25 && status == 0; it++) {
-            const double det = v[0] * v[2] - v[1] * v[1];
-            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
-            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
-            double w[8];
-            int halv = 0;
-            while (true) {
-                rc = pass(c0, c1, nb0, nb1, w);
-                if (rc != CD_OK) return rc;
-                if (w[6] == 0.0 && std::isfinite(w[5])) break;
-                if (++halv > 25) { status = 3; break; }
-                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
-            }
-            if (status) break;
-            b0 = nb0; b1 = nb1;
-            for (int k = 0; k < 8; k++) v[k] = w[k];
-            const double dev = w[5];
-            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
-            devold = dev; ob0 = b0; ob1 = b1;
-        }
-        if (status) break;
-        const double oc0 = c0, oc1 = c1;
-        c0 = b0; c1 = b1;
-        if (!(c0 > 0.0 && c1 > 0.0)) { status = 4; break; }
-        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
-        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
-        iter++;
-        if (iter > 10) { status = 5; break; }
-    }
-    double* h = ctx->h_pinned + 16;
-    h[0] = c0; h[1] = c1; h[2] = (double)status; h[3] = (double)(iter + 1); h[4] = (double)passes;
-    CD_CUDA(ctx, cudaMemcpyAsync(out_dev, h, 5 * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-    return CD_OK;
-}
+struct BatchOut { double a0[kMaxBatch], a1[kMaxBatch], varLogDispEsts[kMaxBatch], dispPriorVar[kMaxBatch], sum_deviance[kMaxBatch]; };
 
-struct PipeOut { double a0, a1, varLogDispEsts, dispPriorVar, sum_deviance; };
-
-// estimateDispersions + nbinomWaldTest for one normalisation (mode / theta) and one design
-int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, double prior_var_override, int grid_len,
-                 bool want_cooks, PipeOut& po, const cd_options* opt)
+// estimateDispersions + nbinomWaldTest for a batch of G fits of one design that differ in their normalisation
+// (mode, theta[g]): the theta grid (G = 5, design ~ 1, only the total deviances are wanted) or the final fit (G = 1).
+// All per-region arrays of the batch are indexed by the virtual region g * n + i.
+int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, int mode, const double* theta,
+              double prior_var_override, int grid_len, bool final_fit, BatchOut& bo, const cd_options* opt)
 {
     const int S = des.S, p = des.p;
-    const int64_t n = ctx->n, off = ctx->g_off;
+    const int64_t n = ctx->n, nv = (int64_t)G * n;
     cudaStream_t st = ctx->st;
     const int df = S - p;
     const bool ask_caller = std::isnan(prior_var_override) && df <= 3 && opt && opt->prior_var_fn;
@@ -1077,124 +1036,139 @@ int run_pipeline(cd_ctx* ctx, const CdDesign& des, int mode, double theta, doubl
         return ctx->fail(CD_ENUMERIC, "S - p = %d <= 3: DESeq2 estimates the dispersion prior variance by a seeded Monte-Carlo "
                                       "match here (set.seed(2), rchisq, loess), which is not implemented; pass disp_prior_var "
                                       "or a prior_var_fn callback", df);
-    CD_CUDA(ctx, set_design_dispersion(des, st));
-    CD_CUDA(ctx, set_design_wald(des, st));
-    double* baseMean = ctx->g_baseMean.p + off;
-    double* dispGeneEst = ctx->g_dispGeneEst.p + off;
-    double* dispFit = ctx->g_dispFit.p + off;
-    uint8_t* flags = ctx->g_flags.p + off;
-    double* sf_dev = ctx->scal.p;                 // size factors live in scal[0..S)
-    double* sums_dev = ctx->scal.p + 48;          // S + 1 offsets sums
-    double* xim_dev = ctx->scal.p + 47;
+    const int32_t* K = (G > 1) ? ctx->Kb.p : ctx->K.p;
+    double* baseMean = ctx->g_baseMean.p;
+    double* dispGeneEst = ctx->g_dispGeneEst.p;
+    double* dispFit = ctx->g_dispFit.p;
+    uint8_t* flags = ctx->g_flags.p;
+    double* sf_dev = ctx->scal.p + kScalSf;
+    double* sums_dev = ctx->scal.p + kScalSums;
+    double* xim_dev = ctx->scal.p + kScalXim;
+    double* trend_dev = ctx->scal.p + kScalTrend;
+    unsigned long long* err_dev = ctx->counters.p + 10;
 
-    CD_LAUNCHN(ctx, 1, launch_norm_factors(n, S, ctx->FM.p, sf_dev, mode, theta, ctx->nf.p, st));
-    CD_LAUNCHN(ctx, 1, launch_base_stats(n, S, ctx->K.p, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, st));
-    CD_LAUNCHN(ctx, 2, launch_masked_colsums(n, S, ctx->nf.p, flags, ctx->partial.p, sums_dev, st));
-    CD_COMM(ctx, ctx->comm.allreduce_sum(sums_dev, (size_t)S + 1, st));
-    xim_kernel<<<1, 32, 0, st>>>(S, sums_dev, xim_dev);
-    ctx->launches++;
-    CD_LAUNCHN(ctx, 1, launch_gene_init(n, S, ctx->K.p, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev,
+    BatchScalars th{};
+    for (int g = 0; g < G; g++) th.v[g] = theta[g];
+    CD_LAUNCHN(ctx, 1, launch_norm_factors(n, S, G, ctx->FM.p, sf_dev, mode, th, ctx->nf.p, ctx->K.p, G > 1 ? ctx->Kb.p : nullptr, st));
+    CD_LAUNCHN(ctx, 1, launch_base_stats(nv, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, st));
+    CD_LAUNCHN(ctx, 2, launch_masked_colsums(n, G, S, ctx->nf.p, flags, ctx->partial.p, sums_dev, st));
+    CD_COMM(ctx, ctx->comm.allreduce_sum(sums_dev, (size_t)G * (S + 1), st));
+    CD_LAUNCHN(ctx, 1, launch_xim(G, S, sums_dev, xim_dev, st));
+    CD_LAUNCHN(ctx, 1, launch_gene_init(nv, n, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev,
                                         ctx->alpha_init.p, ctx->mu.p, st));
     if (!des.linear_mu) {
         // mu from an NB GLM fitted with the rough dispersion (fitNbinomGLMs(alpha_hat = alpha_init)$mu)
-        CD_LAUNCHN(ctx, 3, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->alpha_init.p, flags, ctx->wald_ws, nullptr, nullptr,
+        CD_LAUNCHN(ctx, 3, launch_wald(nv, S, p, des_dev, K, ctx->nf.p, ctx->alpha_init.p, flags, ctx->wald_ws, nullptr, nullptr,
                                        nullptr, nullptr, nullptr, nullptr, nullptr, ctx->mu.p, st));
     }
+    BatchScalars none{};
+    for (int g = 0; g < kMaxBatch; g++) none.v[g] = 1.0;
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 2, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, ctx->alpha_init.p, nullptr, 1.0, ctx->log_alpha.p,
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, ctx->alpha_init.p, nullptr, none, ctx->log_alpha.p,
                                        ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
-    CD_LAUNCHN(ctx, 1, launch_gene_post(n, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
+    CD_LAUNCHN(ctx, 1, launch_gene_post(nv, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
                                         ctx->last_lp.p, flags, dispGeneEst, ctx->refit_list.p, ctx->refit_count.p, st));
     ctx->tm_begin(4);
-    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, nullptr, 1.0,
+    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(nv, n, S, p, des_dev, ctx->refit_count.p, ctx->refit_list.p, K, ctx->mu.p, nullptr, none,
                                             grid_len, dispGeneEst, nullptr, flags, dispGeneEst, st));
     ctx->tm_end();
-    // trend + MAD over the regions of all ranks.  Nothing is gathered: the trend passes all-reduce 8 sums, the
-    // medians all-reduce histogram counters.  One host sync for both on a single GPU.
+    // trend + MAD of every fit over the regions of all ranks.  Nothing is gathered: the trend passes all-reduce 8 sums
+    // per fit, the medians all-reduce histogram counters, both inside their kernels.  One host sync for both.
     ctx->tm_begin(5);
-    double* trend_dev = ctx->scal.p + 110;        // coefs[2], status, outer iterations, passes
-    int rc;
-    if (ctx->comm.active() && !ctx->p2p_ok) {
-        rc = trend_fit_sharded(ctx, trend_dev);                 // NCCL all-reduce per pass, host-driven
-        if (rc != CD_OK) return rc;
+    const bool trend_given = final_fit && opt && opt->trend_a0 > 0.0 && opt->trend_a1 > 0.0;
+    const bool vld_given = final_fit && opt && opt->var_log_disp > 0.0;
+    if (trend_given) {
+        double* h = ctx->h_pinned + kPinTrendIn;
+        for (int g = 0; g < G; g++) { h[8 * g] = opt->trend_a0; h[8 * g + 1] = opt->trend_a1; h[8 * g + 2] = 0.0; h[8 * g + 3] = 0.0; h[8 * g + 4] = 0.0; }
+        CD_CUDA(ctx, cudaMemcpyAsync(trend_dev, h, sizeof(double) * 8 * G, cudaMemcpyHostToDevice, st));
     } else {
-        // one cooperative kernel; in a sharded run it all-reduces the 8 sums of every pass through peer memory
+        // one cooperative kernel; in a sharded run it all-reduces the sums of every pass through peer memory
         TrendP2P pp{};
         pp.nranks = ctx->comm.active() ? ctx->comm.nranks : 1;
         pp.rank = ctx->comm.rank;
         pp.peers = ctx->p2p_peers_dev.p; pp.mymail = ctx->p2p_mail.p;
         pp.epoch = ++ctx->p2p_epoch;
-        CD_LAUNCHN(ctx, 1, launch_trend_fit(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, ctx->g_resid.p, ctx->partial.p,
+        pp.err = err_dev;
+        CD_LAUNCHN(ctx, 1, launch_trend_fit(n, G, baseMean, dispGeneEst, flags, ctx->trend_xs.p, ctx->partial.p,
                                             reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, pp, st));
     }
-    CD_LAUNCHN(ctx, 1, launch_trend_apply(n, ctx->g_baseMean.p, ctx->g_dispGeneEst.p, ctx->g_flags.p, trend_dev,
-                                          ctx->g_dispFit.p, ctx->g_resid.p, st));
-    double* med_dev = ctx->scal.p + 44;
-    rc = medians(ctx, ctx->g_resid.p, n, n, 1, nullptr, med_dev, 0, 1.0);
+    CD_LAUNCHN(ctx, 1, launch_trend_apply(nv, n, baseMean, dispGeneEst, flags, trend_dev, dispFit, ctx->g_resid.p, st));
+    int rc = medians(ctx, ctx->g_resid.p, n, n, G, nullptr, ctx->scal.p + kScalMed, 0, 1.0);
     if (rc != CD_OK) return rc;
-    rc = medians(ctx, ctx->g_resid.p, n, n, 1, med_dev, ctx->scal.p + 45, 0, 1.4826);
+    rc = medians(ctx, ctx->g_resid.p, n, n, G, ctx->scal.p + kScalMed, ctx->scal.p + kScalMad, 0, 1.4826);
     if (rc != CD_OK) return rc;
     ctx->tm_end();
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, trend_dev, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->scal.p + 45, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->counters.p + 10, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinTrend, trend_dev, sizeof(double) * 8 * G, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinMad, ctx->scal.p + kScalMad, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinErr, err_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaStreamSynchronize(st));
     unsigned long long errw;
-    memcpy(&errw, ctx->h_pinned + 9, sizeof(errw));
+    memcpy(&errw, ctx->h_pinned + kPinErr, sizeof(errw));
     if ((rc = check_peer_exchange(ctx, errw)) != CD_OK) return rc;
-    const double coefs[2] = {ctx->h_pinned[0], ctx->h_pinned[1]};
-    const int tstatus = (int)ctx->h_pinned[2];
-    if (tstatus != 0) {
-        static const char* why[] = {"", "fewer than 2 usable regions", "invalid starting values", "no valid step",
-                                    "non-positive coefficients", "did not converge"};
-        return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (%s); the reference would switch to a local "
-                                      "regression fit (locfit), which is not implemented", why[tstatus < 6 ? tstatus : 0]);
+    BatchScalars prior{}, thr{};
+    for (int g = 0; g < kMaxBatch; g++) { prior.v[g] = 1.0; thr.v[g] = 0.0; }
+    for (int g = 0; g < G; g++) {
+        const double* t = ctx->h_pinned + kPinTrend + 8 * g;
+        const int tstatus = (int)t[2];
+        if (tstatus == 6) return check_peer_exchange(ctx, 1ull);
+        if (tstatus != 0) {
+            static const char* why[] = {"", "fewer than 2 usable regions", "invalid starting values", "no valid step",
+                                        "non-positive coefficients", "did not converge"};
+            return ctx->fail(CD_ENUMERIC, "parametric dispersion fit failed (%s); the reference would switch to a local "
+                                          "regression fit (locfit), which is not implemented", why[tstatus < 6 ? tstatus : 0]);
+        }
+        const double mad = ctx->h_pinned[kPinMad + g];
+        if (std::isnan(mad) && !vld_given)
+            return ctx->fail(CD_ENUMERIC, "all gene-wise dispersion estimates are within 2 orders of magnitude of the minimum");
+        const double varLogDispEsts = vld_given ? opt->var_log_disp : mad * mad;
+        double dispPriorVar;
+        if (!std::isnan(prior_var_override)) dispPriorVar = prior_var_override;
+        else if (ask_caller) {
+            // the residuals are in g_resid (+inf where the region is excluded); the caller's rule sees the finite ones
+            if (ctx->comm.active() && ctx->comm.nranks > 1)
+                return ctx->fail(CD_EINVAL, "prior_var_fn needs the residuals of all regions: not available in a sharded run, pass "
+                                            "disp_prior_var");
+            std::vector<double> resid((size_t)n);
+            CD_CUDA(ctx, cudaMemcpyAsync(resid.data(), ctx->g_resid.p + (size_t)g * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            CD_CUDA(ctx, cudaStreamSynchronize(st));
+            size_t m = 0;
+            for (size_t i = 0; i < (size_t)n; i++) if (std::isfinite(resid[i])) resid[m++] = resid[i];
+            dispPriorVar = opt->prior_var_fn(opt->prior_var_user, df, (int64_t)m, resid.data());
+            if (!(dispPriorVar > 0.0) || !std::isfinite(dispPriorVar))
+                return ctx->fail(CD_ENUMERIC, "prior_var_fn returned %g for df = %d (%lld residuals)", dispPriorVar, df, (long long)m);
+        } else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
+        bo.a0[g] = t[0]; bo.a1[g] = t[1]; bo.varLogDispEsts[g] = varLogDispEsts; bo.dispPriorVar[g] = dispPriorVar;
+        prior.v[g] = dispPriorVar;
+        thr.v[g] = 2.0 * sqrt(varLogDispEsts);
     }
-    const double mad = ctx->h_pinned[8];
-    if (std::isnan(mad))
-        return ctx->fail(CD_ENUMERIC, "all gene-wise dispersion estimates are within 2 orders of magnitude of the minimum");
-    const double varLogDispEsts = mad * mad;
-    double dispPriorVar;
-    if (!std::isnan(prior_var_override)) dispPriorVar = prior_var_override;
-    else if (ask_caller) {
-        // the residuals are in g_resid (+inf where the region is excluded); the caller's rule sees the finite ones
-        if (ctx->comm.active() && ctx->comm.nranks > 1)
-            return ctx->fail(CD_EINVAL, "prior_var_fn needs the residuals of all regions: not available in a sharded run, pass "
-                                        "disp_prior_var");
-        std::vector<double> resid((size_t)n);
-        CD_CUDA(ctx, cudaMemcpyAsync(resid.data(), ctx->g_resid.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        CD_CUDA(ctx, cudaStreamSynchronize(st));
-        size_t m = 0;
-        for (size_t i = 0; i < (size_t)n; i++) if (std::isfinite(resid[i])) resid[m++] = resid[i];
-        dispPriorVar = opt->prior_var_fn(opt->prior_var_user, df, (int64_t)m, resid.data());
-        if (!(dispPriorVar > 0.0) || !std::isfinite(dispPriorVar))
-            return ctx->fail(CD_ENUMERIC, "prior_var_fn returned %g for df = %d (%lld residuals)", dispPriorVar, df, (long long)m);
-    } else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
 
     // MAP
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 2, launch_fit_disp(n, S, p, ctx->K.p, ctx->mu.p, flags, dispGeneEst, dispFit, dispPriorVar, ctx->log_alpha.p,
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, dispGeneEst, dispFit, prior, ctx->log_alpha.p,
                                        ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
-    CD_LAUNCHN(ctx, 1, launch_map_post(n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, 2.0 * sqrt(varLogDispEsts),
+    CD_LAUNCHN(ctx, 1, launch_map_post(nv, n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, thr,
                                        flags, ctx->dispMAP.p, ctx->dispersion.p, ctx->refit_list.p, ctx->refit_count.p, st));
     ctx->tm_begin(4);
-    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(n, S, p, ctx->refit_count.p, ctx->refit_list.p, ctx->K.p, ctx->mu.p, dispFit,
-                                            dispPriorVar, grid_len, ctx->dispMAP.p, ctx->dispersion.p, flags, dispGeneEst, st));
+    CD_LAUNCHN(ctx, 1, launch_fit_disp_grid(nv, n, S, p, des_dev, ctx->refit_count.p, ctx->refit_list.p, K, ctx->mu.p, dispFit,
+                                            prior, grid_len, ctx->dispMAP.p, ctx->dispersion.p, flags, dispGeneEst, st));
     ctx->tm_end();
-    // NB GLM + Wald
+    // NB GLM + Wald (final fit) / total deviance only (theta-grid fits)
     ctx->tm_begin(3);
-    CD_LAUNCHN(ctx, p > 1 ? 3 : 2, launch_wald(n, S, p, ctx->K.p, ctx->nf.p, ctx->dispersion.p, flags, ctx->wald_ws, ctx->beta.p, ctx->betaSE.p, ctx->stat.p,
-                                   ctx->pvalue.p, ctx->deviance.p, want_cooks ? ctx->maxCooks.p : nullptr, ctx->betaIter.p,
-                                   nullptr, st));
+    if (final_fit) {
+        CD_LAUNCHN(ctx, p > 1 ? 3 : 2, launch_wald(nv, S, p, des_dev, K, ctx->nf.p, ctx->dispersion.p, flags, ctx->wald_ws, ctx->beta.p,
+                                                   ctx->betaSE.p, ctx->stat.p, ctx->pvalue.p, ctx->deviance.p, ctx->maxCooks.p,
+                                                   ctx->betaIter.p, nullptr, st));
+    } else {
+        CD_LAUNCHN(ctx, 1, launch_wald_deviance_p1(nv, S, K, ctx->nf.p, ctx->dispersion.p, flags, ctx->deviance.p, st));
+    }
     ctx->tm_end();
-    CD_LAUNCHN(ctx, 2, launch_sum_nan(n, ctx->deviance.p, ctx->partial.p, ctx->scal.p + 46, st));
-    CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + 46, 1, st));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->scal.p + 46, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CD_LAUNCHN(ctx, 2, launch_segment_sums(n, G, ctx->deviance.p, ctx->partial.p, ctx->scal.p + kScalDev, st));
+    CD_COMM(ctx, ctx->comm.allreduce_sum(ctx->scal.p + kScalDev, (size_t)G, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + kPinDev, ctx->scal.p + kScalDev, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaStreamSynchronize(st));
-    po.a0 = coefs[0]; po.a1 = coefs[1]; po.varLogDispEsts = varLogDispEsts; po.dispPriorVar = dispPriorVar;
-    po.sum_deviance = ctx->h_pinned[0];
+    for (int g = 0; g < G; g++) bo.sum_deviance[g] = ctx->h_pinned[kPinDev + g];
     return CD_OK;
 }
 
@@ -1234,36 +1208,54 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     if (tot > 2147483647LL) return ctx->fail(CD_EINVAL, "more than 2^31-1 regions in total");
     if (tot < 1) return ctx->fail(CD_EINVAL, "cd_region_test: no regions");
 
-    const size_t sn = (size_t)S * (size_t)n;
+    int norm = opt->norm;
+    double theta = opt->theta;
+    if (!std::isnan(theta)) {
+        // chicdiff.R:1511-1521: theta = 1 is "standard", theta = 0 is "fullmean"
+        if (theta == 1.0 && norm != CD_NORM_STANDARD) norm = CD_NORM_STANDARD;
+        if (theta == 0.0 && norm != CD_NORM_FULLMEAN) norm = CD_NORM_FULLMEAN;
+    }
+    static const double default_grid[5] = {0.0, 0.25, 0.5, 0.75, 1.0};
+    const bool use_grid = (norm == CD_NORM_COMBINED && std::isnan(theta));
+    const double* grid = opt->theta_grid ? opt->theta_grid : default_grid;
+    const int ng = opt->theta_grid ? opt->n_theta_grid : 5;
+    if (use_grid && (ng < 1 || ng > kMaxBatch)) return ctx->fail(CD_EINVAL, "theta grid must have 1..%d values", kMaxBatch);
+    // the fits of the theta grid run as one batch of ng * n virtual regions
+    const int Gmax = use_grid ? ng : 1;
+    const int64_t nv = (int64_t)Gmax * n;
+    if (nv > 2147483647LL) return ctx->fail(CD_EINVAL, "theta grid size x regions exceeds 2^31-1: shard the regions over more GPUs");
+
+    const size_t sn = (size_t)S * (size_t)nv, vn = (size_t)nv;
     CD_CUDA(ctx, ctx->nf.ensure(sn));
     CD_CUDA(ctx, ctx->mu.ensure(sn));
-    CD_CUDA(ctx, ctx->baseVar.ensure((size_t)n)); CD_CUDA(ctx, ctx->rough.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->alpha_init.ensure((size_t)n)); CD_CUDA(ctx, ctx->log_alpha.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->initial_lp.ensure((size_t)n)); CD_CUDA(ctx, ctx->last_lp.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->dispMAP.ensure((size_t)n)); CD_CUDA(ctx, ctx->dispersion.ensure((size_t)n));
+    if (Gmax > 1) CD_CUDA(ctx, ctx->Kb.ensure(sn));
+    CD_CUDA(ctx, ctx->baseVar.ensure(vn)); CD_CUDA(ctx, ctx->rough.ensure(vn));
+    CD_CUDA(ctx, ctx->alpha_init.ensure(vn)); CD_CUDA(ctx, ctx->log_alpha.ensure(vn));
+    CD_CUDA(ctx, ctx->initial_lp.ensure(vn)); CD_CUDA(ctx, ctx->last_lp.ensure(vn));
+    CD_CUDA(ctx, ctx->dispMAP.ensure(vn)); CD_CUDA(ctx, ctx->dispersion.ensure(vn));
     CD_CUDA(ctx, ctx->beta.ensure((size_t)CD_MAXP * (size_t)n)); CD_CUDA(ctx, ctx->betaSE.ensure((size_t)CD_MAXP * (size_t)n));
     CD_CUDA(ctx, ctx->stat.ensure((size_t)n)); CD_CUDA(ctx, ctx->pvalue.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->deviance.ensure((size_t)n)); CD_CUDA(ctx, ctx->maxCooks.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->dispGeneIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->dispIter.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->betaIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->refit_list.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->g_baseMean.ensure((size_t)n)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->g_dispFit.ensure((size_t)n)); CD_CUDA(ctx, ctx->g_resid.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->g_flags.ensure((size_t)n));
-    CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * (CD_MAXS + 8)));
-    CD_CUDA(ctx, ctx->scal.ensure(128));
+    CD_CUDA(ctx, ctx->deviance.ensure(vn)); CD_CUDA(ctx, ctx->maxCooks.ensure((size_t)n));
+    CD_CUDA(ctx, ctx->dispGeneIter.ensure(vn)); CD_CUDA(ctx, ctx->dispIter.ensure(vn));
+    CD_CUDA(ctx, ctx->betaIter.ensure((size_t)n)); CD_CUDA(ctx, ctx->refit_list.ensure(vn));
+    CD_CUDA(ctx, ctx->g_baseMean.ensure(vn)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure(vn));
+    CD_CUDA(ctx, ctx->g_dispFit.ensure(vn)); CD_CUDA(ctx, ctx->g_resid.ensure(vn));
+    CD_CUDA(ctx, ctx->g_flags.ensure(vn)); CD_CUDA(ctx, ctx->trend_xs.ensure(vn));
+    CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * kMaxBatch * (CD_MAXS + 1)));
+    CD_CUDA(ctx, ctx->scal.ensure(kScalSize));
     if (!ctx->counters.p) {
         CD_CUDA(ctx, ctx->counters.ensure(16));
         CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, 16 * sizeof(unsigned long long), st));
     }
     CD_CUDA(ctx, ctx->refit_count.ensure(1));
-    CD_CUDA(ctx, ctx->wald_c.ensure(sn));
+    CD_CUDA(ctx, ctx->wald_c.ensure((size_t)S * (size_t)n));
     CD_CUDA(ctx, ctx->wald_b0.ensure((size_t)CD_MAXP * (size_t)n));
     CD_CUDA(ctx, ctx->wald_b.ensure((size_t)CD_MAXP * (size_t)n));
     CD_CUDA(ctx, ctx->wald_iter.ensure((size_t)n));
     ctx->wald_ws.cmat = ctx->wald_c.p; ctx->wald_ws.beta0 = ctx->wald_b0.p; ctx->wald_ws.beta_nat = ctx->wald_b.p;
     ctx->wald_ws.iter = ctx->wald_iter.p; ctx->wald_ws.work_counter = ctx->counters.p + 15;
     {
-        const int64_t cap = n / 4 + 4096;
+        const int64_t cap = nv / 4 + 4096;
         CD_CUDA(ctx, ctx->park_row.ensure((size_t)cap));
         CD_CUDA(ctx, ctx->park_d.ensure((size_t)cap * 5));
         CD_CUDA(ctx, ctx->park_i.ensure((size_t)cap * 2));
@@ -1283,30 +1275,20 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     if (rc != CD_OK) return rc;
     ctx->tm_end();
 
-    int norm = opt->norm;
-    double theta = opt->theta;
     out->n_deviances = 0;
-    if (!std::isnan(theta)) {
-        // chicdiff.R:1511-1521: theta = 1 is "standard", theta = 0 is "fullmean"
-        if (theta == 1.0 && norm != CD_NORM_STANDARD) norm = CD_NORM_STANDARD;
-        if (theta == 0.0 && norm != CD_NORM_FULLMEAN) norm = CD_NORM_FULLMEAN;
-    }
-    PipeOut po{};
-    if (norm == CD_NORM_COMBINED && std::isnan(theta)) {
-        static const double default_grid[5] = {0.0, 0.25, 0.5, 0.75, 1.0};
-        const double* grid = opt->theta_grid ? opt->theta_grid : default_grid;
-        const int ng = opt->theta_grid ? opt->n_theta_grid : 5;
-        if (ng < 1 || ng > 16) return ctx->fail(CD_EINVAL, "theta grid must have 1..16 values");
-        int best = -1, nbest = 0;
+    BatchOut bo{};
+    if (use_grid) {
+        // chicdiff.R:1633-1647: the ng intercept-only fits, as one batch; only their total deviances are wanted
+        rc = run_batch(ctx, ctx->des1, ctx->des_dev.p + 1, ng, CD_NORM_COMBINED, grid, opt->disp_prior_var_grid, grid_len, false, bo, opt);
+        if (rc != CD_OK) return rc;
         for (int k = 0; k < ng; k++) {
-            rc = run_pipeline(ctx, ctx->des1, CD_NORM_COMBINED, grid[k], opt->disp_prior_var_grid, grid_len, false, po, opt);
-            if (rc != CD_OK) return rc;
-            out->deviances[k] = po.sum_deviance;
-            if (std::isnan(po.sum_deviance))
+            out->deviances[k] = bo.sum_deviance[k];
+            if (std::isnan(bo.sum_deviance[k]))
                 return ctx->fail(CD_ENUMERIC, "theta grid: total deviance is NA (an all-zero region is present and chicdiff.R:1647 "
                                               "sums without na.rm); pass theta explicitly, as chicdiffPipeline does for the control set");
         }
         out->n_deviances = ng;
+        int best = -1, nbest = 0;
         for (int k = 0; k < ng; k++) {
             if (best < 0 || out->deviances[k] < out->deviances[best]) { best = k; nbest = 1; }
             else if (out->deviances[k] == out->deviances[best]) nbest++;
@@ -1314,9 +1296,11 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
         if (nbest != 1) return ctx->fail(CD_ENUMERIC, "theta grid: the minimum total deviance is tied");
         theta = grid[best];
     }
-    rc = run_pipeline(ctx, ctx->des, norm, std::isnan(theta) ? 0.0 : theta, opt->disp_prior_var, grid_len, true, po, opt);
+    const double theta_final = std::isnan(theta) ? 0.0 : theta;
+    rc = run_batch(ctx, ctx->des, ctx->des_dev.p, 1, norm, &theta_final, opt->disp_prior_var, grid_len, true, bo, opt);
     if (rc != CD_OK) return rc;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    struct { double a0, a1, varLogDispEsts, dispPriorVar; } po = {bo.a0[0], bo.a1[0], bo.varLogDispEsts[0], bo.dispPriorVar[0]};
 
     out->theta = (norm == CD_NORM_COMBINED) ? theta : NAN;
     out->trend_a0 = po.a0; out->trend_a1 = po.a1;
@@ -1345,8 +1329,8 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     if ((rc = d2h(ctx, out->pvalue, ctx->pvalue.p, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->deviance, ctx->deviance.p, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->maxCooks, ctx->maxCooks.p, nn)) != CD_OK) return rc;
-    if ((rc = d2h(ctx, out->normFactors, ctx->nf.p, sn)) != CD_OK) return rc;
-    if ((rc = d2h(ctx, out->mu, ctx->mu.p, sn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->normFactors, ctx->nf.p, (size_t)S * nn)) != CD_OK) return rc;
+    if ((rc = d2h(ctx, out->mu, ctx->mu.p, (size_t)S * nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->dispGeneIter, ctx->dispGeneIter.p, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->dispIter, ctx->dispIter.p, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->betaIter, ctx->betaIter.p, nn)) != CD_OK) return rc;

@@ -6,37 +6,100 @@
 // log(alpha) over the Cox-Reid adjusted profile likelihood (DESeq2.cpp fitDisp), and the
 // two-level grid refit (fitDispGrid) for rows whose search did not converge.
 //
-// Mapping: one thread per region; per-sample columns are read coalesced from the
-// sample-major matrices and the region's replicates (y_j, mu_j) are staged per thread in a
+// Mapping: one lane per region; per-sample columns are read coalesced from the
+// sample-major matrices and the region's replicates (y_j, mu_j) are staged per lane in a
 // conflict-free shared-memory column.
+//
+// Batches.  The theta grid of DESeq2Wrap (chicdiff.R:1633-1647) fits the SAME counts G = 5 times with different
+// normalisation factors.  Those fits run as ONE problem of G * n "virtual regions": every per-region array of the
+// batch is sample-major over the virtual index v = g * n + i (the counts are replicated G times), so every kernel
+// here works on a batch unchanged; the few per-fit scalars (theta, moments offset, trend coefficients, prior
+// variance, outlier threshold) are looked up with g = v / n.  One launch per stage instead of G, and the uneven
+// tails of the line searches overlap across the fits.
+//
+// The design of the running fit is read through a pointer into the context's own device copy (no __constant__
+// globals: two contexts of one process, on one or several devices, do not share state).
 #include "kernels.h"
 #include <cuda_pipeline.h>
+#include "posterior.cuh"
 
 namespace cd {
-
-__constant__ CdDesign c_des;
-
-}  // namespace cd
-
-#include "posterior.cuh"     // eval_post: needs c_des
-
-namespace cd {
-
-cudaError_t set_design_dispersion(const CdDesign& d, cudaStream_t st)
-{
-    return cudaMemcpyToSymbolAsync(c_des, &d, sizeof(CdDesign), 0, cudaMemcpyHostToDevice, st);
-}
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------
+// normalisation factors for a batch: fit g mixes the FullMean scaling factors with the size factors at theta_g
+// (chicdiff.R:1583-1589, 1614-1615, 1635-1638, 1666-1669); also replicates the counts into the batch layout
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+norm_factors_kernel(int64_t n, int S, int G, const double* __restrict__ FMagg, const double* __restrict__ sf,
+                    int mode, BatchScalars theta, double* __restrict__ nf, const int32_t* __restrict__ K,
+                    int32_t* __restrict__ Kb)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t nv = (int64_t)G * n;
+    if (Kb) {
+        for (int s = 0; s < S; s++) {
+            const int32_t k = K[(int64_t)s * n + i];
+            for (int g = 0; g < G; g++) Kb[(int64_t)s * nv + (int64_t)g * n + i] = k;
+        }
+    }
+    if (mode == 0) {
+        for (int s = 0; s < S; s++)
+            for (int g = 0; g < G; g++) nf[(int64_t)s * nv + (int64_t)g * n + i] = sf[s];
+        return;
+    }
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) acc += log(FMagg[(int64_t)s * n + i]);
+    const double gm = exp(acc / S);
+    bool anyna = false;
+    for (int s = 0; s < S; s++) {
+        const double m3 = FMagg[(int64_t)s * n + i] / gm;
+        anyna = anyna || isnan(m3);
+    }
+    if (mode == 1) {
+        for (int s = 0; s < S; s++) {
+            const double v = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
+            for (int g = 0; g < G; g++) nf[(int64_t)s * nv + (int64_t)g * n + i] = v;
+        }
+        return;
+    }
+    for (int g = 0; g < G; g++) {
+        const double th = theta.v[g];
+        double acc2 = 0.0;
+        for (int s = 0; s < S; s++) {
+            const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
+            acc2 += log(m3 * (1.0 - th) + sf[s] * th);
+        }
+        const double g2 = exp(acc2 / S);
+        for (int s = 0; s < S; s++) {
+            const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
+            nf[(int64_t)s * nv + (int64_t)g * n + i] = (m3 * (1.0 - th) + sf[s] * th) / g2;
+        }
+    }
+}
+
+cudaError_t launch_norm_factors(int64_t n, int S, int G, const double* FMagg, const double* sf, int mode,
+                                const BatchScalars& theta, double* nf, const int32_t* K, int32_t* Kb, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    norm_factors_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, G, FMagg, sf, mode, theta, nf, K, Kb);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------------------
 // base statistics, linear mu, rough dispersion
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-base_stats_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
-                  double* __restrict__ baseMean, double* __restrict__ baseVar,
+base_stats_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
+                  const double* __restrict__ nf, double* __restrict__ baseMean, double* __restrict__ baseVar,
                   double* __restrict__ rough, uint8_t* __restrict__ flags)
 {
+    __shared__ double hat[CD_MAXS * CD_MAXS];
+    for (int k = threadIdx.x; k < S * S; k += blockDim.x) hat[k] = des->hat[k];
+    __syncthreads();
+    const int p = des->p;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double q[CD_MAXS];
@@ -58,29 +121,32 @@ base_stats_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
     double est = 0.0;
     for (int a = 0; a < S; a++) {
         double mul = 0.0;
-        for (int b = 0; b < S; b++) mul += c_des.hat[a * S + b] * q[b];
+        for (int b = 0; b < S; b++) mul += hat[a * S + b] * q[b];
         const double mm = fmax(1.0, mul);
         est += ((q[a] - mm) * (q[a] - mm) - mm) / (mm * mm);
     }
-    rough[i] = fmax(est / (S - c_des.p), 0.0);
+    rough[i] = fmax(est / (S - p), 0.0);
 }
 
-cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf, double* baseMean,
+cudaError_t launch_base_stats(int64_t n, int S, const CdDesign* des, const int32_t* K, const double* nf, double* baseMean,
                               double* baseVar, double* rough, uint8_t* flags, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    base_stats_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, baseMean, baseVar, rough, flags);
+    base_stats_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, des, K, nf, baseMean, baseVar, rough, flags);
     return cudaGetLastError();
 }
 
-// alpha_init = clamp(min(rough, moments)); mu = linearModelMu(q) * nf floored at minmu
+// alpha_init = clamp(min(rough, moments)); mu = linearModelMu(q) * nf floored at minmu.  xim_dev[g] per fit.
 __global__ void __launch_bounds__(256)
-gene_init_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
-                 const double* __restrict__ baseMean, const double* __restrict__ baseVar,
+gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
+                 const double* __restrict__ nf, const double* __restrict__ baseMean, const double* __restrict__ baseVar,
                  const double* __restrict__ rough, const uint8_t* __restrict__ flags,
                  const double* __restrict__ xim_dev, double* __restrict__ alpha_init,
                  double* __restrict__ mu)
 {
+    __shared__ double hat[CD_MAXS * CD_MAXS];
+    for (int k = threadIdx.x; k < S * S; k += blockDim.x) hat[k] = des->hat[k];
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) {
@@ -88,7 +154,7 @@ gene_init_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* 
         if (mu) for (int j = 0; j < S; j++) mu[(int64_t)j * n + i] = NAN;
         return;
     }
-    const double xim = *xim_dev;
+    const double xim = xim_dev[i / n_fit];
     const double bm = baseMean[i], bv = baseVar[i];
     const double moments = (bv - xim * bm) / (bm * bm);
     const double maxDisp = fmax(10.0, (double)S);
@@ -98,28 +164,19 @@ gene_init_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* 
     for (int j = 0; j < S; j++) q[j] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
     for (int a = 0; a < S; a++) {
         double mul = 0.0;
-        for (int b = 0; b < S; b++) mul += c_des.hat[a * S + b] * q[b];
+        for (int b = 0; b < S; b++) mul += hat[a * S + b] * q[b];
         mu[(int64_t)a * n + i] = fmax(mul * nf[(int64_t)a * n + i], kMinMu);
     }
 }
 
-cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* nf, const double* baseMean,
-                             const double* baseVar, const double* rough, const uint8_t* flags,
+cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
+                             const double* baseMean, const double* baseVar, const double* rough, const uint8_t* flags,
                              const double* xim_dev, double* alpha_init, double* mu, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, baseMean, baseVar, rough, flags,
+    gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, S, des, K, nf, baseMean, baseVar, rough, flags,
                                                        xim_dev, alpha_init, mu);
     return cudaGetLastError();
-}
-
-template <int P>
-__device__ __forceinline__ double eval_lp(double a, const double* ys, const double* mus, int stride, int S,
-                                          double prior_mean, double prior_sigmasq, bool use_prior)
-{
-    double lp, unused;
-    eval_post<P, false>(a, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior, lp, unused);
-    return lp;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -135,19 +192,27 @@ __device__ __forceinline__ double eval_lp(double a, const double* ys, const doub
 constexpr int kFitDispThreads = 128;
 constexpr int kFitDispTripCap = 24;     // first pass: a region still searching after this many trips is parked
 
+// shared memory of the line-search kernels, in doubles: two staging columns and the prefetch slot per lane, the model
+// matrix and the logarithm table
+static inline size_t fit_disp_smem_doubles(int S, int P, int threads)
+{
+    return (size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads +
+           (size_t)S * P + 256;
+}
+
 // Two passes.  ~2-3 % of the regions run the full 100 trips while the average is below 10; in a
 // single persistent pass such a region pulled near the end keeps its warp alive long after the
 // work queue is empty.  Pass 1 therefore parks every region that is still searching after
 // kFitDispTripCap trips (its scalar search state goes to the FitDispPark arrays); pass 2 resumes
 // all parked regions at once, one per lane, so the long searches overlap each other.
 #ifndef CD_FITDISP_MINBLOCKS
-#define CD_FITDISP_MINBLOCKS 4      /* <= 128 registers; measured: 5 blocks (<= 102) and 6 blocks (80) are not faster */
+#define CD_FITDISP_MINBLOCKS 4      /* <= 128 registers; measured in round 1: 5 blocks (<= 102) and 6 blocks (80) are not faster */
 #endif
-template <int P, bool RESUME>
+template <int P, bool RESUME, bool TABLOG>
 __global__ void __launch_bounds__(kFitDispThreads, CD_FITDISP_MINBLOCKS)
-fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
-                const uint8_t* __restrict__ flags, const double* __restrict__ disp_init,
-                const double* __restrict__ prior_mean_disp, double prior_sigmasq,
+fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
+                const double* __restrict__ mu_g, const double* __restrict__ disp_init,
+                const double* __restrict__ prior_mean_disp, BatchScalars prior_sigmasq_g,
                 double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
                 double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
@@ -169,19 +234,23 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
 
     bool active = false, exhausted = false, fresh = false;
     int64_t i = 0;
-    double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0;
+    double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0, prior_sigmasq = 1.0;
     int iter = 0, iter_accept = 0;
 
-    // First pass: the refill is software-pipelined per lane.  ncu showed a quarter of all stall samples in
-    // the old refill (global atomic -> shuffle -> scattered loads -> convert, executed by ~3 lanes while the
-    // other 29 wait).  Now every lane always owns `pending` (a region whose replicates are already on their
-    // way into its prefetch column by cp.async) and `queued` (a region index claimed by an atomic whose
-    // result is not needed before the lane's next refill), so becoming idle costs one shared-memory copy.
-    // pf layout per lane: S int32 counts, S double means, start value, prior mean.
+    // First pass: the refill is software-pipelined per lane.  Every lane always owns `pending` (a region whose
+    // replicates are already on their way into its prefetch column by cp.async) and `queued` (a region index claimed
+    // by an atomic whose result is not needed before the lane's next refill), so becoming idle costs one
+    // shared-memory copy.  pf layout per lane: S int32 counts, S double means, start value, prior mean.
     int* pf_k = reinterpret_cast<int*>(smem + (size_t)2 * S * stride) + threadIdx.x;
     double* pf_mu = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + threadIdx.x;
     double* pf_init = pf_mu + (size_t)S * stride;
     double* pf_prior = pf_init + stride;
+    double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
+    double* tab = Xs + S * P;
+    for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) tab[k] = kLogTab[k];
+    __syncthreads();
+
     int64_t pending = 0, queued = 0;
     auto prefetch = [&](int64_t r) {
         if (r < n) {
@@ -228,10 +297,11 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
                             // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more
                             // than an order of magnitude below the trend
                             const double ft = *pf_prior;
-                            a = log((d0 > 0.1 * ft) ? d0 : ft);
-                            prior_mean = log(ft);
+                            a = log_pos((d0 > 0.1 * ft) ? d0 : ft);
+                            prior_mean = log_pos(ft);
+                            prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
                         } else {
-                            a = log(d0);
+                            a = log_pos(d0);
                         }
                         active = true; fresh = true;
                         iter = 0; iter_accept = 0; kappa = kappa_0;
@@ -262,7 +332,10 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
                     i = park.row[w];
                     a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
                     iter = park.iter[w]; iter_accept = park.iter_accept[w];
-                    if (use_prior) prior_mean = log(prior_mean_disp[i]);
+                    if (use_prior) {
+                        prior_mean = log_pos(prior_mean_disp[i]);
+                        prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
+                    }
                     for (int j = 0; j < S; j++) {
                         ys[j * stride] = (double)K[(int64_t)j * n + i];
                         mus[j * stride] = mu_g[(int64_t)j * n + i];
@@ -291,7 +364,7 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
         // fitDisp evaluates the posterior at the proposal twice (Armijo test, then "lpnew") and, when
         // the proposal is accepted, the derivative at the same point; the arguments are the same
         // double, so one fused evaluation serves all three
-        if (active) eval_post<P, true>(x, ys, mus, stride, S, prior_mean, prior_sigmasq, use_prior, lpx, dlpx);
+        if (active) eval_post<P, true, TABLOG>(x, ys, mus, stride, S, Xs, tab, prior_mean, prior_sigmasq, use_prior, lpx, dlpx);
         __syncwarp();
         // ---- decision ----
         bool finished = false;
@@ -349,9 +422,9 @@ fit_disp_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* _
 // ---------------------------------------------------------------------------------------
 template <int P, int G>
 __global__ void __launch_bounds__(128)
-fit_disp_resume_tile_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
-                            const double* __restrict__ prior_mean_disp, double prior_sigmasq,
-                            double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
+fit_disp_resume_tile_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
+                            const double* __restrict__ mu_g, const double* __restrict__ prior_mean_disp,
+                            BatchScalars prior_sigmasq_g, double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
                             double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out, FitDispPark park)
 {
     constexpr int NS = P * (P + 1) / 2;
@@ -367,19 +440,19 @@ fit_disp_resume_tile_kernel(int64_t n, int S, const int32_t* __restrict__ K, con
     const bool has_sample = lane_g < S;
     double xrow[P];
 #pragma unroll
-    for (int u = 0; u < P; u++) xrow[u] = has_sample ? c_des.X[lane_g * P + u] : 0.0;
+    for (int u = 0; u < P; u++) xrow[u] = has_sample ? des->X[lane_g * P + u] : 0.0;
 
     for (int64_t w0 = 0; w0 < n_work; w0 += n_groups) {
         const int64_t w = w0 + group;
         bool active = w < n_work;
         int64_t i = 0;
-        double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 1.0, kappa = kappa_0, prior_mean = 0.0, y = 0.0, mu = 1.0;
+        double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 1.0, kappa = kappa_0, prior_mean = 0.0, prior_sigmasq = 1.0, y = 0.0, mu = 1.0;
         int iter = 0, iter_accept = 0;
         if (active) {
             i = park.row[w];
             a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
             iter = park.iter[w]; iter_accept = park.iter_accept[w];
-            if (use_prior) prior_mean = log(prior_mean_disp[i]);
+            if (use_prior) { prior_mean = log_pos(prior_mean_disp[i]); prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)]; }
             if (has_sample) { y = (double)K[(int64_t)lane_g * n + i]; mu = mu_g[(int64_t)lane_g * n + i]; }
         }
         while (__any_sync(0xffffffffu, active)) {
@@ -468,8 +541,16 @@ fit_disp_resume_tile_kernel(int64_t n, int S, const int32_t* __restrict__ K, con
     }
 }
 
-cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu, const uint8_t* flags,
-                            const double* disp_init, const double* prior_mean_disp, double prior_sigmasq,
+// CHICDIFF_B200_TABLE_LOG=0 selects the build of the line search that takes its logarithms with log_pos (fdlibm scheme)
+// instead of the shared-memory table; read at every launch so that a measurement script can switch between the two
+static bool table_log_enabled()
+{
+    const char* e = getenv("CHICDIFF_B200_TABLE_LOG");
+    return !(e && e[0] == '0');
+}
+
+cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* K, const double* mu,
+                            const double* disp_init, const double* prior_mean_disp, const BatchScalars& prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
                             unsigned long long* work_counter, const FitDispPark& park, cudaStream_t st)
 {
@@ -481,7 +562,7 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
     if (e != cudaSuccess) return e;
     const int threads = kFitDispThreads;
     const int64_t want = (n + threads - 1) / threads;
-    const size_t smem = ((size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads) * sizeof(double);
+    const size_t smem = fit_disp_smem_doubles(S, p, threads) * sizeof(double);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -489,43 +570,41 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
     // problem -> sample-parallel tile kernel; with many it is a throughput problem -> one region per lane again.
     const int G = S <= 8 ? 8 : (S <= 16 ? 16 : 32);
     const bool tile = (double)n * 0.04 * G <= (double)sms * 1024.0;
+    const bool tl = table_log_enabled();
     // persistent grids: exactly the number of CTAs that are resident at once
-#define CD_LAUNCH(P_)                                                                                          \
+#define CD_LAUNCH_T(P_, TL_)                                                                                   \
     {                                                                                                          \
         int per_sm = 1;                                                                                        \
-        if (smem > 48 * 1024) {                                                                                \
-            e = cudaFuncSetAttribute(fit_disp_kernel<P_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                    \
-        }                                                                                                      \
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_disp_kernel<P_, false>, threads, smem); \
+        e = cudaFuncSetAttribute(fit_disp_kernel<P_, false, TL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                        \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fit_disp_kernel<P_, false, TL_>, threads, smem); \
         if (e != cudaSuccess) return e;                                                                        \
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                     \
         const int blocks = (int)(want < resident ? want : resident);                                           \
-        fit_disp_kernel<P_, false><<<blocks, threads, smem, st>>>(n, S, K, mu, flags, disp_init,               \
+        fit_disp_kernel<P_, false, TL_><<<blocks, threads, smem, st>>>(n, n_fit, S, des, K, mu, disp_init,     \
             prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);         \
         if (tile) {                                                                                            \
             const int blocks2 = sms * 8;                                                                       \
             if (S <= 8)                                                                                        \
-                fit_disp_resume_tile_kernel<P_, 8><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,      \
+                fit_disp_resume_tile_kernel<P_, 8><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
             else if (S <= 16)                                                                                  \
-                fit_disp_resume_tile_kernel<P_, 16><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,     \
+                fit_disp_resume_tile_kernel<P_, 16><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
             else                                                                                               \
-                fit_disp_resume_tile_kernel<P_, 32><<<blocks2, 128, 0, st>>>(n, S, K, mu, prior_mean_disp,     \
+                fit_disp_resume_tile_kernel<P_, 32><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
         } else {                                                                                               \
-            if (smem > 48 * 1024) {                                                                            \
-                e = cudaFuncSetAttribute(fit_disp_kernel<P_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                if (e != cudaSuccess) return e;                                                                \
-            }                                                                                                  \
+            e = cudaFuncSetAttribute(fit_disp_kernel<P_, true, TL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                    \
             const int64_t want2 = (park.capacity + threads - 1) / threads;                                     \
             const int blocks2 = (int)(want2 < resident ? want2 : resident);                                    \
-            fit_disp_kernel<P_, true><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, S, K, mu, flags,    \
+            fit_disp_kernel<P_, true, TL_><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, n_fit, S, des, K, mu, \
                 disp_init, prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp,               \
                 work_counter + 1, park);                                                                       \
         }                                                                                                      \
     }
+#define CD_LAUNCH(P_) { if (tl) CD_LAUNCH_T(P_, true) else CD_LAUNCH_T(P_, false) }
     switch (p) {
         case 1: CD_LAUNCH(1); break;
         case 2: CD_LAUNCH(2); break;
@@ -534,6 +613,7 @@ cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const dou
         default: return cudaErrorInvalidValue;
     }
 #undef CD_LAUNCH
+#undef CD_LAUNCH_T
     return cudaGetLastError();
 }
 
@@ -577,9 +657,10 @@ cudaError_t launch_gene_post(int64_t n, int S, const double* alpha_init, const d
     return cudaGetLastError();
 }
 
+// outlier_thr[g] = 2 sqrt(varLogDispEsts) of fit g
 __global__ void __launch_bounds__(256)
-map_post_kernel(int64_t n, int S, const double* __restrict__ log_alpha, const int32_t* __restrict__ iter,
-                const double* __restrict__ dispGeneEst, const double* __restrict__ dispFit, double outlier_thr,
+map_post_kernel(int64_t n, int64_t n_fit, int S, const double* __restrict__ log_alpha, const int32_t* __restrict__ iter,
+                const double* __restrict__ dispGeneEst, const double* __restrict__ dispFit, BatchScalars outlier_thr,
                 uint8_t* __restrict__ flags, double* __restrict__ dispMAP, double* __restrict__ dispersion,
                 int32_t* __restrict__ refit_list, int32_t* __restrict__ refit_count)
 {
@@ -595,20 +676,20 @@ map_post_kernel(int64_t n, int S, const double* __restrict__ log_alpha, const in
     }
     const double dmap = fmin(fmax(exp(log_alpha[i]), kMinDisp), maxDisp);
     const double ge = dispGeneEst[i], ft = dispFit[i];
-    const bool outl = log(ge) > log(ft) + outlier_thr;
+    const bool outl = log(ge) > log(ft) + outlier_thr.v[(int)(i / n_fit)];
     if (outl) f |= CD_FLAG_OUTLIER;
     dispMAP[i] = dmap;
     dispersion[i] = outl ? ge : dmap;
     flags[i] = f;
 }
 
-cudaError_t launch_map_post(int64_t n, int S, const double* log_alpha, const int32_t* iter, const double* dispGeneEst,
-                            const double* dispFit, double outlier_thr, uint8_t* flags, double* dispMAP,
-                            double* dispersion, int32_t* refit_list, int32_t* refit_count, cudaStream_t st)
+cudaError_t launch_map_post(int64_t n, int64_t n_fit, int S, const double* log_alpha, const int32_t* iter,
+                            const double* dispGeneEst, const double* dispFit, const BatchScalars& outlier_thr, uint8_t* flags,
+                            double* dispMAP, double* dispersion, int32_t* refit_list, int32_t* refit_count, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(refit_count, 0, sizeof(int32_t), st);
     if (e != cudaSuccess || n == 0) return e;
-    map_post_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, log_alpha, iter, dispGeneEst, dispFit, outlier_thr,
+    map_post_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, S, log_alpha, iter, dispGeneEst, dispFit, outlier_thr,
                                                       flags, dispMAP, dispersion, refit_list, refit_count);
     return cudaGetLastError();
 }
@@ -618,13 +699,17 @@ cudaError_t launch_map_post(int64_t n, int S, const double* log_alpha, const int
 // ---------------------------------------------------------------------------------------
 template <int P>
 __global__ void __launch_bounds__(128)
-fit_disp_grid_kernel(int64_t n, int S, const int32_t* __restrict__ n_list_dev, const int32_t* __restrict__ list,
-                     const int32_t* __restrict__ K, const double* __restrict__ mu_g,
-                     const double* __restrict__ prior_mean_disp, double prior_sigmasq, int grid_len,
+fit_disp_grid_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ n_list_dev,
+                     const int32_t* __restrict__ list, const int32_t* __restrict__ K, const double* __restrict__ mu_g,
+                     const double* __restrict__ prior_mean_disp, BatchScalars prior_sigmasq_g, int grid_len,
                      double* __restrict__ disp_out, double* __restrict__ dispersion_out,
                      const uint8_t* __restrict__ flags, const double* __restrict__ dispGeneEst)
 {
     __shared__ double sh[4][2 * CD_MAXS];
+    __shared__ double Xs[CD_MAXS * CD_MAXP];
+    for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
+    __syncthreads();
+    const double* tab = nullptr;                 // the grid evaluations use log_pos (no table)
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -641,6 +726,7 @@ fit_disp_grid_kernel(int64_t n, int S, const int32_t* __restrict__ n_list_dev, c
         __syncwarp();
         const bool use_prior = (prior_mean_disp != nullptr);
         const double prior_mean = use_prior ? log(prior_mean_disp[i]) : 0.0;
+        const double prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
         const double maxDisp = fmax(10.0, (double)S);
         const double lo = log(1e-8), hi = log(maxDisp);
         const double step = (hi - lo) / (grid_len - 1);
@@ -648,8 +734,8 @@ fit_disp_grid_kernel(int64_t n, int S, const int32_t* __restrict__ n_list_dev, c
         double from = lo, to = hi, by = step;
         for (int level = 0; level < 2; level++) {
             const double a = (lane == grid_len - 1) ? to : from + lane * by;
-            double v = -INFINITY;
-            if (lane < grid_len) v = eval_lp<P>(a, ys, mus, 1, S, prior_mean, prior_sigmasq, use_prior);
+            double v = -INFINITY, unused;
+            if (lane < grid_len) eval_post<P, false, false>(a, ys, mus, 1, S, Xs, tab, prior_mean, prior_sigmasq, use_prior, v, unused);
             int idx = lane;
             // arg max, first maximum wins
 #pragma unroll
@@ -674,16 +760,16 @@ fit_disp_grid_kernel(int64_t n, int S, const int32_t* __restrict__ n_list_dev, c
     }
 }
 
-cudaError_t launch_fit_disp_grid(int64_t n, int S, int p, const int32_t* n_list_dev, const int32_t* list,
-                                 const int32_t* K, const double* mu, const double* prior_mean_disp,
-                                 double prior_sigmasq, int grid_len, double* disp_out, double* dispersion_out,
+cudaError_t launch_fit_disp_grid(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* n_list_dev,
+                                 const int32_t* list, const int32_t* K, const double* mu, const double* prior_mean_disp,
+                                 const BatchScalars& prior_sigmasq, int grid_len, double* disp_out, double* dispersion_out,
                                  const uint8_t* flags, const double* dispGeneEst, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     if (grid_len < 2 || grid_len > 32) return cudaErrorInvalidValue;
     const int threads = 128, blocks = 148 * 4;
 #define CD_LAUNCH(P_)                                                                                          \
-    fit_disp_grid_kernel<P_><<<blocks, threads, 0, st>>>(n, S, n_list_dev, list, K, mu, prior_mean_disp,       \
+    fit_disp_grid_kernel<P_><<<blocks, threads, 0, st>>>(n, n_fit, S, des, n_list_dev, list, K, mu, prior_mean_disp, \
                                                          prior_sigmasq, grid_len, disp_out, dispersion_out,    \
                                                          flags, dispGeneEst)
     switch (p) {

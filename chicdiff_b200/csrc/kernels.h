@@ -6,9 +6,10 @@
 
 namespace cd {
 
-// design constants live in __constant__ memory of each translation unit that needs them
-cudaError_t set_design_dispersion(const CdDesign& d, cudaStream_t st);
-cudaError_t set_design_wald(const CdDesign& d, cudaStream_t st);
+// Batches: G fits of the same counts (the theta grid) run as one problem of G * n virtual regions, sample-major over
+// v = g * n + i (dispersion.cu).  Per-fit scalars travel by value.
+constexpr int kMaxBatch = 16;
+struct BatchScalars { double v[kMaxBatch]; };
 
 // ---- stage 1: aggregation (chicdiff.R:1540-1547) --------------------------------------
 cudaError_t launch_aggregate(int64_t n, int S, const int64_t* row_off, int64_t R,
@@ -70,47 +71,42 @@ cudaError_t launch_assemble(int64_t n, int S, const int64_t* row_off, int64_t R,
 // ---- size factors + stage 2: offsets (chicdiff.R:1561-1562, 1583-1589, 1635-1638) ------
 cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR /*S x n, +inf = excluded*/,
                               cudaStream_t st);
-cudaError_t launch_norm_factors(int64_t n, int S, const double* FMagg, const double* sf /*S, device*/,
-                                int mode, double theta, double* nf, cudaStream_t st);
+// nf (S x G*n) for the G fits of a batch (mode 2: fit g at theta.v[g]); Kb != null also replicates K (S x n) into the
+// batch layout (S x G*n)
+cudaError_t launch_norm_factors(int64_t n, int S, int G, const double* FMagg, const double* sf /*S, device*/,
+                                int mode, const BatchScalars& theta, double* nf, const int32_t* K, int32_t* Kb, cudaStream_t st);
 
 // ---- deterministic reductions -----------------------------------------------------------
-// column sums of a sample-major S x n matrix over rows where mask[i]==0 (mask may be null);
-// out[s] (device, S doubles) and, if count != null, the number of unmasked rows
-cudaError_t launch_masked_colsums(int64_t n, int S, const double* M, const uint8_t* mask,
-                                  double* partial /*>= kReduceBlocks*(S+1)*/, double* out, cudaStream_t st);
-cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* out /*[0]=sum incl. NaN*/,
-                           cudaStream_t st);
+// per fit g: column sums of the sample-major S x G*n matrix over the rows of fit g where mask[row]==0 (mask may be
+// null): out[g * (S + 1) + s], and the number of such rows in out[g * (S + 1) + S]
+cudaError_t launch_masked_colsums(int64_t n, int G, int S, const double* M, const uint8_t* mask,
+                                  double* partial /*>= kReduceBlocks*G*(S+1)*/, double* out, cudaStream_t st);
+// out[g] = sum over the rows of fit g (NaN propagates)
+cudaError_t launch_segment_sums(int64_t n, int G, const double* v, double* partial, double* out, cudaStream_t st);
+// xim[g] from the masked column sums of the normalisation factors (momentsDispEstimate)
+cudaError_t launch_xim(int G, int S, const double* sums, double* xim, cudaStream_t st);
 constexpr int kReduceBlocks = 592;      // 148 SMs x 4
 
 // ---- exact medians by radix selection (select.cu); B columns at base + c*stride, length n each ----
-// state: B x 8 words, hist: B x 2048 words, counts / le / mg: B words each (device).  A sharded run needs
-// `counts` (sum) all-reduced between count and init, `hist` (sum) between every hist and scan, and `le` (sum) /
-// `mg` (min) between next and finish.  With a SelP2P of nranks > 1 the init / scan / finish kernels do that
-// exchange themselves through peer memory (one sequence number per kernel); with nranks == 1 they do not, and
-// the caller either runs alone or all-reduces the buffers on the stream (NCCL) before those kernels.
+// One cooperative kernel per batch of B <= 32 medians.  state: B x 8 words, hist: B x 2048 words, aux: 3 B words,
+// bar: one word (all device scratch).  out[c] = scale * median of the finite entries of column c (of |x - center[c]|
+// when center != null), exp'ed when do_exp.  In a sharded run (pp.nranks > 1) the kernel all-reduces its counters
+// through peer memory itself: 8 exchanges, sequence numbers pp.seq .. pp.seq + 7.
 constexpr int kSelBinsHost = 2048;
 constexpr int kSelStateHost = 8;
 constexpr int kSelP2PMaxCols = 32;
+constexpr int kSelExchanges = 8;
 struct SelP2P {
     int nranks, rank;                       // nranks == 1: no exchange
     unsigned long long* const* peers;       // device array of nranks mailbox pointers (own one included)
     unsigned long long* mymail;             // 2 x nranks x kSelP2PMaxCols slots of 2048 words, then as many flag words
-    unsigned long long seq;                 // nonzero, +1 per exchanging kernel, identical on all ranks
-    unsigned long long* err;                // set to 1 when a peer never answered
+    unsigned long long seq;                 // first sequence number of this launch (nonzero), identical on all ranks
+    unsigned long long* err;                // device word, never null: raised when a peer never answered; ends every spin loop
 };
 inline size_t sel_p2p_mail_words(int nranks) { return (size_t)2 * nranks * kSelP2PMaxCols * (kSelBinsHost + 1); }
-cudaError_t sel_launch_count(int64_t n, int B, const double* base, int64_t stride, const double* center,
-                             unsigned long long* counts, cudaStream_t st);
-cudaError_t sel_launch_init(int B, unsigned long long* counts, unsigned long long* state, unsigned long long* hist,
-                            unsigned long long* le, unsigned long long* mg, const SelP2P& pp, cudaStream_t st);
-cudaError_t sel_launch_hist(int64_t n, int B, const double* base, int64_t stride, const double* center,
-                            const unsigned long long* state, int pass, unsigned long long* hist, cudaStream_t st);
-cudaError_t sel_launch_scan(int B, int pass, unsigned long long* state, unsigned long long* hist, const SelP2P& pp,
-                            cudaStream_t st);
-cudaError_t sel_launch_next(int64_t n, int B, const double* base, int64_t stride, const double* center,
-                            const unsigned long long* state, unsigned long long* le, unsigned long long* mg, cudaStream_t st);
-cudaError_t sel_launch_finish(int B, const unsigned long long* state, const unsigned long long* le, const unsigned long long* mg,
-                              double* out, int do_exp, double scale, const SelP2P& pp, cudaStream_t st);
+cudaError_t sel_launch_fused(int64_t n, int B, const double* base, int64_t stride, const double* center, double* out,
+                             int do_exp, double scale, unsigned long long* state, unsigned long long* hist,
+                             unsigned long long* aux, unsigned int* bar, const SelP2P& pp, cudaStream_t st);
 
 // ---- results() on resident arrays (results_resident.cu) ----
 // counts: [0] rows with a p-value after the Cook's filter, [1] rows with baseMean == 0
@@ -129,13 +125,13 @@ cudaError_t res_launch_bh(int64_t n, const unsigned long long* counts, const dou
                           const unsigned int* sorted_idx, const double* cut, int j, const unsigned int* off,
                           const unsigned long long* m_tot, double* cmin, double* smin, double* padj, cudaStream_t st);
 
-// ---- stage 4a: gene-wise dispersion -----------------------------------------------------
-cudaError_t launch_base_stats(int64_t n, int S, const int32_t* K, const double* nf,
+// ---- stage 4a: gene-wise dispersion (n = virtual regions of the batch, n_fit = regions per fit) --------------
+cudaError_t launch_base_stats(int64_t n, int S, const CdDesign* des, const int32_t* K, const double* nf,
                               double* baseMean, double* baseVar, double* rough, uint8_t* flags,
                               cudaStream_t st);
-cudaError_t launch_gene_init(int64_t n, int S, const int32_t* K, const double* nf,
+cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
                              const double* baseMean, const double* baseVar, const double* rough,
-                             const uint8_t* flags, const double* xim_dev, double* alpha_init, double* mu,
+                             const uint8_t* flags, const double* xim_dev /*per fit*/, double* alpha_init, double* mu,
                              cudaStream_t st);
 // scalar search state of regions parked by the first line-search pass (see dispersion.cu)
 struct FitDispPark {
@@ -145,10 +141,10 @@ struct FitDispPark {
     int32_t *iter, *iter_accept;
     unsigned long long* count;
 };
-// line search; prior_mean == null => no prior (gene-wise); log_alpha0 in/out
-cudaError_t launch_fit_disp(int64_t n, int S, int p, const int32_t* K, const double* mu,
-                            const uint8_t* flags, const double* disp_init /*alpha scale*/,
-                            const double* prior_mean_disp /*alpha scale or null*/, double prior_sigmasq,
+// line search; prior_mean_disp == null => no prior (gene-wise); prior_sigmasq.v[g] per fit
+cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* K, const double* mu,
+                            const double* disp_init /*alpha scale*/,
+                            const double* prior_mean_disp /*alpha scale or null*/, const BatchScalars& prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
                             unsigned long long* work_counter /*device scratch, 2 words*/, const FitDispPark& park,
                             cudaStream_t st);
@@ -157,15 +153,15 @@ cudaError_t launch_gene_post(int64_t n, int S, const double* alpha_init, const d
                              const int32_t* iter, const double* initial_lp, const double* last_lp,
                              uint8_t* flags, double* dispGeneEst, int32_t* refit_list, int32_t* refit_count,
                              cudaStream_t st);
-cudaError_t launch_map_post(int64_t n, int S, const double* log_alpha, const int32_t* iter,
-                            const double* dispGeneEst, const double* dispFit, double outlier_thr,
+cudaError_t launch_map_post(int64_t n, int64_t n_fit, int S, const double* log_alpha, const int32_t* iter,
+                            const double* dispGeneEst, const double* dispFit, const BatchScalars& outlier_thr,
                             uint8_t* flags, double* dispMAP, double* dispersion,
                             int32_t* refit_list, int32_t* refit_count, cudaStream_t st);
 // grid refit of listed rows, one warp per row; writes disp_out[row] (clamped) and, for MAP,
 // re-applies the outlier rule through dispersion_out
-cudaError_t launch_fit_disp_grid(int64_t n, int S, int p, const int32_t* n_list_dev, const int32_t* list,
-                                 const int32_t* K, const double* mu, const double* prior_mean_disp,
-                                 double prior_sigmasq, int grid_len, double* disp_out,
+cudaError_t launch_fit_disp_grid(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* n_list_dev,
+                                 const int32_t* list, const int32_t* K, const double* mu, const double* prior_mean_disp,
+                                 const BatchScalars& prior_sigmasq, int grid_len, double* disp_out,
                                  double* dispersion_out /*null for gene-wise*/, const uint8_t* flags,
                                  const double* dispGeneEst, cudaStream_t st);
 
@@ -176,19 +172,22 @@ cudaError_t launch_fit_disp_grid(int64_t n, int S, int p, const int32_t* n_list_
 cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* dispGeneEst,
                               const uint8_t* flags, double c0, double c1, double b0, double b1,
                               double* partial, double* out, cudaStream_t st);
-// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded
 // peer-memory description for the in-kernel all-reduce of the sharded trend fit (nranks == 1: unused)
 struct TrendP2P {
     int nranks, rank;
     double* const* peers;       // device array of nranks pointers: every rank's mailbox (own one included)
-    double* mymail;             // this rank's mailbox: 2 x nranks slots of 16 doubles (8 sums, sequence word, pad)
+    double* mymail;             // this rank's mailbox: 2 x nranks slots of (8 kMaxBatch + 8) doubles
     unsigned long long epoch;   // distinct per launch, identical on all ranks
+    unsigned long long* err;    // device word, never null (see SelP2P)
 };
-// the whole parametricDispersionFit in one cooperative kernel; out[0..1] coefs, out[2] status, out[3] outer
-// iterations, out[4] passes; xs = n doubles of scratch, partial >= 16 * #SMs doubles, bar = one zero-initialised word
-cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+inline size_t trend_p2p_mail_doubles(int nranks) { return (size_t)2 * nranks * (8 * kMaxBatch + 8); }
+// the whole parametricDispersionFit of the G fits of a batch in one cooperative kernel; out[g * 8 + 0..1] coefs,
+// [2] status, [3] outer iterations, [4] passes; xs = one double of scratch per virtual region,
+// partial >= 16 * G * #SMs doubles, bar = one word
+cudaError_t launch_trend_fit(int64_t n, int G, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
                              double* xs, double* partial, unsigned int* bar, double* out, const TrendP2P& pp, cudaStream_t st);
-cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst,
+// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded ; coefs_dev[g * 8 + 0..1]
+cudaError_t launch_trend_apply(int64_t n, int64_t n_fit, const double* baseMean, const double* dispGeneEst,
                                const uint8_t* flags, const double* coefs_dev, double* dispFit, double* resid,
                                cudaStream_t st);
 
@@ -202,10 +201,15 @@ struct WaldScratch {
 };
 // prep + persistent IRLS (p >= 2) + finalisation.  Also used for the IRLS-mu variant of the gene-wise
 // step (mu_out != null => only mu is written).  maxCooks == null skips Cook's distances.
-cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double* nf,
+cudaError_t launch_wald(int64_t n, int S, int p, const CdDesign* des, const int32_t* K, const double* nf,
                         const double* dispersion, uint8_t* flags, const WaldScratch& ws,
                         double* beta /*p x n, log2*/, double* betaSE, double* stat, double* pvalue,
                         double* deviance, double* maxCooks, int32_t* betaIter, double* mu_out,
                         cudaStream_t st);
+
+// total deviance input of the theta-grid fits (design ~ 1): -2 logLik per virtual region at the intercept-only
+// shortcut's coefficients; nothing else of nbinomWaldTest is needed there (chicdiff.R:1644-1647)
+cudaError_t launch_wald_deviance_p1(int64_t n, int S, const int32_t* K, const double* nf, const double* dispersion,
+                                    const uint8_t* flags, double* deviance, cudaStream_t st);
 
 }  // namespace cd

@@ -1,13 +1,14 @@
-// offsets.cu -- size factors, stage 2 (per-region normalisation offsets), the parametric
-// dispersion trend passes and the deterministic reductions they need.
+// offsets.cu -- size factors, the parametric dispersion trend of a batch of fits, and the deterministic
+// reductions the global steps need.
 //
-//   chicdiff.R:1561-1562  estimateSizeFactors: log-ratio matrix (medians are taken by the host
-//                         orchestration after a device sort)
-//   chicdiff.R:1583-1589  FullMean scaling factors, rows with NA replaced by the size factors
-//   chicdiff.R:1614-1615, theta mix with the size factors and row geometric-mean rescale
-//              1635-1638
+//   chicdiff.R:1561-1562  estimateSizeFactors: log-ratio matrix (medians by radix selection, select.cu)
+//   DESeq2 momentsDispEstimate: mean over samples of 1 / colMeans(normalisation factors of the non-zero rows)
 //   DESeq2 parametricDispersionFit / dispersionFunction<-: Gamma(identity) IRLS sums, fitted
 //                         trend and log residuals
+//   chicdiff.R:1647       sum of deviances per theta-grid fit
+//
+// (the per-region normalisation offsets of stage 2, chicdiff.R:1583-1589 / 1614-1615 / 1635-1638, are in
+// dispersion.cu: norm_factors_kernel writes them for every fit of a batch.)
 //
 // All reductions are two-stage with a fixed block count and fixed summation order, so results
 // are bit-reproducible from run to run (no floating-point atomics).
@@ -16,6 +17,8 @@
 namespace cd {
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+constexpr long long kSpinLimit = 20000000000LL;      // ~10 s of SM clocks: a peer died; give up
 
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* dst)
@@ -53,41 +56,79 @@ __global__ void __launch_bounds__(32) final_reduce_kernel(int nblocks, int nv, c
 }
 
 // ---------------------------------------------------------------------------------------
-// masked column sums: out[s] = sum_i M[s][i] over rows with mask[i] == 0 ; out[S] = #rows
+// masked column sums per fit of a batch: M is sample-major over the G * n virtual regions;
+// out[g * (S + 1) + s] = sum over the rows of fit g with mask == 0 of M[s][.] ; out[g * (S + 1) + S] = #rows
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-masked_colsums_kernel(int64_t n, int S, const double* __restrict__ M, const uint8_t* __restrict__ mask,
+masked_colsums_kernel(int64_t n, int G, int S, const double* __restrict__ M, const uint8_t* __restrict__ mask,
                       double* __restrict__ partial)
+{
+    const int64_t nv = (int64_t)G * n;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
+    for (int g = 0; g < G; g++)
+        for (int s = 0; s <= S; s++) {
+            double v[1] = {0.0};
+            for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+                const int64_t r = (int64_t)g * n + i;
+                const bool use = (mask == nullptr) || ((mask[r] & CD_FLAG_ALLZERO) == 0);
+                if (use) v[0] += (s < S) ? M[(int64_t)s * nv + r] : 1.0;
+            }
+            block_reduce_store<1>(v, partial + ((size_t)blockIdx.x * G + g) * (S + 1) + s);
+        }
+}
+
+cudaError_t launch_masked_colsums(int64_t n, int G, int S, const double* M, const uint8_t* mask, double* partial,
+                                  double* out, cudaStream_t st)
+{
+    masked_colsums_kernel<<<kReduceBlocks, 256, 0, st>>>(n, G, S, M, mask, partial);
+    final_reduce_kernel<<<G * (S + 1), 32, 0, st>>>(kReduceBlocks, G * (S + 1), partial, out);
+    return cudaGetLastError();
+}
+
+// out[g] = sum of v over the rows of fit g (NaN propagates: chicdiff.R:1647 sums without na.rm)
+__global__ void __launch_bounds__(256)
+segment_sums_kernel(int64_t n, int G, const double* __restrict__ v_in, double* __restrict__ partial)
 {
     const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * chunk;
     const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
-    for (int s = 0; s <= S; s++) {
+    for (int g = 0; g < G; g++) {
         double v[1] = {0.0};
-        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const bool use = (mask == nullptr) || ((mask[i] & CD_FLAG_ALLZERO) == 0);
-            if (use) v[0] += (s < S) ? M[(int64_t)s * n + i] : 1.0;
-        }
-        block_reduce_store<1>(v, partial + (size_t)blockIdx.x * (S + 1) + s);
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) v[0] += v_in[(int64_t)g * n + i];
+        block_reduce_store<1>(v, partial + (size_t)blockIdx.x * G + g);
     }
 }
 
-cudaError_t launch_masked_colsums(int64_t n, int S, const double* M, const uint8_t* mask, double* partial,
-                                  double* out, cudaStream_t st)
+cudaError_t launch_segment_sums(int64_t n, int G, const double* v, double* partial, double* out, cudaStream_t st)
 {
-    masked_colsums_kernel<<<kReduceBlocks, 256, 0, st>>>(n, S, M, mask, partial);
-    final_reduce_kernel<<<S + 1, 32, 0, st>>>(kReduceBlocks, S + 1, partial, out);
+    segment_sums_kernel<<<kReduceBlocks, 256, 0, st>>>(n, G, v, partial);
+    final_reduce_kernel<<<G, 32, 0, st>>>(kReduceBlocks, G, partial, out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_sum_nan(int64_t n, const double* v, double* partial, double* out, cudaStream_t st)
+// xim[g] = mean_s 1 / (colsum_s / count)   (momentsDispEstimate), sums laid out as masked_colsums writes them
+__global__ void xim_kernel(int G, int S, const double* __restrict__ sums, double* __restrict__ xim)
 {
-    return launch_masked_colsums(n, 1, v, nullptr, partial, out, st);
+    const int g = threadIdx.x;
+    if (g >= G) return;
+    const double* sg = sums + (size_t)g * (S + 1);
+    const double cnt = sg[S];
+    double acc = 0.0;
+    for (int s = 0; s < S; s++) acc += 1.0 / (sg[s] / cnt);
+    xim[g] = acc / S;
+}
+
+cudaError_t launch_xim(int G, int S, const double* sums, double* xim, cudaStream_t st)
+{
+    xim_kernel<<<1, 32, 0, st>>>(G, S, sums, xim);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
 // size factors: LR[s][i] = log K[s][i] - mean_s' log K[s'][i] for rows with every K > 0,
-// +inf otherwise (sorted to the end; the host reads the median of the finite prefix)
+// +inf otherwise (excluded from the medians)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 log_ratios_kernel(int64_t n, int S, const int32_t* __restrict__ K, double* __restrict__ LR)
@@ -114,52 +155,8 @@ cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR, cu
 }
 
 // ---------------------------------------------------------------------------------------
-// stage 2: normalisation factors.  mode 0 standard, 1 fullmean, 2 combined(theta)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-norm_factors_kernel(int64_t n, int S, const double* __restrict__ FMagg, const double* __restrict__ sf,
-                    int mode, double theta, double* __restrict__ nf)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (mode == 0) {
-        for (int s = 0; s < S; s++) nf[(int64_t)s * n + i] = sf[s];
-        return;
-    }
-    double acc = 0.0;
-    for (int s = 0; s < S; s++) acc += log(FMagg[(int64_t)s * n + i]);
-    const double g = exp(acc / S);
-    bool anyna = false;
-    for (int s = 0; s < S; s++) {
-        const double m3 = FMagg[(int64_t)s * n + i] / g;
-        anyna = anyna || isnan(m3);
-    }
-    if (mode == 1) {
-        for (int s = 0; s < S; s++) nf[(int64_t)s * n + i] = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
-        return;
-    }
-    double acc2 = 0.0;
-    for (int s = 0; s < S; s++) {
-        const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
-        acc2 += log(m3 * (1.0 - theta) + sf[s] * theta);
-    }
-    const double g2 = exp(acc2 / S);
-    for (int s = 0; s < S; s++) {
-        const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / g;
-        nf[(int64_t)s * n + i] = (m3 * (1.0 - theta) + sf[s] * theta) / g2;
-    }
-}
-
-cudaError_t launch_norm_factors(int64_t n, int S, const double* FMagg, const double* sf, int mode, double theta,
-                                double* nf, cudaStream_t st)
-{
-    if (n == 0) return cudaSuccess;
-    norm_factors_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, FMagg, sf, mode, theta, nf);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------
-// parametric trend: one pass of glm.fit(family = Gamma(link = "identity")) at coefficients b
+// parametric trend: one pass of glm.fit(family = Gamma(link = "identity")) at coefficients b (host-driven
+// variant, used when a sharded run has no peer memory: NCCL all-reduces the 8 sums between the passes)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 trend_pass_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
@@ -198,88 +195,168 @@ cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* d
 }
 
 // ---------------------------------------------------------------------------------------
-// The whole parametricDispersionFit on the device: one cooperative kernel, one CTA per SM.
-// Every pass (sums + deviance at coefficients b over the rows kept by the outer coefficients c)
-// is a chunked block reduction, a grid barrier, and a fixed-order sum of the per-CTA partials
-// that every CTA repeats for itself, so all CTAs take the same branch of glm.fit's control flow
-// (start validity, IRLS <= 25, step halving, outer loop <= 11) without a host round trip.
-// out[0..1] = coefficients, out[2] = status (0 ok; >0 = reason the reference would fall back to
-// a local fit), out[3] = outer iterations, out[4] = passes.
+// The whole parametricDispersionFit of a batch of G fits on the device: one cooperative kernel, one CTA per SM.
+// Every pass (sums + deviance at coefficients b over the rows kept by the outer coefficients c, for every fit that
+// is still running) is a chunked block reduction, a grid barrier, and a fixed-order sum of the per-CTA partials
+// that every CTA repeats for itself, so all CTAs take the same branch of glm.fit's control flow (start validity,
+// IRLS <= 25, step halving, outer loop <= 11) without a host round trip.  Thread g of every CTA runs fit g's control
+// flow; the G fits advance in lock step, so a batch costs max_g(passes) barriers, not their sum.
+// out[g * 8 + 0..1] = coefficients, [2] = status (0 ok; 1..5 = reason the reference would fall back to a local fit;
+// 6 = the exchange with another rank failed), [3] = outer iterations, [4] = passes.
 // ---------------------------------------------------------------------------------------
 constexpr int kTrendThreads = 512;
+constexpr int kTrendSlot = 8 * kMaxBatch + 8;      // doubles per mailbox slot: 8 sums per fit, then the sequence word
 
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& phase)
+__device__ __forceinline__ bool trend_grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& phase,
+                                                   unsigned long long* err)
 {
+    __shared__ int ok_sh;
     __syncthreads();
     phase++;                                   // every thread keeps the same phase count
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
-        while (atomicAdd(bar, 0u) < phase * nblocks) { }
+        int ok = 1;
+        const long long t0 = clock64();
+        while (atomicAdd(bar, 0u) < phase * nblocks) {
+            if (*reinterpret_cast<volatile unsigned long long*>(err) != 0ull) { ok = 0; break; }
+            if (clock64() - t0 > kSpinLimit) { ok = 0; atomicExch(err, 1ull); break; }
+        }
         __threadfence();
+        ok_sh = ok;
     }
     __syncthreads();
+    return ok_sh != 0;
 }
 
-// Cross-GPU part of a pass (sharded runs): CTA 0 stores this rank's 8 sums straight into every peer's
-// mailbox over NVLink (peer pointers from cudaIpcOpenMemHandle), then a sequence word.  EVERY CTA then waits
-// until all ranks' slots of the local mailbox carry this pass's sequence and adds them in rank order, so all
-// CTAs of all ranks obtain bit-identical totals and follow the same control flow, without a second grid
-// barrier.  Slots are double-buffered by pass parity: a peer can only be one pass ahead, because finishing a
-// pass needs everybody's contribution to it, and CTA 0 contributes to pass k+1 only after the grid barrier of
-// pass k+1, i.e. after all local CTAs have read pass k.  (Between two launches the stream carries other
-// collectives -- the medians -- so a peer cannot start the next launch while this one still reads.)
-__device__ __forceinline__ void p2p_allreduce8(const TrendP2P& pp, unsigned long long seq, unsigned int parity, double* sh_tot)
+// Cross-GPU part of a pass (sharded runs): CTA 0 stores this rank's sums straight into every peer's mailbox over
+// NVLink, then a sequence word.  EVERY CTA then waits until all ranks' slots of the local mailbox carry this pass's
+// sequence and adds them in rank order, so all CTAs of all ranks obtain bit-identical totals and follow the same
+// control flow, without a second grid barrier.  Slots are double-buffered by pass parity: a peer can only be one pass
+// ahead, because finishing a pass needs everybody's contribution to it, and CTA 0 contributes to pass k+1 only after
+// the grid barrier of pass k+1, i.e. after all local CTAs have read pass k.  A CTA that gives up raises the error
+// word, which ends every other spin loop (here and in the grid barrier) of this and of the following kernels.
+__device__ __forceinline__ bool p2p_allreduce(const TrendP2P& pp, unsigned long long seq, unsigned int parity, int nvals,
+                                              double* sh_tot)
 {
     __shared__ int timed_out;
     if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
-    if (blockIdx.x == 0 && (int)threadIdx.x < pp.nranks) {
-        double* dst = pp.peers[threadIdx.x] + ((size_t)parity * pp.nranks + pp.rank) * 16;
-#pragma unroll
-        for (int k = 0; k < 8; k++) dst[k] = sh_tot[k];
+    if (blockIdx.x == 0) {
+        for (int r = 0; r < pp.nranks; r++) {
+            double* dst = pp.peers[r] + ((size_t)parity * pp.nranks + pp.rank) * kTrendSlot;
+            for (int k = threadIdx.x; k < nvals; k += blockDim.x) dst[k] = sh_tot[k];
+        }
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(dst + 8) = seq;
+        __syncthreads();
+        if ((int)threadIdx.x < pp.nranks) {
+            double* dst = pp.peers[threadIdx.x] + ((size_t)parity * pp.nranks + pp.rank) * kTrendSlot;
+            *reinterpret_cast<volatile unsigned long long*>(dst + 8 * kMaxBatch) = seq;
+        }
     }
     if ((int)threadIdx.x < pp.nranks) {
         volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(
-            pp.mymail + ((size_t)parity * pp.nranks + threadIdx.x) * 16 + 8);
+            pp.mymail + ((size_t)parity * pp.nranks + threadIdx.x) * kTrendSlot + 8 * kMaxBatch);
         const long long t0 = clock64();
         while (*f != seq) {
-            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }      // ~10 s: a peer died; give up
+            if (*reinterpret_cast<volatile unsigned long long*>(pp.err) != 0ull) { timed_out = 1; break; }
+            if (clock64() - t0 > kSpinLimit) { timed_out = 1; atomicExch(pp.err, 1ull); break; }
         }
         __threadfence_system();
     }
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if ((int)threadIdx.x < nvals) {
         double x = 0.0;
         for (int r = 0; r < pp.nranks; r++)
-            x += *reinterpret_cast<volatile double*>(pp.mymail + ((size_t)parity * pp.nranks + r) * 16 + threadIdx.x);
-        if (timed_out) x = (threadIdx.x == 6) ? 1.0 : NAN;          // reads as "invalid" in the control flow below
+            x += *reinterpret_cast<volatile double*>(pp.mymail + ((size_t)parity * pp.nranks + r) * kTrendSlot + threadIdx.x);
         sh_tot[threadIdx.x] = x;
     }
     __syncthreads();
+    return timed_out == 0;
 }
 
-// One pass: the sums glm.fit needs at coefficients b over the rows kept by the outer coefficients c.
-// xs is n doubles of scratch that carries 1/baseMean between passes: NaN = row never used (all-zero region or
-// dispersion at the floor), negative = excluded by the current outer coefficients.  `refresh` = 2 on the first
+// what one pass evaluates for one fit
+struct TrendPass { double c0, c1, b0, b1; int refresh, active; };
+
+// glm.fit's control flow for one fit, advanced by one pass at a time (thread g of every CTA holds fit g's copy)
+struct TrendFit {
+    double c0, c1, b0, b1, ob0, ob1, nb0, nb1, devold;
+    double v[8];
+    int iter, it, halv, passes, status, stage;       // stage 0: first pass of an outer iteration, 1: IRLS proposal, 2: done
+    bool conv;
+
+    __device__ void init()
+    {
+        c0 = 0.1; c1 = 1.0; b0 = c0; b1 = c1; ob0 = c0; ob1 = c1; nb0 = c0; nb1 = c1; devold = 0.0;
+        iter = 0; it = 0; halv = 0; passes = 0; status = 0; stage = 0; conv = false;
+    }
+    __device__ void next_pass(TrendPass& p) const
+    {
+        p.c0 = c0; p.c1 = c1;
+        p.active = (stage != 2);
+        if (stage == 0) { p.b0 = c0; p.b1 = c1; p.refresh = (passes == 0) ? 2 : 1; }
+        else { p.b0 = nb0; p.b1 = nb1; p.refresh = 0; }
+    }
+    __device__ void propose()
+    {
+        const double det = v[0] * v[2] - v[1] * v[1];
+        nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
+        nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
+        halv = 0;
+    }
+    __device__ void outer_end()
+    {
+        const double oc0 = c0, oc1 = c1;
+        c0 = b0; c1 = b1;
+        if (!(c0 > 0.0 && c1 > 0.0)) { status = 4; stage = 2; return; }
+        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
+        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) { stage = 2; return; }
+        iter++;
+        if (iter > 10) { status = 5; stage = 2; return; }
+        stage = 0;
+    }
+    // w: the 8 totals of the pass that next_pass() described
+    __device__ void advance(const double* w)
+    {
+        passes++;
+        if (stage == 0) {
+            b0 = c0; b1 = c1; ob0 = c0; ob1 = c1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = w[k];
+            if (v[7] < 2.0) { status = 1; stage = 2; return; }
+            if (v[6] > 0.0) { status = 2; stage = 2; return; }
+            devold = v[5]; conv = false; it = 0;
+            propose();
+            stage = 1;
+            return;
+        }
+        if (!(w[6] == 0.0 && isfinite(w[5]))) {
+            if (++halv > 25) { status = 3; stage = 2; return; }
+            nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
+            return;
+        }
+        b0 = nb0; b1 = nb1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = w[k];
+        const double dev = w[5];
+        if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; outer_end(); return; }
+        devold = dev; ob0 = b0; ob1 = b1;
+        if (++it < 25) { propose(); return; }
+        outer_end();
+    }
+};
+
+// One pass for one fit: the sums glm.fit needs at coefficients b over the rows kept by the outer coefficients c.
+// xs is scratch (one double per virtual region) that carries 1/baseMean between passes: NaN = row never used (all-zero
+// region or dispersion at the floor), negative = excluded by the current outer coefficients.  refresh = 2 on the first
 // pass of the launch (fill xs), 1 on the first pass of an outer iteration (re-decide the sign), 0 otherwise.
 // Every row is always handled by the same thread, so xs needs no synchronisation.
-__device__ __forceinline__ void trend_pass_device(int64_t n, const double* __restrict__ baseMean,
-                                                  const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
-                                                  double* __restrict__ xs, int refresh,
-                                                  double c0, double c1, double b0, double b1, double* partial_base,
-                                                  unsigned int* bar, unsigned int& phase, double* sh_tot /*8, shared*/,
-                                                  const TrendP2P& pp, unsigned long long& pass_no)
+__device__ __forceinline__ void trend_pass_rows(int64_t lo, int64_t hi, const double* __restrict__ baseMean,
+                                                const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
+                                                double* __restrict__ xs, const TrendPass& p, double (&v)[8])
 {
-    // partials are double-buffered by pass parity: a CTA can be at most one pass ahead of the slowest
-    // one (there is a barrier in every pass), so one barrier per pass is enough
-    double* partial = partial_base + (size_t)(phase & 1u) * 8 * gridDim.x;
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
-    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
-    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int refresh = p.refresh;
+    const double c0 = p.c0, c1 = p.c1, b0 = p.b0, b1 = p.b1;
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         double xv;
         const double d = dispGeneEst[i];
@@ -311,100 +388,92 @@ __device__ __forceinline__ void trend_pass_device(int64_t n, const double* __res
         const double lt = (t > 1e-300 && t < 1e300) ? log_pos(t) : log(t);
         v[5] += -2.0 * (lt - (t - 1.0));
     }
-    // block reduction (fixed order)
-    __shared__ double sh[8][kTrendThreads / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        double x = v[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0) sh[k][wid] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        double x = 0.0;
-        for (int w = 0; w < kTrendThreads / 32; w++) x += sh[threadIdx.x][w];
-        __stcg(partial + (size_t)blockIdx.x * 8 + threadIdx.x, x);
-    }
-    grid_barrier(bar, gridDim.x, phase);
-    // fixed-order sum of the per-CTA partials, one warp per value; every CTA repeats it for itself
-    if (wid < 8) {
-        double x = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) x += __ldcg(partial + (size_t)b * 8 + wid);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-        if (lane == 0) sh_tot[wid] = x;
-    }
-    __syncthreads();
-    if (pp.nranks > 1) {
-        pass_no++;
-        p2p_allreduce8(pp, (pp.epoch << 32) | pass_no, (unsigned int)(pass_no & 1ull), sh_tot);
-    }
 }
 
 __global__ void __launch_bounds__(kTrendThreads)
-trend_fit_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
+trend_fit_kernel(int64_t n, int G, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
                  const uint8_t* __restrict__ flags, double* __restrict__ xs, double* partial, unsigned int* bar, double* out,
                  TrendP2P pp)
 {
-    __shared__ double tot[8];
+    __shared__ double tot[8 * kMaxBatch];
+    __shared__ double shw[8 * kMaxBatch][kTrendThreads / 32];
+    __shared__ TrendPass sp[kMaxBatch];
+    __shared__ int any_active, failed;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nvals = 8 * G;
     unsigned int phase = 0;
     unsigned long long pass_no = 0;
-    double c0 = 0.1, c1 = 1.0;
-    int iter = 0, status = 0, passes = 0;
+    TrendFit fit;
+    fit.init();
+    if (threadIdx.x == 0) failed = 0;
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
     while (true) {
-        double b0 = c0, b1 = c1, ob0 = c0, ob1 = c1;
-        trend_pass_device(n, baseMean, dispGeneEst, flags, xs, passes == 0 ? 2 : 1, c0, c1, b0, b1, partial, bar, phase, tot, pp,
-                          pass_no);
-        passes++;
-        double v[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = tot[k];
-        if (v[7] < 2.0) { status = 1; break; }
-        if (v[6] > 0.0) { status = 2; break; }
-        double devold = v[5];
-        bool conv = false;
-        for (int it = 0; it < 25 && status == 0; it++) {
-            const double det = v[0] * v[2] - v[1] * v[1];
-            double nb0 = (v[2] * v[3] - v[1] * v[4]) / det;
-            double nb1 = (v[0] * v[4] - v[1] * v[3]) / det;
-            double w[8];
-            int halv = 0;
-            while (true) {
-                trend_pass_device(n, baseMean, dispGeneEst, flags, xs, 0, c0, c1, nb0, nb1, partial, bar, phase, tot, pp, pass_no);
-                passes++;
-#pragma unroll
-                for (int k = 0; k < 8; k++) w[k] = tot[k];
-                if (w[6] == 0.0 && isfinite(w[5])) break;
-                if (++halv > 25) { status = 3; break; }
-                nb0 = 0.5 * (nb0 + ob0); nb1 = 0.5 * (nb1 + ob1);
+        if ((int)threadIdx.x < G) fit.next_pass(sp[threadIdx.x]);
+        if (threadIdx.x == 0) any_active = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < G && sp[threadIdx.x].active) any_active = 1;
+        __syncthreads();
+        if (!any_active) break;
+        // partials are double-buffered by pass parity: a CTA can be at most one pass ahead of the slowest
+        // one (there is a barrier in every pass), so one barrier per pass is enough
+        double* part = partial + (size_t)(phase & 1u) * nvals * gridDim.x;
+        for (int g = 0; g < G; g++) {
+            double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (sp[g].active) {
+                const int64_t off = (int64_t)g * n;
+                trend_pass_rows(off + lo, off + hi, baseMean, dispGeneEst, flags, xs, sp[g], v);
             }
-            if (status) break;
-            b0 = nb0; b1 = nb1;
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = w[k];
-            const double dev = w[5];
-            if (fabs(dev - devold) / (fabs(dev) + 0.1) < 1e-8) { conv = true; break; }
-            devold = dev; ob0 = b0; ob1 = b1;
+            for (int k = 0; k < 8; k++) {
+                double x = v[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                if (lane == 0) shw[g * 8 + k][wid] = x;
+            }
         }
-        if (status) break;
-        const double oc0 = c0, oc1 = c1;
-        c0 = b0; c1 = b1;
-        if (!(c0 > 0.0 && c1 > 0.0)) { status = 4; break; }
-        const double l0 = log(c0 / oc0), l1 = log(c1 / oc1);
-        if ((l0 * l0 + l1 * l1 < 1e-6) && conv) break;
-        iter++;
-        if (iter > 10) { status = 5; break; }
+        __syncthreads();
+        if ((int)threadIdx.x < nvals) {
+            double x = 0.0;
+            for (int w = 0; w < kTrendThreads / 32; w++) x += shw[threadIdx.x][w];
+            __stcg(part + (size_t)blockIdx.x * nvals + threadIdx.x, x);
+        }
+        bool ok = trend_grid_barrier(bar, gridDim.x, phase, pp.err);
+        if (ok) {
+            // fixed-order sum of the per-CTA partials, one warp per value; every CTA repeats it for itself
+            for (int k = wid; k < nvals; k += kTrendThreads / 32) {
+                double x = 0.0;
+                for (unsigned b = lane; b < gridDim.x; b += 32) x += __ldcg(part + (size_t)b * nvals + k);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+                if (lane == 0) tot[k] = x;
+            }
+            __syncthreads();
+            if (pp.nranks > 1) {
+                pass_no++;
+                ok = p2p_allreduce(pp, (pp.epoch << 32) | pass_no, (unsigned int)(pass_no & 1ull), nvals, tot);
+            }
+        }
+        if (!ok) {
+            if (threadIdx.x == 0) failed = 1;
+            __syncthreads();
+            break;
+        }
+        if ((int)threadIdx.x < G && sp[threadIdx.x].active) fit.advance(tot + 8 * threadIdx.x);
+        __syncthreads();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        out[0] = c0; out[1] = c1; out[2] = (double)status; out[3] = (double)(iter + 1); out[4] = (double)passes;
+    if (blockIdx.x == 0 && (int)threadIdx.x < G) {
+        double* o = out + 8 * threadIdx.x;
+        o[0] = fit.c0; o[1] = fit.c1; o[2] = failed ? 6.0 : (double)fit.status; o[3] = (double)(fit.iter + 1);
+        o[4] = (double)fit.passes;
     }
 }
 
-cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+cudaError_t launch_trend_fit(int64_t n, int G, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
                              double* xs, double* partial, unsigned int* bar, double* out, const TrendP2P& pp_in, cudaStream_t st)
 {
+    if (G < 1 || G > kMaxBatch) return cudaErrorInvalidValue;
     TrendP2P pp = pp_in;
     int dev = 0, sms = 148, coop = 0;
     cudaGetDevice(&dev);
@@ -413,31 +482,32 @@ cudaError_t launch_trend_fit(int64_t n, const double* baseMean, const double* di
     if (!coop) return cudaErrorNotSupported;
     cudaError_t e = cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
-    void* args[] = {(void*)&n, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&xs, (void*)&partial, (void*)&bar, (void*)&out,
-                    (void*)&pp};
+    void* args[] = {(void*)&n, (void*)&G, (void*)&baseMean, (void*)&dispGeneEst, (void*)&flags, (void*)&xs, (void*)&partial, (void*)&bar,
+                    (void*)&out, (void*)&pp};
     return cudaLaunchCooperativeKernel((const void*)trend_fit_kernel, dim3((unsigned)sms), dim3(kTrendThreads), args, 0, st);
 }
 
-// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded ; coefficients on device
+// dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded ; coefs[g * 8 + 0..1] on device
 __global__ void __launch_bounds__(256)
-trend_apply_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
+trend_apply_kernel(int64_t n, int64_t n_fit, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
                    const uint8_t* __restrict__ flags, const double* __restrict__ coefs, double* __restrict__ dispFit,
                    double* __restrict__ resid)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) { dispFit[i] = NAN; resid[i] = INFINITY; return; }
-    const double f = coefs[0] + coefs[1] / baseMean[i];
+    const double* c = coefs + 8 * (i / n_fit);
+    const double f = c[0] + c[1] / baseMean[i];
     const double d = dispGeneEst[i];
     dispFit[i] = f;
     resid[i] = (d >= 100.0 * kMinDisp) ? log(d) - log(f) : INFINITY;
 }
 
-cudaError_t launch_trend_apply(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
+cudaError_t launch_trend_apply(int64_t n, int64_t n_fit, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
                                const double* coefs_dev, double* dispFit, double* resid, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, baseMean, dispGeneEst, flags, coefs_dev, dispFit, resid);
+    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, baseMean, dispGeneEst, flags, coefs_dev, dispFit, resid);
     return cudaGetLastError();
 }
 

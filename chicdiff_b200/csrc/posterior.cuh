@@ -6,12 +6,6 @@
 
 namespace cd {
 
-// c_des, the design of the running fit, must be visible here: dispersion.cu defines it in constant memory before
-// including this header (set_design_dispersion fills it); the host build of the accuracy tests supplies a plain global.
-#ifndef __CUDACC__
-extern CdDesign c_des;
-#endif
-
 // ---------------------------------------------------------------------------------------
 // Cox-Reid adjusted profile log-posterior of log(alpha) (DESeq2.cpp log_posterior) and its
 // derivative (dlog_posterior), evaluated together at one point.  The line search needs the
@@ -19,24 +13,72 @@ extern CdDesign c_des;
 // share exp(a), w_j = 1/(1/mu_j + alpha), log(1 + mu_j alpha), log(y_j + r + 10) and the shifted
 // gamma-function rationals, so the pair costs ~1.3x the posterior alone, and the lanes of a warp
 // never split into "needs the derivative" and "does not".
-// ys / mus point at the region's replicates in shared memory, element j at [j * stride].
+// ys / mus point at the region's replicates in shared memory, element j at [j * stride];
+// Xd is the S x P model matrix (row-major; shared memory on the device: every lane reads the same entry).
 // WANT_D = false (grid refit) skips the derivative.
+//
+// Formulation (what the per-source-line profile of round 1 led to; profiles/r01_final_fit_disp_source_lines.txt):
+//   * log Gamma and digamma of x = y_j + r come from the shift-10 scheme of common.cuh, but the logarithm of the
+//     rational's denominator is not taken per replicate: with q_j = den_j / den_r (>= 1, the ratio against the rational
+//     of r = 1/alpha alone) the sum over replicates of [log den_j - log den_r] is log(q_a q_b) per PAIR of replicates:
+//     2.5 instead of 3 logarithms per replicate, and a zero count still contributes (almost) exactly zero;
+//   * p = 1 and p = 2 (every fit of the default pipeline) use the closed-form determinant and inverse of X'WX with
+//     one Newton reciprocal and one logarithm; p = 3, 4 keep the packed Cholesky;
+//   * TABLOG = true takes every logarithm with log_pos_v2 (table in shared memory, no reciprocal); false with log_pos.
 // ---------------------------------------------------------------------------------------
-template <int P, bool WANT_D>
+struct GammaParts { double st, dgs, num, den; };      // st: Stirling part of lgamma; dgs: series part of digamma
+
+template <bool TABLOG>
+__device__ __forceinline__ double post_log(double x, const double* tab)
+{
+    return TABLOG ? log_pos_v2(x, tab) : log_pos(x);
+}
+
+// the pieces of lgamma_digamma_pos, with the rational's denominator handed back instead of logged
+template <bool TABLOG>
+__device__ __forceinline__ GammaParts gamma_parts(double x, const double* tab)
+{
+    GammaParts g;
+    double num = 1.0, den = x;
+#pragma unroll
+    for (int k = 1; k < 10; k++) {
+        const double t = x + (double)k;
+        num = fma(num, t, den);
+        den *= t;
+    }
+    const double xs = x + 10.0;
+    const double xi = rcp_pos(xs);
+    const double f = xi * xi;
+    const double lxs = post_log<TABLOG>(xs, tab);
+    double t = kLgamC[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) t = fma(f, t, kLgamC[k]);
+    g.st = ((xs - 0.5) * lxs - xs) + xi * t;
+    double u = kDigamC[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) u = fma(f, u, kDigamC[k]);
+    g.dgs = (lxs - 0.5 * xi) + f * u;
+    g.num = num; g.den = den;
+    return g;
+}
+
+template <int P, bool WANT_D, bool TABLOG>
 __device__ __forceinline__ void eval_post(double a, const double* ys, const double* mus, int stride, int S,
+                                          const double* Xd, const double* tab,
                                           double prior_mean, double prior_sigmasq, bool use_prior,
                                           double& lp_out, double& dlp_out)
 {
     const double alpha = exp(a);
     const double r = rcp_pos(alpha);
     const double log_r = -a;                            // log(1/alpha)
-    double lgr, dgr;
-    lgamma_digamma_pos(r, lgr, dgr);
+    const GammaParts gr = gamma_parts<TABLOG>(r, tab);
+    const double inv_den_r = rcp_pos(gr.den);
+    const double dgr = gr.dgs - gr.num * inv_den_r;
     Sym<P> B, dB;
 #pragma unroll
     for (int k = 0; k < P * (P + 1) / 2; k++) { B.v[k] = 0.0; dB.v[k] = 0.0; }
-    double ll = 0.0, ds = 0.0;
-    // (measured: unrolling this loop by 2 doubles the registers to 188 and is 24 % slower)
+    double ll = 0.0, ds = 0.0, qprod = 1.0;
+    // (measured in round 1: unrolling this loop by 2 doubles the registers and is 24 % slower)
 #pragma unroll 1
     for (int j = 0; j < S; j++) {
         const double yj = ys[j * stride], muj = mus[j * stride];
@@ -44,19 +86,107 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
         const double ropm = rcp_pos(1.0 + ma);
         const double w = muj * ropm;                    // = 1 / (1/mu + alpha)
         const double dw = -w * w;
+        if (P == 1) {
+            B.v[0] += w;
+            if (WANT_D) dB.v[0] += dw;
+        } else {
+#pragma unroll
+            for (int u = 0; u < P; u++)
+#pragma unroll
+                for (int v = 0; v <= u; v++) {
+                    const double xx = Xd[j * P + u] * Xd[j * P + v];
+                    B.v[u * (u + 1) / 2 + v] += w * xx;
+                    if (WANT_D) dB.v[u * (u + 1) / 2 + v] += dw * xx;
+                }
+        }
+        const double l1 = post_log<TABLOG>(1.0 + ma, tab);
+        const GammaParts g = gamma_parts<TABLOG>(yj + r, tab);
+        qprod *= g.den * inv_den_r;                       // den_j / den_r >= 1
+        if (j & 1) { ll -= post_log<TABLOG>(qprod, tab); qprod = 1.0; }      // one logarithm per pair of replicates
+        // mu + r = r (1 + mu alpha): log(mu + r) = log r + log(1 + mu alpha), 1/(mu + r) = alpha / (1 + mu alpha)
+        // for a zero count g.st - gr.st and dgr - dg are exactly zero (same instruction sequence, same input)
+        ll += ((g.st - gr.st) - yj * (log_r + l1)) - r * l1;
+        if (WANT_D) {
+            const double dg = g.dgs - g.num * rcp_pos(g.den);
+            ds += ((dgr - dg) + (l1 - ma * ropm)) + yj * (alpha * ropm);
+        }
+    }
+    if (S & 1) ll -= post_log<TABLOG>(qprod, tab);
+    double cr, dcr = 0.0;
+    if (P == 1) {
+        const double b = B.v[0];
+        cr = -0.5 * ((b > 0.0) ? post_log<TABLOG>(b, tab) : NAN);
+        if (WANT_D) dcr = -0.5 * (dB.v[0] * rcp_pos(b));
+    } else if (P == 2) {
+        const double det = B.v[0] * B.v[2] - B.v[1] * B.v[1];
+        const bool ok = (B.v[0] > 0.0) && (det > 0.0);
+        cr = -0.5 * (ok ? post_log<TABLOG>(det, tab) : NAN);
+        if (WANT_D) {
+            // tr(B^-1 dB) = (B11 dB00 - 2 B10 dB10 + B00 dB11) / det
+            const double tr = (B.v[2] * dB.v[0] - 2.0 * B.v[1] * dB.v[1] + B.v[0] * dB.v[2]) * rcp_pos(det);
+            dcr = -0.5 * tr;
+        }
+    } else {
+        Sym<P> L = B;
+        cr = -0.5 * chol_logdet<P>(L);
+        if (WANT_D) {
+            Sym<P> Bi;
+            chol_inverse<P>(L, Bi);
+            double tr = 0.0;
+#pragma unroll
+            for (int u = 0; u < P; u++)
+#pragma unroll
+                for (int v = 0; v < P; v++) tr += Bi.v[sidx<P>(u, v)] * dB.v[sidx<P>(v, u)];
+            dcr = -0.5 * tr;
+        }
+    }
+    double pr = 0.0;
+    if (use_prior) {
+        const double d = a - prior_mean;
+        pr = -0.5 * d * d / prior_sigmasq;
+    }
+    lp_out = ll + pr + cr;
+    if (WANT_D) {
+        const double dpr = use_prior ? -1.0 * (a - prior_mean) / prior_sigmasq : 0.0;
+        dlp_out = ((r * r) * ds + dcr) * alpha + dpr;
+    }
+}
+
+// The first formulation (round 1): one lgamma_digamma_pos per replicate with its own log of the rational's denominator,
+// Cholesky for every p.  Kept as the reference the accuracy tests compare eval_post with (tests/test_device_math.py);
+// the kernels do not use it.
+template <int P, bool WANT_D>
+__device__ __forceinline__ void eval_post_ref(double a, const double* ys, const double* mus, int stride, int S,
+                                              const double* Xd, double prior_mean, double prior_sigmasq, bool use_prior,
+                                              double& lp_out, double& dlp_out)
+{
+    const double alpha = exp(a);
+    const double r = rcp_pos(alpha);
+    const double log_r = -a;
+    double lgr, dgr;
+    lgamma_digamma_pos(r, lgr, dgr);
+    Sym<P> B, dB;
+#pragma unroll
+    for (int k = 0; k < P * (P + 1) / 2; k++) { B.v[k] = 0.0; dB.v[k] = 0.0; }
+    double ll = 0.0, ds = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < S; j++) {
+        const double yj = ys[j * stride], muj = mus[j * stride];
+        const double ma = muj * alpha;
+        const double ropm = rcp_pos(1.0 + ma);
+        const double w = muj * ropm;
+        const double dw = -w * w;
 #pragma unroll
         for (int u = 0; u < P; u++)
 #pragma unroll
             for (int v = 0; v <= u; v++) {
-                const double xx = c_des.X[j * P + u] * c_des.X[j * P + v];
+                const double xx = Xd[j * P + u] * Xd[j * P + v];
                 B.v[u * (u + 1) / 2 + v] += w * xx;
                 if (WANT_D) dB.v[u * (u + 1) / 2 + v] += dw * xx;
             }
         const double l1 = log_pos(1.0 + ma);
         double lg, dg;
         lgamma_digamma_pos(yj + r, lg, dg);
-        // mu + r = r (1 + mu alpha): log(mu + r) = log r + log(1 + mu alpha), 1/(mu + r) = alpha / (1 + mu alpha)
-        // for a zero count lg - lgr and dgr - dg are exactly zero (same instruction sequence, same input)
         ll += ((lg - lgr) - yj * (log_r + l1)) - r * l1;
         if (WANT_D) ds += ((dgr - dg) + (l1 - ma * ropm)) + yj * (alpha * ropm);
     }

@@ -28,12 +28,8 @@
 
 namespace cd {
 
-__constant__ CdDesign c_desw;
-
-cudaError_t set_design_wald(const CdDesign& d, cudaStream_t st)
-{
-    return cudaMemcpyToSymbolAsync(c_desw, &d, sizeof(CdDesign), 0, cudaMemcpyHostToDevice, st);
-}
+// The design of the running fit is read through a pointer into the context's own device copy and staged in shared
+// memory (every lane reads the same entry); no __constant__ globals, so contexts of one process do not share state.
 
 constexpr int kWaldThreads = 128;
 constexpr double kHalfLn2Pi = 0.918938533204672741780329736406;
@@ -54,10 +50,13 @@ __device__ __forceinline__ double nb_logdens(double y, double size, double alpha
 // prep
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-wald_prep_kernel(int64_t n, int S, int P, const int32_t* __restrict__ K, const double* __restrict__ nf,
-                 const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
+wald_prep_kernel(int64_t n, int S, int P, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
+                 const double* __restrict__ nf, const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
                  double* __restrict__ cmat, double* __restrict__ beta0)
 {
+    __shared__ double ls[CD_MAXP * CD_MAXS];
+    for (int k = threadIdx.x; k < P * S; k += blockDim.x) ls[k] = des->ls[k];
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) return;
@@ -71,7 +70,7 @@ wald_prep_kernel(int64_t n, int S, int P, const int32_t* __restrict__ K, const d
         cmat[(int64_t)j * n + i] = ((lgamma_c_pos(y + size) - lgs) - lgamma_c_pos(y + 1.0)) - kHalfLn2Pi;
         if (beta0) {
             const double l = log_pos(y * rcp_pos(nf[(int64_t)j * n + i]) + 0.1);
-            for (int u = 0; u < P; u++) b[u] += c_desw.ls[u * S + j] * l;
+            for (int u = 0; u < P; u++) b[u] += ls[u * S + j] * l;
         }
     }
     if (beta0) for (int u = 0; u < P; u++) beta0[(int64_t)u * n + i] = b[u];
@@ -83,7 +82,7 @@ wald_prep_kernel(int64_t n, int S, int P, const int32_t* __restrict__ K, const d
 // one sweep over the samples at coefficients beta: X'WX (packed, no ridge), X'Wz and the deviance
 template <int P>
 __device__ __forceinline__ void irls_pass(const double* beta, double alpha, double size, int S, int stride,
-                                          const double* ys, const double* nfs, const double* cs,
+                                          const double* ys, const double* nfs, const double* cs, const double* Xs,
                                           Sym<P>& A, double* b, double& dev)
 {
 #pragma unroll
@@ -96,7 +95,7 @@ __device__ __forceinline__ void irls_pass(const double* beta, double alpha, doub
         const double yj = ys[j * stride], nfj = nfs[j * stride];
         double eta = 0.0;
 #pragma unroll
-        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+        for (int u = 0; u < P; u++) eta += Xs[j * P + u] * beta[u];
         double mu = nfj * exp(eta);
         double lmn = eta;
         if (!(mu >= kMinMu)) { mu = kMinMu; lmn = log_pos(kMinMu * rcp_pos(nfj)); }     // fmax(mu, minmu)
@@ -105,10 +104,10 @@ __device__ __forceinline__ void irls_pass(const double* beta, double alpha, doub
         const double z = lmn + (yj - mu) * rcp_pos(mu);
 #pragma unroll
         for (int u = 0; u < P; u++) {
-            const double xu = c_desw.X[j * P + u];
+            const double xu = Xs[j * P + u];
             b[u] += w * z * xu;
 #pragma unroll
-            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * xu * c_desw.X[j * P + v];
+            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * xu * Xs[j * P + v];
         }
     }
     dev = -2.0 * ll;
@@ -116,7 +115,7 @@ __device__ __forceinline__ void irls_pass(const double* beta, double alpha, doub
 
 template <int P>
 __global__ void __launch_bounds__(kWaldThreads)
-wald_irls_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+wald_irls_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K, const double* __restrict__ nf,
                  const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
                  const double* __restrict__ cmat, const double* __restrict__ beta0,
                  double* __restrict__ beta_out /*P x n, natural log scale*/, int32_t* __restrict__ iter_out,
@@ -127,6 +126,9 @@ wald_irls_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* 
     double* ys = smem + threadIdx.x;
     double* nfs = smem + (size_t)S * stride + threadIdx.x;
     double* cs = smem + (size_t)2 * S * stride + threadIdx.x;
+    double* Xs = smem + (size_t)3 * S * stride;
+    for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const double lambda = 1e-6 / (kLn2 * kLn2);
 
@@ -196,7 +198,7 @@ wald_irls_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* 
         __syncwarp();
         // ---- one sweep over the replicates at the current coefficients ----
         double dev = 0.0;
-        if (active && !finished) irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, A, rhs, dev);
+        if (active && !finished) irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, Xs, A, rhs, dev);
         __syncwarp();
         if (active && !finished) {
             if (fresh) {
@@ -240,7 +242,7 @@ __device__ __forceinline__ int trim_bin(int n) { return n <= 3 ? 0 : (n <= 23 ? 
 
 template <int P>
 __global__ void __launch_bounds__(kWaldThreads)
-wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+wald_final_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K, const double* __restrict__ nf,
                   const double* __restrict__ dispersion, uint8_t* __restrict__ flags,
                   const double* __restrict__ cmat, const double* __restrict__ beta_nat,
                   const int32_t* __restrict__ iter_in,
@@ -248,6 +250,12 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
                   double* __restrict__ pvalue_out, double* __restrict__ deviance_out, double* __restrict__ maxCooks_out,
                   int32_t* __restrict__ betaIter_out, double* __restrict__ mu_out)
 {
+    __shared__ double Xs[CD_MAXS * CD_MAXP];
+    __shared__ int cell[CD_MAXS], cell_size[CD_MAXS];
+    for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
+    for (int k = threadIdx.x; k < S; k += blockDim.x) { cell[k] = des->cell[k]; cell_size[k] = des->cell_size[k]; }
+    __syncthreads();
+    const int ncell = des->ncell, any3 = des->any3;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const bool mu_only = (mu_out != nullptr);
@@ -276,7 +284,7 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
         for (int j = 0; j < S; j++) {
             double eta = 0.0;
 #pragma unroll
-            for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+            for (int u = 0; u < P; u++) eta += Xs[j * P + u] * beta[u];
             mu_out[(int64_t)j * n + i] = fmax(nf[(int64_t)j * n + i] * exp(eta), kMinMu);
         }
         return;
@@ -290,7 +298,7 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
         const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
         double eta = 0.0;
 #pragma unroll
-        for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+        for (int u = 0; u < P; u++) eta += Xs[j * P + u] * beta[u];
         const double muw = nfj * exp(eta);                   // unfloored, as stored by nbinomWaldTest
         loglike += nb_logdens(yj, size, alpha, muw, cmat[(int64_t)j * n + i]);
         const double muc = (P == 1) ? muw : fmax(muw, kMinMu);
@@ -298,7 +306,7 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
 #pragma unroll
         for (int u = 0; u < P; u++)
 #pragma unroll
-            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * c_desw.X[j * P + u] * c_desw.X[j * P + v];
+            for (int v = 0; v <= u; v++) A.v[u * (u + 1) / 2 + v] += w * Xs[j * P + u] * Xs[j * P + v];
     }
     Sym<P> Ar = A, Ari;
     if (P > 1) {
@@ -323,18 +331,18 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
     if (maxCooks_out) {
         // robust method-of-moments dispersion for Cook's distance
         double v, tmp[CD_MAXS];
-        if (c_desw.any3) {
+        if (any3) {
             v = -INFINITY;
-            for (int c = 0; c < c_desw.ncell; c++) {
-                const int nc = c_desw.cell_size[c];
+            for (int c = 0; c < ncell; c++) {
+                const int nc = cell_size[c];
                 if (nc < 3) continue;
                 const double trimr = (trim_bin(nc) == 0) ? 1.0 / 3.0 : (trim_bin(nc) == 1 ? 1.0 / 4.0 : 1.0 / 8.0);
                 const double scalec = (trim_bin(nc) == 0) ? 2.04 : (trim_bin(nc) == 1 ? 1.86 : 1.51);
                 int k = 0;
-                for (int j = 0; j < S; j++) if (c_desw.cell[j] == c) tmp[k++] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
+                for (int j = 0; j < S; j++) if (cell[j] == c) tmp[k++] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
                 const double cm = trimmed_mean_dev(tmp, nc, trimr);
                 k = 0;
-                for (int j = 0; j < S; j++) if (c_desw.cell[j] == c) {
+                for (int j = 0; j < S; j++) if (cell[j] == c) {
                     const double d = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i] - cm;
                     tmp[k++] = d * d;
                 }
@@ -354,7 +362,7 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
             const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
             double eta = 0.0;
 #pragma unroll
-            for (int u = 0; u < P; u++) eta += c_desw.X[j * P + u] * beta[u];
+            for (int u = 0; u < P; u++) eta += Xs[j * P + u] * beta[u];
             const double muw = nfj * exp(eta);
             const double muc = (P == 1) ? muw : fmax(muw, kMinMu);
             const double w = muc / (1.0 + alpha * muc);
@@ -363,17 +371,17 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
             for (int u = 0; u < P; u++)
 #pragma unroll
                 for (int v2 = 0; v2 < P; v2++)
-                    h += c_desw.X[j * P + u] * Ari.v[sidx<P>(u, v2)] * c_desw.X[j * P + v2];
+                    h += Xs[j * P + u] * Ari.v[sidx<P>(u, v2)] * Xs[j * P + v2];
             h *= w;
             const double V = muw + ar * muw * muw;
             const double ck = (yj - muw) * (yj - muw) / V / (double)P * h / ((1.0 - h) * (1.0 - h));
-            if (c_desw.cell_size[c_desw.cell[j]] >= 3 && ck > mc) mc = ck;
+            if (cell_size[cell[j]] >= 3 && ck > mc) mc = ck;
             if (ck > ck_best) { ck_best = ck; y_best = yj; }        // which.max: first maximum
         }
         int greater = 0;
         for (int j = 0; j < S; j++) greater += ((double)K[(int64_t)j * n + i] > y_best);
         if (greater >= 3) f |= CD_FLAG_COOKS_KEEP;
-        maxCooks_out[i] = (S > P && c_desw.any3) ? mc : NAN;
+        maxCooks_out[i] = (S > P && any3) ? mc : NAN;
     }
     flags[i] = f;
 #pragma unroll
@@ -388,16 +396,52 @@ wald_final_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double*
     betaIter_out[i] = iter;
 }
 
-cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double* nf, const double* dispersion,
+// ---------------------------------------------------------------------------------------
+// The theta-grid fits (design ~ 1, chicdiff.R:1641-1647) are only asked for their total deviance: fitNbinomGLMs'
+// intercept-only shortcut (beta = log mean(K / nf)) and -2 log-likelihood at mu = nf exp(beta), in one kernel over the
+// virtual regions of the batch, with the arithmetic of wald_prep_kernel + wald_final_kernel<1>.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wald_deviance_p1_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
+                        const double* __restrict__ dispersion, const uint8_t* __restrict__ flags, double* __restrict__ deviance_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] & CD_FLAG_ALLZERO) { deviance_out[i] = NAN; return; }
+    const double alpha = dispersion[i];
+    const double size = rcp_pos(alpha);
+    const double lgs = lgamma_c_pos(size);
+    double qsum = 0.0;
+    for (int j = 0; j < S; j++) qsum += (double)K[(int64_t)j * n + i] * rcp_pos(nf[(int64_t)j * n + i]);
+    const double beta = log_pos(qsum / S);
+    const double eb = exp(beta);
+    double loglike = 0.0;
+    for (int j = 0; j < S; j++) {
+        const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
+        const double c = ((lgamma_c_pos(yj + size) - lgs) - lgamma_c_pos(yj + 1.0)) - kHalfLn2Pi;
+        loglike += nb_logdens(yj, size, alpha, nfj * eb, c);
+    }
+    deviance_out[i] = -2.0 * loglike;
+}
+
+cudaError_t launch_wald_deviance_p1(int64_t n, int S, const int32_t* K, const double* nf, const double* dispersion,
+                                    const uint8_t* flags, double* deviance, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    wald_deviance_p1_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, dispersion, flags, deviance);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wald(int64_t n, int S, int p, const CdDesign* des, const int32_t* K, const double* nf, const double* dispersion,
                         uint8_t* flags, const WaldScratch& ws, double* beta, double* betaSE, double* stat,
                         double* pvalue, double* deviance, double* maxCooks, int32_t* betaIter, double* mu_out,
                         cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     cudaError_t e;
-    wald_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, p, K, nf, dispersion, flags, ws.cmat, p > 1 ? ws.beta0 : nullptr);
+    wald_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, p, des, K, nf, dispersion, flags, ws.cmat, p > 1 ? ws.beta0 : nullptr);
     const int threads = kWaldThreads;
-    const size_t smem = (size_t)3 * S * threads * sizeof(double);
+    const size_t smem = ((size_t)3 * S * threads + (size_t)S * p) * sizeof(double);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -413,10 +457,10 @@ cudaError_t launch_wald(int64_t n, int S, int p, const int32_t* K, const double*
         if (e != cudaSuccess) return e;                                                                          \
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                       \
         wald_irls_kernel<P_><<<(int)(want < resident ? want : resident), threads, smem, st>>>(                   \
-            n, S, K, nf, dispersion, flags, ws.cmat, ws.beta0, ws.beta_nat, ws.iter, ws.work_counter);        \
+            n, S, des, K, nf, dispersion, flags, ws.cmat, ws.beta0, ws.beta_nat, ws.iter, ws.work_counter);   \
     }
 #define CD_FINAL(P_)                                                                                             \
-    wald_final_kernel<P_><<<blocks_for(n, threads), threads, 0, st>>>(n, S, K, nf, dispersion, flags, ws.cmat,   \
+    wald_final_kernel<P_><<<blocks_for(n, threads), threads, 0, st>>>(n, S, des, K, nf, dispersion, flags, ws.cmat, \
         ws.beta_nat, ws.iter, beta, betaSE, stat, pvalue, deviance, maxCooks, betaIter, mu_out)
     switch (p) {
         case 1: CD_FINAL(1); break;

@@ -35,7 +35,8 @@ PRIOR_VAR_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int64, C.POINTER
 class CdOptions(C.Structure):
     _fields_ = [("norm", C.c_int), ("theta", C.c_double), ("theta_grid", C.POINTER(C.c_double)),
                 ("n_theta_grid", C.c_int), ("disp_prior_var", C.c_double), ("disp_prior_var_grid", C.c_double),
-                ("disp_grid_len", C.c_int), ("prior_var_fn", PRIOR_VAR_FN), ("prior_var_user", C.c_void_p)]
+                ("disp_grid_len", C.c_int), ("prior_var_fn", PRIOR_VAR_FN), ("prior_var_user", C.c_void_p),
+                ("trend_a0", C.c_double), ("trend_a1", C.c_double), ("var_log_disp", C.c_double)]
 
 
 class CdSampleTables(C.Structure):
@@ -361,7 +362,8 @@ class Engine:
         return None
 
     def region_test(self, norm="combined", theta=None, theta_grid=None, disp_prior_var=None,
-                    disp_prior_var_grid=None, disp_grid_len=20, fetch="all", prior_var_fn=None):
+                    disp_prior_var_grid=None, disp_grid_len=20, fetch="all", prior_var_fn=None, trend=None,
+                    var_log_disp=None):
         """cd_region_test.  fetch: "all" | "table" (columns of the output table only) | "none".
         prior_var_fn(df, residuals) -> dispPriorVar is asked once per dispersion fit whose design has S - p <= 3 and no
         disp_prior_var* given (the place where an R front end evaluates DESeq2's Monte-Carlo rule)."""
@@ -377,6 +379,9 @@ class Engine:
         opt.disp_prior_var = float("nan") if disp_prior_var is None else float(disp_prior_var)
         opt.disp_prior_var_grid = float("nan") if disp_prior_var_grid is None else float(disp_prior_var_grid)
         opt.disp_grid_len = disp_grid_len
+        nan = float("nan")
+        opt.trend_a0, opt.trend_a1 = (nan, nan) if trend is None else (float(trend[0]), float(trend[1]))
+        opt.var_log_disp = nan if var_log_disp is None else float(var_log_disp)
         cb_error = []
         if prior_var_fn is not None:
             def _cb(_user, df, m, ptr):

@@ -189,6 +189,14 @@ typedef struct {
      * dispPriorVar; an R front end evaluates DESeq2's own rule there.  NaN return = failure. */
     double (*prior_var_fn)(void* user, int df, int64_t n_resid, const double* resid);
     void* prior_var_user;
+    /* Global scalars of the FINAL fit taken from the caller instead of being estimated (NaN or 0 = estimate, so a
+     * zero-initialised struct behaves as before): the parametric trend dispFit = trend_a0 + trend_a1 / baseMean
+     * (DESeq2 dispersionFunction coefficients asymptDisp, extraPois) and varLogDispEsts (the squared MAD of the log
+     * residuals).  Like disp_prior_var they exist so that a fit can be repeated with known scalars -- a control set
+     * fitted with the test set's trend, or a parity check that hands both implementations the same values so that
+     * per-region agreement is not blurred by the coupling through the global fits. */
+    double trend_a0, trend_a1;
+    double var_log_disp;
 } cd_options;
 
 typedef struct {

@@ -454,27 +454,55 @@ static void design_init(design_t* d, int S, int p, const double* X)
 
 typedef struct { int64_t lp_evals, dlp_evals, irls_iters, disp_iters; } orc_counters;
 
-/* DESeq2.cpp log_posterior */
-static double log_posterior(double log_alpha, const double* y, const double* mu, const design_t* d,
-                            double prior_mean, double prior_sigmasq, int use_prior, int use_cr)
+/* Arithmetic of the posterior.  The default is plain double, like DESeq2.cpp.  -DORC_LD evaluates the same
+ * expressions in long double (x87 80-bit: lgammal, logl, expl) and rounds once at the end: a variant used ONLY by
+ * scripts/oracle_flip_evidence.py to show which rows' line-search decisions depend on the rounding of the
+ * reference's own double arithmetic. */
+#ifdef ORC_LD
+typedef long double orc_real;
+#define ORC_LGAMMA lgammal
+#define ORC_LOG logl
+#define ORC_EXP expl
+#else
+typedef double orc_real;
+#define ORC_LGAMMA lgamma
+#define ORC_LOG log
+#define ORC_EXP exp
+#endif
+
+/* DESeq2.cpp log_posterior.  noise_out (may be NULL) receives 2^-53 x the sum of the magnitudes of the terms that
+ * are added up: the size of one rounding error of the value in double arithmetic. */
+static double log_posterior_n(double log_alpha, const double* y, const double* mu, const design_t* d,
+                              double prior_mean, double prior_sigmasq, int use_prior, int use_cr, double* noise_out)
 {
     int S = d->S, p = d->p;
-    double alpha = exp(log_alpha);
+    orc_real alpha = ORC_EXP((orc_real)log_alpha);
     double w[ORC_MAXS];
-    for (int j = 0; j < S; j++) w[j] = 1.0 / (1.0 / mu[j] + alpha);
-    double cr = 0;
+    for (int j = 0; j < S; j++) w[j] = (double)(1.0 / (1.0 / (orc_real)mu[j] + alpha));
+    orc_real cr = 0;
     if (use_cr) {
         double B[ORC_MAXP * ORC_MAXP];
         xtwx(d->X, w, S, p, B);
-        cr = -0.5 * log(det_inv(B, p, NULL));
+        cr = -0.5 * ORC_LOG((orc_real)det_inv(B, p, NULL));
     }
-    double an1 = 1.0 / alpha;
-    double lgr = lgamma(an1);
-    double ll = 0;
-    for (int j = 0; j < S; j++)
-        ll += lgamma(y[j] + an1) - lgr - y[j] * log(mu[j] + an1) - an1 * log(1.0 + mu[j] * alpha);
-    double pr = use_prior ? -0.5 * (log_alpha - prior_mean) * (log_alpha - prior_mean) / prior_sigmasq : 0.0;
-    return ll + pr + cr;
+    orc_real an1 = 1.0 / alpha;
+    orc_real lgr = ORC_LGAMMA(an1);
+    orc_real ll = 0;
+    double mag = 0;
+    for (int j = 0; j < S; j++) {
+        orc_real t1 = ORC_LGAMMA(y[j] + an1), t3 = y[j] * ORC_LOG(mu[j] + an1), t4 = an1 * ORC_LOG(1.0 + mu[j] * alpha);
+        ll += t1 - lgr - t3 - t4;
+        mag += fabs((double)t1) + fabs((double)lgr) + fabs((double)t3) + fabs((double)t4);
+    }
+    orc_real pr = use_prior ? -0.5 * ((orc_real)log_alpha - prior_mean) * ((orc_real)log_alpha - prior_mean) / prior_sigmasq : 0.0;
+    if (noise_out) *noise_out = 0x1p-53 * (mag + fabs((double)cr) + fabs((double)pr));
+    return (double)(ll + pr + cr);
+}
+
+static double log_posterior(double log_alpha, const double* y, const double* mu, const design_t* d,
+                            double prior_mean, double prior_sigmasq, int use_prior, int use_cr)
+{
+    return log_posterior_n(log_alpha, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, NULL);
 }
 
 /* DESeq2.cpp dlog_posterior */
@@ -511,9 +539,14 @@ static double dlog_posterior(double log_alpha, const double* y, const double* mu
     return (ll + cr) * alpha + pr;
 }
 
-typedef struct { double log_alpha; int iter, iter_accept; double initial_lp, last_lp; } fitdisp_res;
+typedef struct { double log_alpha; int iter, iter_accept; double initial_lp, last_lp; double margin, margin_keep; } fitdisp_res;
 
-/* DESeq2.cpp fitDisp, one row */
+/* DESeq2.cpp fitDisp, one row.
+ * r.margin: the smallest distance of any accept / stop comparison of this search from equality, in units of the
+ * rounding error of the compared log-posteriors (log_posterior_n's noise).  A search whose margin is of order 1 takes
+ * a branch that double rounding decides: any other correctly rounded evaluation of the same formulas (another libm,
+ * fused multiply-adds, long double) may take the other one.  The parity tests use it to separate such rows from real
+ * disagreements; it does not influence the search. */
 static fitdisp_res fit_disp_row(const double* y, const double* mu, const design_t* d, double log_alpha0,
                                 double prior_mean, double prior_sigmasq, double min_log_alpha,
                                 double kappa_0, double tol, int maxit, int use_prior, int use_cr,
@@ -522,9 +555,11 @@ static fitdisp_res fit_disp_row(const double* y, const double* mu, const design_
     const double epsilon = 1.0e-4;
     fitdisp_res r;
     double a = log_alpha0;
-    double lp = log_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
+    double nz0 = 0, nz = 0;
+    double lp = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz0);
     double dlp = dlog_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
     double kappa = kappa_0;
+    double margin = INFINITY;
     r.initial_lp = lp; r.iter = 0; r.iter_accept = 0;
     cnt->lp_evals++; cnt->dlp_evals++;
     for (int t = 0; t < maxit; t++) {
@@ -532,18 +567,25 @@ static fitdisp_res fit_disp_row(const double* y, const double* mu, const design_
         double a_propose = a + kappa * dlp;
         if (a_propose < -30.0) kappa = (-30.0 - a) / dlp;
         if (a_propose > 10.0) kappa = (10.0 - a) / dlp;
-        double theta_kappa = -1.0 * log_posterior(a + kappa * dlp, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
+        double theta_kappa = -1.0 * log_posterior_n(a + kappa * dlp, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz);
         double theta_hat_kappa = -1.0 * lp - kappa * epsilon * dlp * dlp;
         cnt->lp_evals++;
+        {
+            /* a proposal that no longer moves a (kappa halved away) is rejected by exact arithmetic, not by noise */
+            double u = fmax(nz, nz0);
+            if (a + kappa * dlp != a) margin = fmin(margin, fabs(theta_hat_kappa - theta_kappa) / u);
+        }
         if (theta_kappa <= theta_hat_kappa) {
             r.iter_accept++;
             a = a + kappa * dlp;
             double lpnew = log_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
             cnt->lp_evals++;
             double change = lpnew - lp;
+            margin = fmin(margin, fabs(change - tol) / fmax(nz, nz0));
             if (change < tol) { lp = lpnew; break; }
             if (a < min_log_alpha) break;
             lp = lpnew;
+            nz0 = nz;
             dlp = dlog_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
             cnt->dlp_evals++;
             kappa = fmin(kappa * 1.1, kappa_0);
@@ -554,31 +596,41 @@ static fitdisp_res fit_disp_row(const double* y, const double* mu, const design_
     }
     r.last_lp = lp;
     r.log_alpha = a;
+    /* estimateDispersionsGeneEst keeps the start value when last_lp < initial_lp + |initial_lp| / 1e6 */
+    r.margin_keep = fabs(r.last_lp - (r.initial_lp + fabs(r.initial_lp) / 1e6)) / fmax(nz, nz0);
+    r.margin = margin;
     return r;
 }
 
-/* DESeq2.cpp fitDispGrid, one row */
+/* DESeq2.cpp fitDispGrid, one row.  margin_out (may be NULL): the gap between the best and the second-best grid value
+ * on either level, in rounding-error units -- an arg max over a plateau flatter than that is decided by rounding. */
 static double fit_disp_grid_row(const double* y, const double* mu, const design_t* d, int grid_n,
                                 double min_la, double max_la, double prior_mean, double prior_sigmasq,
-                                int use_prior, int use_cr, orc_counters* cnt)
+                                int use_prior, int use_cr, orc_counters* cnt, double* margin_out)
 {
     double step = (max_la - min_la) / (grid_n - 1);
-    double best = -INFINITY, a_hat = min_la;
+    double best = -INFINITY, second = -INFINITY, a_hat = min_la, nz = 0, nzb = 1, margin = INFINITY;
     for (int t = 0; t < grid_n; t++) {
         double a = (t == grid_n - 1) ? max_la : min_la + t * step;
-        double v = log_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
+        double v = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz);
         cnt->lp_evals++;
-        if (v > best) { best = v; a_hat = a; }
+        if (v > best) { second = best; best = v; a_hat = a; nzb = nz; }
+        else if (v > second) second = v;
     }
+    margin = fmin(margin, (best - second) / nzb);
     double delta = (min_la + step) - min_la;
     double lo = a_hat - delta, hi = a_hat + delta, fstep = (hi - lo) / (grid_n - 1);
     double best2 = -INFINITY, a2 = lo;
+    second = -INFINITY;
     for (int t = 0; t < grid_n; t++) {
         double a = (t == grid_n - 1) ? hi : lo + t * fstep;
-        double v = log_posterior(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr);
+        double v = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz);
         cnt->lp_evals++;
-        if (v > best2) { best2 = v; a2 = a; }
+        if (v > best2) { second = best2; best2 = v; a2 = a; nzb = nz; }
+        else if (v > second) second = v;
     }
+    margin = fmin(margin, (best2 - second) / nzb);
+    if (margin_out) *margin_out = margin;
     return a2;
 }
 
@@ -772,8 +824,26 @@ static int parametric_fit(const double* means, const double* disps, int64_t m, d
  * (closed form needs S - p > 3; otherwise returns -2 unless overridden).
  * grid_n: fitDispGrid length (20 in current DESeq2).
  */
+/* Extras of orc_deseq_ex (all optional).  trend_a0 / trend_a1 / var_log_disp: not NaN = take these instead of fitting
+ * the trend / taking the MAD (the parity tests hand both sides the same global scalars so that per-region agreement can
+ * be checked without the coupling through the global fits).  gene_margin / map_margin (n doubles each, may be NULL):
+ * fit_disp_row's decision margin of the gene-wise and MAP searches, in rounding-error units (see fit_disp_row). */
+typedef struct {
+    double trend_a0, trend_a1, var_log_disp;
+    double *gene_margin, *map_margin;
+} orc_ext;
+
+int orc_deseq_ex(int64_t n, int S, int p, const double* X, const int32_t* K, const double* nf,
+                 double prior_var_override, int grid_n, int nthreads, const orc_ext* ext, orc_out* o);
+
 int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const double* nf,
               double prior_var_override, int grid_n, int nthreads, orc_out* o)
+{
+    return orc_deseq_ex(n, S, p, X, K, nf, prior_var_override, grid_n, nthreads, NULL, o);
+}
+
+int orc_deseq_ex(int64_t n, int S, int p, const double* X, const int32_t* K, const double* nf,
+                 double prior_var_override, int grid_n, int nthreads, const orc_ext* ext, orc_out* o)
 {
     const double minDisp = 1e-8, kappa_0 = 1.0, dispTol = 1e-6, betaTol = 1e-8, minmu = 0.5;
     const int maxit = 100;
@@ -828,6 +898,7 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         if (o->allZero[i]) {
             o->dispGeneEst[i] = NA; o->dispGeneIter[i] = 0;
             for (int j = 0; j < S; j++) o->mu[(int64_t)j * n + i] = NA;
+            if (ext && ext->gene_margin) ext->gene_margin[i] = NA;
             continue;
         }
         double y[ORC_MAXS], nfr[ORC_MAXS], q[ORC_MAXS], mul[ORC_MAXS], mu[ORC_MAXS];
@@ -874,6 +945,7 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         double la0 = log(alpha_init);
         fitdisp_res fr = fit_disp_row(y, mu, &d, la0, la0, 1.0, log(minDisp / 10), kappa_0, dispTol,
                                       maxit, 0, 1, &cnt);
+        if (ext && ext->gene_margin) ext->gene_margin[i] = fmin(fr.margin, fr.margin_keep);
         double disp = fmin(exp(fr.log_alpha), maxDisp);
         if (fr.last_lp < fr.initial_lp + fabs(fr.initial_lp) / 1e6) {
             disp = alpha_init;
@@ -881,7 +953,9 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         }
         int conv = (fr.iter < maxit) && !(fr.iter == 1);
         if (!conv && disp > minDisp * 10) {
-            double la = fit_disp_grid_row(y, mu, &d, grid_n, log(1e-8), log(maxDisp), 0.0, 1.0, 0, 1, &cnt);
+            double gmargin = INFINITY;
+            double la = fit_disp_grid_row(y, mu, &d, grid_n, log(1e-8), log(maxDisp), 0.0, 1.0, 0, 1, &cnt, &gmargin);
+            if (ext && ext->gene_margin) ext->gene_margin[i] = fmin(ext->gene_margin[i], gmargin);
             disp = exp(la);
             o->flags[i] |= ORC_FLAG_GENE_GRID;
             n_refit_gene++;
@@ -902,7 +976,9 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         }
     double coefs[2] = {NA, NA};
     int outer = 0;
-    int tstat = (m_fit == 0) ? 9 : parametric_fit(means, disps, m_fit, coefs, &outer);
+    int tstat;
+    if (ext && !isnan(ext->trend_a0) && !isnan(ext->trend_a1)) { coefs[0] = ext->trend_a0; coefs[1] = ext->trend_a1; tstat = 0; }
+    else tstat = (m_fit == 0) ? 9 : parametric_fit(means, disps, m_fit, coefs, &outer);
     o->scalars[0] = coefs[0]; o->scalars[1] = coefs[1]; o->scalars[4] = tstat; o->scalars[5] = outer;
     if (tstat != 0) { free(means); free(disps); return -3; }   /* local-regression fallback not restated */
     int64_t m_res = 0;
@@ -917,6 +993,7 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
     for (int64_t k = 0; k < m_res; k++) disps[k] = fabs(means[k] - med);
     double mad = 1.4826 * median_inplace(disps, m_res);
     double varLogDispEsts = mad * mad;
+    if (ext && !isnan(ext->var_log_disp)) varLogDispEsts = ext->var_log_disp;
     free(means); free(disps);
     o->scalars[2] = varLogDispEsts;
 
@@ -936,6 +1013,7 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         orc_counters cnt = {0, 0, 0, 0};
         if (o->allZero[i]) {
             o->dispMAP[i] = NA; o->dispersion[i] = NA; o->dispIter[i] = 0; o->dispOutlier[i] = 0;
+            if (ext && ext->map_margin) ext->map_margin[i] = NA;
             continue;
         }
         double y[ORC_MAXS], mu[ORC_MAXS];
@@ -944,9 +1022,12 @@ int orc_deseq(int64_t n, int S, int p, const double* X, const int32_t* K, const 
         double init = (ge > 0.1 * ft) ? ge : ft;
         fitdisp_res fr = fit_disp_row(y, mu, &d, log(init), log(ft), dispPriorVar, log(minDisp / 10),
                                       kappa_0, dispTol, maxit, 1, 1, &cnt);
+        if (ext && ext->map_margin) ext->map_margin[i] = fr.margin;
         double dmap = exp(fr.log_alpha);
         if (!(fr.iter < maxit)) {
-            double la = fit_disp_grid_row(y, mu, &d, grid_n, log(1e-8), log(maxDisp), log(ft), dispPriorVar, 1, 1, &cnt);
+            double gmargin = INFINITY;
+            double la = fit_disp_grid_row(y, mu, &d, grid_n, log(1e-8), log(maxDisp), log(ft), dispPriorVar, 1, 1, &cnt, &gmargin);
+            if (ext && ext->map_margin) ext->map_margin[i] = fmin(ext->map_margin[i], gmargin);
             dmap = exp(la);
             o->flags[i] |= ORC_FLAG_MAP_GRID;
             n_refit_map++;

@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_VARIANTS = {}
 
 FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLAG_GENE_NOINCREASE = 1, 2, 4, 8, 16, 32
 
@@ -20,11 +21,20 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
 
 
+def variant(name):
+    """The same source built differently (oracle/Makefile: "O0", "fma", "ld"); only orc_deseq_ex is bound.  Used by
+    scripts/oracle_flip_evidence.py to show which rows depend on the rounding of the reference's own arithmetic."""
+    if name not in _VARIANTS:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle_%s.so" % name])
+        _VARIANTS[name] = C.CDLL(os.path.join(_HERE, "liboracle_%s.so" % name))
+    return _VARIANTS[name]
+
+
 def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "liboracle.so")
-        if not os.path.exists(path):
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(_HERE, "chicdiff_oracle.c")):
             build()
         L = C.CDLL(path)
         d = C.c_double
@@ -91,8 +101,15 @@ def norm_factors(FMagg, sf, norm, theta=0.0):
     return nf
 
 
-def deseq(K, nf, X, prior_var=float("nan"), grid_n=20, nthreads=0):
-    """estimateDispersions + nbinomWaldTest.  K int32[S,n], nf float64[S,n], X float64[S,p]."""
+class _OrcExt(C.Structure):
+    _fields_ = [("trend_a0", C.c_double), ("trend_a1", C.c_double), ("var_log_disp", C.c_double),
+                ("gene_margin", C.c_void_p), ("map_margin", C.c_void_p)]
+
+
+def deseq(K, nf, X, prior_var=float("nan"), grid_n=20, nthreads=0, trend=None, var_log_disp=None, margins=False, L=None):
+    """estimateDispersions + nbinomWaldTest.  K int32[S,n], nf float64[S,n], X float64[S,p].
+    trend = (a0, a1) / var_log_disp: take these global scalars instead of fitting them; margins: also return
+    geneMargin / mapMargin (decision margins of the two line searches in rounding-error units); L: a variant build."""
     K = np.ascontiguousarray(K, dtype=np.int32)
     nf = np.ascontiguousarray(nf, dtype=np.float64)
     X = np.ascontiguousarray(X, dtype=np.float64)
@@ -107,8 +124,17 @@ def deseq(K, nf, X, prior_var=float("nan"), grid_n=20, nthreads=0):
         allZero=np.zeros(n, np.uint8), dispOutlier=np.zeros(n, np.uint8), betaConv=np.zeros(n, np.uint8),
         flags=np.zeros(n, np.uint8), scalars=f8(16))
     out = _OrcOut(**{k: _p(v) for k, v in res.items()})
-    rc = lib().orc_deseq(C.c_int64(n), C.c_int(S), C.c_int(p), _p(X), _p(K), _p(nf), C.c_double(prior_var),
-                         C.c_int(grid_n), C.c_int(nthreads), C.byref(out))
+    nan = float("nan")
+    ext = _OrcExt(nan, nan, nan, None, None)
+    if trend is not None:
+        ext.trend_a0, ext.trend_a1 = float(trend[0]), float(trend[1])
+    if var_log_disp is not None:
+        ext.var_log_disp = float(var_log_disp)
+    if margins:
+        res["geneMargin"], res["mapMargin"] = f8(n), f8(n)
+        ext.gene_margin, ext.map_margin = res["geneMargin"].ctypes.data, res["mapMargin"].ctypes.data
+    rc = (L or lib()).orc_deseq_ex(C.c_int64(n), C.c_int(S), C.c_int(p), _p(X), _p(K), _p(nf), C.c_double(prior_var),
+                                   C.c_int(grid_n), C.c_int(nthreads), C.byref(ext), C.byref(out))
     res["rc"] = rc
     sc = res["scalars"]
     res.update(trend_a0=sc[0], trend_a1=sc[1], varLogDispEsts=sc[2], dispPriorVar=sc[3], trend_status=int(sc[4]) if sc[4] == sc[4] else -1,
@@ -120,8 +146,9 @@ def deseq(K, nf, X, prior_var=float("nan"), grid_n=20, nthreads=0):
 
 
 def region_test(K, FMagg, X, norm="combined", theta=None, theta_grid=(0, .25, .5, .75, 1), prior_var=float("nan"),
-                prior_var_grid=float("nan"), nthreads=0):
-    """DESeq2Wrap numerics (chicdiff.R:1551-1674): size factors, offsets, theta grid, final fit."""
+                prior_var_grid=float("nan"), nthreads=0, trend=None, var_log_disp=None, margins=False, L=None):
+    """DESeq2Wrap numerics (chicdiff.R:1551-1674): size factors, offsets, theta grid, final fit.
+    trend / var_log_disp / margins / L apply to the final fit only (see deseq)."""
     S, n = K.shape
     sf = size_factors(K)
     out = {"sizeFactors": sf, "deviances": None}
@@ -149,7 +176,8 @@ def region_test(K, FMagg, X, norm="combined", theta=None, theta_grid=(0, .25, .5
     out["theta"] = theta if norm == "combined" else None
     nf = norm_factors(FMagg, sf, norm, 0.0 if theta is None else theta)
     out["nf"] = nf
-    out.update(deseq(K, nf, X, prior_var=prior_var, nthreads=nthreads))
+    out.update(deseq(K, nf, X, prior_var=prior_var, nthreads=nthreads, trend=trend, var_log_disp=var_log_disp,
+                     margins=margins, L=L))
     return out
 
 
@@ -438,13 +466,28 @@ def countput(reps, frag_start, frag_end, frag_id0=1):
 
 
 def parse_chinput(data):
-    """fread() of a .chinput (chicdiff.R:828): skip the '#' comment line and the header, five columns, NA -> NaN."""
+    """fread() of a .chinput (chicdiff.R:828): skip the '#' comment line and the header, five columns, NA -> NaN.
+    baitID / otherEndID / N are integer columns: a row where one of them is not a whole number (or not a number) is not
+    a .chinput row and is dropped, never truncated; numbers may carry a fraction or an exponent ("12.0", "1e5")."""
+    def num(tok):
+        if tok.upper().startswith("N"):
+            return np.nan
+        try:
+            return float(tok)
+        except ValueError:
+            return np.nan
     rows = []
     for line in data.decode().splitlines():
         f = line.replace(",", "\t").split()
         if not f or not f[0][0].isdigit():
             continue
-        rows.append(f)
-    col = lambda k, na: np.array([na if (len(r) <= k or r[k].upper().startswith("N")) else float(r[k]) for r in rows])
-    return dict(baitID=col(0, np.nan).astype(np.int32), otherEndID=col(1, np.nan).astype(np.int32), N=col(2, np.nan).astype(np.int32),
-                otherEndLen=np.where(np.isnan(col(3, np.nan)), -2147483648, col(3, 0)).astype(np.int32), distSign=col(4, np.nan))
+        v = [num(t) for t in f[:5]] + [np.nan] * (5 - min(len(f), 5))
+        if any(np.isnan(x) or x != np.floor(x) or abs(x) > 2147483647 for x in v[:3]):
+            continue
+        rows.append(v)
+    a = np.array(rows, dtype=np.float64).reshape(-1, 5)
+    ln = a[:, 3]
+    with np.errstate(invalid="ignore"):
+        ln_ok = ~np.isnan(ln) & (ln == np.floor(ln)) & (np.abs(ln) <= 2147483647)
+    return dict(baitID=a[:, 0].astype(np.int32), otherEndID=a[:, 1].astype(np.int32), N=a[:, 2].astype(np.int32),
+                otherEndLen=np.where(ln_ok, np.nan_to_num(ln), -2147483648).astype(np.int32), distSign=a[:, 4].copy())

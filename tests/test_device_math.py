@@ -162,22 +162,19 @@ def test_fused_posterior_and_derivative_follow_the_oracle(dm):
         assert abs(num - f(a)[1]) < 1e-6 * max(1.0, abs(num))
 
 
-@pytest.mark.parametrize("variant", ["v2", "v3"])
-def test_experimental_posterior_is_the_same_function(dm, variant):
-    """experiments/posterior_v2.cuh (one logarithm per pair of samples for the gamma rationals, closed-form 1x1 / 2x2
-    Cox-Reid term) and posterior_v3.cuh (the same with the table-assisted logarithm, p <= 2) against eval_post on the
-    host: same value and derivative up to the rounding of the lgamma-sized terms."""
-    candidate = dm.dm_eval_post_v2 if variant == "v2" else dm.dm_eval_post_v3
-    for f in (dm.dm_eval_post, candidate):
-        f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
-                      C.c_void_p, C.c_void_p]
+@pytest.mark.parametrize("variant", [1, 2])
+def test_posterior_formulations_are_the_same_function(dm, variant):
+    """eval_post (posterior.cuh: one logarithm per pair of replicates for the gamma rationals, closed-form 1x1 / 2x2
+    Cox-Reid term; variant 2 = with the table-assisted logarithm, which is what the kernel runs) against the first
+    formulation eval_post_ref on the host: same value and derivative up to the rounding of the lgamma-sized terms."""
+    f = dm.dm_eval_post_variant
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                  C.c_void_p, C.c_void_p]
     rng = np.random.default_rng(7)
     designs = [np.ones((6, 1)), np.ones((5, 1)), np.column_stack([np.ones(6), [0, 0, 0, 1, 1, 1]]).astype(float),
                np.column_stack([np.ones(8), [0, 1, 0, 1, 0, 1, 0, 1], [0, 0, 0, 0, 1, 1, 1, 1]]).astype(float)]
     for X in designs:
         S, p = X.shape
-        if variant == "v3" and p > 2:
-            continue
         X = np.ascontiguousarray(X)
         worst_lp = worst_dlp = 0.0
         for _ in range(1500):
@@ -189,9 +186,9 @@ def test_experimental_posterior_is_the_same_function(dm, variant):
             a = rng.uniform(np.log(1e-8), np.log(10.0))
             use_prior = int(rng.random() < 0.5)
             out = []
-            for f in (dm.dm_eval_post, candidate):
+            for v in (0, variant):
                 lp, dlp = C.c_double(), C.c_double()
-                f(S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, -2.0, 0.7, use_prior, C.byref(lp), C.byref(dlp))
+                f(v, S, p, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, -2.0, 0.7, use_prior, C.byref(lp), C.byref(dlp))
                 out.append((lp.value, dlp.value))
             scale = 1.0 + np.sum(np.abs(special.gammaln(y + np.exp(-a))))
             worst_lp = max(worst_lp, abs(out[0][0] - out[1][0]) / scale)
@@ -203,8 +200,8 @@ def test_experimental_posterior_is_the_same_function(dm, variant):
         assert worst_dlp < 1e-12, (S, p, worst_dlp)
 
 
-def test_experimental_table_log(dm):
-    """experiments/log_v2.cuh: within 1.5 ulp for every argument >= 1 (all the kernel's logarithms except the determinant's)
+def test_table_log(dm):
+    """log_pos_v2 (common.cuh): within 1.5 ulp for every argument >= 1 (all the kernel's logarithms except the determinant's)
     and within 3e-16 of max(1, |log x|) below 1, where the table entry and k ln2 cancel near x = 1."""
     rng = np.random.default_rng(8)
     for x in (np.exp(rng.uniform(0, np.log(1e300), 200000)), rng.uniform(1, 4, 200000),

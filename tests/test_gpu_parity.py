@@ -1,46 +1,22 @@
 """Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
 
 Bars (BASELINE.json north_star): aggregated counts bit-exact; dispersions, log2FC and p-values within 1e-6
-relative, checked per region.  Two caveats that are properties of the reference algorithm, not of this port,
-are made explicit in the assertions:
-  * gene-wise estimates at the dispersion floor (< 1e-6; DESeq2 excludes them from the trend with
-    `dispGeneEst > 100*minDisp`) are rounding noise of lgamma(1/alpha) at 1/alpha >= 1e6 in the reference
-    itself; they are required to be at the floor on both sides, not equal;
-  * fitDisp's accept / stop decisions compare log-posteriors that differ by less than their rounding error
-    on a few rows per 1e5 (a start value already at the optimum); such a row can take a different branch on
-    any two libm implementations.  Because the trend fit and the MAD are global, one such row perturbs every
-    region by ~1e-7, which z^2 amplifies in far-tail p-values.  Sizes with no such row must pass at 100 %;
-    larger sizes must pass on >= 99.9 % of regions (at 1e-6 plus that measured coupling, itself bounded by
-    2e-4) and make identical significance calls.  There the p-value
-    bound is the one its conditioning allows: d log p / d log z = z^2 in the normal tail, so a statistic that
-    agrees to 1e-6 bounds the p-value to 1e-6 * max(1, z^2) (checked with that factor, raw 1e-6 on `tiny`).
+relative, checked per region.  How that is checked at scale -- shared global scalars to take the coupling through
+the trend fit out of the per-region comparison, and the oracle's own record of which line searches are decided by
+rounding -- is described in tests/parity.py; the gate is parity.assert_parity:
+  * every region whose search decisions are not within rounding noise: 1e-6 in EVERY column, no exception;
+  * the others: 1e-6 as well, except a bounded number of branch flips (<= 1e-4 n + 2), none on the small inputs;
+  * free run: same theta, same filter, identical significance calls, trend coupling < 1e-4.
 """
 import numpy as np
 import pytest
 
+import parity
 from chicdiff_b200 import engine, synth
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-6
-
-
-def run_both(d, prior=None, prior_grid=None, **kw):
-    e = engine.Engine(0)
-    e.set_design(d.X)
-    e.set_regions(d.row_off)
-    for s in range(d.S):
-        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
-    K, FM = e.aggregate()
-    Ko, FMo = O.aggregate(d.row_off, d.N_rows, d.FM_rows)
-    r = e.region_test(disp_prior_var=prior, disp_prior_var_grid=prior_grid, **kw)
-    nan = float("nan")
-    ro = O.region_test(Ko, FMo, d.X, prior_var=nan if prior is None else prior,
-                       prior_var_grid=nan if prior_grid is None else prior_grid,
-                       **{k: v for k, v in kw.items() if k in ("norm", "theta", "theta_grid")})
-    launches = e.launch_count()
-    e.close()
-    return K, FM, Ko, FMo, r, ro, launches
 
 
 def frac_ok(a, b, scale=None, tol=TOL):
@@ -52,90 +28,78 @@ def frac_ok(a, b, scale=None, tol=TOL):
     return ok.mean(), ok
 
 
-def check(d, K, FM, Ko, FMo, r, ro, min_frac, strict_p=False):
-    assert np.array_equal(K, Ko), "aggregated counts must be bit-exact"
-    assert np.array_equal(np.isnan(FM), np.isnan(FMo))
-    okm = ~np.isnan(FMo)
-    assert np.max(np.abs(FM[okm] - FMo[okm]) / np.abs(FMo[okm])) < 1e-14
-    assert np.max(np.abs(r["sizeFactors"] - ro["sizeFactors"]) / ro["sizeFactors"]) < 1e-12
-    assert r["theta"] == ro["theta"]
-    if ro["deviances"] is not None:
-        assert np.max(np.abs(r["deviances"] - ro["deviances"]) / ro["deviances"]) < 1e-5
-    assert frac_ok(r["normFactors"], ro["nf"])[0] == 1.0
-    assert frac_ok(r["baseMean"], ro["baseMean"])[0] == 1.0
-    # gene-wise estimates: compare above the floor, require "at the floor" on both sides below it
-    ge, geo = r["dispGeneEst"], ro["dispGeneEst"]
-    floor = (geo < 1e-6)
-    assert np.all(ge[floor] < 1e-6 * (1 + 1e-9)) or (ge[floor] >= 1e-6).mean() < 1e-4
-    f, _ = frac_ok(np.where(floor, geo, ge), geo)
-    assert f >= min_frac, ("dispGeneEst", f)
-    # A region whose gene-wise search takes a different branch (see the module docstring) moves the global
-    # trend coefficients by ~0.06/n; every downstream quantity inherits that.  The coupling is measured and
-    # bounded, and the per-region tolerance is 1e-6 plus the propagated coupling.
-    coupling = max(abs(r["trend_a0"] - ro["trend_a0"]) / ro["trend_a0"], abs(r["trend_a1"] - ro["trend_a1"]) / ro["trend_a1"])
-    assert coupling < (1e-9 if strict_p else 2e-4), ("trend coefficients", coupling)
-    tol = TOL + 3.0 * coupling
-    report = {"coupling": coupling}
-    for k, ko, scale in [("dispFit", "dispFit", None), ("dispMAP", "dispMAP", None), ("dispersion", "dispersion", None),
-                         ("lfcSE", None, None), ("log2FoldChange", None, "se"), ("stat", "stat", 1.0),
-                         ("pvalue", "pvalue", None), ("deviance", "deviance", None)]:
-        p = d.X.shape[1]
-        if k == "lfcSE":
-            b = ro["betaSE"][p - 1]
-        elif k == "log2FoldChange":
-            b = ro["beta"][p - 1]
-        else:
-            b = ro[ko]
-        sc = ro["betaSE"][p - 1] if scale == "se" else scale
-        if k == "pvalue" and not strict_p:
-            with np.errstate(invalid="ignore"):
-                sc = np.abs(b) * np.maximum(1.0, ro["stat"] ** 2)
-        f, _ = frac_ok(r[k], b, sc, tol)
-        report[k] = f
-        assert f >= min_frac, (k, f, coupling)
-    # identical significant-interaction calls
-    p = d.X.shape[1]
-    adj = engine.results_adjust(r["baseMean"], r["maxCooks"], r["flags"], r["pvalue"], d.S, p)
-    res_o = O.results(ro, Ko, d.X)
-    assert np.array_equal(np.isnan(adj["padj"]), np.isnan(res_o["padj"]))
-    with np.errstate(invalid="ignore"):
-        sig_g, sig_o = adj["padj"] < 0.05, res_o["padj"] < 0.05
-        near = np.abs(res_o["padj"] - 0.05) < 1e-5
-    assert np.array_equal(sig_g | near, sig_o | near), "significant-interaction calls differ"
-    assert adj["filterIndex"] == res_o["filterIndex"] + 1
-    return report
+_C3_FULL = []
+
+
+def c3_full():
+    """the full-size bench workload, generated once per test session (a minute of NumPy)"""
+    if not _C3_FULL:
+        _C3_FULL.append(synth.generate("c3"))
+    return _C3_FULL[0]
+
+
+def run_and_check(d, all_rows=False, **kw):
+    t = parity.run_three(d, **kw)
+    report = []
+    S = parity.compare(d, t, report)
+    try:
+        parity.assert_parity(S, all_rows=all_rows)
+    except AssertionError:
+        print("\n".join(report))
+        raise
+    return t, S
 
 
 def test_tiny_3v3_all_regions_within_tolerance():
     d = synth.generate("tiny")
-    K, FM, Ko, FMo, r, ro, launches = run_both(d)
-    rep = check(d, K, FM, Ko, FMo, r, ro, min_frac=1.0, strict_p=True)
-    assert launches > 50
+    t, S = run_and_check(d, all_rows=True)
+    r, ro = t["shared"], t["oracle"]
+    assert S["rows_bad"] == 0
+    # one launch per stage of a batch, not per fit: the five theta-grid fits run as one problem (round 1: 330 launches)
+    assert 30 < t["launches"] / 2 < 120
     # same search paths: identical IRLS iteration counts; the MAP line search may stop one trip apart on a
     # region whose last gain sits at the 1e-6 stopping threshold (values then agree to ~1e-7)
     assert np.array_equal(r["betaIter"], ro["betaIter"])
     assert (r["dispIter"] != ro["dispIter"]).mean() <= 0.002
     assert np.array_equal(r["flags"] & 63, ro["flags"])
+    # the free run as well (no branch flip on this input: the coupling is zero)
+    f = t["free"]
+    p = d.X.shape[1]
+    for k, b, sc in (("dispersion", ro["dispersion"], None), ("lfcSE", ro["betaSE"][p - 1], None), ("stat", ro["stat"], 1.0),
+                     ("pvalue", ro["pvalue"], None), ("log2FoldChange", ro["beta"][p - 1], ro["betaSE"][p - 1])):
+        assert frac_ok(f[k], b, sc)[0] == 1.0, k
 
 
 def test_c1_shape_2v2_with_given_prior_variance():
     """chr19-shaped 2-vs-2 (BASELINE configs[0] shape).  S - p = 2: DESeq2's seeded Monte-Carlo prior-variance
     estimator is not restated, so both sides receive the same dispPriorVar."""
-    d = synth.generate("c1")
-    K, FM, Ko, FMo, r, ro, _ = run_both(d, prior=0.5, prior_grid=0.5)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.999)
+    run_and_check(synth.generate("c1"), prior=0.5, prior_grid=0.5)
 
 
 def test_c2_one_chromosome_2v2():
-    d = synth.generate("c2")
-    K, FM, Ko, FMo, r, ro, _ = run_both(d, prior=0.6, prior_grid=0.6)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.999)
+    run_and_check(synth.generate("c2"), prior=0.6, prior_grid=0.6)
 
 
 def test_c3_subset_3v3_100k():
-    d = synth.generate("c3", n_regions=100000)
-    K, FM, Ko, FMo, r, ro, _ = run_both(d)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.999)
+    run_and_check(synth.generate("c3", n_regions=100000))
+
+
+def test_c3_full_size_against_the_oracle():
+    """BASELINE configs[2] at full size (2.1 M regions, 23 M rows, 3-vs-3), the configuration the bench line is quoted on,
+    against the oracle (about a minute on the box's cores); the per-column table goes to gpurun_out/ when it exists
+    (committed copy: profiles/r02_parity_c3_full.txt)."""
+    import os
+    d = c3_full()
+    assert d.n > 2_000_000
+    t = parity.run_three(d)
+    report = ["== c3 full size: n = %d regions, R = %d rows, S = %d, p = %d" % (d.n, d.R, d.S, d.X.shape[1])]
+    S = parity.compare(d, t, report)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.path.isdir(os.path.join(root, "gpurun_out")):
+        with open(os.path.join(root, "gpurun_out", "parity_c3_full_from_pytest.txt"), "w") as fh:
+            fh.write("\n".join(report) + "\n")
+    print("\n".join(report[:24]))
+    parity.assert_parity(S)
 
 
 def test_c4_batch_covariate_8v8_three_column_glm():
@@ -143,16 +107,14 @@ def test_c4_batch_covariate_8v8_three_column_glm():
     NB GLM (IRLS) and the Wald fit is the 3-column IRLS."""
     d = synth.generate("c4", n_regions=20000)
     assert d.X.shape == (16, 3)
-    K, FM, Ko, FMo, r, ro, _ = run_both(d)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.999)
-    assert frac_ok(r["mu"], ro["mu"])[0] >= 0.999
+    t, S = run_and_check(d)
+    assert frac_ok(t["shared"]["mu"], t["oracle"]["mu"])[0] >= 0.999
 
 
 @pytest.mark.parametrize("norm,theta", [("standard", None), ("fullmean", None), ("combined", 0.5), ("combined", 1.0), ("combined", 0.0)])
 def test_norm_modes_and_fixed_theta(norm, theta):
     d = synth.generate("tiny", seed_offset=3)
-    K, FM, Ko, FMo, r, ro, _ = run_both(d, norm=norm, theta=theta)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.999)
+    run_and_check(d, norm=norm, theta=theta)
 
 
 def test_all_zero_region_gives_na_and_poisons_theta_grid():
@@ -475,8 +437,7 @@ def test_other_designs(reps, extra_cols):
         c2 = ((np.arange(S) // 2) % 2).astype(float)
         X = np.column_stack([X[:, 0], c1, c2, X[:, 1]])
         d.X = X
-    K, FM, Ko, FMo, r, ro, _ = run_both(d)
-    check(d, K, FM, Ko, FMo, r, ro, min_frac=0.998)
+    run_and_check(d)
 
 
 def test_full_size_c3_properties():
@@ -485,7 +446,7 @@ def test_full_size_c3_properties():
     whole region test (bitwise), output identities (stat = LFC / SE, p = 2 Phi(-|stat|)), value ranges, and the
     fused-assembly route giving the same counts."""
     from scipy import special
-    d = synth.generate("c3")
+    d = c3_full()
     assert d.n > 2_000_000
     e = engine.Engine(0)
     e.set_design(d.X)
@@ -583,7 +544,7 @@ def test_chinput_codec_on_device():
     txt = synth.chinput_text(d, 0, max_rows=200000)
     got = e.parse_chinput(txt)
     ref = O.parse_chinput(txt)
-    assert len(ref["N"]) > 50000 and np.isnan(ref["distSign"]).sum() == 0 or True
+    assert len(ref["N"]) > 50000
     for k in ("baitID", "otherEndID", "N", "otherEndLen"):
         assert np.array_equal(got[k], ref[k]), k
     assert np.array_equal(np.isnan(got["distSign"]), np.isnan(ref["distSign"]))
@@ -595,6 +556,14 @@ def test_chinput_codec_on_device():
     assert got["baitID"].tolist() == [5, 7, 8] and got["otherEndID"].tolist() == [9, 12, 13] and got["N"].tolist() == [3, 1, 2]
     assert np.isnan(got["distSign"][0]) and got["distSign"][1:].tolist() == [-4500.0, 15000.0]
     assert e.parse_chinput(b"")["N"].size == 0 and e.parse_chinput(b"# only a comment\n")["N"].size == 0
+    # numbers written with a fraction or an exponent are read as numbers; a row whose ID or count is not a whole number
+    # is dropped (never truncated to 123 or 1)
+    odd = b"baitID\totherEndID\tN\totherEndLen\tdistSign\n1e3\t12.0\t3\t1.2e3\t-4.5e3\n123.5\t7\t1\t10\t5\n9\t1e5x\t1\t10\t5\n8\t2\t4\t7.5\t1250.5\n"
+    got, ref = e.parse_chinput(odd), O.parse_chinput(odd)
+    assert got["baitID"].tolist() == [1000, 8] and got["otherEndID"].tolist() == [12, 2] and got["N"].tolist() == [3, 4]
+    assert got["otherEndLen"].tolist() == [1200, -2147483648] and got["distSign"].tolist() == [-4500.0, 1250.5]
+    for k in ("baitID", "otherEndID", "N", "otherEndLen", "distSign"):
+        assert np.array_equal(got[k], ref[k]), k
     e.close()
 
 
