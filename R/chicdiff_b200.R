@@ -144,6 +144,9 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
     tlb <- rep(-1L, nF); tlb[oe$otherEndID - id0 + 1L] <- ifelse(is.na(oe$tlb), -1L, match(oe$tlb, tl.lv) - 1L)
     dfp <- .chicEstimateDistFun(x)
     cnt <- if (is.null(counts)) x[common, .(baitID, otherEndID, N), nomatch = 0L] else fread(counts[i])[, .(baitID, otherEndID, N)]
+    # rows whose bait is not a fragment of the rmap would be dropped by tabulate() but stay in cnt$otherEndID / cnt$N,
+    # and every offset after them would point at the wrong rows: drop them first
+    cnt <- cnt[baitID >= id0 & baitID < id0 + nF]
     setkey(cnt, baitID, otherEndID)
     cnt_off <- c(0, cumsum(tabulate(cnt$baitID - id0 + 1L, nbins = nF)))
     .Call("cdR_set_sample_tables", ctx, i, s_j, tblb, s_i, tlb, t(tmean),

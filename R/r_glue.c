@@ -75,12 +75,24 @@ SEXP cdR_set_sample_rows(SEXP ptr, SEXP s, SEXP N, SEXP fullmean)
     return R_NilValue;
 }
 
+/* the sizes the context holds: outputs are allocated from these, and a caller whose idea of n / S / R differs is told */
+static void check_dims(cd_ctx* ctx, const char* who, long long n_given, int S_given, long long R_given)
+{
+    int64_t n = 0, R = 0;
+    int S = 0, p = 0;
+    if (cd_get_dims(ctx, &n, &S, &p, &R) != CD_OK) error("chicdiff_b200: %s: bad context", who);
+    if (n_given >= 0 && n_given != (long long)n) error("chicdiff_b200: %s: n = %lld but the context holds %lld regions", who, n_given, (long long)n);
+    if (S_given >= 0 && S_given != S) error("chicdiff_b200: %s: S = %d but the context's design has %d samples", who, S_given, S);
+    if (R_given >= 0 && R_given != (long long)R) error("chicdiff_b200: %s: R = %lld but the context holds %lld region rows", who, R_given, (long long)R);
+}
+
 /* returns list(K = integer matrix n x S, FullMean = numeric matrix n x S); R's column-major n x S is the
  * library's sample-major layout, so no transposition happens */
 SEXP cdR_aggregate(SEXP ptr, SEXP n_, SEXP S_)
 {
     cd_ctx* ctx = get_ctx(ptr);
     int n = asInteger(n_), S = asInteger(S_);
+    check_dims(ctx, "cdR_aggregate", n, S, -1);
     SEXP K = PROTECT(allocMatrix(INTSXP, n, S));
     SEXP FM = PROTECT(allocMatrix(REALSXP, n, S));
     CD_CHECK(ctx, cd_aggregate(ctx, (int32_t*)INTEGER(K), REAL(FM)));
@@ -103,11 +115,16 @@ static double prior_var_trampoline(void* user, int df, int64_t n_resid, const do
     memcpy(REAL(r), resid, sizeof(double) * (size_t)n_resid);
     SEXP d = PROTECT(ScalarInteger(df));
     SEXP call = PROTECT(lang3(fn, d, r));
-    SEXP val = PROTECT(eval(call, R_GlobalEnv));
-    double v = asReal(val);
-    UNPROTECT(4);
+    /* an R error must not longjmp through the C++ frames of cd_region_test (they own heap buffers): evaluate under
+     * R_tryEvalSilent and report failure as NaN, which the library turns into CD_ENUMERIC */
+    int failed = 0;
+    SEXP val = R_tryEvalSilent(call, R_GlobalEnv, &failed);
+    double v = NA_REAL;
+    if (!failed) { PROTECT(val); v = asReal(val); UNPROTECT(1); }
+    UNPROTECT(3);
     return v;
 }
+
 
 /* norm: 0/1/2; theta, priorVar, priorVarGrid: NA_real_ = let the library decide; grid: numeric vector;
  * priorVarFn: NULL or function(df, resid) returning dispPriorVar for designs with S - p <= 3 */
@@ -117,6 +134,7 @@ SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta,
     cd_ctx* ctx = get_ctx(ptr);
     int n = asInteger(n_), S = asInteger(S_);
     (void)p_;
+    check_dims(ctx, "cdR_region_test", n, S, -1);
     cd_options opt;
     memset(&opt, 0, sizeof(opt));
     opt.norm = asInteger(norm);
@@ -176,6 +194,7 @@ SEXP cdR_results_resident(SEXP ptr, SEXP n_)
 {
     cd_ctx* ctx = get_ctx(ptr);
     R_xlen_t n = (R_xlen_t)asReal(n_);
+    check_dims(ctx, "cdR_results_resident", (long long)n, -1, -1);
     SEXP pv = PROTECT(allocVector(REALSXP, n));
     SEXP padj = PROTECT(allocVector(REALSXP, n));
     SEXP thr = PROTECT(allocVector(REALSXP, 1));
@@ -286,6 +305,7 @@ SEXP cdR_assemble(SEXP ptr, SEXP n_, SEXP S_, SEXP keep_rows)
     cd_ctx* ctx = get_ctx(ptr);
     R_xlen_t n = (R_xlen_t)asReal(n_);
     int S = asInteger(S_);
+    check_dims(ctx, "cdR_assemble", (long long)n, S, -1);
     SEXP K = PROTECT(allocMatrix(INTSXP, (int)n, S));
     SEXP FM = PROTECT(allocMatrix(REALSXP, (int)n, S));
     SEXP av = PROTECT(allocVector(REALSXP, n));
@@ -304,6 +324,7 @@ SEXP cdR_get_sample_rows(SEXP ptr, SEXP s, SEXP R_)
 {
     cd_ctx* ctx = get_ctx(ptr);
     R_xlen_t R = (R_xlen_t)asReal(R_);
+    check_dims(ctx, "cdR_get_sample_rows", -1, -1, (long long)R);
     SEXP N = PROTECT(allocVector(INTSXP, R));
     SEXP FM = PROTECT(allocVector(REALSXP, R));
     SEXP BM = PROTECT(allocVector(REALSXP, R));

@@ -124,6 +124,19 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double m, dou
     if (r == 123.456) *sink = r;
 }
 
+// line-search evaluations of one fit_disp call: every searched region evaluates the fused posterior once to start and
+// once per trip (the count the FP64 roofline of the bench line is built from)
+__global__ void count_evals_kernel(int64_t n, const int32_t* __restrict__ iter, unsigned long long* __restrict__ out)
+{
+    unsigned long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int it = iter[i];
+        if (it > 0) local += (unsigned long long)it + 1ull;
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
 __global__ void count_flags_kernel(int64_t n, const uint8_t* __restrict__ flags, unsigned long long* __restrict__ out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,8 +173,20 @@ struct cd_ctx {
     bool have_results = false;       // the arrays of a successful cd_region_test are in device memory
     std::vector<uint8_t> sample_set;
     DevBuf<int64_t> row_off;
-    DevBuf<int32_t> N_rows;
-    DevBuf<double> FM_rows;
+    // Per-row columns, double-buffered: cd_set_sample_rows uploads on a copy stream of its own into the buffer the last
+    // cd_aggregate did NOT read, so the rows of the next batch cross the bus while the region test of the current
+    // one runs (a caller pipelines by setting the next batch's rows between cd_aggregate and cd_region_test).
+    DevBuf<int32_t> N_rows, N_rows_alt;
+    DevBuf<double> FM_rows, FM_rows_alt;
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr;                 // last upload of the staging round
+    cudaEvent_t ev_read[2] = {nullptr, nullptr};   // last aggregation kernel that read buffer b
+    int front = 0;                                 // buffer the last cd_aggregate consumed
+    bool front_used = false;
+    std::vector<uint8_t> staged;                   // samples uploaded since then
+    int32_t* nbuf(int b) { return b ? N_rows_alt.p : N_rows.p; }
+    double* fbuf(int b) { return b ? FM_rows_alt.p : FM_rows.p; }
+    int back() const { return front_used ? 1 - front : front; }
     DevBuf<double> BM_rows;          // per-row Bmean, only after cd_assemble(keep_rows)
     bool have_bm_rows = false;
     const int32_t* N_rows_p = nullptr;
@@ -182,6 +207,11 @@ struct cd_ctx {
     DevBuf<double> trend_xs;         // scratch of the trend fit: one double per virtual region
     DevBuf<double> partial, scal;    // reduction scratch ; device scalars
     DevBuf<unsigned long long> counters;
+    DevBuf<unsigned long long> eval_counts;       // per fit_disp call of the last cd_region_test: evaluations
+    int n_eval_calls = 0;
+    int eval_call_p[16] = {0};                     // design columns of that call
+    int64_t eval_call_regions[16] = {0};           // virtual regions of that call
+    unsigned long long eval_counts_host[16] = {0};
     DevBuf<int32_t> refit_count;
     DevBuf<int64_t> park_row;
     DevBuf<double> park_d;           // 5 x capacity
@@ -313,6 +343,9 @@ int cd_create(cd_ctx** out, int device)
         delete c;
         return CD_ECUDA;
     }
+    cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&c->ev_read[k], cudaEventDisableTiming);
     for (int k = 0; k < 4; k++) cudaEventCreate(&c->ev[k]);
     for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev_user[k]);
     *out = c;
@@ -324,6 +357,9 @@ void cd_destroy(cd_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
+    if (ctx->st_copy) { cudaStreamSynchronize(ctx->st_copy); cudaStreamDestroy(ctx->st_copy); }
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    for (int k = 0; k < 2; k++) if (ctx->ev_read[k]) cudaEventDestroy(ctx->ev_read[k]);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->ev_user[k]) cudaEventDestroy(ctx->ev_user[k]);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -495,6 +531,8 @@ int cd_set_design(cd_ctx* ctx, int S, int p, const double* X)
     ctx->have_design = true;
     ctx->have_regions = ctx->have_agg = false;
     ctx->sample_set.assign((size_t)S, 0);
+    ctx->staged.assign((size_t)S, 0);
+    ctx->front_used = false;
     return CD_OK;
 }
 
@@ -519,6 +557,9 @@ int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off)
     ctx->rows_borrowed = false;
     ctx->N_rows_p = nullptr; ctx->FM_rows_p = nullptr;
     std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 0);
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st_copy));
+    std::fill(ctx->staged.begin(), ctx->staged.end(), 0);
+    ctx->front_used = false;
     return CD_OK;
 }
 
@@ -531,14 +572,21 @@ int cd_set_sample_rows(cd_ctx* ctx, int s, int64_t R, const int32_t* N, const do
         return ctx->fail(CD_EINVAL, "cd_set_sample_rows: sample index or row count does not match the regions");
     if (ctx->rows_borrowed) return ctx->fail(CD_EINVAL, "cd_set_sample_rows: rows were set with cd_set_rows_device");
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
-    CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R));
-    CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->N_rows.p + (size_t)s * R, N, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
-    CD_CUDA(ctx, cudaMemcpyAsync(ctx->FM_rows.p + (size_t)s * R, fullmean, sizeof(double) * (size_t)R, cudaMemcpyHostToDevice, ctx->st));
-    ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
+    const int b = ctx->back();
+    if (b == 0) { CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R)); CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R)); }
+    else { CD_CUDA(ctx, ctx->N_rows_alt.ensure((size_t)S * (size_t)R)); CD_CUDA(ctx, ctx->FM_rows_alt.ensure((size_t)S * (size_t)R)); }
+    bool first_of_round = true;
+    for (uint8_t f : ctx->staged) if (f) first_of_round = false;
+    // the buffer being filled was read by the aggregation two batches ago: that kernel must be done
+    if (first_of_round) CD_CUDA(ctx, cudaStreamWaitEvent(ctx->st_copy, ctx->ev_read[b], 0));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->nbuf(b) + (size_t)s * R, N, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, ctx->st_copy));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->fbuf(b) + (size_t)s * R, fullmean, sizeof(double) * (size_t)R, cudaMemcpyHostToDevice, ctx->st_copy));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->st_copy));
+    ctx->staged[(size_t)s] = 1;
     ctx->sample_set[(size_t)s] = 1;
-    ctx->have_agg = false;
-    return CD_OK;            // the copies are ordered before any kernel on the context's stream
+    // (the matrices of the last cd_aggregate stay valid: these rows belong to the NEXT cd_aggregate, and a region test of
+    //  the current batch may run while they are on their way)
+    return CD_OK;            // asynchronous: the host buffers must stay valid until the next cd_aggregate has returned
 }
 
 int cd_set_rows_device(cd_ctx* ctx, int64_t R, const int32_t* N_dev, const double* fullmean_dev)
@@ -622,6 +670,9 @@ int cd_region_universe(cd_ctx* ctx, int64_t m, const int32_t* peak_bait, const i
     ctx->have_regions = true; ctx->have_region_rows = true; ctx->have_agg = false; ctx->rows_borrowed = false;
     ctx->N_rows_p = nullptr; ctx->FM_rows_p = nullptr;
     std::fill(ctx->sample_set.begin(), ctx->sample_set.end(), 0);
+    CD_CUDA(ctx, cudaStreamSynchronize(ctx->st_copy));
+    std::fill(ctx->staged.begin(), ctx->staged.end(), 0);
+    ctx->front_used = false;
     if (R_out) *R_out = R;
     return CD_OK;
 }
@@ -868,6 +919,9 @@ int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out
         CD_CUDA(ctx, ctx->N_rows.ensure((size_t)S * (size_t)R));
         CD_CUDA(ctx, ctx->FM_rows.ensure((size_t)S * (size_t)R));
         CD_CUDA(ctx, ctx->BM_rows.ensure((size_t)S * (size_t)R));
+        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st_copy));          // no upload may still target the buffer written here
+        std::fill(ctx->staged.begin(), ctx->staged.end(), 0);
+        ctx->front = 0; ctx->front_used = true;
         ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
     }
     ctx->have_bm_rows = keep_rows != 0;
@@ -900,12 +954,18 @@ int cd_get_sample_rows(cd_ctx* ctx, int s, int32_t* N_out, double* fullmean_out)
 {
     if (!ctx) return CD_EINVAL;
     const int S = ctx->des.S;
-    if (s < 0 || s >= S || !ctx->have_regions || !ctx->N_rows_p || ctx->rows_borrowed || !ctx->sample_set[(size_t)s])
+    if (s < 0 || s >= S || !ctx->have_regions || (!ctx->N_rows_p && !ctx->staged[(size_t)s]) || ctx->rows_borrowed || !ctx->sample_set[(size_t)s])
         return ctx->fail(CD_EINVAL, "cd_get_sample_rows: no per-row columns on the device (cd_assemble with keep_rows, or cd_set_sample_rows)");
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t R = (size_t)ctx->R;
-    if (N_out) CD_CUDA(ctx, cudaMemcpyAsync(N_out, ctx->N_rows_p + (size_t)s * R, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, ctx->st));
-    if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM_rows_p + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->st));
+    const int32_t* Np = ctx->N_rows_p;
+    const double* Fp = ctx->FM_rows_p;
+    if (ctx->staged[(size_t)s]) {               // uploaded since the last aggregation: still in the staging buffer
+        CD_CUDA(ctx, cudaStreamSynchronize(ctx->st_copy));
+        Np = ctx->nbuf(ctx->back()); Fp = ctx->fbuf(ctx->back());
+    }
+    if (N_out) CD_CUDA(ctx, cudaMemcpyAsync(N_out, Np + (size_t)s * R, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, ctx->st));
+    if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, Fp + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     return CD_OK;
 }
@@ -933,9 +993,32 @@ int cd_aggregate(cd_ctx* ctx, int32_t* K_out, double* fullmean_out)
     const int64_t n = ctx->n;
     CD_CUDA(ctx, ctx->K.ensure((size_t)S * (size_t)n));
     CD_CUDA(ctx, ctx->FM.ensure((size_t)S * (size_t)n));
+    if (!ctx->rows_borrowed) {
+        int n_staged = 0;
+        for (uint8_t f : ctx->staged) n_staged += f ? 1 : 0;
+        if (n_staged > 0) {
+            const int b = ctx->back();
+            CD_CUDA(ctx, cudaStreamWaitEvent(ctx->st, ctx->ev_copy, 0));
+            if (b != ctx->front || !ctx->front_used) {
+                // samples that were not uploaded again keep the rows of the previous batch
+                if (ctx->front_used && n_staged < S) {
+                    const size_t R = (size_t)ctx->R;
+                    for (int s = 0; s < S; s++) if (!ctx->staged[(size_t)s]) {
+                        CD_CUDA(ctx, cudaMemcpyAsync(ctx->nbuf(b) + (size_t)s * R, ctx->nbuf(ctx->front) + (size_t)s * R, sizeof(int32_t) * R, cudaMemcpyDeviceToDevice, ctx->st));
+                        CD_CUDA(ctx, cudaMemcpyAsync(ctx->fbuf(b) + (size_t)s * R, ctx->fbuf(ctx->front) + (size_t)s * R, sizeof(double) * R, cudaMemcpyDeviceToDevice, ctx->st));
+                    }
+                }
+                ctx->front = b;
+            }
+            ctx->front_used = true;
+            std::fill(ctx->staged.begin(), ctx->staged.end(), 0);
+        }
+        ctx->N_rows_p = ctx->nbuf(ctx->front); ctx->FM_rows_p = ctx->fbuf(ctx->front);
+    }
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->st));
     CD_LAUNCHN(ctx, n > 0 ? 1 : 0, launch_aggregate(n, S, ctx->row_off.p, ctx->R, ctx->N_rows_p, ctx->FM_rows_p, ctx->K.p, ctx->FM.p, ctx->st));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->st));
+    if (!ctx->rows_borrowed) CD_CUDA(ctx, cudaEventRecord(ctx->ev_read[ctx->front], ctx->st));
     if (K_out) CD_CUDA(ctx, cudaMemcpyAsync(K_out, ctx->K.p, sizeof(int32_t) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     if (fullmean_out) CD_CUDA(ctx, cudaMemcpyAsync(fullmean_out, ctx->FM.p, sizeof(double) * (size_t)S * (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
     CD_CUDA(ctx, cudaStreamSynchronize(ctx->st));
@@ -1067,6 +1150,11 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, ctx->alpha_init.p, nullptr, none, ctx->log_alpha.p,
                                        ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
+    if (ctx->n_eval_calls < 16 && nv > 0) {
+        count_evals_kernel<<<592, 256, 0, st>>>(nv, ctx->dispGeneIter.p, ctx->eval_counts.p + ctx->n_eval_calls);
+        ctx->launches++;
+        ctx->eval_call_p[ctx->n_eval_calls] = p; ctx->eval_call_regions[ctx->n_eval_calls] = nv; ctx->n_eval_calls++;
+    }
     CD_LAUNCHN(ctx, 1, launch_gene_post(nv, S, ctx->alpha_init.p, ctx->log_alpha.p, ctx->dispGeneIter.p, ctx->initial_lp.p,
                                         ctx->last_lp.p, flags, dispGeneEst, ctx->refit_list.p, ctx->refit_count.p, st));
     ctx->tm_begin(4);
@@ -1148,6 +1236,11 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, dispGeneEst, dispFit, prior, ctx->log_alpha.p,
                                        ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
+    if (ctx->n_eval_calls < 16 && nv > 0) {
+        count_evals_kernel<<<592, 256, 0, st>>>(nv, ctx->dispIter.p, ctx->eval_counts.p + ctx->n_eval_calls);
+        ctx->launches++;
+        ctx->eval_call_p[ctx->n_eval_calls] = p; ctx->eval_call_regions[ctx->n_eval_calls] = nv; ctx->n_eval_calls++;
+    }
     CD_LAUNCHN(ctx, 1, launch_map_post(nv, n, S, ctx->log_alpha.p, ctx->dispIter.p, dispGeneEst, dispFit, thr,
                                        flags, ctx->dispMAP.p, ctx->dispersion.p, ctx->refit_list.p, ctx->refit_count.p, st));
     ctx->tm_begin(4);
@@ -1266,6 +1359,9 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
         pk.count = ctx->counters.p + 14;
     }
 
+    CD_CUDA(ctx, ctx->eval_counts.ensure(16));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->eval_counts.p, 0, 16 * sizeof(unsigned long long), st));
+    ctx->n_eval_calls = 0;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     memset(out->sizeFactors, 0, sizeof(out->sizeFactors));
     for (int k = 2; k < 8; k++) ctx->timings[k] = 0.0;
@@ -1314,6 +1410,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     }
     unsigned long long hc[4] = {0, 0, 0, 0};
     CD_CUDA(ctx, cudaMemcpyAsync(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->eval_counts_host, ctx->eval_counts.p, sizeof(ctx->eval_counts_host), cudaMemcpyDeviceToHost, st));
     const size_t nn = (size_t)n;
     if ((rc = d2h(ctx, out->baseMean, ctx->g_baseMean.p + ctx->g_off, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->baseVar, ctx->baseVar.p, nn)) != CD_OK) return rc;
@@ -1413,6 +1510,16 @@ int cd_results_resident(cd_ctx* ctx, double* pvalue_out, double* padj_out, doubl
     return CD_OK;
 }
 
+int cd_get_dims(const cd_ctx* ctx, int64_t* n, int* S, int* p, int64_t* R)
+{
+    if (!ctx) return CD_EINVAL;
+    if (n) *n = ctx->n;
+    if (S) *S = ctx->have_design ? ctx->des.S : 0;
+    if (p) *p = ctx->have_design ? ctx->des.p : 0;
+    if (R) *R = ctx->R;
+    return CD_OK;
+}
+
 int64_t cd_launch_count(const cd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int cd_timer_start(cd_ctx* ctx)
@@ -1462,6 +1569,18 @@ int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmea
     if (!ctx->have_agg) return ctx->fail(CD_EINVAL, "cd_device_buffers: nothing aggregated yet");
     if (K_dev) *K_dev = ctx->K.p;
     if (fullmean_dev) *fullmean_dev = ctx->FM.p;
+    return CD_OK;
+}
+
+int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[16], int design_columns[16], int64_t regions[16])
+{
+    if (!ctx || !n_calls) return CD_EINVAL;
+    *n_calls = ctx->n_eval_calls;
+    for (int k = 0; k < 16; k++) {
+        if (evaluations) evaluations[k] = k < ctx->n_eval_calls ? (int64_t)ctx->eval_counts_host[k] : 0;
+        if (design_columns) design_columns[k] = k < ctx->n_eval_calls ? ctx->eval_call_p[k] : 0;
+        if (regions) regions[k] = k < ctx->n_eval_calls ? ctx->eval_call_regions[k] : 0;
+    }
     return CD_OK;
 }
 

@@ -166,12 +166,8 @@ cudaError_t launch_fit_disp_grid(int64_t n, int64_t n_fit, int S, int p, const C
                                  const double* dispGeneEst, cudaStream_t st);
 
 // ---- stage 4b: trend ---------------------------------------------------------------------
-// one pass of the Gamma(identity) IRLS: at coefficients b, over rows with !allZero,
-// dispGeneEst > 1e-6 and residual ratio (w.r.t. outer coefs c) in (1e-4, 15):
-// out[0..4] = s00,s01,s11,t0,t1 ; out[5] = deviance ; out[6] = #invalid mu ; out[7] = #rows used
-cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* dispGeneEst,
-                              const uint8_t* flags, double c0, double c1, double b0, double b1,
-                              double* partial, double* out, cudaStream_t st);
+// the sums of one pass of the Gamma(identity) IRLS at coefficients b, over rows with !allZero, dispGeneEst > 1e-6 and
+// residual ratio (w.r.t. the outer coefficients c) in (1e-4, 15): s00, s01, s11, t0, t1, deviance, #invalid mu, #rows
 // peer-memory description for the in-kernel all-reduce of the sharded trend fit (nranks == 1: unused)
 struct TrendP2P {
     int nranks, rank;

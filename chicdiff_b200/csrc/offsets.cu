@@ -155,46 +155,6 @@ cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR, cu
 }
 
 // ---------------------------------------------------------------------------------------
-// parametric trend: one pass of glm.fit(family = Gamma(link = "identity")) at coefficients b (host-driven
-// variant, used when a sharded run has no peer memory: NCCL all-reduces the 8 sums between the passes)
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-trend_pass_kernel(int64_t n, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
-                  const uint8_t* __restrict__ flags, double c0, double c1, double b0, double b1,
-                  double* __restrict__ partial)
-{
-    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
-    const int64_t lo = (int64_t)blockIdx.x * chunk;
-    const int64_t hi = (lo + chunk < n) ? lo + chunk : n;
-    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        if (flags[i] & CD_FLAG_ALLZERO) continue;
-        const double d = dispGeneEst[i];
-        if (!(d > 100.0 * kMinDisp)) continue;
-        const double x = 1.0 / baseMean[i];
-        const double r = d / (c0 + c1 * x);
-        if (!((r > 1e-4) && (r < 15.0))) continue;
-        const double mu = b0 + b1 * x;
-        v[7] += 1.0;
-        if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; continue; }
-        const double w = 1.0 / (mu * mu);
-        v[0] += w; v[1] += w * x; v[2] += w * x * x;
-        v[3] += w * d; v[4] += w * x * d;
-        v[5] += -2.0 * (log(d / mu) - (d - mu) / mu);
-    }
-    block_reduce_store<8>(v, partial + (size_t)blockIdx.x * 8);
-}
-
-cudaError_t launch_trend_pass(int64_t n, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                              double c0, double c1, double b0, double b1, double* partial, double* out,
-                              cudaStream_t st)
-{
-    trend_pass_kernel<<<kReduceBlocks, 256, 0, st>>>(n, baseMean, dispGeneEst, flags, c0, c1, b0, b1, partial);
-    final_reduce_kernel<<<8, 32, 0, st>>>(kReduceBlocks, 8, partial, out);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------
 // The whole parametricDispersionFit of a batch of G fits on the device: one cooperative kernel, one CTA per SM.
 // Every pass (sums + deviance at coefficients b over the rows kept by the outer coefficients c, for every fit that
 // is still running) is a chunked block reduction, a grid barrier, and a fixed-order sum of the per-CTA partials
@@ -351,42 +311,67 @@ struct TrendFit {
 // region or dispersion at the floor), negative = excluded by the current outer coefficients.  refresh = 2 on the first
 // pass of the launch (fill xs), 1 on the first pass of an outer iteration (re-decide the sign), 0 otherwise.
 // Every row is always handled by the same thread, so xs needs no synchronisation.
+__device__ __forceinline__ void trend_row(int64_t i, double d, double xv, int refresh, double c0, double c1, double b0, double b1,
+                                          double* __restrict__ xs, double (&v)[8])
+{
+    if (refresh) {
+        if (xv != xv) { if (refresh == 2) xs[i] = xv; return; }
+        const double x = fabs(xv);
+        const double r = d / (c0 + c1 * x);
+        xv = ((r > 1e-4) && (r < 15.0)) ? x : -x;
+        xs[i] = xv;
+    }
+    if (!(xv > 0.0)) return;
+    const double x = xv;
+    const double mu = b0 + b1 * x;
+    v[7] += 1.0;
+    if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; return; }
+    double w, t;
+    if (mu > 1e-100 && mu < 1e100) { const double inv = rcp_pos(mu); w = inv * inv; t = d * inv; }
+    else { w = 1.0 / (mu * mu); t = d / mu; }
+    const double wx = w * x;
+    v[0] += w; v[1] += wx; v[2] += wx * x;
+    v[3] += w * d; v[4] += wx * d;
+    // unit deviance of the Gamma family: -2 (log(d/mu) - (d - mu)/mu)
+    const double lt = (t > 1e-300 && t < 1e300) ? log_pos(t) : log(t);
+    v[5] += -2.0 * (lt - (t - 1.0));
+}
+
+// The pass streams 16 bytes per row; four rows per thread are loaded before any of them is processed so that enough
+// loads are in flight to cover the HBM latency (a thread handles the same rows, in the same order, in every pass, so
+// the sums stay bit-reproducible).
 __device__ __forceinline__ void trend_pass_rows(int64_t lo, int64_t hi, const double* __restrict__ baseMean,
                                                 const double* __restrict__ dispGeneEst, const uint8_t* __restrict__ flags,
                                                 double* __restrict__ xs, const TrendPass& p, double (&v)[8])
 {
     const int refresh = p.refresh;
     const double c0 = p.c0, c1 = p.c1, b0 = p.b0, b1 = p.b1;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        double xv;
-        const double d = dispGeneEst[i];
+    const int64_t bd = blockDim.x;
+    int64_t i = lo + threadIdx.x;
+    for (; i + 3 * bd < hi; i += 4 * bd) {
+        double d[4], xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) d[u] = dispGeneEst[i + u * bd];
         if (refresh == 2) {
-            xv = NAN;
-            if (!(flags[i] & CD_FLAG_ALLZERO) && (d > 100.0 * kMinDisp)) xv = 1.0 / baseMean[i];
+            double bm[4];
+            uint8_t f[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { bm[u] = baseMean[i + u * bd]; f[u] = flags[i + u * bd]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = (!(f[u] & CD_FLAG_ALLZERO) && (d[u] > 100.0 * kMinDisp)) ? 1.0 / bm[u] : NAN;
         } else {
-            xv = xs[i];
+#pragma unroll
+            for (int u = 0; u < 4; u++) xv[u] = xs[i + u * bd];
         }
-        if (refresh) {
-            if (xv != xv) { if (refresh == 2) xs[i] = xv; continue; }
-            const double x = fabs(xv);
-            const double r = d / (c0 + c1 * x);
-            xv = ((r > 1e-4) && (r < 15.0)) ? x : -x;
-            xs[i] = xv;
-        }
-        if (!(xv > 0.0)) continue;
-        const double x = xv;
-        const double mu = b0 + b1 * x;
-        v[7] += 1.0;
-        if (!(mu > 0.0) || !isfinite(mu)) { v[6] += 1.0; continue; }
-        double w, t;
-        if (mu > 1e-100 && mu < 1e100) { const double inv = rcp_pos(mu); w = inv * inv; t = d * inv; }
-        else { w = 1.0 / (mu * mu); t = d / mu; }
-        const double wx = w * x;
-        v[0] += w; v[1] += wx; v[2] += wx * x;
-        v[3] += w * d; v[4] += wx * d;
-        // unit deviance of the Gamma family: -2 (log(d/mu) - (d - mu)/mu)
-        const double lt = (t > 1e-300 && t < 1e300) ? log_pos(t) : log(t);
-        v[5] += -2.0 * (lt - (t - 1.0));
+#pragma unroll
+        for (int u = 0; u < 4; u++) trend_row(i + u * bd, d[u], xv[u], refresh, c0, c1, b0, b1, xs, v);
+    }
+    for (; i < hi; i += bd) {
+        const double d = dispGeneEst[i];
+        double xv;
+        if (refresh == 2) xv = (!(flags[i] & CD_FLAG_ALLZERO) && (d > 100.0 * kMinDisp)) ? 1.0 / baseMean[i] : NAN;
+        else xv = xs[i];
+        trend_row(i, d, xv, refresh, c0, c1, b0, b1, xs, v);
     }
 }
 

@@ -19,7 +19,7 @@ FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLA
 EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident", "cd_ihw_apply",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
-            "cd_device_buffers", "cd_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
+            "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
             "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]
 
 
@@ -434,6 +434,14 @@ class Engine:
         t = C.c_double()
         self._check(self._L.cd_measure_fp64_peak(self._h, C.byref(t)))
         return t.value
+
+    def last_search_counts(self):
+        """[(evaluations, design columns, regions searched)] of the dispersion line-search launches of the last region_test"""
+        k = C.c_int()
+        ev, pc, rg = (C.c_int64 * 16)(), (C.c_int * 16)(), (C.c_int64 * 16)()
+        self._L.cd_last_search_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+        self._check(self._L.cd_last_search_counts(self._h, C.byref(k), ev, pc, rg))
+        return [(int(ev[i]), int(pc[i]), int(rg[i])) for i in range(k.value)]
 
     def last_timings(self):
         t = np.zeros(8, np.float64)

@@ -95,7 +95,12 @@ int cd_set_design(cd_ctx* ctx, int S, int p, const double* X);
 /* regions as CSR segments over region-contiguous rows (sorted by regionID, then otherEndID) */
 int cd_set_regions(cd_ctx* ctx, int64_t n, const int64_t* row_off /* n + 1 */);
 /* per-replicate columns of the long table: N (chicdiff.R:853) and FullMean = Bmean + Tmean
- * (chicdiff.R:896), R = row_off[n] rows, host pointers (copied to the device) */
+ * (chicdiff.R:896), R = row_off[n] rows, host pointers.  The copy is asynchronous on a copy stream of the context: the
+ * buffers must stay valid until the next cd_aggregate has returned (pageable memory is staged by the driver before the
+ * call returns; pinned memory is read by the DMA engine later).  Uploads go to a second device buffer while the rows
+ * of the previous cd_aggregate are still in use, so a caller that processes several batches (test set, control set,
+ * bench steps) can call cd_set_sample_rows for the NEXT batch between cd_aggregate and cd_region_test of the current
+ * one, and the upload crosses the bus under the region test. */
 int cd_set_sample_rows(cd_ctx* ctx, int s, int64_t R, const int32_t* N, const double* fullmean);
 /* same, but the pointers are device pointers holding ALL samples sample-major (S x R); the
  * context borrows them (no copy) until the next cd_set_regions / cd_destroy */
@@ -247,6 +252,9 @@ int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalue, int ngro
                  double* weighted_pvalue_out, double* weighted_padj_out);
 
 /* ---- introspection ------------------------------------------------------------------------ */
+/* sizes of the problem currently set on the context: regions n, samples S, design columns p, region rows R (any pointer
+ * may be NULL).  Bindings size their output buffers from these, not from what their caller believes. */
+int cd_get_dims(const cd_ctx* ctx, int64_t* n, int* S, int* p, int64_t* R);
 /* number of kernel launches issued by this context since creation */
 int64_t cd_launch_count(const cd_ctx* ctx);
 /* device pointers of the aggregated matrices (S x n): for device-resident pipelines */
@@ -255,6 +263,11 @@ int cd_device_buffers(cd_ctx* ctx, const int32_t** K_dev, const double** fullmea
  * stream: [0] aggregation kernel, [1] region_test total, [2] fitDisp line-search kernels (all fits),
  * [3] NB GLM / Wald kernels, [4] grid refits, [5] trend fit + MAD, [6] size factors */
 int cd_last_timings(const cd_ctx* ctx, double out_ms[8]);
+/* The dispersion line searches of the last cd_region_test, one entry per search launch in launch order (theta-grid batch:
+ * gene-wise, MAP; final fit: gene-wise, MAP): fused posterior + derivative evaluations summed over the regions (one to
+ * start a search plus one per trip), the design columns p of that fit and the (virtual) regions searched.  This is the
+ * unit count of the FP64 roofline in bench.py: evaluations x S replicates x flop per replicate-evaluation. */
+int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[16], int design_columns[16], int64_t regions[16]);
 /* CUDA-event stopwatch on the context's stream (what bench.py brackets its timed region with) */
 int cd_timer_start(cd_ctx* ctx);
 int cd_timer_stop(cd_ctx* ctx, double* ms_out);      /* synchronises */

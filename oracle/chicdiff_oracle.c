@@ -602,34 +602,40 @@ static fitdisp_res fit_disp_row(const double* y, const double* mu, const design_
     return r;
 }
 
-/* DESeq2.cpp fitDispGrid, one row.  margin_out (may be NULL): the gap between the best and the second-best grid value
- * on either level, in rounding-error units -- an arg max over a plateau flatter than that is decided by rounding. */
+/* DESeq2.cpp fitDispGrid, one row.  margin_out (may be NULL): the smallest gap between the winning grid value and any
+ * other grid value of the same level, in units of the larger of the two values' rounding errors -- an arg max over a
+ * plateau flatter than that is decided by rounding (the far end of the grid, alpha = 1e-8, carries the rounding error
+ * of lgamma(1e8) ~ 1e-6 even when the winner sits where the posterior is known to 1e-11). */
+static double grid_level(const double* y, const double* mu, const design_t* d, int grid_n, double lo, double hi,
+                         double prior_mean, double prior_sigmasq, int use_prior, int use_cr, orc_counters* cnt, double* margin)
+{
+    double v[64], nz[64];
+    const double step = (hi - lo) / (grid_n - 1);
+    int best = 0;
+    for (int t = 0; t < grid_n; t++) {
+        double a = (t == grid_n - 1) ? hi : lo + t * step;
+        v[t] = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz[t]);
+        cnt->lp_evals++;
+        if (v[t] > v[best]) best = t;            /* first maximum wins, as which.max */
+    }
+    for (int t = 0; t < grid_n; t++) {
+        if (t == best) continue;
+        double m = (v[best] - v[t]) / fmax(nz[best], nz[t]);
+        if (!(m >= *margin)) *margin = m;        /* also takes NaN values to the front */
+    }
+    return (best == grid_n - 1) ? hi : lo + best * step;
+}
+
 static double fit_disp_grid_row(const double* y, const double* mu, const design_t* d, int grid_n,
                                 double min_la, double max_la, double prior_mean, double prior_sigmasq,
                                 int use_prior, int use_cr, orc_counters* cnt, double* margin_out)
 {
+    double margin = INFINITY;
+    if (grid_n > 64) grid_n = 64;
     double step = (max_la - min_la) / (grid_n - 1);
-    double best = -INFINITY, second = -INFINITY, a_hat = min_la, nz = 0, nzb = 1, margin = INFINITY;
-    for (int t = 0; t < grid_n; t++) {
-        double a = (t == grid_n - 1) ? max_la : min_la + t * step;
-        double v = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz);
-        cnt->lp_evals++;
-        if (v > best) { second = best; best = v; a_hat = a; nzb = nz; }
-        else if (v > second) second = v;
-    }
-    margin = fmin(margin, (best - second) / nzb);
+    double a_hat = grid_level(y, mu, d, grid_n, min_la, max_la, prior_mean, prior_sigmasq, use_prior, use_cr, cnt, &margin);
     double delta = (min_la + step) - min_la;
-    double lo = a_hat - delta, hi = a_hat + delta, fstep = (hi - lo) / (grid_n - 1);
-    double best2 = -INFINITY, a2 = lo;
-    second = -INFINITY;
-    for (int t = 0; t < grid_n; t++) {
-        double a = (t == grid_n - 1) ? hi : lo + t * fstep;
-        double v = log_posterior_n(a, y, mu, d, prior_mean, prior_sigmasq, use_prior, use_cr, &nz);
-        cnt->lp_evals++;
-        if (v > best2) { second = best2; best2 = v; a2 = a; nzb = nz; }
-        else if (v > second) second = v;
-    }
-    margin = fmin(margin, (best2 - second) / nzb);
+    double a2 = grid_level(y, mu, d, grid_n, a_hat - delta, a_hat + delta, prior_mean, prior_sigmasq, use_prior, use_cr, cnt, &margin);
     if (margin_out) *margin_out = margin;
     return a2;
 }

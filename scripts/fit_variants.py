@@ -9,12 +9,13 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from chicdiff_b200 import engine, synth  # noqa: E402
+from chicdiff_b200 import engine  # noqa: E402
+from _cache import cached_generate  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "c3"
 nreg = None if len(sys.argv) < 3 or sys.argv[2] == "full" else int(sys.argv[2])
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
-d = synth.generate(workload, n_regions=nreg)
+d = cached_generate(workload, nreg)
 e = engine.Engine(0)
 e.set_design(d.X); e.set_regions(d.row_off)
 for s in range(d.S):

@@ -25,6 +25,19 @@ def run(eng, X, row_off, N, FMr, **kw):
     return r
 
 
+COLS = ("baseMean", "normFactors", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "log2FoldChange", "lfcSE", "stat", "pvalue",
+        "deviance", "maxCooks")
+FLIP_BOUND = 1e-4
+
+
+def relerr(a, b):
+    with np.errstate(invalid="ignore", divide="ignore"):
+        e = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    e[(np.isnan(a) & np.isnan(b)) | (a == b)] = 0
+    e[np.isnan(e)] = np.inf
+    return e
+
+
 def main():
     workload = sys.argv[1] if len(sys.argv) > 1 else "c3"
     nreg = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
@@ -36,36 +49,60 @@ def main():
     off, (N, FMr), (lo, hi) = parallel.take_shard(d.row_off, [d.N_rows, d.FM_rows], bounds, rank)
     eng = engine.Engine(local)
     parallel.init_comm(eng, dist)
-    r = run(eng, d.X, off, N, FMr)
-    cols = {k: v for k, v in r.items() if isinstance(v, np.ndarray) and v.ndim >= 1 and k not in ("sizeFactors", "deviances")}
-    for k in ("sizeFactors", "deviances", "theta", "trend_a0", "trend_a1", "varLogDispEsts", "dispPriorVar"):
-        cols[k] = r[k]
-    full = parallel.gather_columns(cols, dist)
-    ok = True
+    info = eng.comm_info()
+    assert info["peer_memory_allreduce"] and info["peer_memory_medians"], "sharded runs exchange through peer memory"
+
+    def gathered(r):
+        cols = {k: v for k, v in r.items() if isinstance(v, np.ndarray) and v.ndim >= 1 and k not in ("sizeFactors", "deviances")}
+        for k in ("sizeFactors", "deviances", "theta", "trend_a0", "trend_a1", "varLogDispEsts", "dispPriorVar"):
+            cols[k] = r[k]
+        return parallel.gather_columns(cols, dist)
+
+    # 1. free sharded run; 2. single-GPU run of the whole set on rank 0; 3. sharded run with the single-GPU run's global
+    # scalars, which makes every per-region number a function of that region's data alone
+    full = gathered(run(eng, d.X, off, N, FMr))
+    box = [None]
+    ref = None
     if rank == 0:
         ref = run(engine.Engine(local), d.X, d.row_off, d.N_rows, d.FM_rows)
+        box[0] = (ref["theta"], ref["trend_a0"], ref["trend_a1"], ref["varLogDispEsts"], ref["dispPriorVar"])
+    dist.broadcast_object_list(box, src=0)
+    th, a0, a1, vld, pv = box[0]
+    shared = gathered(run(eng, d.X, off, N, FMr, theta_grid=[th], trend=(a0, a1), var_log_disp=vld, disp_prior_var=pv))
+    ok = True
+    if rank == 0:
+        from oracle import oracle as O          # test tooling: the oracle's record of rounding-decided line searches
+        ro = O.region_test(ref["K"], ref["FMagg"], d.X, margins=True)
+        with np.errstate(invalid="ignore"):
+            noisy = (ro["geneMargin"] < 64) | (ro["mapMargin"] < 64)
         assert np.array_equal(full["K"], ref["K"]), "aggregated counts differ"
         print("shards", bounds.tolist(), "theta", full["theta"], ref["theta"])
-        assert full["theta"] == ref["theta"]
-        worst = 0.0
+        ok = ok and full["theta"] == ref["theta"] == th
         for k in ("sizeFactors", "deviances"):
             e = float(np.max(np.abs(full[k] - ref[k]) / np.abs(ref[k])))
-            print("%-14s max rel %.3e" % (k, e)); worst = max(worst, e if k == "sizeFactors" else 0)
+            print("%-14s max rel %.3e" % (k, e))
+            ok = ok and e < (1e-12 if k == "sizeFactors" else 1e-6)
+        coupling = 0.0
         for k in ("trend_a0", "trend_a1", "varLogDispEsts", "dispPriorVar"):
             e = abs(full[k] - ref[k]) / abs(ref[k])
-            print("%-14s rel %.3e" % (k, e)); worst = max(worst, e)
-        for k in ("baseMean", "normFactors", "dispGeneEst", "dispFit", "dispMAP", "dispersion", "log2FoldChange", "lfcSE", "stat", "pvalue", "deviance", "maxCooks"):
-            a, b = full[k], ref[k]
-            assert np.array_equal(np.isnan(a), np.isnan(b)), k
-            with np.errstate(invalid="ignore", divide="ignore"):
-                e = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
-            e[np.isnan(e) | (a == b)] = 0
-            print("%-14s max rel %.3e  #>1e-9: %d" % (k, e.max(), (e > 1e-9).sum()))
-            if k not in ("pvalue", "stat", "log2FoldChange", "dispGeneEst"):
-                worst = max(worst, float(np.quantile(e, 0.999)))
-        print("iters equal:", np.array_equal(full["dispIter"], ref["dispIter"]), np.array_equal(full["betaIter"], ref["betaIter"]))
-        ok = worst < 1e-6
-        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", "world", world, "worst %.3e" % worst)
+            print("%-14s rel %.3e (free run)" % (k, e)); coupling = max(coupling, e)
+        ok = ok and coupling < 1e-4
+        bad = np.zeros(d.n, bool)
+        for k in COLS:
+            a, b = shared[k], ref[k]
+            e = relerr(a, b)
+            e = e.max(axis=0) if e.ndim == 2 else e
+            if k == "dispGeneEst":
+                e[(a < 1e-6) & (b < 1e-6)] = 0           # both at the floor (DESeq2 excludes them from the trend)
+            bad |= e > 1e-6
+            ef = relerr(full[k], ref[k])
+            print("%-14s shared scalars: max rel %.3e  #>1e-6: %d   | free run: max rel %.3e  #>1e-6: %d" % (
+                k, e.max(), (e > 1e-6).sum(), ef.max(), (ef > 1e-6).sum()))
+        print("regions beyond 1e-6 in any column (shared scalars): %d of %d, all rounding-decided per the oracle: %s -> %s" % (
+            bad.sum(), d.n, bool(np.all(noisy[bad])), np.flatnonzero(bad)[:20].tolist()))
+        ok = ok and bool(np.all(noisy[bad])) and bad.sum() <= FLIP_BOUND * d.n + 2
+        print("iters equal:", float((shared["dispIter"] == ref["dispIter"]).mean()), float((shared["betaIter"] == ref["betaIter"]).mean()))
+        print("MULTI_GPU_CHECK", "OK" if ok else "FAILED", "world", world)
     dist.barrier()
     dist.destroy_process_group()
     if not ok:

@@ -47,6 +47,9 @@ SEXP Rf_ScalarReal(double);
 SEXP Rf_ScalarInteger(int);
 SEXP Rf_lang3(SEXP, SEXP, SEXP);
 SEXP Rf_eval(SEXP, SEXP);
+SEXP R_tryEvalSilent(SEXP, SEXP, int*);
+extern double R_NaReal;
+#define NA_REAL R_NaReal
 Rboolean Rf_isNull(SEXP);
 extern SEXP R_GlobalEnv;
 #define error Rf_error
