@@ -217,62 +217,32 @@ def chicEstimateDistFun(distbin, refBinMean, binsize=20000):
     return np.asarray(out, dtype=np.float64)
 
 
-def _first_by(keys, *cols):
-    """data.table's x[, list(v = v[1]), by = key] on a table sorted by (baitID, otherEndID): first row per key."""
-    u, first = np.unique(keys, return_index=True)
-    return (u,) + tuple(np.asarray(c)[first] for c in cols)
+def label_codes(lab):
+    """bin labels (R factor / character; None or NaN = NA) -> (int32 codes with -1 = NA, sorted levels)"""
+    lab = np.asarray(lab, dtype=object)
+    na = np.array([v is None or (isinstance(v, float) and np.isnan(v)) for v in lab])
+    levels = sorted(set(lab[~na].tolist()))
+    lut = {v: k for k, v in enumerate(levels)}
+    return np.array([-1 if m else lut[v] for v, m in zip(lab, na)], dtype=np.int32), levels
 
 
-def replicate_tables(x, rmap_ids, counts=None, binsize=20000):
+def chicago_columns(x, counts=None, binsize=20000):
     """One replicate's CHiCAGO table (dict of columns: baitID, otherEndID, N, s_j, s_i, tblb, tlb, Tmean, distbin,
-    refBinMean) -> the per-fragment look-up tables of cd_sample_tables, exactly the intermediate tables of
-    getFullRegionData1: per-bait first (s_j, tblb) (:659), per-other-end first (s_i, tlb) (:668), first Tmean per
-    (tblb, tlb) (:680), .chicEstimateDistFun (:696), and the count rows (the .chinput, :828-853, or x's own N)."""
-    ids = np.asarray(rmap_ids, dtype=np.int64)
-    id0, F = int(ids[0]), len(ids)
-    if not np.array_equal(ids, np.arange(id0, id0 + F)):
-        raise ValueError("the rmap fragment IDs must be contiguous")
-    bait = np.asarray(x["baitID"], dtype=np.int64)
-    oe = np.asarray(x["otherEndID"], dtype=np.int64)
-    order = np.lexsort((oe, bait))                                   # setkey(x, baitID, otherEndID) (:632)
-    bait, oe = bait[order], oe[order]
-    col = lambda k: np.asarray(x[k])[order]
-    tb_lab, tl_lab = col("tblb"), col("tlb")
-
-    def codes(lab):
-        lab = np.asarray(lab, dtype=object)
-        na = np.array([v is None or (isinstance(v, float) and np.isnan(v)) for v in lab])
-        levels = sorted(set(lab[~na].tolist()))
-        lut = {v: k for k, v in enumerate(levels)}
-        return np.array([-1 if m else lut[v] for v, m in zip(lab, na)], dtype=np.int32), levels
-    tb_code, tb_levels = codes(tb_lab)
-    tl_code, tl_levels = codes(tl_lab)
-    s_j = np.full(F, np.nan); tblb = np.full(F, -1, np.int32)
-    ub, sj1, tb1 = _first_by(bait, col("s_j").astype(np.float64), tb_code)
-    s_j[ub - id0] = sj1; tblb[ub - id0] = tb1
-    s_i = np.full(F, np.nan); tlb = np.full(F, -1, np.int32)
-    o2 = np.lexsort((bait, oe))                                      # first row per otherEndID in (baitID, otherEndID) order
-    uo, first = np.unique(oe[o2], return_index=True)
-    s_i[uo - id0] = col("s_i").astype(np.float64)[o2][first]
-    tlb[uo - id0] = tl_code[o2][first]
-    tmean = np.full((max(1, len(tb_levels)), max(1, len(tl_levels))), np.nan)
-    tm = col("Tmean").astype(np.float64)
-    okc = (tb_code >= 0) & (tl_code >= 0)
-    key = tb_code[okc].astype(np.int64) * max(1, len(tl_levels)) + tl_code[okc]
-    uk, firstk = np.unique(key, return_index=True)
-    tmean.reshape(-1)[uk] = tm[okc][firstk]
-    distfun = chicEstimateDistFun(col("distbin"), col("refBinMean"), binsize)
-    if counts is None:
-        cb, co, cn = bait, oe, np.asarray(x["N"])[order]
-    else:
-        cb = np.asarray(counts["baitID"], dtype=np.int64); co = np.asarray(counts["otherEndID"], dtype=np.int64)
-        o3 = np.lexsort((co, cb))
-        cb, co, cn = cb[o3], co[o3], np.asarray(counts["N"])[o3]
-    inside = (cb >= id0) & (cb < id0 + F)
-    cb, co, cn = cb[inside], co[inside], cn[inside]
-    cnt_off = np.searchsorted(cb, np.arange(id0, id0 + F + 1)).astype(np.int64)
-    return dict(s_j=s_j, tblb=tblb, s_i=s_i, tlb=tlb, tmean=tmean, distfun=distfun, cnt_off=cnt_off,
-                cnt_oe=co.astype(np.int32), cnt_N=cn.astype(np.int32), tblb_levels=tb_levels, tlb_levels=tl_levels)
+    refBinMean) -> the raw columns cd_build_sample_tables takes.  No sort, no join, no first-per-group pass happens
+    here: those are the device's (csrc/tables.cu); the host only turns the bin labels into codes and fits the ~75-point
+    distance function (.chicEstimateDistFun, chicdiff.R:538-573)."""
+    tb, tb_levels = label_codes(x["tblb"])
+    tl, tl_levels = label_codes(x["tlb"])
+    t = dict(baitID=np.asarray(x["baitID"], dtype=np.int32), otherEndID=np.asarray(x["otherEndID"], dtype=np.int32),
+             s_j=np.asarray(x["s_j"], dtype=np.float64), s_i=np.asarray(x["s_i"], dtype=np.float64), tblb=tb, tlb=tl,
+             Tmean=np.asarray(x["Tmean"], dtype=np.float64), N=np.asarray(x["N"], dtype=np.int32),
+             n_tblb=max(1, len(tb_levels)), n_tlb=max(1, len(tl_levels)),
+             distfun=chicEstimateDistFun(x["distbin"], x["refBinMean"], binsize), tblb_levels=tb_levels, tlb_levels=tl_levels)
+    if counts is not None:
+        t["cnt_baitID"] = np.asarray(counts["baitID"], dtype=np.int32)
+        t["cnt_otherEndID"] = np.asarray(counts["otherEndID"], dtype=np.int32)
+        t["cnt_N"] = np.asarray(counts["N"], dtype=np.int32)
+    return t
 
 
 def reconstruct_count_tables(reps):
@@ -337,8 +307,8 @@ def getFullRegionData1(chicdiff_settings, RU, rmap, chicago_tables, count_tables
     tabs = []
     for s in range(S):
         message("\nReading Chicago dataset %d of %d : %s" % (s + 1, S, names[s]))
-        tabs.append(replicate_tables(reps[s], ids, cnts[s]))
-        eng.set_sample_tables(s, tabs[-1])
+        eng.build_sample_tables(s, chicago_columns(reps[s], cnts[s]))          # joins / first-per-key tables on the device
+        tabs.append(eng.get_sample_tables(s))
     message("Processing count data")
     eng.assemble(keep_rows=True, fetch=False)
     R = len(ru_oe)

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 using namespace cd;
 
@@ -388,16 +389,20 @@ static bool open_peer_mailboxes(cd_ctx* ctx, void* mine_ptr, bool local_ok, std:
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     if (ok && cudaIpcGetMemHandle(&mine, mine_ptr) != cudaSuccess) { cudaGetLastError(); ok = false; }
-    // handle + a validity byte per rank
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    // per rank: handle, a validity byte, and -- for peers that live in THIS process (cd_multi: one host thread per GPU) --
+    // the process id, the raw device pointer and the device ordinal: such a peer's buffer is mapped by enabling peer
+    // access and using the pointer as it is (cudaIpc handles cannot be opened by the process that exported them)
+    struct Rec { cudaIpcMemHandle_t h; unsigned char ok; unsigned char pad[7]; long long pid; unsigned long long ptr; int dev; int pad2; };
+    const size_t rec = sizeof(Rec);
     DevBuf<unsigned char> hb;
-    std::vector<unsigned char> all((size_t)nr * rec, 0);
+    std::vector<Rec> all((size_t)nr);
     const bool have_buf = hb.ensure((size_t)nr * rec) == cudaSuccess;
     if (have_buf) {
-        unsigned char mine_rec[sizeof(cudaIpcMemHandle_t) + 8] = {0};
-        memcpy(mine_rec, &mine, sizeof(mine));
-        mine_rec[sizeof(mine)] = ok ? 1 : 0;
-        cudaMemcpy(hb.p + (size_t)rk * rec, mine_rec, rec, cudaMemcpyHostToDevice);
+        Rec mine_rec;
+        memset(&mine_rec, 0, sizeof(mine_rec));
+        mine_rec.h = mine; mine_rec.ok = ok ? 1 : 0; mine_rec.pid = (long long)getpid();
+        mine_rec.ptr = (unsigned long long)(uintptr_t)mine_ptr; mine_rec.dev = ctx->device;
+        cudaMemcpy(hb.p + (size_t)rk * rec, &mine_rec, rec, cudaMemcpyHostToDevice);
     }
     std::vector<int64_t> counts((size_t)nr, 1), displs((size_t)nr);
     for (int r = 0; r < nr; r++) displs[(size_t)r] = r;
@@ -405,16 +410,21 @@ static bool open_peer_mailboxes(cd_ctx* ctx, void* mine_ptr, bool local_ok, std:
     //  device is unusable anyway; the collective below would fail on every rank alike)
     if (!have_buf) return false;
     if (!ctx->comm.allgatherv(hb.p + (size_t)rk * rec, hb.p, counts, displs, rec, ctx->st).empty()) ok = false;
-    if (cudaMemcpyAsync(all.data(), hb.p, all.size(), cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) ok = false;
+    if (cudaMemcpyAsync(all.data(), hb.p, (size_t)nr * rec, cudaMemcpyDeviceToHost, ctx->st) != cudaSuccess) ok = false;
     if (cudaStreamSynchronize(ctx->st) != cudaSuccess) ok = false;
     peers.assign((size_t)nr, nullptr);
     for (int r = 0; r < nr && ok; r++) {
-        if (!all[(size_t)r * rec + sizeof(cudaIpcMemHandle_t)]) { ok = false; break; }        // that rank could not export
+        if (!all[(size_t)r].ok) { ok = false; break; }                                         // that rank could not export
         if (r == rk) { peers[(size_t)r] = mine_ptr; continue; }
-        cudaIpcMemHandle_t h;
-        memcpy(&h, all.data() + (size_t)r * rec, sizeof(h));
+        if (all[(size_t)r].pid == (long long)getpid()) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[(size_t)r].dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = false; break; }
+            cudaGetLastError();
+            peers[(size_t)r] = (void*)(uintptr_t)all[(size_t)r].ptr;
+            continue;
+        }
         void* ptr = nullptr;
-        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
         ctx->p2p_opened.push_back(ptr);
         peers[(size_t)r] = ptr;
     }
@@ -896,6 +906,131 @@ int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* t)
     ctx->tab_set[(size_t)s] = 1;
     ctx->have_agg = false;
     return CD_OK;           // copies are ordered before cd_assemble on the context's stream
+}
+
+int cd_build_sample_tables(cd_ctx* ctx, int s, const cd_chicago_table* t)
+{
+    if (!ctx) return CD_EINVAL;
+    if (!ctx->have_design || !ctx->have_rmap) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: call cd_set_design and cd_set_rmap first");
+    const int S = ctx->des.S;
+    if (s < 0 || s >= S || !t || t->rows < 0 || t->rows > 4000000000LL || t->n_tblb < 1 || t->n_tlb < 1 || t->cnt_rows < 0 || t->cnt_rows > 4000000000LL)
+        return ctx->fail(CD_EINVAL, "cd_build_sample_tables: bad arguments");
+    const int64_t m = t->rows;
+    if (m > 0 && (!t->baitID || !t->otherEndID || !t->s_j || !t->s_i || !t->tblb || !t->tlb || !t->Tmean))
+        return ctx->fail(CD_EINVAL, "cd_build_sample_tables: null column");
+    const bool own_counts = t->cnt_rows == 0;
+    if (own_counts && m > 0 && !t->N) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: neither count rows nor the table's N column given");
+    if (!own_counts && (!t->cnt_baitID || !t->cnt_otherEndID || !t->cnt_N)) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: null count column");
+    const int64_t mc = own_counts ? m : t->cnt_rows;
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const int64_t F = ctx->F;
+    if ((int)ctx->tab_blob.size() != S) { ctx->tab_blob.clear(); ctx->tab_blob.resize((size_t)S); ctx->tabs_host.assign((size_t)S, AssembleTables{}); ctx->tab_set.assign((size_t)S, 0); }
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t nt = (size_t)t->n_tblb * (size_t)t->n_tlb;
+    size_t off[11], pos = 0;
+    const size_t sizes[10] = {sizeof(double) * (size_t)F, sizeof(int32_t) * (size_t)F, sizeof(double) * (size_t)F, sizeof(int32_t) * (size_t)F,
+                              sizeof(double) * nt, sizeof(double) * (size_t)t->n_tblb, sizeof(double) * 10, sizeof(int64_t) * ((size_t)F + 1),
+                              sizeof(int32_t) * (size_t)mc, sizeof(int32_t) * (size_t)mc};
+    for (int k = 0; k < 10; k++) { off[k] = pos; pos += al(sizes[k]); }
+    off[10] = pos;
+    DevBuf<unsigned char>& blob = ctx->tab_blob[(size_t)s];
+    CD_CUDA(ctx, blob.ensure(pos));
+    // raw columns on the device (scratch of this call)
+    DevBuf<int32_t> d_bait, d_oe, d_tblb, d_tlb, d_N, d_cb, d_co;
+    DevBuf<double> d_sj, d_si, d_tm;
+    DevBuf<unsigned long long> best, k0, k1;
+    DevBuf<unsigned int> i0, i1;
+    DevBuf<unsigned char> tmp;
+    const size_t ms = (size_t)m, mcs = (size_t)mc;
+    CD_CUDA(ctx, d_bait.ensure(ms)); CD_CUDA(ctx, d_oe.ensure(ms)); CD_CUDA(ctx, d_tblb.ensure(ms)); CD_CUDA(ctx, d_tlb.ensure(ms));
+    CD_CUDA(ctx, d_sj.ensure(ms)); CD_CUDA(ctx, d_si.ensure(ms)); CD_CUDA(ctx, d_tm.ensure(ms));
+    CD_CUDA(ctx, best.ensure(2 * (size_t)F + 2 * nt));
+    CD_CUDA(ctx, ctx->asm_status.ensure(1));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->asm_status.p, 0, sizeof(int32_t), st));
+    if (m > 0) {
+        CD_CUDA(ctx, cudaMemcpyAsync(d_bait.p, t->baitID, sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_oe.p, t->otherEndID, sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_tblb.p, t->tblb, sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_tlb.p, t->tlb, sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_sj.p, t->s_j, sizeof(double) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_si.p, t->s_i, sizeof(double) * ms, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_tm.p, t->Tmean, sizeof(double) * ms, cudaMemcpyHostToDevice, st));
+    }
+    CD_LAUNCHN(ctx, m > 0 ? 2 : 0, tb_launch_first(m, d_bait.p, d_oe.p, d_tblb.p, d_tlb.p, F, ctx->frag_id0, t->n_tblb, t->n_tlb, best.p,
+                                                  ctx->asm_status.p, st));
+    CD_LAUNCHN(ctx, 1, tb_launch_fill(F, t->n_tblb, t->n_tlb, best.p, d_sj.p, d_tblb.p, d_si.p, d_tlb.p, d_tm.p,
+                                      (double*)(blob.p + off[0]), (int32_t*)(blob.p + off[1]), (double*)(blob.p + off[2]),
+                                      (int32_t*)(blob.p + off[3]), (double*)(blob.p + off[4]), st));
+    CD_CUDA(ctx, cudaMemcpyAsync(blob.p + off[6], t->distfun, sizeof(double) * 10, cudaMemcpyHostToDevice, st));
+    // counts: sort the (bait, other end) keys, cut the rows of baits outside the rmap, CSR offsets by lower bound
+    const int32_t *cb = d_bait.p, *co = d_oe.p, *cN = nullptr;
+    CD_CUDA(ctx, d_N.ensure(mcs));
+    if (own_counts) {
+        if (m > 0) CD_CUDA(ctx, cudaMemcpyAsync(d_N.p, t->N, sizeof(int32_t) * ms, cudaMemcpyHostToDevice, st));
+    } else {
+        CD_CUDA(ctx, d_cb.ensure(mcs)); CD_CUDA(ctx, d_co.ensure(mcs));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_cb.p, t->cnt_baitID, sizeof(int32_t) * mcs, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_co.p, t->cnt_otherEndID, sizeof(int32_t) * mcs, cudaMemcpyHostToDevice, st));
+        CD_CUDA(ctx, cudaMemcpyAsync(d_N.p, t->cnt_N, sizeof(int32_t) * mcs, cudaMemcpyHostToDevice, st));
+        cb = d_cb.p; co = d_co.p;
+    }
+    cN = d_N.p;
+    CD_CUDA(ctx, k0.ensure(mcs)); CD_CUDA(ctx, k1.ensure(mcs)); CD_CUDA(ctx, i0.ensure(mcs)); CD_CUDA(ctx, i1.ensure(mcs));
+    int64_t* cnt_off_dev = (int64_t*)(blob.p + off[7]);
+    if (mc > 0) {
+        CD_LAUNCHN(ctx, 1, tb_launch_count_keys(mc, cb, co, F, ctx->frag_id0, k0.p, i0.p, st));
+        size_t bytes = 0;
+        CD_CUDA(ctx, cp_sort_pairs_u64(nullptr, bytes, k0.p, k1.p, i0.p, i1.p, mc, st));
+        CD_CUDA(ctx, tmp.ensure(bytes));
+        CD_LAUNCHN(ctx, 1, cp_sort_pairs_u64(tmp.p, bytes, k0.p, k1.p, i0.p, i1.p, mc, st));
+    }
+    CD_LAUNCHN(ctx, 1, tb_launch_count_offsets(F, mc, k1.p, cnt_off_dev, st));
+    int64_t valid = 0;
+    int32_t status = 0;
+    CD_CUDA(ctx, cudaMemcpyAsync(&valid, cnt_off_dev + F, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(&status, ctx->asm_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    if (status & 1) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: a baitID / otherEndID of the CHiCAGO table is not a fragment of the rmap");
+    if (status & 2) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: a tblb / tlb code is outside [0, n_tblb) x [0, n_tlb)");
+    CD_LAUNCHN(ctx, valid > 0 ? 1 : 0, tb_launch_count_gather(valid, k1.p, i1.p, cN, (int32_t*)(blob.p + off[8]), (int32_t*)(blob.p + off[9]), st));
+    AssembleTables& a = ctx->tabs_host[(size_t)s];
+    a.s_j = (const double*)(blob.p + off[0]); a.tblb = (const int32_t*)(blob.p + off[1]);
+    a.s_i = (const double*)(blob.p + off[2]); a.tlb = (const int32_t*)(blob.p + off[3]);
+    a.tmean = (const double*)(blob.p + off[4]); a.tmin = (const double*)(blob.p + off[5]);
+    a.distfun = (const double*)(blob.p + off[6]); a.cnt_off = (const int64_t*)(blob.p + off[7]);
+    a.cnt_oe = (const int32_t*)(blob.p + off[8]); a.cnt_N = (const int32_t*)(blob.p + off[9]);
+    a.n_tblb = t->n_tblb; a.n_tlb = t->n_tlb;
+    CD_LAUNCHN(ctx, 1, launch_tmin(t->n_tblb, t->n_tlb, a.tmean, (double*)(blob.p + off[5]), st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));       // the scratch columns of this call are freed on return
+    ctx->tab_set[(size_t)s] = 1;
+    ctx->have_agg = false;
+    return CD_OK;
+}
+
+int cd_get_sample_tables(cd_ctx* ctx, int s, double* s_j, int32_t* tblb, double* s_i, int32_t* tlb, double* tmean,
+                         int64_t* cnt_off, int32_t* cnt_oe, int32_t* cnt_N)
+{
+    if (!ctx) return CD_EINVAL;
+    if (s < 0 || s >= (int)ctx->tab_set.size() || !ctx->tab_set[(size_t)s])
+        return ctx->fail(CD_EINVAL, "cd_get_sample_tables: tables of replicate %d were never set", s);
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const AssembleTables& a = ctx->tabs_host[(size_t)s];
+    const size_t F = (size_t)ctx->F, nt = (size_t)a.n_tblb * (size_t)a.n_tlb;
+    int64_t ncnt = 0;
+    CD_CUDA(ctx, cudaMemcpyAsync(&ncnt, a.cnt_off + F, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    if (s_j) CD_CUDA(ctx, cudaMemcpyAsync(s_j, a.s_j, sizeof(double) * F, cudaMemcpyDeviceToHost, st));
+    if (tblb) CD_CUDA(ctx, cudaMemcpyAsync(tblb, a.tblb, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    if (s_i) CD_CUDA(ctx, cudaMemcpyAsync(s_i, a.s_i, sizeof(double) * F, cudaMemcpyDeviceToHost, st));
+    if (tlb) CD_CUDA(ctx, cudaMemcpyAsync(tlb, a.tlb, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    if (tmean) CD_CUDA(ctx, cudaMemcpyAsync(tmean, a.tmean, sizeof(double) * nt, cudaMemcpyDeviceToHost, st));
+    if (cnt_off) CD_CUDA(ctx, cudaMemcpyAsync(cnt_off, a.cnt_off, sizeof(int64_t) * (F + 1), cudaMemcpyDeviceToHost, st));
+    if (cnt_oe && ncnt > 0) CD_CUDA(ctx, cudaMemcpyAsync(cnt_oe, a.cnt_oe, sizeof(int32_t) * (size_t)ncnt, cudaMemcpyDeviceToHost, st));
+    if (cnt_N && ncnt > 0) CD_CUDA(ctx, cudaMemcpyAsync(cnt_N, a.cnt_N, sizeof(int32_t) * (size_t)ncnt, cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaStreamSynchronize(st));
+    return CD_OK;
 }
 
 int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out, double* avDist_out)

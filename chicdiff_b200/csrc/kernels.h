@@ -68,6 +68,20 @@ cudaError_t launch_assemble(int64_t n, int S, const int64_t* row_off, int64_t R,
                             double* FM_rows /*S x R or null*/, double* BM_rows /*S x R or null*/, int32_t* status,
                             cudaStream_t st);
 
+// ---- per-replicate tables from the raw CHiCAGO columns (tables.cu; chicdiff.R:632-634, 659-692, 828-853) ----
+// best: 2 F + 2 n_tblb n_tlb words of scratch (first-by-key winners); status bit 0: a fragment outside the rmap, bit 1: a bin
+// code outside the table
+cudaError_t tb_launch_first(int64_t m, const int32_t* bait, const int32_t* oe, const int32_t* tblb, const int32_t* tlb, int64_t F,
+                            int32_t id0, int n_tblb, int n_tlb, unsigned long long* best, int32_t* status, cudaStream_t st);
+cudaError_t tb_launch_fill(int64_t F, int n_tblb, int n_tlb, const unsigned long long* best, const double* s_j_rows,
+                           const int32_t* tblb_rows, const double* s_i_rows, const int32_t* tlb_rows, const double* tmean_rows,
+                           double* s_j, int32_t* tblb, double* s_i, int32_t* tlb, double* tmean, cudaStream_t st);
+cudaError_t tb_launch_count_keys(int64_t m, const int32_t* bait, const int32_t* oe, int64_t F, int32_t id0, unsigned long long* keys,
+                                 unsigned int* idx, cudaStream_t st);
+cudaError_t tb_launch_count_offsets(int64_t F, int64_t m, const unsigned long long* sorted_keys, int64_t* cnt_off, cudaStream_t st);
+cudaError_t tb_launch_count_gather(int64_t m_valid, const unsigned long long* sorted_keys, const unsigned int* sorted_idx,
+                                   const int32_t* N_rows, int32_t* cnt_oe, int32_t* cnt_N, cudaStream_t st);
+
 // ---- size factors + stage 2: offsets (chicdiff.R:1561-1562, 1583-1589, 1635-1638) ------
 cudaError_t launch_log_ratios(int64_t n, int S, const int32_t* K, double* LR /*S x n, +inf = excluded*/,
                               cudaStream_t st);

@@ -19,8 +19,10 @@ FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLA
 EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident", "cd_ihw_apply",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
-            "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
-            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]
+            "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims",
+            "cd_multi_create", "cd_multi_destroy", "cd_multi_last_error", "cd_multi_gpus", "cd_multi_set_design", "cd_multi_set_regions",
+            "cd_multi_get_shards", "cd_multi_set_sample_rows", "cd_multi_aggregate", "cd_multi_region_test", "cd_multi_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
+            "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_build_sample_tables", "cd_get_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]
 
 
 class ChicdiffError(RuntimeError):
@@ -43,6 +45,13 @@ class CdSampleTables(C.Structure):
     _fields_ = [("s_j", C.c_void_p), ("tblb", C.c_void_p), ("s_i", C.c_void_p), ("tlb", C.c_void_p),
                 ("n_tblb", C.c_int), ("n_tlb", C.c_int), ("tmean", C.c_void_p), ("distfun", C.c_double * 10),
                 ("cnt_off", C.c_void_p), ("cnt_oe", C.c_void_p), ("cnt_N", C.c_void_p)]
+
+
+class CdChicagoTable(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("baitID", C.c_void_p), ("otherEndID", C.c_void_p), ("s_j", C.c_void_p), ("s_i", C.c_void_p),
+                ("tblb", C.c_void_p), ("tlb", C.c_void_p), ("Tmean", C.c_void_p), ("N", C.c_void_p), ("n_tblb", C.c_int),
+                ("n_tlb", C.c_int), ("distfun", C.c_double * 10), ("cnt_rows", C.c_int64), ("cnt_baitID", C.c_void_p),
+                ("cnt_otherEndID", C.c_void_p), ("cnt_N", C.c_void_p)]
 
 
 class CdChicagoRows(C.Structure):
@@ -99,6 +108,9 @@ def load_library():
     L.cd_set_rmap.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_set_region_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.cd_set_sample_tables.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdSampleTables)]
+    L.cd_build_sample_tables.argtypes = [C.c_void_p, C.c_int, C.POINTER(CdChicagoTable)]
+    L.cd_get_sample_tables.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    L.cd_get_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
     L.cd_assemble.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cd_get_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.cd_get_sample_bmean.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -111,6 +123,19 @@ def load_library():
     L.cd_timer_start.argtypes = [C.c_void_p]
     L.cd_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.cd_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.cd_multi_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    L.cd_multi_destroy.argtypes = [C.c_void_p]
+    L.cd_multi_destroy.restype = None
+    L.cd_multi_last_error.restype = C.c_char_p
+    L.cd_multi_last_error.argtypes = [C.c_void_p]
+    L.cd_multi_gpus.argtypes = [C.c_void_p]
+    L.cd_multi_set_design.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.cd_multi_set_regions.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_multi_get_shards.argtypes = [C.c_void_p, C.c_void_p]
+    L.cd_multi_set_sample_rows.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.cd_multi_aggregate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.cd_multi_region_test.argtypes = [C.c_void_p, C.POINTER(CdOptions), C.POINTER(CdResults)]
+    L.cd_multi_last_timings.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -254,6 +279,7 @@ class Engine:
     # -- per-replicate assembly fused with stage 1 ------------------------------------------------
     def set_rmap(self, chr_codes, start, end, frag_id0=1):
         a = [np.ascontiguousarray(x, dtype=np.int32) for x in (chr_codes, start, end)]
+        self._F = len(a[0])
         self._check(self._L.cd_set_rmap(self._h, len(a[0]), frag_id0, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])))
 
     def region_universe(self, peak_bait, peak_oe, ru_expand=5, fetch=True):
@@ -330,6 +356,44 @@ class Engine:
         self._keep_tabs[s] = keep
         self._check(self._L.cd_set_sample_tables(self._h, s, C.byref(t)))
 
+    def build_sample_tables(self, s, t):
+        """One replicate's raw CHiCAGO columns (api.chicago_columns) -> the per-fragment tables, built on the device
+        (cd_build_sample_tables): first (s_j, tblb) per bait, first (s_i, tlb) per other end, first Tmean per bin pair, counts."""
+        c = CdChicagoTable()
+        keep = {k: np.ascontiguousarray(t[k], dtype=dt) for k, dt in (("baitID", np.int32), ("otherEndID", np.int32), ("s_j", np.float64),
+                ("s_i", np.float64), ("tblb", np.int32), ("tlb", np.int32), ("Tmean", np.float64))}
+        c.rows = len(keep["baitID"])
+        for k, v in keep.items():
+            setattr(c, k, v.ctypes.data)
+        if t.get("N") is not None:
+            keep["N"] = np.ascontiguousarray(t["N"], dtype=np.int32)
+            c.N = keep["N"].ctypes.data
+        c.n_tblb, c.n_tlb = int(t["n_tblb"]), int(t["n_tlb"])
+        for k, v in enumerate(np.asarray(t["distfun"], dtype=np.float64)):
+            c.distfun[k] = float(v)
+        if t.get("cnt_baitID") is not None:
+            for k in ("cnt_baitID", "cnt_otherEndID", "cnt_N"):
+                keep[k] = np.ascontiguousarray(t[k], dtype=np.int32)
+                setattr(c, k, keep[k].ctypes.data)
+            c.cnt_rows = len(keep["cnt_baitID"])
+        self._check(self._L.cd_build_sample_tables(self._h, s, C.byref(c)))
+        self._table_shapes = getattr(self, "_table_shapes", {})
+        self._table_shapes[s] = (c.n_tblb, c.n_tlb)
+
+    def get_sample_tables(self, s, F=None):
+        """the tables of replicate s as they stand on the device (cd_get_sample_tables)"""
+        if F is None:
+            F = self._F
+        nt = self._table_shapes[s]
+        out = dict(s_j=np.empty(F), tblb=np.empty(F, np.int32), s_i=np.empty(F), tlb=np.empty(F, np.int32),
+                   tmean=np.empty(nt), cnt_off=np.empty(F + 1, np.int64))
+        self._check(self._L.cd_get_sample_tables(self._h, s, _ptr(out["s_j"]), _ptr(out["tblb"]), _ptr(out["s_i"]), _ptr(out["tlb"]),
+                                                 _ptr(out["tmean"]), _ptr(out["cnt_off"]), None, None))
+        m = int(out["cnt_off"][-1])
+        out["cnt_oe"], out["cnt_N"] = np.empty(m, np.int32), np.empty(m, np.int32)
+        self._check(self._L.cd_get_sample_tables(self._h, s, None, None, None, None, None, None, _ptr(out["cnt_oe"]), _ptr(out["cnt_N"])))
+        return out
+
     def assemble(self, keep_rows=False, fetch=True):
         if fetch:
             K = np.empty((self.S, self.n), np.int32)
@@ -405,7 +469,7 @@ class Engine:
         for k in want:
             arrays[k] = np.empty(shapes.get(k, (n,)), dtypes.get(k, np.float64))
             setattr(res, k, arrays[k].ctypes.data)
-        rc = self._L.cd_region_test(self._h, C.byref(opt), C.byref(res))
+        rc = self._region_test_entry()(self._h, C.byref(opt), C.byref(res))
         if cb_error:
             raise cb_error[0]
         self._check(rc)
@@ -417,6 +481,9 @@ class Engine:
                   "n_beta_noconv"):
             out[k] = getattr(res, k)
         return out
+
+    def _region_test_entry(self):
+        return self._L.cd_region_test
 
     # -- introspection ------------------------------------------------------------------------
     def launch_count(self):
@@ -446,4 +513,68 @@ class Engine:
     def last_timings(self):
         t = np.zeros(8, np.float64)
         self._L.cd_last_timings(self._h, _ptr(t))
+        return t
+
+
+class MultiEngine(Engine):
+    """Several GPUs from this one process (cd_multi_*): same calls as Engine on the whole problem; the library cuts the
+    regions into bait-aligned shards, one per device, and runs one host thread per device inside every call."""
+
+    def __init__(self, n_gpus, device_ids=None):
+        self._L = load_library()
+        h = C.c_void_p()
+        ids = None if device_ids is None else np.ascontiguousarray(device_ids, dtype=np.int32)
+        rc = self._L.cd_multi_create(C.byref(h), int(n_gpus), _ptr(ids))
+        if rc != 0:
+            raise ChicdiffError(rc, self._L.cd_multi_last_error(None).decode())
+        self._h = h
+        self.S = self.p = None
+        self.n = 0
+        self.n_gpus = int(n_gpus)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cd_multi_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ChicdiffError(rc, self._L.cd_multi_last_error(self._h).decode())
+
+    def set_design(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self.S, self.p = X.shape
+        self._check(self._L.cd_multi_set_design(self._h, self.S, self.p, _ptr(X)))
+
+    def set_regions(self, row_off, region_bait):
+        row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+        region_bait = np.ascontiguousarray(region_bait, dtype=np.int32)
+        self.n = len(row_off) - 1
+        self._check(self._L.cd_multi_set_regions(self._h, self.n, _ptr(row_off), _ptr(region_bait)))
+
+    def shards(self):
+        b = np.zeros(self.n_gpus + 1, np.int64)
+        self._check(self._L.cd_multi_get_shards(self._h, _ptr(b)))
+        return b
+
+    def set_sample_rows(self, s, N, fullmean):
+        N = np.ascontiguousarray(N, dtype=np.int32)
+        fullmean = np.ascontiguousarray(fullmean, dtype=np.float64)
+        self._keep.append((N, fullmean))            # uploads are asynchronous until the next aggregate
+        self._check(self._L.cd_multi_set_sample_rows(self._h, s, len(N), _ptr(N), _ptr(fullmean)))
+
+    def aggregate(self, fetch=True):
+        K = np.empty((self.S, self.n), np.int32) if fetch else None
+        FM = np.empty((self.S, self.n), np.float64) if fetch else None
+        self._check(self._L.cd_multi_aggregate(self._h, _ptr(K), _ptr(FM)))
+        self._keep = []
+        return (K, FM) if fetch else None
+
+    def _region_test_entry(self):
+        return self._L.cd_multi_region_test
+
+    def last_timings(self):
+        t = np.zeros(8, np.float64)
+        self._L.cd_multi_last_timings(self._h, _ptr(t))
         return t

@@ -31,9 +31,11 @@
  *   - NA: integer NA is INT32_MIN (R's NA_integer_); floating NA is any NaN (R's NA_real_ is a
  *     NaN; is.na() is true for both).  All-zero regions get NaN in every output column, as in
  *     DESeq2.
- *   - One context drives one GPU.  For several GPUs run one process per GPU, shard the regions
- *     by bait (cd_plan_shards) and join the contexts with cd_comm_init; the few global steps
- *     (size-factor medians, dispersion trend, theta-grid deviances) then use NCCL over NVLink.
+ *   - One context drives one GPU.  For several GPUs either use cd_multi_* (one process, one host thread per
+ *     GPU inside the library) or run one process per GPU, shard the regions by bait (cd_plan_shards) and join
+ *     the contexts with cd_comm_init.  Either way the few global steps exchange sums and counters only: the
+ *     dispersion-trend sums and the median histograms inside their kernels through NVLink peer memory, the
+ *     moments-offset sums and the theta-grid deviances with NCCL.
  */
 #ifndef CHICDIFF_B200_H
 #define CHICDIFF_B200_H
@@ -145,6 +147,31 @@ int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_
 /* the region universe's rows (RU: baitID, otherEndID), region-contiguous, R = row_off[n] */
 int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe);
 int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);
+/* The same tables built ON THE DEVICE from one replicate's raw CHiCAGO columns, replacing the keyed joins / setkey sorts /
+ * first-per-group passes of getFullRegionData1 (chicdiff.R:632-634 setkey(x, baitID, otherEndID); :659 first (s_j, tblb)
+ * per bait; :668 first (s_i, tlb) per other end; :678-680 first Tmean per (tblb, tlb); :828-853 the per-pair counts).
+ * Rows may come in any order: "first" means first in (baitID, otherEndID, input position) order, as after the
+ * reference's setkey.  tblb / tlb are the bin labels as integer codes (index into the Tmean table, -1 = NA); the
+ * label -> code map and .chicEstimateDistFun's 10 numbers (:538-573, ~75 points) are the caller's.  Counts: the rows of
+ * cnt_* when cnt_rows > 0 (the .chinput file, or the inner join of the replicates' N columns for countData = NULL,
+ * :778), otherwise the table's own N column.  Replaces cd_set_sample_tables for replicate s. */
+typedef struct {
+    int64_t rows;
+    const int32_t* baitID; const int32_t* otherEndID;
+    const double* s_j; const double* s_i;            /* NaN = NA */
+    const int32_t* tblb; const int32_t* tlb;         /* bin codes, -1 = NA */
+    const double* Tmean;
+    const int32_t* N;                                /* may be NULL when cnt_rows > 0 */
+    int n_tblb, n_tlb;
+    double distfun[10];
+    int64_t cnt_rows;
+    const int32_t* cnt_baitID; const int32_t* cnt_otherEndID; const int32_t* cnt_N;
+} cd_chicago_table;
+int cd_build_sample_tables(cd_ctx* ctx, int s, const cd_chicago_table* table);
+/* host copies of replicate s's tables as they stand on the device (any pointer may be NULL): s_j, tblb, s_i, tlb of length
+ * F; tmean n_tblb x n_tlb; cnt_off F + 1; cnt_oe / cnt_N of cnt_off[F] entries (ask for cnt_off first to size them) */
+int cd_get_sample_tables(cd_ctx* ctx, int s, double* s_j, int32_t* tblb, double* s_i, int32_t* tlb, double* tmean,
+                         int64_t* cnt_off, int32_t* cnt_oe, int32_t* cnt_N);
 /* assembly + aggregation.  keep_rows != 0 also materialises the per-row N / FullMean columns on the device
  * (cd_get_sample_rows).  Outputs are host pointers and may be NULL: K, FullMean (S x n sample-major) and
  * avDist[n] = mean over the region's rows of the signed distance of chicdiff.R:878-881 (what
@@ -227,6 +254,29 @@ typedef struct {
 
 /* DESeq2Wrap numerics on the aggregated matrices of this context (this rank's shard) */
 int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out);
+
+/* ---- several GPUs from ONE process ------------------------------------------------------ */
+/* chicdiffPipeline runs in a single R session (chicdiff.R:301-347); a cd_multi lets that one process use n_gpus devices:
+ * it owns one context per device, cuts the regions into contiguous bait-aligned shards (cd_plan_shards), drives the
+ * contexts with one host thread per device for the duration of each call, and returns per-region results in region
+ * order.  The contexts are joined like the ranks of a multi-process run; sharing an address space, their peer-memory
+ * mailboxes are mapped with cudaDeviceEnablePeerAccess.  device_ids == NULL: devices 0 .. n_gpus-1.
+ * Semantics of every call = the single-context call of the same name on the whole problem (matrices S x n sample-major,
+ * vectors of n regions; cd_results scalars from the global steps, counters summed).  region_bait: baitID per region,
+ * non-decreasing (cuts fall between baits).  cd_options.prior_var_fn is not available (it needs all residuals on the
+ * host): pass disp_prior_var for designs with S - p <= 3. */
+typedef struct cd_multi cd_multi;
+int cd_multi_create(cd_multi** out, int n_gpus, const int* device_ids);
+void cd_multi_destroy(cd_multi* m);
+const char* cd_multi_last_error(const cd_multi* m);       /* m may be NULL: last error of cd_multi_create */
+int cd_multi_gpus(const cd_multi* m);
+int cd_multi_set_design(cd_multi* m, int S, int p, const double* X);
+int cd_multi_set_regions(cd_multi* m, int64_t n, const int64_t* row_off /* n + 1 */, const int32_t* region_bait /* n */);
+int cd_multi_get_shards(const cd_multi* m, int64_t* bounds /* n_gpus + 1 */);
+int cd_multi_set_sample_rows(cd_multi* m, int s, int64_t R, const int32_t* N, const double* fullmean);
+int cd_multi_aggregate(cd_multi* m, int32_t* K_out, double* fullmean_out);
+int cd_multi_region_test(cd_multi* m, const cd_options* opt, cd_results* out);
+int cd_multi_last_timings(const cd_multi* m, double out_ms[8]);      /* per stage, the slowest device */
 
 /* results(): Cook's cutoff (+ two-level-factor heuristic via CD_FLAG_COOKS_KEEP), independent
  * filtering on baseMean (alpha = 0.1), BH.  Global over all regions: in a sharded run gather

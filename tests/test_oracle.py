@@ -266,7 +266,7 @@ def test_replicate_tables_from_chicago_table(tiny):
     ids = np.arange(1, len(d.frag_chr) + 1)
     for s in (0, 3):
         x = synth.chicago_table(d, s)
-        t = api.replicate_tables(x, ids, synth.chinput_table(d, s))
+        t = O.replicate_tables(x, ids, synth.chinput_table(d, s))
         g = d.extra["tables"][s]
         baits = np.unique(x["baitID"]); oes = np.unique(x["otherEndID"])
         assert np.array_equal(np.isnan(t["s_j"][baits - 1]), np.isnan(g["s_j"][baits - 1]))
