@@ -251,7 +251,7 @@ struct cd_ctx {
     int64_t cp_pairs = 0;
     DevBuf<int32_t> cp_bait, cp_oe;
     DevBuf<double> cp_nav, cp_bav, cp_score, cp_mid;
-    DevBuf<double> wald_c, wald_b0, wald_b;
+    DevBuf<double> wald_c, wald_b0, wald_b, lfact;
     DevBuf<int32_t> wald_iter;
     WaldScratch wald_ws{};
     double* h_pinned = nullptr;      // pinned host scratch (1024 doubles)
@@ -1389,7 +1389,7 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
                                                    ctx->betaSE.p, ctx->stat.p, ctx->pvalue.p, ctx->deviance.p, ctx->maxCooks.p,
                                                    ctx->betaIter.p, nullptr, st));
     } else {
-        CD_LAUNCHN(ctx, 1, launch_wald_deviance_p1(nv, S, K, ctx->nf.p, ctx->dispersion.p, flags, ctx->deviance.p, st));
+        CD_LAUNCHN(ctx, 1, launch_wald_deviance_p1(nv, S, K, ctx->nf.p, ctx->dispersion.p, flags, ctx->lfact.p, ctx->deviance.p, st));
     }
     ctx->tm_end();
     CD_LAUNCHN(ctx, 2, launch_segment_sums(n, G, ctx->deviance.p, ctx->partial.p, ctx->scal.p + kScalDev, st));
@@ -1480,6 +1480,11 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->wald_b0.ensure((size_t)CD_MAXP * (size_t)n));
     CD_CUDA(ctx, ctx->wald_b.ensure((size_t)CD_MAXP * (size_t)n));
     CD_CUDA(ctx, ctx->wald_iter.ensure((size_t)n));
+    if (!ctx->lfact.p) {
+        CD_CUDA(ctx, ctx->lfact.ensure(kLfactN));
+        CD_LAUNCHN(ctx, 1, launch_lfact_table(ctx->lfact.p, st));
+    }
+    ctx->wald_ws.lfact = ctx->lfact.p;
     ctx->wald_ws.cmat = ctx->wald_c.p; ctx->wald_ws.beta0 = ctx->wald_b0.p; ctx->wald_ws.beta_nat = ctx->wald_b.p;
     ctx->wald_ws.iter = ctx->wald_iter.p; ctx->wald_ws.work_counter = ctx->counters.p + 15;
     {

@@ -234,7 +234,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
 
     bool active = false, exhausted = false, fresh = false;
     int64_t i = 0;
-    double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0, prior_sigmasq = 1.0;
+    double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0, prior_sigmasq = 1.0;   // prior_sigmasq holds 1 / variance
     int iter = 0, iter_accept = 0;
 
     // First pass: the refill is software-pipelined per lane.  Every lane always owns `pending` (a region whose
@@ -299,7 +299,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                             const double ft = *pf_prior;
                             a = log_pos((d0 > 0.1 * ft) ? d0 : ft);
                             prior_mean = log_pos(ft);
-                            prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
+                            prior_sigmasq = 1.0 / prior_sigmasq_g.v[(int)(i / n_fit)];      // eval_post multiplies by the reciprocal
                         } else {
                             a = log_pos(d0);
                         }
@@ -334,7 +334,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                     iter = park.iter[w]; iter_accept = park.iter_accept[w];
                     if (use_prior) {
                         prior_mean = log_pos(prior_mean_disp[i]);
-                        prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
+                        prior_sigmasq = 1.0 / prior_sigmasq_g.v[(int)(i / n_fit)];      // eval_post multiplies by the reciprocal
                     }
                     for (int j = 0; j < S; j++) {
                         ys[j * stride] = (double)K[(int64_t)j * n + i];
@@ -726,7 +726,7 @@ fit_disp_grid_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict
         __syncwarp();
         const bool use_prior = (prior_mean_disp != nullptr);
         const double prior_mean = use_prior ? log(prior_mean_disp[i]) : 0.0;
-        const double prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)];
+        const double prior_sigmasq = 1.0 / prior_sigmasq_g.v[(int)(i / n_fit)];      // eval_post multiplies by the reciprocal
         const double maxDisp = fmax(10.0, (double)S);
         const double lo = log(1e-8), hi = log(maxDisp);
         const double step = (hi - lo) / (grid_len - 1);

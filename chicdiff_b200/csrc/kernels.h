@@ -202,7 +202,10 @@ cudaError_t launch_trend_apply(int64_t n, int64_t n_fit, const double* baseMean,
                                cudaStream_t st);
 
 // ---- stages 3 + 5: NB GLM, Cook's, Wald --------------------------------------------------
+constexpr int kLfactN = 4096;
+cudaError_t launch_lfact_table(double* tab /* kLfactN doubles */, cudaStream_t st);
 struct WaldScratch {
+    const double* lfact; // kLfactN: log Gamma(k + 1) - 0.5 log(2 pi), see launch_lfact_table
     double* cmat;        // S x n: mu-independent part of the NB log density
     double* beta0;       // p x n: least-squares start
     double* beta_nat;    // p x n: IRLS coefficients, natural-log scale
@@ -220,6 +223,6 @@ cudaError_t launch_wald(int64_t n, int S, int p, const CdDesign* des, const int3
 // total deviance input of the theta-grid fits (design ~ 1): -2 logLik per virtual region at the intercept-only
 // shortcut's coefficients; nothing else of nbinomWaldTest is needed there (chicdiff.R:1644-1647)
 cudaError_t launch_wald_deviance_p1(int64_t n, int S, const int32_t* K, const double* nf, const double* dispersion,
-                                    const uint8_t* flags, double* deviance, cudaStream_t st);
+                                    const uint8_t* flags, const double* lfact, double* deviance, cudaStream_t st);
 
 }  // namespace cd

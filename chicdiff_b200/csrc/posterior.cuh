@@ -62,10 +62,11 @@ __device__ __forceinline__ GammaParts gamma_parts(double x, const double* tab)
     return g;
 }
 
+// prior_inv_sigmasq = 1 / prior variance of log(alpha) (the caller takes the reciprocal once per region)
 template <int P, bool WANT_D, bool TABLOG>
 __device__ __forceinline__ void eval_post(double a, const double* ys, const double* mus, int stride, int S,
                                           const double* Xd, const double* tab,
-                                          double prior_mean, double prior_sigmasq, bool use_prior,
+                                          double prior_mean, double prior_inv_sigmasq, bool use_prior,
                                           double& lp_out, double& dlp_out)
 {
     const double alpha = exp(a);
@@ -143,11 +144,11 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
     double pr = 0.0;
     if (use_prior) {
         const double d = a - prior_mean;
-        pr = -0.5 * d * d / prior_sigmasq;
+        pr = (-0.5 * d * d) * prior_inv_sigmasq;
     }
     lp_out = ll + pr + cr;
     if (WANT_D) {
-        const double dpr = use_prior ? -1.0 * (a - prior_mean) / prior_sigmasq : 0.0;
+        const double dpr = use_prior ? (-1.0 * (a - prior_mean)) * prior_inv_sigmasq : 0.0;
         dlp_out = ((r * r) * ds + dcr) * alpha + dpr;
     }
 }

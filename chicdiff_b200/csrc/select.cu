@@ -40,15 +40,31 @@ __device__ __forceinline__ double value_of(unsigned long long k)
     return __longlong_as_double((long long)b);
 }
 
-// value of column c, element i, after the optional |x - center[c]| transform; +inf / NaN = excluded
-__device__ __forceinline__ bool sel_load(const double* __restrict__ base, int64_t stride, int c, int64_t i,
-                                         const double* __restrict__ center, double& v)
+// value after the optional |x - center[c]| transform; +inf / NaN = excluded
+__device__ __forceinline__ bool sel_xform(double x, const double* __restrict__ center, int c, double& v)
 {
-    double x = base[(int64_t)c * stride + i];
     if (!isfinite(x)) return false;
     if (center) x = fabs(x - center[c]);
     v = x;
     return true;
+}
+
+// Every pass streams 8 bytes per value; four values per thread are loaded before any is processed so that enough loads are
+// in flight to cover the HBM / L2 latency.  f(value) is called for every included value of column c.
+template <typename F>
+__device__ __forceinline__ void sel_for_each(const double* __restrict__ base, int64_t stride, int c, int64_t n, int64_t tid, int64_t nthr,
+                                             const double* __restrict__ center, F f)
+{
+    const double* col = base + (int64_t)c * stride;
+    int64_t i = tid;
+    for (; i + 3 * nthr < n; i += 4 * nthr) {
+        double x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) x[u] = col[i + u * nthr];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { double v; if (sel_xform(x[u], center, c, v)) f(v); }
+    }
+    for (; i < n; i += nthr) { double v; if (sel_xform(col[i], center, c, v)) f(v); }
 }
 
 // state per column: [0] prefix (finally the key of the k1-th value), [1] remaining rank k, [2] total finite count m
@@ -147,10 +163,7 @@ sel_fused_kernel(int64_t n, int B, const double* __restrict__ base, int64_t stri
     // ---- finite values per column ----
     for (int c = 0; c < B; c++) {
         unsigned long long local = 0;
-        for (int64_t i = tid; i < n; i += nthr) {
-            double v;
-            local += sel_load(base, stride, c, i, center, v) ? 1ull : 0ull;
-        }
+        sel_for_each(base, stride, c, n, tid, nthr, center, [&](double) { local++; });
         for (int off = 16; off > 0; off >>= 1) local += __shfl_down_sync(0xffffffffu, local, off);
         if (lane == 0 && local) atomicAdd(counts + c, local);
     }
@@ -178,13 +191,11 @@ sel_fused_kernel(int64_t n, int B, const double* __restrict__ base, int64_t stri
             for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) sh[b] = 0u;
             __syncthreads();
             const unsigned long long prefix = __ldcg(state + (size_t)c * kSelState);
-            for (int64_t i = tid; i < n; i += nthr) {
-                double v;
-                if (!sel_load(base, stride, c, i, center, v)) continue;
+            sel_for_each(base, stride, c, n, tid, nthr, center, [&](double v) {
                 const unsigned long long k = key_of(v);
                 const bool match = (hi_shift >= 64) ? true : ((k >> hi_shift) == prefix);
                 if (match) atomicAdd(&sh[(unsigned)((k >> shift) & mask)], 1u);
-            }
+            });
             __syncthreads();
             for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
                 if (sh[b]) atomicAdd(hist + (size_t)c * kSelBins + b, (unsigned long long)sh[b]);
@@ -223,12 +234,10 @@ sel_fused_kernel(int64_t n, int B, const double* __restrict__ base, int64_t stri
     for (int c = 0; c < B; c++) {
         const unsigned long long v1 = __ldcg(state + (size_t)c * kSelState);
         unsigned long long l = 0, g = ~0ull;
-        for (int64_t i = tid; i < n; i += nthr) {
-            double v;
-            if (!sel_load(base, stride, c, i, center, v)) continue;
+        sel_for_each(base, stride, c, n, tid, nthr, center, [&](double v) {
             const unsigned long long k = key_of(v);
             if (k <= v1) l++; else if (k < g) g = k;
-        }
+        });
         for (int off = 16; off > 0; off >>= 1) {
             l += __shfl_down_sync(0xffffffffu, l, off);
             const unsigned long long o = __shfl_down_sync(0xffffffffu, g, off);

@@ -32,6 +32,26 @@ namespace cd {
 // memory (every lane reads the same entry); no __constant__ globals, so contexts of one process do not share state.
 
 constexpr int kWaldThreads = 128;
+
+// log Gamma(k + 1) - 0.5 log(2 pi) for the counts k < kLfactN, filled once per context with lgamma_c_pos itself, so a
+// look-up returns the very double the direct evaluation would: a third of the special-function work of the NB log
+// density does not depend on the fit at all
+__global__ void lfact_table_kernel(double* __restrict__ tab)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < kLfactN) tab[k] = lgamma_c_pos((double)k + 1.0);
+}
+
+cudaError_t launch_lfact_table(double* tab, cudaStream_t st)
+{
+    lfact_table_kernel<<<(kLfactN + 255) / 256, 256, 0, st>>>(tab);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ double lfact_c(double y, const double* __restrict__ lfact)
+{
+    return (y < (double)kLfactN) ? __ldg(lfact + (int)y) : lgamma_c_pos(y + 1.0);
+}
 constexpr double kHalfLn2Pi = 0.918938533204672741780329736406;
 constexpr double kHugeSize = 1e6;
 
@@ -52,7 +72,7 @@ __device__ __forceinline__ double nb_logdens(double y, double size, double alpha
 __global__ void __launch_bounds__(256)
 wald_prep_kernel(int64_t n, int S, int P, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
                  const double* __restrict__ nf, const double* __restrict__ dispersion, const uint8_t* __restrict__ flags,
-                 double* __restrict__ cmat, double* __restrict__ beta0)
+                 const double* __restrict__ lfact, double* __restrict__ cmat, double* __restrict__ beta0)
 {
     __shared__ double ls[CD_MAXP * CD_MAXS];
     for (int k = threadIdx.x; k < P * S; k += blockDim.x) ls[k] = des->ls[k];
@@ -67,7 +87,7 @@ wald_prep_kernel(int64_t n, int S, int P, const CdDesign* __restrict__ des, cons
     for (int u = 0; u < P; u++) b[u] = 0.0;
     for (int j = 0; j < S; j++) {
         const double y = (double)K[(int64_t)j * n + i];
-        cmat[(int64_t)j * n + i] = ((lgamma_c_pos(y + size) - lgs) - lgamma_c_pos(y + 1.0)) - kHalfLn2Pi;
+        cmat[(int64_t)j * n + i] = ((lgamma_c_pos(y + size) - lgs) - lfact_c(y, lfact)) - kHalfLn2Pi;
         if (beta0) {
             const double l = log_pos(y * rcp_pos(nf[(int64_t)j * n + i]) + 0.1);
             for (int u = 0; u < P; u++) b[u] += ls[u * S + j] * l;
@@ -403,7 +423,8 @@ wald_final_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int3
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 wald_deviance_p1_kernel(int64_t n, int S, const int32_t* __restrict__ K, const double* __restrict__ nf,
-                        const double* __restrict__ dispersion, const uint8_t* __restrict__ flags, double* __restrict__ deviance_out)
+                        const double* __restrict__ dispersion, const uint8_t* __restrict__ flags, const double* __restrict__ lfact,
+                        double* __restrict__ deviance_out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -418,17 +439,17 @@ wald_deviance_p1_kernel(int64_t n, int S, const int32_t* __restrict__ K, const d
     double loglike = 0.0;
     for (int j = 0; j < S; j++) {
         const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
-        const double c = ((lgamma_c_pos(yj + size) - lgs) - lgamma_c_pos(yj + 1.0)) - kHalfLn2Pi;
+        const double c = ((lgamma_c_pos(yj + size) - lgs) - lfact_c(yj, lfact)) - kHalfLn2Pi;
         loglike += nb_logdens(yj, size, alpha, nfj * eb, c);
     }
     deviance_out[i] = -2.0 * loglike;
 }
 
 cudaError_t launch_wald_deviance_p1(int64_t n, int S, const int32_t* K, const double* nf, const double* dispersion,
-                                    const uint8_t* flags, double* deviance, cudaStream_t st)
+                                    const uint8_t* flags, const double* lfact, double* deviance, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    wald_deviance_p1_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, dispersion, flags, deviance);
+    wald_deviance_p1_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, K, nf, dispersion, flags, lfact, deviance);
     return cudaGetLastError();
 }
 
@@ -439,7 +460,7 @@ cudaError_t launch_wald(int64_t n, int S, int p, const CdDesign* des, const int3
 {
     if (n == 0) return cudaSuccess;
     cudaError_t e;
-    wald_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, p, des, K, nf, dispersion, flags, ws.cmat, p > 1 ? ws.beta0 : nullptr);
+    wald_prep_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, p, des, K, nf, dispersion, flags, ws.lfact, ws.cmat, p > 1 ? ws.beta0 : nullptr);
     const int threads = kWaldThreads;
     const size_t smem = ((size_t)3 * S * threads + (size_t)S * p) * sizeof(double);
     int dev = 0, sms = 148;

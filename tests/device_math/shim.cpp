@@ -11,8 +11,8 @@ static void eval_variant(int variant, int S, const double* X, const double* y, c
                          double prior_sigmasq, bool use_prior, double* lp, double* dlp)
 {
     if (variant == 0) cd::eval_post_ref<P, true>(a, y, mu, 1, S, X, prior_mean, prior_sigmasq, use_prior, *lp, *dlp);
-    else if (variant == 1) cd::eval_post<P, true, false>(a, y, mu, 1, S, X, cd::kLogTab, prior_mean, prior_sigmasq, use_prior, *lp, *dlp);
-    else cd::eval_post<P, true, true>(a, y, mu, 1, S, X, cd::kLogTab, prior_mean, prior_sigmasq, use_prior, *lp, *dlp);
+    else if (variant == 1) cd::eval_post<P, true, false>(a, y, mu, 1, S, X, cd::kLogTab, prior_mean, 1.0 / prior_sigmasq, use_prior, *lp, *dlp);
+    else cd::eval_post<P, true, true>(a, y, mu, 1, S, X, cd::kLogTab, prior_mean, 1.0 / prior_sigmasq, use_prior, *lp, *dlp);
 }
 extern "C" {
 double dm_rcp_pos(double x) { return cd::rcp_pos(x); }
