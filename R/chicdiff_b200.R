@@ -55,33 +55,56 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
   samples <- unique(fragData$sample)
   setkey(fragData, regionID, otherEndID)
   conditions <- sapply(samples, function(s) fragData[sample == s, condition[1]])
-  X <- model.matrix(~ condition, data.frame(condition = factor(conditions)))
+  ## chicdiff.R:1559 hard-codes `~ condition`; chicdiff.settings$batch (one label per sample, in sample order) adds the
+  ## covariate of BASELINE.json configs[3]: `~ batch + condition`, the tested coefficient stays the last column
+  batch <- chicdiff.settings[["batch"]]
+  X <- if (is.null(batch)) model.matrix(~ condition, data.frame(condition = factor(conditions)))
+       else model.matrix(~ batch + condition, data.frame(batch = factor(batch), condition = factor(conditions)))
   one <- fragData[sample == samples[1]]
   row_off <- c(0, cumsum(as.numeric(one[, .N, by = regionID]$N)))
   n <- length(row_off) - 1L; S <- length(samples); p <- ncol(X)
-
-  ctx <- .Call("cdR_create", as.integer(if (is.null(chicdiff.settings[["gpu"]])) 0L else chicdiff.settings[["gpu"]]))
-  .Call("cdR_set_design", ctx, X)
-  .Call("cdR_set_regions", ctx, row_off)
-  for (i in seq_along(samples)) {
-    x <- fragData[sample == samples[i]]
-    .Call("cdR_set_sample_rows", ctx, i, as.integer(x$N), as.numeric(x$FullMean))
-  }
-  .Call("cdR_aggregate", ctx, n, S)
-  if (norm == "combined" && is.null(theta)) message("Optimising scaling factors...")
+  norm_code <- match(norm, c("standard", "fullmean", "combined")) - 1L
   na <- NA_real_
+  theta_arg <- if (is.null(theta) || norm != "combined") na else as.numeric(theta)
   pv <- chicdiff.settings[["dispPriorVar"]]; pvg <- chicdiff.settings[["dispPriorVarGrid"]]
-  fit <- .Call("cdR_region_test", ctx, n, S, p, match(norm, c("standard", "fullmean", "combined")) - 1L,
-               if (is.null(theta) || norm != "combined") na else as.numeric(theta), as.numeric(Grid),
-               if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg, dispPriorVarSmallDf)
+  gpus <- if (is.null(chicdiff.settings[["gpus"]])) 1L else as.integer(chicdiff.settings[["gpus"]])
+
+  if (gpus > 1L) {
+    ## several GPUs from this one R session: the library shards the regions by bait and runs one host thread per GPU
+    ## (cd_multi_*).  The Monte-Carlo prior-variance rule needs all residuals in R: pass dispPriorVar for 2-vs-2 designs.
+    ctx <- .Call("cdR_multi_create", gpus)
+    .Call("cdR_multi_set_design", ctx, X)
+    .Call("cdR_multi_set_regions", ctx, row_off, as.integer(one[, baitID[1], by = regionID]$V1))
+    for (i in seq_along(samples)) {
+      x <- fragData[sample == samples[i]]
+      .Call("cdR_multi_set_sample_rows", ctx, i, as.integer(x$N), as.numeric(x$FullMean))
+    }
+    .Call("cdR_multi_aggregate", ctx, n, S)
+    if (norm == "combined" && is.null(theta)) message("Optimising scaling factors...")
+    fit <- .Call("cdR_multi_region_test", ctx, n, S, norm_code, theta_arg, as.numeric(Grid),
+                 if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg)
+  } else {
+    ctx <- .Call("cdR_create", as.integer(if (is.null(chicdiff.settings[["gpu"]])) 0L else chicdiff.settings[["gpu"]]))
+    .Call("cdR_set_design", ctx, X)
+    .Call("cdR_set_regions", ctx, row_off)
+    for (i in seq_along(samples)) {
+      x <- fragData[sample == samples[i]]
+      .Call("cdR_set_sample_rows", ctx, i, as.integer(x$N), as.numeric(x$FullMean))
+    }
+    .Call("cdR_aggregate", ctx, n, S)
+    if (norm == "combined" && is.null(theta)) message("Optimising scaling factors...")
+    fit <- .Call("cdR_region_test", ctx, n, S, p, norm_code, theta_arg, as.numeric(Grid),
+                 if (is.null(pv)) na else pv, if (is.null(pvg)) na else pvg, dispPriorVarSmallDf)
+  }
   if (length(fit$deviances)) {
     message("Total deviances by theta (Fullmean --> Standard):")
     cat(sprintf("%f", fit$deviances), "\n", file = stderr())
   }
   if (norm == "combined") message("Theta=", fit$theta)
   message("Processing model output")
-  ## results() on the arrays still in device memory (cdR_results_adjust is the host routine for gathered columns)
-  adj <- .Call("cdR_results_resident", ctx, n)
+  ## results() on the arrays still in device memory; with several GPUs the columns were gathered: host routine
+  adj <- if (gpus > 1L) .Call("cdR_results_adjust", S, p, fit$baseMean, fit$maxCooks, fit$flags, fit$pvalue)
+         else .Call("cdR_results_resident", ctx, n)
   adj$pvalue[is.nan(adj$pvalue)] <- NA_real_; adj$padj[is.nan(adj$padj)] <- NA_real_
 
   ## annotation columns of the output table (what chicdiff.R:1700-1717 derives by three merges): one row per region,
@@ -107,10 +130,13 @@ DESeq2Wrap.cuda <- function(chicdiff.settings, RU, FullRegionData, suffix = "", 
 
 
 ## getFullRegionData1() on the CUDA backend (chicdiff.R:577-948) -- marshalling only.
-## Per replicate it builds the same small intermediate tables the reference builds (first s_j/tblb per bait :659,
-## first s_i/tlb per other end :668, first Tmean per (tblb, tlb) :680, .chicEstimateDistFun :696) as dense
-## per-fragment vectors, hands them and the .chinput counts to cd_set_sample_tables, and lets cd_assemble do the
-## joins, Bmean/Tmean reconstruction, count merge and region sums (stubs in r_glue.c).
+## Per replicate the raw CHiCAGO columns go to the device as they are (cdR_build_sample_tables): the keyed joins, the
+## setkey sorts and the first-per-bait / per-other-end / per-(tblb, tlb) passes of chicdiff.R:632-634, 659-692 happen
+## there; R only turns the bin labels into integer codes and fits the ~75-point distance function.  cd_assemble then
+## does Bmean/Tmean reconstruction, count merge and region sums.  Returns the reference's long table: a data.table keyed
+## by regionID with columns baitID, otherEndID, regionID, distSign, sample, N, s_j, Bmean, Tmean, score, FullMean,
+## condition (chicdiff.R:912-925), plus attr "aggregated" = list(K, FullMean, avDist) so that DESeq2Wrap.cuda need
+## not re-aggregate.
 getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, ctx) {
   rmap <- Chicago:::.readRmap(list(rmapfile = chicdiff.settings[["rmapfile"]]))
   colnames(rmap) <- c("chr", "start", "end", "ID"); setkey(rmap, ID)
@@ -121,6 +147,7 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
   .Call("cdR_set_regions", ctx, c(0, cumsum(as.numeric(RU[, .N, by = regionID]$N))))
   .Call("cdR_set_region_rows", ctx, as.integer(RU$baitID), as.integer(RU$otherEndID))
   files <- unlist(chicdiff.settings[["chicagoData"]]); counts <- unlist(chicdiff.settings[["countData"]])
+  conds <- rep(names(chicdiff.settings[["chicagoData"]]), lengths(chicdiff.settings[["chicagoData"]]))
   ## countData = NULL: the reference reads the counts back from Reduce(merge, ...) over the replicates' CHiCAGO tables,
   ## an inner join (chicdiff.R:778): only pairs with a row in every replicate keep their counts
   common <- NULL
@@ -130,31 +157,61 @@ getFullRegionData1.cuda <- function(chicdiff.settings, RU, is_control = FALSE, c
     common <- Reduce(function(a, b) merge(a, b, by = c("baitID", "otherEndID")), pairs)
     setkey(common, baitID, otherEndID)
   }
+  scores <- vector("list", length(files)); sj <- vector("list", length(files)); tm <- vector("list", length(files))
+  mid <- round(0.5 * (rmap$start + rmap$end))                               # chicdiff.R:871 (R rounds half to even)
   for (i in seq_along(files)) {
     x <- readRDSorRDA(files[i]); x <- if ("chicagoData" %in% class(x)) as.data.table(x@x) else setDT(x)
-    setkey(x, baitID, otherEndID)
-    bait <- x[, list(s_j = s_j[1], tblb = tblb[1]), by = "baitID"]
-    oe <- x[, list(s_i = s_i[1], tlb = tlb[1]), by = "otherEndID"]
-    tb.lv <- sort(unique(na.omit(x$tblb))); tl.lv <- sort(unique(na.omit(x$tlb)))
-    tm <- x[!is.na(tblb) & !is.na(tlb), list(Tmean = Tmean[1]), by = c("tblb", "tlb")]
-    tmean <- matrix(NA_real_, length(tb.lv), length(tl.lv)); tmean[cbind(match(tm$tblb, tb.lv), match(tm$tlb, tl.lv))] <- tm$Tmean
-    s_j <- rep(NA_real_, nF); s_j[bait$baitID - id0 + 1L] <- bait$s_j
-    tblb <- rep(-1L, nF); tblb[bait$baitID - id0 + 1L] <- ifelse(is.na(bait$tblb), -1L, match(bait$tblb, tb.lv) - 1L)
-    s_i <- rep(NA_real_, nF); s_i[oe$otherEndID - id0 + 1L] <- oe$s_i
-    tlb <- rep(-1L, nF); tlb[oe$otherEndID - id0 + 1L] <- ifelse(is.na(oe$tlb), -1L, match(oe$tlb, tl.lv) - 1L)
+    tb <- factor(x$tblb); tl <- factor(x$tlb)
+    code <- function(f) { v <- as.integer(f) - 1L; v[is.na(v)] <- -1L; v }
     dfp <- .chicEstimateDistFun(x)
-    cnt <- if (is.null(counts)) x[common, .(baitID, otherEndID, N), nomatch = 0L] else fread(counts[i])[, .(baitID, otherEndID, N)]
-    # rows whose bait is not a fragment of the rmap would be dropped by tabulate() but stay in cnt$otherEndID / cnt$N,
-    # and every offset after them would point at the wrong rows: drop them first
-    cnt <- cnt[baitID >= id0 & baitID < id0 + nF]
-    setkey(cnt, baitID, otherEndID)
-    cnt_off <- c(0, cumsum(tabulate(cnt$baitID - id0 + 1L, nbins = nF)))
-    .Call("cdR_set_sample_tables", ctx, i, s_j, tblb, s_i, tlb, t(tmean),
+    cnt <- if (is.null(counts)) x[common, .(baitID, otherEndID, N), on = c("baitID", "otherEndID"), nomatch = 0L]
+           else fread(counts[i])[, .(baitID, otherEndID, N)]
+    .Call("cdR_build_sample_tables", ctx, i, as.integer(x$baitID), as.integer(x$otherEndID), as.numeric(x$s_j), as.numeric(x$s_i),
+          code(tb), code(tl), as.numeric(x$Tmean), NULL, max(1L, nlevels(tb)), max(1L, nlevels(tl)),
           c(dfp$cubicFit, dfp$obs.min, dfp$obs.max, dfp$head.coef, dfp$tail.coef),
-          as.numeric(cnt_off), as.integer(cnt$otherEndID), as.integer(cnt$N))
+          as.integer(cnt$baitID), as.integer(cnt$otherEndID), as.integer(cnt$N))
+    ## columns of the long table that are plain look-ups in x (chicdiff.R:634, 659): score of the pair, s_j of the bait
+    scores[[i]] <- x[RU, score, on = c("baitID", "otherEndID")]
+    sj[[i]] <- x[, .(s_j = s_j[1]), keyby = baitID][RU, s_j, on = "baitID"]
   }
-  n <- length(unique(RU$regionID))
-  .Call("cdR_assemble", ctx, n, length(files), TRUE)      # -> list(K, FullMean, avDist); per-row columns via cdR_get_sample_rows
+  n <- length(unique(RU$regionID)); S <- length(files); R <- nrow(RU)
+  agg <- .Call("cdR_assemble", ctx, n, S, TRUE)        # list(K, FullMean, avDist); per-row columns stay on the device
+  same <- rmap$chr[RU$otherEndID - id0 + 1L] == rmap$chr[RU$baitID - id0 + 1L]
+  distSign <- ifelse(same, mid[RU$otherEndID - id0 + 1L] - mid[RU$baitID - id0 + 1L], NA_real_)   # :878-881
+  long <- rbindlist(lapply(seq_along(files), function(i) {
+    rows <- .Call("cdR_get_sample_rows", ctx, i, R)    # list(N, FullMean, Bmean)
+    fm <- rows$FullMean; fm[is.nan(fm)] <- NA_real_; bm <- rows$Bmean; bm[is.nan(bm)] <- NA_real_
+    data.table(baitID = RU$baitID, otherEndID = RU$otherEndID, regionID = RU$regionID, distSign = distSign,
+               sample = paste0(conds[i], ".", basename(files[i])), N = rows$N, s_j = sj[[i]], Bmean = bm, Tmean = fm - bm,
+               score = scores[[i]], FullMean = fm, condition = conds[i])
+  }))
+  setkey(long, regionID)                                                    # chicdiff.R:925
+  attr(long, "aggregated") <- agg
+  long
+}
+
+## getFullRegionData() (chicdiff.R:1460-1478): list(FullRegionData, FullControlRegionData, countput) and the same files:
+## <outprefix>_countput<suffix>.Rds always, the two long tables when saveAuxData.
+getFullRegionData.cuda <- function(chicdiff.settings, RU, RUcontrol, suffix = "") {
+  ctx <- .Call("cdR_create", as.integer(if (is.null(chicdiff.settings[["gpu"]])) 0L else chicdiff.settings[["gpu"]]))
+  files <- chicdiff.settings[["chicagoData"]]
+  .Call("cdR_set_design", ctx, model.matrix(~ condition, data.frame(condition = factor(rep(names(files), lengths(files))))))
+  FullRegionData <- getFullRegionData1.cuda(chicdiff.settings, RU, FALSE, ctx)
+  ## countput (chicdiff.R:708-735, 755-770): per condition, over the replicates' CHiCAGO rows that have a distance
+  countput <- rbindlist(lapply(names(files), function(cond) {
+    reps <- lapply(files[[cond]], function(f) { x <- readRDSorRDA(f); x <- if ("chicagoData" %in% class(x)) as.data.table(x@x) else setDT(x)
+                                                x <- x[!is.na(distSign)]
+                                                list(as.integer(x$baitID), as.integer(x$otherEndID), as.integer(x$N), as.numeric(x$Bmean), as.numeric(x$score)) })
+    cp <- as.data.table(.Call("cdR_countput", ctx, reps)); cp[, condition := cond]; cp
+  }))
+  FullControlRegionData <- getFullRegionData1.cuda(chicdiff.settings, RUcontrol, TRUE, ctx)
+  outprefix <- chicdiff.settings[["outprefix"]]
+  saveRDS(countput, paste0(outprefix, "_countput", suffix, ".Rds"))
+  if (isTRUE(chicdiff.settings[["saveAuxData"]])) {
+    saveRDS(FullRegionData, paste0(outprefix, "_FullRegionData", suffix, ".Rds"))
+    saveRDS(FullControlRegionData, paste0(outprefix, "_FullControlRegionData", suffix, ".Rds"))
+  }
+  list(FullRegionData, FullControlRegionData, countput)
 }
 
 

@@ -127,16 +127,17 @@ static double prior_var_trampoline(void* user, int df, int64_t n_resid, const do
 
 
 /* norm: 0/1/2; theta, priorVar, priorVarGrid: NA_real_ = let the library decide; grid: numeric vector;
- * priorVarFn: NULL or function(df, resid) returning dispPriorVar for designs with S - p <= 3 */
-SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta, SEXP grid, SEXP priorVar, SEXP priorVarGrid,
-                     SEXP priorVarFn)
+ * priorVarFn: NULL or function(df, resid) returning dispPriorVar for designs with S - p <= 3.
+ * run: cd_region_test on a context or cd_multi_region_test on a multi-GPU handle (same contract). */
+typedef int (*region_test_fn)(void* handle, const cd_options* opt, cd_results* out);
+static int run_single(void* h, const cd_options* opt, cd_results* out) { return cd_region_test((cd_ctx*)h, opt, out); }
+static int run_multi(void* h, const cd_options* opt, cd_results* out) { return cd_multi_region_test((cd_multi*)h, opt, out); }
+
+static SEXP region_test_common(region_test_fn run, void* handle, const char* (*last_error)(void*), int n, int S, SEXP norm, SEXP theta,
+                               SEXP grid, SEXP priorVar, SEXP priorVarGrid, SEXP priorVarFn)
 {
-    cd_ctx* ctx = get_ctx(ptr);
-    int n = asInteger(n_), S = asInteger(S_);
-    (void)p_;
-    check_dims(ctx, "cdR_region_test", n, S, -1);
     cd_options opt;
-    memset(&opt, 0, sizeof(opt));
+    memset(&opt, 0, sizeof(opt));              /* trend_a0 / trend_a1 / var_log_disp = 0: estimate */
     opt.norm = asInteger(norm);
     opt.theta = asReal(theta);                 /* NA_real_ is a NaN */
     opt.theta_grid = REAL(grid); opt.n_theta_grid = LENGTH(grid);
@@ -155,7 +156,7 @@ SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta,
     SEXP flags = PROTECT(allocVector(RAWSXP, n));
     res.flags = RAW(flags);
     SET_VECTOR_ELT(out, 11, flags);
-    CD_CHECK(ctx, cd_region_test(ctx, &opt, &res));
+    if (run(handle, &opt, &res) != CD_OK) error("chicdiff_b200: %s", last_error(handle));
     SET_VECTOR_ELT(out, 12, ScalarReal(res.theta));
     SEXP dv = PROTECT(allocVector(REALSXP, res.n_deviances));
     for (int k = 0; k < res.n_deviances; k++) REAL(dv)[k] = res.deviances[k];
@@ -168,6 +169,97 @@ SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta,
     setAttrib(out, R_NamesSymbol, nm);
     UNPROTECT(16);
     return out;
+}
+
+static const char* last_error_single(void* h) { return cd_last_error((cd_ctx*)h); }
+static const char* last_error_multi(void* h) { return cd_multi_last_error((cd_multi*)h); }
+
+SEXP cdR_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP p_, SEXP norm, SEXP theta, SEXP grid, SEXP priorVar, SEXP priorVarGrid,
+                     SEXP priorVarFn)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    int n = asInteger(n_), S = asInteger(S_);
+    (void)p_;
+    check_dims(ctx, "cdR_region_test", n, S, -1);
+    return region_test_common(run_single, ctx, last_error_single, n, S, norm, theta, grid, priorVar, priorVarGrid, priorVarFn);
+}
+
+/* ---- several GPUs from this one R session (cd_multi_*): same calls on the whole problem ---- */
+static void multi_finalizer(SEXP ptr)
+{
+    cd_multi* m = (cd_multi*)R_ExternalPtrAddr(ptr);
+    if (m) { cd_multi_destroy(m); R_ClearExternalPtr(ptr); }
+}
+
+static cd_multi* get_multi(SEXP ptr)
+{
+    cd_multi* m = (cd_multi*)R_ExternalPtrAddr(ptr);
+    if (!m) error("chicdiff_b200: multi-GPU handle was destroyed");
+    return m;
+}
+
+#define CD_MCHECK(m, call) do { int rc_ = (call); if (rc_ != CD_OK) error("chicdiff_b200: %s", cd_multi_last_error(m)); } while (0)
+
+SEXP cdR_multi_create(SEXP n_gpus)
+{
+    cd_multi* m = NULL;
+    if (cd_multi_create(&m, asInteger(n_gpus), NULL) != CD_OK) error("chicdiff_b200: %s", cd_multi_last_error(NULL));
+    SEXP ptr = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(ptr, multi_finalizer, TRUE);
+    UNPROTECT(1);
+    return ptr;
+}
+
+SEXP cdR_multi_set_design(SEXP ptr, SEXP X)
+{
+    cd_multi* m = get_multi(ptr);
+    int S = nrows(X), p = ncols(X);
+    double* rowmajor = (double*)R_alloc((size_t)S * p, sizeof(double));
+    for (int j = 0; j < S; j++) for (int u = 0; u < p; u++) rowmajor[j * p + u] = REAL(X)[u * S + j];
+    CD_MCHECK(m, cd_multi_set_design(m, S, p, rowmajor));
+    return R_NilValue;
+}
+
+/* row_off: numeric n + 1; region_bait: integer n (baitID of every region, regions in regionID order) */
+SEXP cdR_multi_set_regions(SEXP ptr, SEXP row_off, SEXP region_bait)
+{
+    cd_multi* m = get_multi(ptr);
+    R_xlen_t len = XLENGTH(row_off);
+    if (XLENGTH(region_bait) != len - 1) error("chicdiff_b200: cdR_multi_set_regions: one baitID per region");
+    int64_t* off = (int64_t*)R_alloc((size_t)len, sizeof(int64_t));
+    for (R_xlen_t i = 0; i < len; i++) off[i] = (int64_t)REAL(row_off)[i];
+    CD_MCHECK(m, cd_multi_set_regions(m, (int64_t)len - 1, off, (const int32_t*)INTEGER(region_bait)));
+    return R_NilValue;
+}
+
+SEXP cdR_multi_set_sample_rows(SEXP ptr, SEXP s, SEXP N, SEXP fullmean)
+{
+    cd_multi* m = get_multi(ptr);
+    CD_MCHECK(m, cd_multi_set_sample_rows(m, asInteger(s) - 1, (int64_t)XLENGTH(N), (const int32_t*)INTEGER(N), REAL(fullmean)));
+    return R_NilValue;
+}
+
+SEXP cdR_multi_aggregate(SEXP ptr, SEXP n_, SEXP S_)
+{
+    cd_multi* m = get_multi(ptr);
+    int n = asInteger(n_), S = asInteger(S_);
+    SEXP K = PROTECT(allocMatrix(INTSXP, n, S));
+    SEXP FM = PROTECT(allocMatrix(REALSXP, n, S));
+    CD_MCHECK(m, cd_multi_aggregate(m, (int32_t*)INTEGER(K), REAL(FM)));
+    SEXP out = PROTECT(allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, K); SET_VECTOR_ELT(out, 1, FM);
+    SEXP nm = PROTECT(allocVector(STRSXP, 2));
+    SET_STRING_ELT(nm, 0, mkChar("K")); SET_STRING_ELT(nm, 1, mkChar("FullMean"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(4);
+    return out;
+}
+
+SEXP cdR_multi_region_test(SEXP ptr, SEXP n_, SEXP S_, SEXP norm, SEXP theta, SEXP grid, SEXP priorVar, SEXP priorVarGrid)
+{
+    cd_multi* m = get_multi(ptr);
+    return region_test_common(run_multi, m, last_error_multi, asInteger(n_), asInteger(S_), norm, theta, grid, priorVar, priorVarGrid,
+                              R_NilValue);
 }
 
 /* returns list(pvalue, padj) after Cook's cutoff + independent filtering + BH */
@@ -296,6 +388,30 @@ SEXP cdR_set_sample_tables(SEXP ptr, SEXP s, SEXP s_j, SEXP tblb, SEXP s_i, SEXP
     memcpy(t.distfun, REAL(distfun), sizeof(t.distfun));
     t.cnt_off = offsets_from_real(cnt_off); t.cnt_oe = INTEGER(cnt_oe); t.cnt_N = INTEGER(cnt_N);
     CD_CHECK(ctx, cd_set_sample_tables(ctx, asInteger(s) - 1, &t));
+    return R_NilValue;
+}
+
+/* One replicate's raw CHiCAGO columns -> the per-fragment tables, built on the device (cd_build_sample_tables): no setkey,
+ * no first-per-group pass in R.  tblb / tlb: integer codes (factor codes - 1, NA -> -1); cnt_*: the .chinput rows, or
+ * NULL to take the table's own N column. */
+SEXP cdR_build_sample_tables(SEXP ptr, SEXP s, SEXP baitID, SEXP otherEndID, SEXP s_j, SEXP s_i, SEXP tblb, SEXP tlb, SEXP Tmean,
+                             SEXP N, SEXP n_tblb, SEXP n_tlb, SEXP distfun, SEXP cnt_bait, SEXP cnt_oe, SEXP cnt_N)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    cd_chicago_table t;
+    memset(&t, 0, sizeof(t));
+    t.rows = (int64_t)XLENGTH(baitID);
+    t.baitID = INTEGER(baitID); t.otherEndID = INTEGER(otherEndID); t.s_j = REAL(s_j); t.s_i = REAL(s_i);
+    t.tblb = INTEGER(tblb); t.tlb = INTEGER(tlb); t.Tmean = REAL(Tmean);
+    t.N = isNull(N) ? NULL : INTEGER(N);
+    t.n_tblb = asInteger(n_tblb); t.n_tlb = asInteger(n_tlb);
+    if (XLENGTH(distfun) != 10) error("chicdiff_b200: distfun must hold 10 numbers");
+    memcpy(t.distfun, REAL(distfun), sizeof(t.distfun));
+    if (!isNull(cnt_bait)) {
+        t.cnt_rows = (int64_t)XLENGTH(cnt_bait);
+        t.cnt_baitID = INTEGER(cnt_bait); t.cnt_otherEndID = INTEGER(cnt_oe); t.cnt_N = INTEGER(cnt_N);
+    }
+    CD_CHECK(ctx, cd_build_sample_tables(ctx, asInteger(s) - 1, &t));
     return R_NilValue;
 }
 
