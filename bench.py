@@ -494,6 +494,17 @@ def main():
     dev_ms, wall_ms, tm = R.timed(step_resident, args.steps)
     clocks = sampler.stop() if sampler else None
     launches = (e.launch_count() - launches0) / args.steps
+    rendezvous = None
+    if world > 1:
+        passes, wait_peers, wait_self = e.last_rendezvous()
+        mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        rendezvous = {"what": "trend-fit passes of one step: every pass ends with an all-reduce of 8 sums per fit through NVLink peer-memory "
+                              "mailboxes inside the kernel; wait = SM cycles CTA 0 of this rank spent polling for a peer's sequence word "
+                              "(arrival skew of the ranks + store-to-visibility latency), per pass and peer",
+                      "trend_passes_per_step": passes, "ranks": world,
+                      "mean_wait_us_per_pass_and_peer": wait_peers / max(passes * (world - 1), 1) / mhz,
+                      "own_slot_us_per_pass": wait_self / max(passes, 1) / mhz,
+                      "median_kernel_exchanges_per_step": 8 * 5}
     flop_tab, flop_src = read_flop_table()
     fp64 = fp64_roofline(e, d, tm[2], fp64_peak, flop_tab, flop_src)
     fp64["kernel"] = "fit_disp_kernel (dispersion line searches: %.0f %% of the step)" % (100.0 * tm[2] / dev_ms)
@@ -598,6 +609,8 @@ def main():
             line["results_step"] = res_step
         if strong is not None:
             line["strong"] = strong
+        if rendezvous is not None:
+            line["rendezvous"] = rendezvous
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             rate, dt, m = cpu_reference_rate(d, args.cpu_sample, threads)

@@ -107,9 +107,11 @@ __device__ __forceinline__ double log_pos(double x)
 // log(1 + mu alpha) at small alpha needs.  <= 1.5 ulp for x >= 1, <= 3e-16 max(1, |log x|) below
 // (tests/test_device_math.py).  tab = 128 x {rc, -log rc}: kLogTab copied to shared memory by the kernel (the lanes of
 // a warp index it with unrelated mantissas, which constant memory would serialise).
-static __constant__ double kLogTab[256] = {
+alignas(16) static __constant__ double kLogTab[256] = {
 #include "log_table.inc"
 };
+
+struct alignas(16) LogTabEntry { double rc, lc; };      // one 16-byte shared-memory load per logarithm
 
 __device__ __forceinline__ double log_pos_v2(double x, const double* tab)
 {
@@ -122,7 +124,8 @@ __device__ __forceinline__ double log_pos_v2(double x, const double* tab)
     hi |= (up ^ 0x3ff00000);
     k += (up >> 20);
     const double m = __hiloint2double(hi, lo);
-    const double rc = tab[2 * idx], lc = tab[2 * idx + 1];
+    const LogTabEntry e = reinterpret_cast<const LogTabEntry*>(tab)[idx];      // tab is 16-byte aligned
+    const double rc = e.rc, lc = e.lc;
     const double r = fma(m, rc, -1.0);
     double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
     q = fma(r, q, -1.0 / 6.0);

@@ -213,6 +213,9 @@ struct cd_ctx {
     int eval_call_p[16] = {0};                     // design columns of that call
     int64_t eval_call_regions[16] = {0};           // virtual regions of that call
     unsigned long long eval_counts_host[16] = {0};
+    double trend_passes_batch = 0;
+    double trend_passes = 0;                       // trend passes (= cross-rank rendezvous of the trend fits) of the last region test
+    unsigned long long wait_host[2] = {0, 0};
     DevBuf<int32_t> refit_count;
     DevBuf<int64_t> park_row;
     DevBuf<double> park_d;           // 5 x capacity
@@ -1313,6 +1316,7 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
         pp.peers = ctx->p2p_peers_dev.p; pp.mymail = ctx->p2p_mail.p;
         pp.epoch = ++ctx->p2p_epoch;
         pp.err = err_dev;
+        pp.wait_cycles = ctx->comm.active() ? ctx->counters.p + 4 : nullptr;
         CD_LAUNCHN(ctx, 1, launch_trend_fit(n, G, baseMean, dispGeneEst, flags, ctx->trend_xs.p, ctx->partial.p,
                                             reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, pp, st));
     }
@@ -1362,9 +1366,13 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
                 return ctx->fail(CD_ENUMERIC, "prior_var_fn returned %g for df = %d (%lld residuals)", dispPriorVar, df, (long long)m);
         } else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
         bo.a0[g] = t[0]; bo.a1[g] = t[1]; bo.varLogDispEsts[g] = varLogDispEsts; bo.dispPriorVar[g] = dispPriorVar;
+        if (g == 0 || t[4] > ctx->trend_passes_batch) ctx->trend_passes_batch = t[4];
         prior.v[g] = dispPriorVar;
         thr.v[g] = 2.0 * sqrt(varLogDispEsts);
     }
+
+    ctx->trend_passes += ctx->trend_passes_batch;          // the fits of a batch advance in lock step: max over the fits
+    ctx->trend_passes_batch = 0;
 
     // MAP
     ctx->tm_begin(2);
@@ -1501,7 +1509,9 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
 
     CD_CUDA(ctx, ctx->eval_counts.ensure(16));
     CD_CUDA(ctx, cudaMemsetAsync(ctx->eval_counts.p, 0, 16 * sizeof(unsigned long long), st));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
     ctx->n_eval_calls = 0;
+    ctx->trend_passes = 0;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     memset(out->sizeFactors, 0, sizeof(out->sizeFactors));
     for (int k = 2; k < 8; k++) ctx->timings[k] = 0.0;
@@ -1551,6 +1561,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     unsigned long long hc[4] = {0, 0, 0, 0};
     CD_CUDA(ctx, cudaMemcpyAsync(hc, ctx->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->eval_counts_host, ctx->eval_counts.p, sizeof(ctx->eval_counts_host), cudaMemcpyDeviceToHost, st));
+    CD_CUDA(ctx, cudaMemcpyAsync(ctx->wait_host, ctx->counters.p + 4, sizeof(ctx->wait_host), cudaMemcpyDeviceToHost, st));
     const size_t nn = (size_t)n;
     if ((rc = d2h(ctx, out->baseMean, ctx->g_baseMean.p + ctx->g_off, nn)) != CD_OK) return rc;
     if ((rc = d2h(ctx, out->baseVar, ctx->baseVar.p, nn)) != CD_OK) return rc;
@@ -1721,6 +1732,15 @@ int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[1
         if (design_columns) design_columns[k] = k < ctx->n_eval_calls ? ctx->eval_call_p[k] : 0;
         if (regions) regions[k] = k < ctx->n_eval_calls ? ctx->eval_call_regions[k] : 0;
     }
+    return CD_OK;
+}
+
+int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self)
+{
+    if (!ctx) return CD_EINVAL;
+    if (trend_passes) *trend_passes = ctx->trend_passes;
+    if (wait_cycles_peers) *wait_cycles_peers = (double)ctx->wait_host[0];
+    if (wait_cycles_self) *wait_cycles_self = (double)ctx->wait_host[1];
     return CD_OK;
 }
 

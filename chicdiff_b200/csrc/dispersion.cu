@@ -217,7 +217,11 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                 double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem_all[];
+    // layout: logarithm table (256 doubles, 16-byte aligned: one LDS.128 per logarithm), staging columns, prefetch slots,
+    // model matrix
+    double* tab = smem_all;
+    double* smem = smem_all + 256;
     const int stride = kFitDispThreads;
     double* ys = smem + threadIdx.x;
     double* mus = smem + (size_t)S * stride + threadIdx.x;
@@ -246,7 +250,6 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double* pf_init = pf_mu + (size_t)S * stride;
     double* pf_prior = pf_init + stride;
     double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
-    double* tab = Xs + S * P;
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
     for (int k = threadIdx.x; k < 256; k += blockDim.x) tab[k] = kLogTab[k];
     __syncthreads();

@@ -223,6 +223,8 @@ __device__ __forceinline__ bool p2p_allreduce(const TrendP2P& pp, unsigned long 
             if (clock64() - t0 > kSpinLimit) { timed_out = 1; atomicExch(pp.err, 1ull); break; }
         }
         __threadfence_system();
+        // how long this rank waited for the slowest peer's sums (CTA 0, per peer): the rendezvous cost the bench reports
+        if (blockIdx.x == 0 && pp.wait_cycles) atomicAdd(pp.wait_cycles + ((int)threadIdx.x == pp.rank ? 1 : 0), (unsigned long long)(clock64() - t0));
     }
     __syncthreads();
     if ((int)threadIdx.x < nvals) {

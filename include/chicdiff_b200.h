@@ -318,6 +318,12 @@ int cd_last_timings(const cd_ctx* ctx, double out_ms[8]);
  * start a search plus one per trip), the design columns p of that fit and the (virtual) regions searched.  This is the
  * unit count of the FP64 roofline in bench.py: evaluations x S replicates x flop per replicate-evaluation. */
 int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[16], int design_columns[16], int64_t regions[16]);
+/* Cross-rank rendezvous of the trend fits of the last cd_region_test on a sharded context: the number of trend passes (each
+ * pass ends with every rank storing its sums into every peer's mailbox over NVLink and waiting for everybody's), and
+ * the SM cycles CTA 0 spent waiting for the peers' sequence words, summed over passes and peers (wait_cycles_self: the
+ * same for its own slot, i.e. the cost of the store + fence alone).  wait / (passes x (ranks - 1)) / SM clock = the mean
+ * wait per rendezvous and peer: arrival skew of the ranks plus the NVLink store-to-visibility latency. */
+int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self);
 /* CUDA-event stopwatch on the context's stream (what bench.py brackets its timed region with) */
 int cd_timer_start(cd_ctx* ctx);
 int cd_timer_stop(cd_ctx* ctx, double* ms_out);      /* synchronises */
