@@ -206,6 +206,7 @@ struct cd_ctx {
     DevBuf<double> g_LR;
     DevBuf<unsigned long long> sel_state, sel_hist, sel_aux;
     DevBuf<double> trend_xs;         // scratch of the trend fit: one double per virtual region
+    DevBuf<double> start_log, log_fit;   // line-search start values and prior means as logarithms
     DevBuf<double> partial, scal;    // reduction scratch ; device scalars
     DevBuf<unsigned long long> counters;
     DevBuf<unsigned long long> eval_counts;       // per fit_disp call of the last cd_region_test: evaluations
@@ -1276,7 +1277,7 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     CD_COMM(ctx, ctx->comm.allreduce_sum(sums_dev, (size_t)G * (S + 1), st));
     CD_LAUNCHN(ctx, 1, launch_xim(G, S, sums_dev, xim_dev, st));
     CD_LAUNCHN(ctx, 1, launch_gene_init(nv, n, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev,
-                                        ctx->alpha_init.p, ctx->mu.p, st));
+                                        ctx->alpha_init.p, ctx->start_log.p, ctx->mu.p, st));
     if (!des.linear_mu) {
         // mu from an NB GLM fitted with the rough dispersion (fitNbinomGLMs(alpha_hat = alpha_init)$mu)
         CD_LAUNCHN(ctx, 3, launch_wald(nv, S, p, des_dev, K, ctx->nf.p, ctx->alpha_init.p, flags, ctx->wald_ws, nullptr, nullptr,
@@ -1285,7 +1286,7 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     BatchScalars none{};
     for (int g = 0; g < kMaxBatch; g++) none.v[g] = 1.0;
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, ctx->alpha_init.p, nullptr, none, ctx->log_alpha.p,
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, ctx->start_log.p, nullptr, none, ctx->log_alpha.p,
                                        ctx->dispGeneIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
     if (ctx->n_eval_calls < 16 && nv > 0) {
@@ -1320,7 +1321,8 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
         CD_LAUNCHN(ctx, 1, launch_trend_fit(n, G, baseMean, dispGeneEst, flags, ctx->trend_xs.p, ctx->partial.p,
                                             reinterpret_cast<unsigned int*>(ctx->counters.p + 9), trend_dev, pp, st));
     }
-    CD_LAUNCHN(ctx, 1, launch_trend_apply(nv, n, baseMean, dispGeneEst, flags, trend_dev, dispFit, ctx->g_resid.p, st));
+    CD_LAUNCHN(ctx, 1, launch_trend_apply(nv, n, baseMean, dispGeneEst, flags, trend_dev, dispFit, ctx->g_resid.p,
+                                          ctx->start_log.p, ctx->log_fit.p, st));
     int rc = medians(ctx, ctx->g_resid.p, n, n, G, nullptr, ctx->scal.p + kScalMed, 0, 1.0);
     if (rc != CD_OK) return rc;
     rc = medians(ctx, ctx->g_resid.p, n, n, G, ctx->scal.p + kScalMed, ctx->scal.p + kScalMad, 0, 1.4826);
@@ -1376,7 +1378,7 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
 
     // MAP
     ctx->tm_begin(2);
-    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, dispGeneEst, dispFit, prior, ctx->log_alpha.p,
+    CD_LAUNCHN(ctx, 2, launch_fit_disp(nv, n, S, p, des_dev, K, ctx->mu.p, ctx->start_log.p, ctx->log_fit.p, prior, ctx->log_alpha.p,
                                        ctx->dispIter.p, ctx->initial_lp.p, ctx->last_lp.p, ctx->counters.p + 12, ctx->park, st));
     ctx->tm_end();
     if (ctx->n_eval_calls < 16 && nv > 0) {
@@ -1477,6 +1479,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
     CD_CUDA(ctx, ctx->g_baseMean.ensure(vn)); CD_CUDA(ctx, ctx->g_dispGeneEst.ensure(vn));
     CD_CUDA(ctx, ctx->g_dispFit.ensure(vn)); CD_CUDA(ctx, ctx->g_resid.ensure(vn));
     CD_CUDA(ctx, ctx->g_flags.ensure(vn)); CD_CUDA(ctx, ctx->trend_xs.ensure(vn));
+    CD_CUDA(ctx, ctx->start_log.ensure(vn)); CD_CUDA(ctx, ctx->log_fit.ensure(vn));
     CD_CUDA(ctx, ctx->partial.ensure((size_t)kReduceBlocks * kMaxBatch * (CD_MAXS + 1)));
     CD_CUDA(ctx, ctx->scal.ensure(kScalSize));
     if (!ctx->counters.p) {

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256)
 gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
                  const double* __restrict__ nf, const double* __restrict__ baseMean, const double* __restrict__ baseVar,
                  const double* __restrict__ rough, const uint8_t* __restrict__ flags,
-                 const double* __restrict__ xim_dev, double* __restrict__ alpha_init,
+                 const double* __restrict__ xim_dev, double* __restrict__ alpha_init, double* __restrict__ start_log,
                  double* __restrict__ mu)
 {
     __shared__ double hat[CD_MAXS * CD_MAXS];
@@ -151,6 +151,7 @@ gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ d
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) {
         alpha_init[i] = NAN;
+        start_log[i] = NAN;                      // the line search recognises an all-zero region by this
         if (mu) for (int j = 0; j < S; j++) mu[(int64_t)j * n + i] = NAN;
         return;
     }
@@ -158,7 +159,9 @@ gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ d
     const double bm = baseMean[i], bv = baseVar[i];
     const double moments = (bv - xim * bm) / (bm * bm);
     const double maxDisp = fmax(10.0, (double)S);
-    alpha_init[i] = fmin(fmax(kMinDisp, fmin(rough[i], moments)), maxDisp);
+    const double a0 = fmin(fmax(kMinDisp, fmin(rough[i], moments)), maxDisp);
+    alpha_init[i] = a0;
+    start_log[i] = log_pos(a0);                  // where the gene-wise line search starts (taken here, off its refill path)
     if (!mu) return;
     double q[CD_MAXS];
     for (int j = 0; j < S; j++) q[j] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
@@ -171,11 +174,11 @@ gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ d
 
 cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
                              const double* baseMean, const double* baseVar, const double* rough, const uint8_t* flags,
-                             const double* xim_dev, double* alpha_init, double* mu, cudaStream_t st)
+                             const double* xim_dev, double* alpha_init, double* start_log, double* mu, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
     gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, S, des, K, nf, baseMean, baseVar, rough, flags,
-                                                       xim_dev, alpha_init, mu);
+                                                       xim_dev, alpha_init, start_log, mu);
     return cudaGetLastError();
 }
 
@@ -211,8 +214,8 @@ static inline size_t fit_disp_smem_doubles(int S, int P, int threads)
 template <int P, bool RESUME, bool TABLOG>
 __global__ void __launch_bounds__(kFitDispThreads, CD_FITDISP_MINBLOCKS)
 fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
-                const double* __restrict__ mu_g, const double* __restrict__ disp_init,
-                const double* __restrict__ prior_mean_disp, BatchScalars prior_sigmasq_g,
+                const double* __restrict__ mu_g, const double* __restrict__ start_log,
+                const double* __restrict__ prior_log_mean, BatchScalars prior_sigmasq_g,
                 double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
                 double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
@@ -226,7 +229,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double* ys = smem + threadIdx.x;
     double* mus = smem + (size_t)S * stride + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    const bool use_prior = (prior_mean_disp != nullptr);
+    const bool use_prior = (prior_log_mean != nullptr);
     const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
     const double min_log_alpha = log(kMinDisp / 10.0);
     const int maxit = 100;
@@ -257,12 +260,15 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     int64_t pending = 0, queued = 0;
     auto prefetch = [&](int64_t r) {
         if (r < n) {
+            const int32_t* kp = K + r;
+            const double* mp = mu_g + r;
             for (int j = 0; j < S; j++) {
-                __pipeline_memcpy_async(pf_k + j * stride, K + (int64_t)j * n + r, sizeof(int32_t));
-                __pipeline_memcpy_async(pf_mu + j * stride, mu_g + (int64_t)j * n + r, sizeof(double));
+                __pipeline_memcpy_async(pf_k + j * stride, kp, sizeof(int32_t));
+                __pipeline_memcpy_async(pf_mu + j * stride, mp, sizeof(double));
+                kp += n; mp += n;
             }
-            __pipeline_memcpy_async(pf_init, disp_init + r, sizeof(double));
-            if (use_prior) __pipeline_memcpy_async(pf_prior, prior_mean_disp + r, sizeof(double));
+            __pipeline_memcpy_async(pf_init, start_log + r, sizeof(double));
+            if (use_prior) __pipeline_memcpy_async(pf_prior, prior_log_mean + r, sizeof(double));
         }
         __pipeline_commit();
     };
@@ -287,8 +293,8 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                 } else {
                     __pipeline_wait_prior(0);
                     i = pending;
-                    const double d0 = *pf_init;
-                    if (isnan(d0)) {
+                    const double a_start = *pf_init;
+                    if (isnan(a_start)) {
                         // all-zero region: every estimate is NA (its start value was written as NaN upstream)
                         log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
                     } else {
@@ -296,15 +302,13 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                             ys[j * stride] = (double)pf_k[j * stride];
                             mus[j * stride] = pf_mu[j * stride];
                         }
+                        // the logarithms of the start value and of the prior mean were taken by the kernels that produced
+                        // them (gene_init / trend_apply): the refill path runs with 2-3 of 32 lanes on almost every trip
+                        a = a_start;
                         if (use_prior) {
-                            // estimateDispersionsMAP: start at the gene-wise estimate unless it sits more
-                            // than an order of magnitude below the trend
-                            const double ft = *pf_prior;
-                            a = log_pos((d0 > 0.1 * ft) ? d0 : ft);
-                            prior_mean = log_pos(ft);
-                            prior_sigmasq = 1.0 / prior_sigmasq_g.v[(int)(i / n_fit)];      // eval_post multiplies by the reciprocal
-                        } else {
-                            a = log_pos(d0);
+                            prior_mean = *pf_prior;
+                            // n < 2^31 virtual regions: a 32-bit division finds the fit; eval_post multiplies by the reciprocal
+                            prior_sigmasq = 1.0 / prior_sigmasq_g.v[(unsigned)i / (unsigned)n_fit];
                         }
                         active = true; fresh = true;
                         iter = 0; iter_accept = 0; kappa = kappa_0;
@@ -336,8 +340,8 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                     a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
                     iter = park.iter[w]; iter_accept = park.iter_accept[w];
                     if (use_prior) {
-                        prior_mean = log_pos(prior_mean_disp[i]);
-                        prior_sigmasq = 1.0 / prior_sigmasq_g.v[(int)(i / n_fit)];      // eval_post multiplies by the reciprocal
+                        prior_mean = prior_log_mean[i];
+                        prior_sigmasq = 1.0 / prior_sigmasq_g.v[(unsigned)i / (unsigned)n_fit];      // eval_post multiplies by the reciprocal
                     }
                     for (int j = 0; j < S; j++) {
                         ys[j * stride] = (double)K[(int64_t)j * n + i];
@@ -426,7 +430,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
 template <int P, int G>
 __global__ void __launch_bounds__(128)
 fit_disp_resume_tile_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
-                            const double* __restrict__ mu_g, const double* __restrict__ prior_mean_disp,
+                            const double* __restrict__ mu_g, const double* __restrict__ prior_log_mean,
                             BatchScalars prior_sigmasq_g, double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
                             double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out, FitDispPark park)
 {
@@ -434,7 +438,7 @@ fit_disp_resume_tile_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __r
     const int lane_g = threadIdx.x & (G - 1);                     // replicate handled by this lane
     const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
-    const bool use_prior = (prior_mean_disp != nullptr);
+    const bool use_prior = (prior_log_mean != nullptr);
     const unsigned long long parked = *park.count;
     const int64_t n_work = (int64_t)(parked < (unsigned long long)park.capacity ? parked : (unsigned long long)park.capacity);
     const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
@@ -455,7 +459,7 @@ fit_disp_resume_tile_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __r
             i = park.row[w];
             a = park.a[w]; lp = park.lp[w]; dlp = park.dlp[w]; kappa = park.kappa[w]; lp0 = park.lp0[w];
             iter = park.iter[w]; iter_accept = park.iter_accept[w];
-            if (use_prior) { prior_mean = log_pos(prior_mean_disp[i]); prior_sigmasq = prior_sigmasq_g.v[(int)(i / n_fit)]; }
+            if (use_prior) { prior_mean = prior_log_mean[i]; prior_sigmasq = prior_sigmasq_g.v[(unsigned)i / (unsigned)n_fit]; }
             if (has_sample) { y = (double)K[(int64_t)lane_g * n + i]; mu = mu_g[(int64_t)lane_g * n + i]; }
         }
         while (__any_sync(0xffffffffu, active)) {
@@ -553,7 +557,7 @@ static bool table_log_enabled()
 }
 
 cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* K, const double* mu,
-                            const double* disp_init, const double* prior_mean_disp, const BatchScalars& prior_sigmasq,
+                            const double* start_log, const double* prior_log_mean, const BatchScalars& prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
                             unsigned long long* work_counter, const FitDispPark& park, cudaStream_t st)
 {
@@ -584,18 +588,18 @@ cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesi
         if (e != cudaSuccess) return e;                                                                        \
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                     \
         const int blocks = (int)(want < resident ? want : resident);                                           \
-        fit_disp_kernel<P_, false, TL_><<<blocks, threads, smem, st>>>(n, n_fit, S, des, K, mu, disp_init,     \
-            prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);         \
+        fit_disp_kernel<P_, false, TL_><<<blocks, threads, smem, st>>>(n, n_fit, S, des, K, mu, start_log,     \
+            prior_log_mean, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);          \
         if (tile) {                                                                                            \
             const int blocks2 = sms * 8;                                                                       \
             if (S <= 8)                                                                                        \
-                fit_disp_resume_tile_kernel<P_, 8><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
+                fit_disp_resume_tile_kernel<P_, 8><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_log_mean, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
             else if (S <= 16)                                                                                  \
-                fit_disp_resume_tile_kernel<P_, 16><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
+                fit_disp_resume_tile_kernel<P_, 16><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_log_mean, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
             else                                                                                               \
-                fit_disp_resume_tile_kernel<P_, 32><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_mean_disp, \
+                fit_disp_resume_tile_kernel<P_, 32><<<blocks2, 128, 0, st>>>(n, n_fit, S, des, K, mu, prior_log_mean, \
                     prior_sigmasq, log_alpha, iter, initial_lp, last_lp, park);                                \
         } else {                                                                                               \
             e = cudaFuncSetAttribute(fit_disp_kernel<P_, true, TL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -603,7 +607,7 @@ cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesi
             const int64_t want2 = (park.capacity + threads - 1) / threads;                                     \
             const int blocks2 = (int)(want2 < resident ? want2 : resident);                                    \
             fit_disp_kernel<P_, true, TL_><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, n_fit, S, des, K, mu, \
-                disp_init, prior_mean_disp, prior_sigmasq, log_alpha, iter, initial_lp, last_lp,               \
+                start_log, prior_log_mean, prior_sigmasq, log_alpha, iter, initial_lp, last_lp,                \
                 work_counter + 1, park);                                                                       \
         }                                                                                                      \
     }

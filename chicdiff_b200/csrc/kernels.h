@@ -145,8 +145,8 @@ cudaError_t launch_base_stats(int64_t n, int S, const CdDesign* des, const int32
                               cudaStream_t st);
 cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
                              const double* baseMean, const double* baseVar, const double* rough,
-                             const uint8_t* flags, const double* xim_dev /*per fit*/, double* alpha_init, double* mu,
-                             cudaStream_t st);
+                             const uint8_t* flags, const double* xim_dev /*per fit*/, double* alpha_init,
+                             double* start_log /*log(alpha_init), NaN = all-zero region*/, double* mu, cudaStream_t st);
 // scalar search state of regions parked by the first line-search pass (see dispersion.cu)
 struct FitDispPark {
     int64_t capacity;
@@ -155,10 +155,10 @@ struct FitDispPark {
     int32_t *iter, *iter_accept;
     unsigned long long* count;
 };
-// line search; prior_mean_disp == null => no prior (gene-wise); prior_sigmasq.v[g] per fit
+// line search from start_log (log alpha; NaN = all-zero region); prior_log_mean == null => no prior (gene-wise), else the
+// prior is N(prior_log_mean, prior_sigmasq.v[g]) on log alpha
 cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesign* des, const int32_t* K, const double* mu,
-                            const double* disp_init /*alpha scale*/,
-                            const double* prior_mean_disp /*alpha scale or null*/, const BatchScalars& prior_sigmasq,
+                            const double* start_log, const double* prior_log_mean, const BatchScalars& prior_sigmasq,
                             double* log_alpha, int32_t* iter, double* initial_lp, double* last_lp,
                             unsigned long long* work_counter /*device scratch, 2 words*/, const FitDispPark& park,
                             cudaStream_t st);
@@ -198,9 +198,10 @@ inline size_t trend_p2p_mail_doubles(int nranks) { return (size_t)2 * nranks * (
 cudaError_t launch_trend_fit(int64_t n, int G, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
                              double* xs, double* partial, unsigned int* bar, double* out, const TrendP2P& pp, cudaStream_t st);
 // dispFit = a0 + a1/baseMean ; resid = log(dispGeneEst) - log(dispFit) or +inf when excluded ; coefs_dev[g * 8 + 0..1]
+// also the MAP search's start value and prior mean as logarithms
 cudaError_t launch_trend_apply(int64_t n, int64_t n_fit, const double* baseMean, const double* dispGeneEst,
                                const uint8_t* flags, const double* coefs_dev, double* dispFit, double* resid,
-                               cudaStream_t st);
+                               double* map_start_log, double* log_fit, cudaStream_t st);
 
 // ---- stages 3 + 5: NB GLM, Cook's, Wald --------------------------------------------------
 constexpr int kLfactN = 4096;

@@ -478,23 +478,30 @@ cudaError_t launch_trend_fit(int64_t n, int G, const double* baseMean, const dou
 __global__ void __launch_bounds__(256)
 trend_apply_kernel(int64_t n, int64_t n_fit, const double* __restrict__ baseMean, const double* __restrict__ dispGeneEst,
                    const uint8_t* __restrict__ flags, const double* __restrict__ coefs, double* __restrict__ dispFit,
-                   double* __restrict__ resid)
+                   double* __restrict__ resid, double* __restrict__ map_start_log, double* __restrict__ log_fit)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (flags[i] & CD_FLAG_ALLZERO) { dispFit[i] = NAN; resid[i] = INFINITY; return; }
+    if (flags[i] & CD_FLAG_ALLZERO) { dispFit[i] = NAN; resid[i] = INFINITY; map_start_log[i] = NAN; log_fit[i] = NAN; return; }
     const double* c = coefs + 8 * (i / n_fit);
     const double f = c[0] + c[1] / baseMean[i];
     const double d = dispGeneEst[i];
     dispFit[i] = f;
     resid[i] = (d >= 100.0 * kMinDisp) ? log(d) - log(f) : INFINITY;
+    // estimateDispersionsMAP: the search starts at the gene-wise estimate unless that sits more than an order of magnitude
+    // below the trend; its prior is centred on the trend.  Both as logarithms, for the line search's refill path.
+    const double lf = log_pos(f);
+    log_fit[i] = lf;
+    map_start_log[i] = (d > 0.1 * f) ? log_pos(d) : lf;
 }
 
 cudaError_t launch_trend_apply(int64_t n, int64_t n_fit, const double* baseMean, const double* dispGeneEst, const uint8_t* flags,
-                               const double* coefs_dev, double* dispFit, double* resid, cudaStream_t st)
+                               const double* coefs_dev, double* dispFit, double* resid, double* map_start_log, double* log_fit,
+                               cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, baseMean, dispGeneEst, flags, coefs_dev, dispFit, resid);
+    trend_apply_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, baseMean, dispGeneEst, flags, coefs_dev, dispFit, resid,
+                                                         map_start_log, log_fit);
     return cudaGetLastError();
 }
 

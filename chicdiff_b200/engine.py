@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libchicdiff_b200.so")
+# (CHICDIFF_B200_LIB: development hook of scripts/fit_variants.py to time alternative builds of the same library)
+_LIB_PATH = os.environ.get("CHICDIFF_B200_LIB") or os.path.join(_HERE, "libchicdiff_b200.so")
 _lib = None
 
 CD_NORM = {"standard": 0, "fullmean": 1, "combined": 2}

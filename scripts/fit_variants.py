@@ -22,7 +22,10 @@ for s in range(d.S):
     e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
 names = ["aggregate", "region_test", "fit_disp", "wald", "grid_refits", "trend_mad", "size_factors"]
 ref = None
-for label, env in [("table log", "1"), ("fdlibm log", "0"), ("table log", "1")]:
+variants = [("table log", "1")] if os.environ.get("CHICDIFF_B200_LIB") else [("table log", "1"), ("fdlibm log", "0"), ("table log", "1")]
+if os.environ.get("CHICDIFF_B200_LIB"):
+    print("library:", os.environ["CHICDIFF_B200_LIB"])
+for label, env in variants:
     os.environ["CHICDIFF_B200_TABLE_LOG"] = env
     for _ in range(2):
         e.aggregate(fetch=False); r = e.region_test(fetch="none")
