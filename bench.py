@@ -178,6 +178,20 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPU cores next to its GPU (NVML's ideal affinity) before any pinned host buffer is
+    allocated, so that the buffers land on that NUMA node and eight ranks' host->device copies do not all cross the
+    socket interconnect.  Best effort: returns the number of cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 class Runner:
     """one rank's context + the timing helpers"""
 
@@ -192,6 +206,7 @@ class Runner:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; chicdiff_b200 has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
+        self.affinity = bind_to_gpu_numa_node(self.local_rank)
         self.e = engine.Engine(self.local_rank)
         if self.world > 1:
             with stdout_to_stderr():
@@ -304,19 +319,23 @@ def run_strong(R, args, d_full):
     ms, _, tm = R.timed(step, args.steps)
     e.aggregate(fetch=False)
     r = e.region_test(fetch="table")
-    # gather the p-values of all shards on rank 0 (rank order = region order)
-    pv_loc = torch.from_numpy(r["pvalue"]).cuda()
     sizes = [int(bounds[k + 1] - bounds[k]) for k in range(R.world)]
-    m = max(sizes)                                  # shards are ragged: pad to the longest
-    pad = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
-    pad[: sizes[R.rank]] = pv_loc
-    padded = [torch.empty(m, dtype=torch.float64, device="cuda") for _ in sizes]
-    dist.all_gather(padded, pad)
-    bufs = [q[:k] for q, k in zip(padded, sizes)]
-    out = None
+
+    def gather_pvalues(res):
+        """p-values of all shards on every rank, in region order (rank order = region order; shards are ragged)"""
+        m = max(sizes)
+        pad = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+        pad[: sizes[R.rank]] = torch.from_numpy(res["pvalue"]).cuda()
+        padded = [torch.empty(m, dtype=torch.float64, device="cuda") for _ in sizes]
+        dist.all_gather(padded, pad)
+        return torch.cat([q[:k] for q, k in zip(padded, sizes)]).cpu().numpy()
+
+    pv = gather_pvalues(r)
+    # the same set on one GPU (rank 0, a context of its own without communicator); its global scalars go to every rank
+    box = [None]
+    e1 = r1 = None
+    one_ms = None
     if R.rank == 0:
-        pv = torch.cat(bufs).cpu().numpy()
-        # the same set on one GPU, on a context of its own (no communicator)
         e1 = R.engine.Engine(R.local_rank)
         e1.set_design(d.X); e1.set_regions(d.row_off)
         for s in range(d.S):
@@ -327,9 +346,19 @@ def run_strong(R, args, d_full):
         e1.aggregate(fetch=False)
         r1 = e1.region_test(fetch="table")
         one_ms = e1.last_timings()[0] + e1.last_timings()[1]
+        box[0] = (r1["theta"], r1["trend_a0"], r1["trend_a1"], r1["varLogDispEsts"], r1["dispPriorVar"])
+    dist.broadcast_object_list(box, src=0)
+    th, a0, a1, vld, pvar = box[0]
+    # second sharded run with the single-GPU run's global scalars: per-region numbers then depend on the region's data only
+    rs = e.region_test(fetch="table", theta_grid=[th], trend=(a0, a1), var_log_disp=vld, disp_prior_var=pvar)
+    pv_shared = gather_pvalues(rs)
+    out = None
+    if R.rank == 0:
         with np.errstate(invalid="ignore", divide="ignore"):
             rel = np.abs(pv - r1["pvalue"]) / np.maximum(np.abs(r1["pvalue"]), 1e-300)
+            rel_s = np.abs(pv_shared - r1["pvalue"]) / np.maximum(np.abs(r1["pvalue"]), 1e-300)
         rel[np.isnan(rel)] = 0.0
+        rel_s[np.isnan(rel_s)] = 0.0
         adj_s = R.engine.results_adjust(r1["baseMean"], r1["maxCooks"], r1["flags"], pv, d.S, int(d.X.shape[1]))
         adj_1 = R.engine.results_adjust(r1["baseMean"], r1["maxCooks"], r1["flags"], r1["pvalue"], d.S, int(d.X.shape[1]))
         with np.errstate(invalid="ignore"):
@@ -338,7 +367,13 @@ def run_strong(R, args, d_full):
                "ms_per_step": ms, "value": d.n / (ms * 1e-3), "unit": UNIT, "regions_per_gpu": sizes,
                "one_gpu_ms_per_step_same_set": one_ms, "speedup_vs_one_gpu": one_ms / ms,
                "stage_ms": stage_dict(tm),
-               "check_vs_single_gpu": {"pvalue_max_rel": float(rel.max()), "regions_beyond_1e-6": int((rel > 1e-6).sum()),
+               "check_vs_single_gpu": {"what": "p-values of the sharded run against a single-GPU run of the same set.  free: each run fits its own "
+                                               "dispersion trend (the sharded sums add up in another order; one region whose line search takes "
+                                               "the other branch of a rounding-level comparison moves the trend by ~1e-6 and with it every far-tail "
+                                               "p-value); shared_scalars: the sharded run repeated with the single-GPU run's trend / MAD / prior, "
+                                               "which leaves only per-region differences (DESIGN.md section 5)",
+                                       "free": {"pvalue_max_rel": float(rel.max()), "regions_beyond_1e-6": int((rel > 1e-6).sum())},
+                                       "shared_scalars": {"pvalue_max_rel": float(rel_s.max()), "regions_beyond_1e-6": int((rel_s > 1e-6).sum())},
                                        "pvalue_checksum_sharded": float(np.nansum(pv)), "pvalue_checksum_single": float(np.nansum(r1["pvalue"])),
                                        "theta_equal": bool(r["theta"] == r1["theta"]),
                                        "significant_calls_identical": same_calls}}
@@ -585,7 +620,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_label(args, d),
                            "regions_total": n_tot, "design_columns": p, "norm": "combined", "theta_grid": 5,
-                           "fits_per_step": 6, "l2": "inputs (%.2f GB per GPU) larger than L2; no flush" % ((N_host.numel() * 4 + FM_host.numel() * 8) / 1e9),
+                           "fits_per_step": 6, "host_cores_bound_to_this_gpu": R.affinity, "l2": "inputs (%.2f GB per GPU) larger than L2; no flush" % ((N_host.numel() * 4 + FM_host.numel() * 8) / 1e9),
                            "parallelism": "regions sharded by bait, %d rank(s); global steps by all-reduce only (trend sums and median "
                                           "histograms: %s; offsets sums, deviances: NCCL); nothing is gathered"
                                           % (world, "inside the kernels over NVLink peer memory" if info["peer_memory_allreduce"] else "single rank")},
