@@ -98,16 +98,20 @@ __device__ __forceinline__ double log_pos(double x)
     return dk * kLogC[0] - ((hfsq - fma(s, hfsq + R, dk * kLogC[1])) - f);
 }
 
-// Table-assisted natural logarithm for the line-search kernel, where the logarithm runs 2.5 times per replicate and
-// evaluation.  The mantissa is reduced multiplicatively with a 128-entry table instead of the division s = f / (2 + f):
-// x = 2^k m, m rc_i = 1 + r with |r| <= 2^-7, log x = k ln2 - log rc_i + log1p(r), log1p by a degree-8 Taylor
-// polynomial.  No reciprocal, 13 FP64 instructions (log_pos: ~25 + the MUFU seed).  rc_i has 20 significant bits, so
-// fma(m, rc_i, -1) is exact up to its single rounding.  The first interval uses rc = 1 (r = m - 1) and the last one is
-// moved to the next binade (r = m/2 - 1), so the result keeps full relative accuracy around x = 1, which
-// log(1 + mu alpha) at small alpha needs.  <= 1.5 ulp for x >= 1, <= 3e-16 max(1, |log x|) below
-// (tests/test_device_math.py).  tab = 128 x {rc, -log rc}: kLogTab copied to shared memory by the kernel (the lanes of
-// a warp index it with unrelated mantissas, which constant memory would serialise).
-alignas(16) static __constant__ double kLogTab[256] = {
+// Table-assisted natural logarithm for the line-search kernel, where the logarithm runs 2 + 1/S times per replicate
+// and evaluation.  The mantissa is reduced multiplicatively with a 512-entry table instead of the division
+// s = f / (2 + f): x = 2^k m, m rc_i = 1 + r with |r| <= 2^-9, log x = k ln2 - log rc_i + log1p(r), log1p by a degree-6
+// Taylor polynomial (the first dropped term, r^7 / 7, is below 1e-17 of the result even where the result is r itself;
+// its two highest coefficients are rounded to 21 bits, which costs 2^-58 relative, so that they are instruction
+// immediates).  No reciprocal, 11 FP64 + 7 integer instructions (log_pos: ~25 FP64 + the MUFU seed).  rc_i has 20
+// significant bits, so fma(m, rc_i, -1) is exact up to its single rounding.  The first interval uses rc = 1 (r = m - 1),
+// the last one rc = 1/2 with lc = ln2 (r = m/2 - 1, exact), so the result keeps its relative accuracy at and above
+// x = 1, which log(1 + mu alpha) at small alpha needs; just below 1 the absolute error is that of ln2 as a double
+// (2.3e-17).  <= 1.5 ulp for x >= 1, <= 3e-16 max(1, |log x|) below (tests/test_device_math.py).
+// tab = kLogTabN x {rc, -log rc}: kLogTab copied to shared memory by the kernel (the lanes of a warp index it with
+// unrelated mantissas, which constant memory would serialise), 16-byte aligned.
+constexpr int kLogTabN = 512;
+alignas(16) static __constant__ double kLogTab[2 * kLogTabN] = {
 #include "log_table.inc"
 };
 
@@ -115,21 +119,15 @@ struct alignas(16) LogTabEntry { double rc, lc; };      // one 16-byte shared-me
 
 __device__ __forceinline__ double log_pos_v2(double x, const double* tab)
 {
-    int hi = __double2hiint(x);
+    const int hi = __double2hiint(x);
     const int lo = __double2loint(x);
-    int k = (hi >> 20) - 1023;
-    hi &= 0x000fffff;
-    const int idx = hi >> 13;                         // top 7 bits of the mantissa
-    const int up = (hi + 0x2000) & 0x100000;          // set iff idx == 127: treat [2 - 1/64, 2) as [1 - 1/128, 1) of the next binade
-    hi |= (up ^ 0x3ff00000);
-    k += (up >> 20);
-    const double m = __hiloint2double(hi, lo);
+    const int k = (hi >> 20) - 1023;
+    const int idx = (hi >> 11) & (kLogTabN - 1);      // top 9 bits of the mantissa
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const LogTabEntry e = reinterpret_cast<const LogTabEntry*>(tab)[idx];      // tab is 16-byte aligned
     const double rc = e.rc, lc = e.lc;
     const double r = fma(m, rc, -1.0);
-    double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
-    q = fma(r, q, -1.0 / 6.0);
-    q = fma(r, q, 1.0 / 5.0);
+    double q = fma(r, -0x1.55555p-3 /* -1/6 */, 0x1.9999ap-3 /* 1/5 */);
     q = fma(r, q, -1.0 / 4.0);
     q = fma(r, q, 1.0 / 3.0);
     q = fma(r, q, -0.5);

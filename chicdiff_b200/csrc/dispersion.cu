@@ -200,7 +200,7 @@ constexpr int kFitDispTripCap = 24;     // first pass: a region still searching 
 static inline size_t fit_disp_smem_doubles(int S, int P, int threads)
 {
     return (size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads +
-           (size_t)S * P + 256;
+           (size_t)S * P + 2 * kLogTabN;
 }
 
 // Two passes.  ~2-3 % of the regions run the full 100 trips while the average is below 10; in a
@@ -215,16 +215,16 @@ template <int P, bool RESUME, bool TABLOG>
 __global__ void __launch_bounds__(kFitDispThreads, CD_FITDISP_MINBLOCKS)
 fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
                 const double* __restrict__ mu_g, const double* __restrict__ start_log,
-                const double* __restrict__ prior_log_mean, BatchScalars prior_sigmasq_g,
+                const double* __restrict__ prior_log_mean, BatchScalars prior_inv_sigmasq_g,
                 double* __restrict__ log_alpha_out, int32_t* __restrict__ iter_out,
                 double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
 {
     extern __shared__ __align__(16) double smem_all[];
-    // layout: logarithm table (256 doubles, 16-byte aligned: one LDS.128 per logarithm), staging columns, prefetch slots,
+    // layout: logarithm table (2 x kLogTabN doubles, 16-byte aligned: one LDS.128 per logarithm), staging columns, prefetch slots,
     // model matrix
     double* tab = smem_all;
-    double* smem = smem_all + 256;
+    double* smem = smem_all + 2 * kLogTabN;
     const int stride = kFitDispThreads;
     double* ys = smem + threadIdx.x;
     double* mus = smem + (size_t)S * stride + threadIdx.x;
@@ -254,7 +254,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double* pf_prior = pf_init + stride;
     double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) tab[k] = kLogTab[k];
+    for (int k = threadIdx.x; k < 2 * kLogTabN; k += blockDim.x) tab[k] = kLogTab[k];
     __syncthreads();
 
     int64_t pending = 0, queued = 0;
@@ -307,8 +307,12 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                         a = a_start;
                         if (use_prior) {
                             prior_mean = *pf_prior;
-                            // n < 2^31 virtual regions: a 32-bit division finds the fit; eval_post multiplies by the reciprocal
-                            prior_sigmasq = 1.0 / prior_sigmasq_g.v[(unsigned)i / (unsigned)n_fit];
+                            // the fit of virtual region i by counting (<= kMaxBatch fits; this path runs with 2-3 of 32
+                            // lanes on almost every trip, so no division of either kind here); eval_post multiplies
+                            // by the reciprocal of the prior variance, which the launcher took
+                            int g = 0;
+                            for (int64_t t = n_fit; t <= i; t += n_fit) g++;
+                            prior_sigmasq = prior_inv_sigmasq_g.v[g];
                         }
                         active = true; fresh = true;
                         iter = 0; iter_accept = 0; kappa = kappa_0;
@@ -341,7 +345,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                     iter = park.iter[w]; iter_accept = park.iter_accept[w];
                     if (use_prior) {
                         prior_mean = prior_log_mean[i];
-                        prior_sigmasq = 1.0 / prior_sigmasq_g.v[(unsigned)i / (unsigned)n_fit];      // eval_post multiplies by the reciprocal
+                        prior_sigmasq = prior_inv_sigmasq_g.v[(unsigned)i / (unsigned)n_fit];      // eval_post multiplies by the reciprocal
                     }
                     for (int j = 0; j < S; j++) {
                         ys[j * stride] = (double)K[(int64_t)j * n + i];
@@ -578,6 +582,8 @@ cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesi
     const int G = S <= 8 ? 8 : (S <= 16 ? 16 : 32);
     const bool tile = (double)n * 0.04 * G <= (double)sms * 1024.0;
     const bool tl = table_log_enabled();
+    BatchScalars prior_inv;                           // 1 / prior variance per fit (IEEE division, as the kernel's own would be)
+    for (int g = 0; g < kMaxBatch; g++) prior_inv.v[g] = 1.0 / prior_sigmasq.v[g];
     // persistent grids: exactly the number of CTAs that are resident at once
 #define CD_LAUNCH_T(P_, TL_)                                                                                   \
     {                                                                                                          \
@@ -589,7 +595,7 @@ cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesi
         const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);                                     \
         const int blocks = (int)(want < resident ? want : resident);                                           \
         fit_disp_kernel<P_, false, TL_><<<blocks, threads, smem, st>>>(n, n_fit, S, des, K, mu, start_log,     \
-            prior_log_mean, prior_sigmasq, log_alpha, iter, initial_lp, last_lp, work_counter, park);          \
+            prior_log_mean, prior_inv, log_alpha, iter, initial_lp, last_lp, work_counter, park);              \
         if (tile) {                                                                                            \
             const int blocks2 = sms * 8;                                                                       \
             if (S <= 8)                                                                                        \
@@ -607,7 +613,7 @@ cudaError_t launch_fit_disp(int64_t n, int64_t n_fit, int S, int p, const CdDesi
             const int64_t want2 = (park.capacity + threads - 1) / threads;                                     \
             const int blocks2 = (int)(want2 < resident ? want2 : resident);                                    \
             fit_disp_kernel<P_, true, TL_><<<blocks2 > 0 ? blocks2 : 1, threads, smem, st>>>(n, n_fit, S, des, K, mu, \
-                start_log, prior_log_mean, prior_sigmasq, log_alpha, iter, initial_lp, last_lp,                \
+                start_log, prior_log_mean, prior_inv, log_alpha, iter, initial_lp, last_lp,                    \
                 work_counter + 1, park);                                                                       \
         }                                                                                                      \
     }

@@ -20,8 +20,12 @@ namespace cd {
 // Formulation (what the per-source-line profile of round 1 led to; profiles/r01_final_fit_disp_source_lines.txt):
 //   * log Gamma and digamma of x = y_j + r come from the shift-10 scheme of common.cuh, but the logarithm of the
 //     rational's denominator is not taken per replicate: with q_j = den_j / den_r (>= 1, the ratio against the rational
-//     of r = 1/alpha alone) the sum over replicates of [log den_j - log den_r] is log(q_a q_b) per PAIR of replicates:
-//     2.5 instead of 3 logarithms per replicate, and a zero count still contributes (almost) exactly zero;
+//     of r = 1/alpha alone) the sum over replicates of [log den_j - log den_r] is the logarithm of the PRODUCT of the
+//     q_j, taken once per evaluation (earlier only if the running product passes 2^511; one q_j is below 2e89 for any
+//     32-bit count and alpha <= 32): 2 + 1/S instead of 3 logarithms per replicate, and a zero count still contributes
+//     (almost) exactly zero;
+//   * the four highest coefficients of the Stirling and of the digamma series are rounded to 21 bits (they multiply
+//     f^3 <= 1e-6 and higher: <= 3e-17 absolute), which makes them instruction immediates instead of constant loads;
 //   * p = 1 and p = 2 (every fit of the default pipeline) use the closed-form determinant and inverse of X'WX with
 //     one Newton reciprocal and one logarithm; p = 3, 4 keep the packed Cholesky;
 //   * TABLOG = true takes every logarithm with log_pos_v2 (table in shared memory, no reciprocal); false with log_pos.
@@ -50,13 +54,18 @@ __device__ __forceinline__ GammaParts gamma_parts(double x, const double* tab)
     const double xi = rcp_pos(xs);
     const double f = xi * xi;
     const double lxs = post_log<TABLOG>(xs, tab);
-    double t = kLgamC[6];
+    // kLgamC[6..3] and kDigamC[6..3] with the low word zero
+    double t = fma(f, 0x1.a41a4p-8, -0x1.f6ab1p-10);
+    t = fma(f, t, 0x1.b951ep-11);
+    t = fma(f, t, -0x1.38138p-11);
 #pragma unroll
-    for (int k = 5; k >= 0; k--) t = fma(f, t, kLgamC[k]);
+    for (int k = 2; k >= 0; k--) t = fma(f, t, kLgamC[k]);
     g.st = ((xs - 0.5) * lxs - xs) + xi * t;
-    double u = kDigamC[6];
+    double u = fma(f, -0x1.55555p-4, 0x1.5995ap-6);
+    u = fma(f, u, -0x1.f07c2p-8);
+    u = fma(f, u, 0x1.11111p-8);
 #pragma unroll
-    for (int k = 5; k >= 0; k--) u = fma(f, u, kDigamC[k]);
+    for (int k = 2; k >= 0; k--) u = fma(f, u, kDigamC[k]);
     g.dgs = (lxs - 0.5 * xi) + f * u;
     g.num = num; g.den = den;
     return g;
@@ -103,7 +112,7 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
         const double l1 = post_log<TABLOG>(1.0 + ma, tab);
         const GammaParts g = gamma_parts<TABLOG>(yj + r, tab);
         qprod *= g.den * inv_den_r;                       // den_j / den_r >= 1
-        if (j & 1) { ll -= post_log<TABLOG>(qprod, tab); qprod = 1.0; }      // one logarithm per pair of replicates
+        if (__double2hiint(qprod) > 0x5fe00000) { ll -= post_log<TABLOG>(qprod, tab); qprod = 1.0; }      // > 2^511: rare
         // mu + r = r (1 + mu alpha): log(mu + r) = log r + log(1 + mu alpha), 1/(mu + r) = alpha / (1 + mu alpha)
         // for a zero count g.st - gr.st and dgr - dg are exactly zero (same instruction sequence, same input)
         ll += ((g.st - gr.st) - yj * (log_r + l1)) - r * l1;
@@ -112,7 +121,7 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
             ds += ((dgr - dg) + (l1 - ma * ropm)) + yj * (alpha * ropm);
         }
     }
-    if (S & 1) ll -= post_log<TABLOG>(qprod, tab);
+    ll -= post_log<TABLOG>(qprod, tab);                  // one logarithm for the gamma rationals of all replicates
     double cr, dcr = 0.0;
     if (P == 1) {
         const double b = B.v[0];
