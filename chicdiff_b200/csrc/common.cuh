@@ -103,7 +103,7 @@ __device__ __forceinline__ double log_pos(double x)
 // s = f / (2 + f): x = 2^k m, m rc_i = 1 + r with |r| <= 2^-9, log x = k ln2 - log rc_i + log1p(r), log1p by a degree-6
 // Taylor polynomial (the first dropped term, r^7 / 7, is below 1e-17 of the result even where the result is r itself;
 // its two highest coefficients are rounded to 21 bits, which costs 2^-58 relative, so that they are instruction
-// immediates).  No reciprocal, 11 FP64 + 7 integer instructions (log_pos: ~25 FP64 + the MUFU seed).  rc_i has 20
+// immediates).  No reciprocal, 11 FP64 + 6 integer instructions + the load (log_pos: ~25 FP64 + the MUFU seed).  rc_i has 20
 // significant bits, so fma(m, rc_i, -1) is exact up to its single rounding.  The first interval uses rc = 1 (r = m - 1),
 // the last one rc = 1/2 with lc = ln2 (r = m/2 - 1, exact), so the result keeps its relative accuracy at and above
 // x = 1, which log(1 + mu alpha) at small alpha needs; just below 1 the absolute error is that of ln2 as a double
@@ -117,16 +117,32 @@ alignas(16) static __constant__ double kLogTab[2 * kLogTabN] = {
 
 struct alignas(16) LogTabEntry { double rc, lc; };      // one 16-byte shared-memory load per logarithm
 
-__device__ __forceinline__ double log_pos_v2(double x, const double* tab)
+// The table as the device code names it: its 32-bit shared-memory address (log_tab_handle), so that the look-up is a
+// single LDS.128 [offset + base] -- through a generic pointer the compiler rebuilds the shared window's base on the way.
+// The host build of the accuracy tests uses the pointer.
+#ifdef __CUDA_ARCH__
+typedef unsigned LogTab;
+__device__ __forceinline__ LogTab log_tab_handle(const double* tab_in_shared) { return (unsigned)__cvta_generic_to_shared(tab_in_shared); }
+#else
+typedef const double* LogTab;
+__device__ __forceinline__ LogTab log_tab_handle(const double* tab) { return tab; }
+#endif
+
+__device__ __forceinline__ double log_pos_v2(double x, LogTab tab)
 {
     const int hi = __double2hiint(x);
-    const int lo = __double2loint(x);
     const int k = (hi >> 20) - 1023;
-    const int idx = (hi >> 11) & (kLogTabN - 1);      // top 9 bits of the mantissa
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-    const LogTabEntry e = reinterpret_cast<const LogTabEntry*>(tab)[idx];      // tab is 16-byte aligned
-    const double rc = e.rc, lc = e.lc;
-    const double r = fma(m, rc, -1.0);
+    LogTabEntry e;
+#ifdef __CUDA_ARCH__
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.rc), "=d"(e.lc) : "r"(tab + ((unsigned)(hi & ((kLogTabN - 1) << 11)) >> 7)));
+#else
+    e = reinterpret_cast<const LogTabEntry*>(tab)[(hi >> 11) & (kLogTabN - 1)];      // top 9 bits of the mantissa
+#endif
+    // m rc = x (2^-k rc): the exponent of x is taken off rc's (two integer instructions on rc's high word; rc's low
+    // word is zero) instead of building m.  Needs 2^-1020 < x < 2^1021, far beyond what the posterior produces.
+    const double rcs = __hiloint2double(__double2hiint(e.rc) - (hi & 0x7ff00000) + 0x3ff00000, __double2loint(e.rc));
+    const double lc = e.lc;
+    const double r = fma(x, rcs, -1.0);
     double q = fma(r, -0x1.55555p-3 /* -1/6 */, 0x1.9999ap-3 /* 1/5 */);
     q = fma(r, q, -1.0 / 4.0);
     q = fma(r, q, 1.0 / 3.0);
@@ -135,6 +151,22 @@ __device__ __forceinline__ double log_pos_v2(double x, const double* tab)
     const double t = fma(dk, kLogC[0], lc);           // k ln2_hi is exact (ln2_hi has 32 trailing zero bits)
     const double u = fma(r * r, q, dk * kLogC[1]);
     return t + (r + u);
+}
+
+// 1/b for the posterior: the same seed and ONE cubic step, y0 (1 + e + e^2) = (1 - e^3) / b with e = 1 - b y0: three
+// DFMAs instead of rcp_pos's four; |e| <= 2^-19 (the seed has ~20 bits) leaves 2^-57 plus the final rounding (<= 1 ulp,
+// not always correctly rounded, which nothing in the posterior needs)
+__device__ __forceinline__ double rcp_fast(double b)
+{
+    double r;
+#ifdef __CUDA_ARCH__
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#else
+    r = (1.0 / b) * (1.0 + 0x1p-20);   // host build of the accuracy tests: a seed at the low end of the quality assumed
+#endif
+    const double e = fma(-b, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 }
 
 // log Gamma(x) - 0.5 log(2 pi) and digamma(x) for x > 0 in one go, same instruction sequence for every

@@ -1272,12 +1272,13 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     BatchScalars th{};
     for (int g = 0; g < G; g++) th.v[g] = theta[g];
     CD_LAUNCHN(ctx, 1, launch_norm_factors(n, S, G, ctx->FM.p, sf_dev, mode, th, ctx->nf.p, ctx->K.p, G > 1 ? ctx->Kb.p : nullptr, st));
-    CD_LAUNCHN(ctx, 1, launch_base_stats(nv, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, st));
+    CD_LAUNCHN(ctx, 1, launch_base_stats(nv, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags,
+                                         des.linear_mu ? ctx->mu.p : nullptr, st));
     CD_LAUNCHN(ctx, 2, launch_masked_colsums(n, G, S, ctx->nf.p, flags, ctx->partial.p, sums_dev, st));
     CD_COMM(ctx, ctx->comm.allreduce_sum(sums_dev, (size_t)G * (S + 1), st));
     CD_LAUNCHN(ctx, 1, launch_xim(G, S, sums_dev, xim_dev, st));
-    CD_LAUNCHN(ctx, 1, launch_gene_init(nv, n, S, des_dev, K, ctx->nf.p, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev,
-                                        ctx->alpha_init.p, ctx->start_log.p, ctx->mu.p, st));
+    CD_LAUNCHN(ctx, 1, launch_gene_init(nv, n, S, baseMean, ctx->baseVar.p, ctx->rough.p, flags, xim_dev, ctx->alpha_init.p,
+                                        ctx->start_log.p, st));
     if (!des.linear_mu) {
         // mu from an NB GLM fitted with the rough dispersion (fitNbinomGLMs(alpha_hat = alpha_init)$mu)
         CD_LAUNCHN(ctx, 3, launch_wald(nv, S, p, des_dev, K, ctx->nf.p, ctx->alpha_init.p, flags, ctx->wald_ws, nullptr, nullptr,

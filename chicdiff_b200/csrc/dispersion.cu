@@ -53,30 +53,26 @@ norm_factors_kernel(int64_t n, int S, int G, const double* __restrict__ FMagg, c
     double acc = 0.0;
     for (int s = 0; s < S; s++) acc += log(FMagg[(int64_t)s * n + i]);
     const double gm = exp(acc / S);
+    double m3[CD_MAXS];                          // the scaling factors, taken once (every fit of the batch uses them)
     bool anyna = false;
     for (int s = 0; s < S; s++) {
-        const double m3 = FMagg[(int64_t)s * n + i] / gm;
-        anyna = anyna || isnan(m3);
+        m3[s] = FMagg[(int64_t)s * n + i] / gm;
+        anyna = anyna || isnan(m3[s]);
     }
+    if (anyna)
+        for (int s = 0; s < S; s++) m3[s] = sf[s];
     if (mode == 1) {
-        for (int s = 0; s < S; s++) {
-            const double v = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
-            for (int g = 0; g < G; g++) nf[(int64_t)s * nv + (int64_t)g * n + i] = v;
-        }
+        for (int s = 0; s < S; s++)
+            for (int g = 0; g < G; g++) nf[(int64_t)s * nv + (int64_t)g * n + i] = m3[s];
         return;
     }
     for (int g = 0; g < G; g++) {
         const double th = theta.v[g];
         double acc2 = 0.0;
-        for (int s = 0; s < S; s++) {
-            const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
-            acc2 += log(m3 * (1.0 - th) + sf[s] * th);
-        }
+        for (int s = 0; s < S; s++) acc2 += log(m3[s] * (1.0 - th) + sf[s] * th);
         const double g2 = exp(acc2 / S);
-        for (int s = 0; s < S; s++) {
-            const double m3 = anyna ? sf[s] : FMagg[(int64_t)s * n + i] / gm;
-            nf[(int64_t)s * nv + (int64_t)g * n + i] = (m3 * (1.0 - th) + sf[s] * th) / g2;
-        }
+        for (int s = 0; s < S; s++)
+            nf[(int64_t)s * nv + (int64_t)g * n + i] = (m3[s] * (1.0 - th) + sf[s] * th) / g2;
     }
 }
 
@@ -89,12 +85,13 @@ cudaError_t launch_norm_factors(int64_t n, int S, int G, const double* FMagg, co
 }
 
 // ---------------------------------------------------------------------------------------
-// base statistics, linear mu, rough dispersion
+// base statistics, rough dispersion, and the linear-model means mu = max(hat q * nf, minmu) (the hat products serve
+// both; mu may be null: the caller fits it by IRLS then)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 base_stats_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
                   const double* __restrict__ nf, double* __restrict__ baseMean, double* __restrict__ baseVar,
-                  double* __restrict__ rough, uint8_t* __restrict__ flags)
+                  double* __restrict__ rough, uint8_t* __restrict__ flags, double* __restrict__ mu)
 {
     __shared__ double hat[CD_MAXS * CD_MAXS];
     for (int k = threadIdx.x; k < S * S; k += blockDim.x) hat[k] = des->hat[k];
@@ -124,35 +121,30 @@ base_stats_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int3
         for (int b = 0; b < S; b++) mul += hat[a * S + b] * q[b];
         const double mm = fmax(1.0, mul);
         est += ((q[a] - mm) * (q[a] - mm) - mm) / (mm * mm);
+        if (mu) mu[(int64_t)a * n + i] = (tot == 0) ? NAN : fmax(mul * nf[(int64_t)a * n + i], kMinMu);
     }
     rough[i] = fmax(est / (S - p), 0.0);
 }
 
 cudaError_t launch_base_stats(int64_t n, int S, const CdDesign* des, const int32_t* K, const double* nf, double* baseMean,
-                              double* baseVar, double* rough, uint8_t* flags, cudaStream_t st)
+                              double* baseVar, double* rough, uint8_t* flags, double* mu, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    base_stats_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, des, K, nf, baseMean, baseVar, rough, flags);
+    base_stats_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, S, des, K, nf, baseMean, baseVar, rough, flags, mu);
     return cudaGetLastError();
 }
 
-// alpha_init = clamp(min(rough, moments)); mu = linearModelMu(q) * nf floored at minmu.  xim_dev[g] per fit.
+// alpha_init = clamp(min(rough, moments)) and its logarithm, where the gene-wise line search starts.  xim_dev[g] per fit.
 __global__ void __launch_bounds__(256)
-gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ des, const int32_t* __restrict__ K,
-                 const double* __restrict__ nf, const double* __restrict__ baseMean, const double* __restrict__ baseVar,
+gene_init_kernel(int64_t n, int64_t n_fit, int S, const double* __restrict__ baseMean, const double* __restrict__ baseVar,
                  const double* __restrict__ rough, const uint8_t* __restrict__ flags,
-                 const double* __restrict__ xim_dev, double* __restrict__ alpha_init, double* __restrict__ start_log,
-                 double* __restrict__ mu)
+                 const double* __restrict__ xim_dev, double* __restrict__ alpha_init, double* __restrict__ start_log)
 {
-    __shared__ double hat[CD_MAXS * CD_MAXS];
-    for (int k = threadIdx.x; k < S * S; k += blockDim.x) hat[k] = des->hat[k];
-    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) {
         alpha_init[i] = NAN;
         start_log[i] = NAN;                      // the line search recognises an all-zero region by this
-        if (mu) for (int j = 0; j < S; j++) mu[(int64_t)j * n + i] = NAN;
         return;
     }
     const double xim = xim_dev[i / n_fit];
@@ -161,24 +153,16 @@ gene_init_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ d
     const double maxDisp = fmax(10.0, (double)S);
     const double a0 = fmin(fmax(kMinDisp, fmin(rough[i], moments)), maxDisp);
     alpha_init[i] = a0;
-    start_log[i] = log_pos(a0);                  // where the gene-wise line search starts (taken here, off its refill path)
-    if (!mu) return;
-    double q[CD_MAXS];
-    for (int j = 0; j < S; j++) q[j] = (double)K[(int64_t)j * n + i] / nf[(int64_t)j * n + i];
-    for (int a = 0; a < S; a++) {
-        double mul = 0.0;
-        for (int b = 0; b < S; b++) mul += hat[a * S + b] * q[b];
-        mu[(int64_t)a * n + i] = fmax(mul * nf[(int64_t)a * n + i], kMinMu);
-    }
+    start_log[i] = log_pos(a0);                  // taken here, off the line search's refill path
 }
 
-cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
-                             const double* baseMean, const double* baseVar, const double* rough, const uint8_t* flags,
-                             const double* xim_dev, double* alpha_init, double* start_log, double* mu, cudaStream_t st)
+cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const double* baseMean, const double* baseVar,
+                             const double* rough, const uint8_t* flags, const double* xim_dev, double* alpha_init,
+                             double* start_log, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, S, des, K, nf, baseMean, baseVar, rough, flags,
-                                                       xim_dev, alpha_init, start_log, mu);
+    gene_init_kernel<<<blocks_for(n, 256), 256, 0, st>>>(n, n_fit, S, baseMean, baseVar, rough, flags, xim_dev, alpha_init,
+                                                       start_log);
     return cudaGetLastError();
 }
 
@@ -195,12 +179,12 @@ cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* de
 constexpr int kFitDispThreads = 128;
 constexpr int kFitDispTripCap = 24;     // first pass: a region still searching after this many trips is parked
 
-// shared memory of the line-search kernels, in doubles: two staging columns and the prefetch slot per lane, the model
-// matrix and the logarithm table
+// dynamic shared memory of the line-search kernels, in doubles: two staging columns and the prefetch slot per lane and
+// the model matrix (the logarithm table is a static array: its address is an instruction immediate)
 static inline size_t fit_disp_smem_doubles(int S, int P, int threads)
 {
     return (size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads +
-           (size_t)S * P + 2 * kLogTabN;
+           (size_t)S * P;
 }
 
 // Two passes.  ~2-3 % of the regions run the full 100 trips while the average is below 10; in a
@@ -220,11 +204,9 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                 double* __restrict__ initial_lp_out, double* __restrict__ last_lp_out,
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
 {
-    extern __shared__ __align__(16) double smem_all[];
-    // layout: logarithm table (2 x kLogTabN doubles, 16-byte aligned: one LDS.128 per logarithm), staging columns, prefetch slots,
-    // model matrix
-    double* tab = smem_all;
-    double* smem = smem_all + 2 * kLogTabN;
+    extern __shared__ __align__(16) double smem[];
+    // logarithm table (16-byte aligned: one LDS.128 per logarithm); dynamic part: staging columns, prefetch slots, model matrix
+    __shared__ __align__(16) double tab[TABLOG ? 2 * kLogTabN : 2];
     const int stride = kFitDispThreads;
     double* ys = smem + threadIdx.x;
     double* mus = smem + (size_t)S * stride + threadIdx.x;
@@ -254,7 +236,9 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double* pf_prior = pf_init + stride;
     double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
-    for (int k = threadIdx.x; k < 2 * kLogTabN; k += blockDim.x) tab[k] = kLogTab[k];
+    if (TABLOG)
+        for (int k = threadIdx.x; k < 2 * kLogTabN; k += blockDim.x) tab[k] = kLogTab[k];
+    const LogTab tabh = log_tab_handle(tab);
     __syncthreads();
 
     int64_t pending = 0, queued = 0;
@@ -375,7 +359,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
         // fitDisp evaluates the posterior at the proposal twice (Armijo test, then "lpnew") and, when
         // the proposal is accepted, the derivative at the same point; the arguments are the same
         // double, so one fused evaluation serves all three
-        if (active) eval_post<P, true, TABLOG>(x, ys, mus, stride, S, Xs, tab, prior_mean, prior_sigmasq, use_prior, lpx, dlpx);
+        if (active) eval_post<P, true, TABLOG>(x, ys, mus, stride, S, Xs, tabh, prior_mean, prior_sigmasq, use_prior, lpx, dlpx);
         __syncwarp();
         // ---- decision ----
         bool finished = false;
@@ -722,7 +706,7 @@ fit_disp_grid_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict
     __shared__ double Xs[CD_MAXS * CD_MAXP];
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
     __syncthreads();
-    const double* tab = nullptr;                 // the grid evaluations use log_pos (no table)
+    const LogTab tab = 0;                        // the grid evaluations use log_pos (no table)
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;

@@ -142,11 +142,11 @@ cudaError_t res_launch_bh(int64_t n, const unsigned long long* counts, const dou
 // ---- stage 4a: gene-wise dispersion (n = virtual regions of the batch, n_fit = regions per fit) --------------
 cudaError_t launch_base_stats(int64_t n, int S, const CdDesign* des, const int32_t* K, const double* nf,
                               double* baseMean, double* baseVar, double* rough, uint8_t* flags,
-                              cudaStream_t st);
-cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const CdDesign* des, const int32_t* K, const double* nf,
-                             const double* baseMean, const double* baseVar, const double* rough,
-                             const uint8_t* flags, const double* xim_dev /*per fit*/, double* alpha_init,
-                             double* start_log /*log(alpha_init), NaN = all-zero region*/, double* mu, cudaStream_t st);
+                              double* mu /*linear-model means, or null*/, cudaStream_t st);
+cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const double* baseMean, const double* baseVar,
+                             const double* rough, const uint8_t* flags, const double* xim_dev /*per fit*/,
+                             double* alpha_init, double* start_log /*log(alpha_init), NaN = all-zero region*/,
+                             cudaStream_t st);
 // scalar search state of regions parked by the first line-search pass (see dispersion.cu)
 struct FitDispPark {
     int64_t capacity;

@@ -33,25 +33,31 @@ namespace cd {
 struct GammaParts { double st, dgs, num, den; };      // st: Stirling part of lgamma; dgs: series part of digamma
 
 template <bool TABLOG>
-__device__ __forceinline__ double post_log(double x, const double* tab)
+__device__ __forceinline__ double post_log(double x, LogTab tab)
 {
     return TABLOG ? log_pos_v2(x, tab) : log_pos(x);
 }
 
 // the pieces of lgamma_digamma_pos, with the rational's denominator handed back instead of logged
 template <bool TABLOG>
-__device__ __forceinline__ GammaParts gamma_parts(double x, const double* tab)
+__device__ __forceinline__ GammaParts gamma_parts(double x, LogTab tab)
 {
     GammaParts g;
-    double num = 1.0, den = x;
-#pragma unroll
-    for (int k = 1; k < 10; k++) {
-        const double t = x + (double)k;
-        num = fma(num, t, den);
-        den *= t;
+    // den = x (x+1) ... (x+9) and num = d den / dx (num / den = sum of 1 / (x+k)) through u = x (x+9):
+    // (x+k)(x+9-k) = u + k (9-k), so den = u (u+8) (u+14) (u+18) (u+20), and num = d den / du (2x + 9):
+    // 16 FP64 instructions instead of the 27 of the factor-by-factor recurrence, all terms positive
+    const double u9 = x * (x + 9.0);
+    double den = u9, num = 1.0;
+    {
+        const double t8 = u9 + 8.0, t14 = u9 + 14.0, t18 = u9 + 18.0, t20 = u9 + 20.0;
+        num = t8 + den;           den *= t8;
+        num = fma(num, t14, den); den *= t14;
+        num = fma(num, t18, den); den *= t18;
+        num = fma(num, t20, den); den *= t20;
     }
+    num *= fma(x, 2.0, 9.0);
     const double xs = x + 10.0;
-    const double xi = rcp_pos(xs);
+    const double xi = rcp_fast(xs);
     const double f = xi * xi;
     const double lxs = post_log<TABLOG>(xs, tab);
     // kLgamC[6..3] and kDigamC[6..3] with the low word zero
@@ -74,15 +80,15 @@ __device__ __forceinline__ GammaParts gamma_parts(double x, const double* tab)
 // prior_inv_sigmasq = 1 / prior variance of log(alpha) (the caller takes the reciprocal once per region)
 template <int P, bool WANT_D, bool TABLOG>
 __device__ __forceinline__ void eval_post(double a, const double* ys, const double* mus, int stride, int S,
-                                          const double* Xd, const double* tab,
+                                          const double* Xd, LogTab tab,
                                           double prior_mean, double prior_inv_sigmasq, bool use_prior,
                                           double& lp_out, double& dlp_out)
 {
     const double alpha = exp(a);
-    const double r = rcp_pos(alpha);
+    const double r = rcp_fast(alpha);
     const double log_r = -a;                            // log(1/alpha)
     const GammaParts gr = gamma_parts<TABLOG>(r, tab);
-    const double inv_den_r = rcp_pos(gr.den);
+    const double inv_den_r = rcp_fast(gr.den);
     const double dgr = gr.dgs - gr.num * inv_den_r;
     Sym<P> B, dB;
 #pragma unroll
@@ -93,7 +99,7 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
     for (int j = 0; j < S; j++) {
         const double yj = ys[j * stride], muj = mus[j * stride];
         const double ma = muj * alpha;
-        const double ropm = rcp_pos(1.0 + ma);
+        const double ropm = rcp_fast(1.0 + ma);
         const double w = muj * ropm;                    // = 1 / (1/mu + alpha)
         const double dw = -w * w;
         if (P == 1) {
@@ -117,7 +123,7 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
         // for a zero count g.st - gr.st and dgr - dg are exactly zero (same instruction sequence, same input)
         ll += ((g.st - gr.st) - yj * (log_r + l1)) - r * l1;
         if (WANT_D) {
-            const double dg = g.dgs - g.num * rcp_pos(g.den);
+            const double dg = g.dgs - g.num * rcp_fast(g.den);
             ds += ((dgr - dg) + (l1 - ma * ropm)) + yj * (alpha * ropm);
         }
     }
@@ -126,14 +132,14 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
     if (P == 1) {
         const double b = B.v[0];
         cr = -0.5 * ((b > 0.0) ? post_log<TABLOG>(b, tab) : NAN);
-        if (WANT_D) dcr = -0.5 * (dB.v[0] * rcp_pos(b));
+        if (WANT_D) dcr = -0.5 * (dB.v[0] * rcp_fast(b));
     } else if (P == 2) {
         const double det = B.v[0] * B.v[2] - B.v[1] * B.v[1];
         const bool ok = (B.v[0] > 0.0) && (det > 0.0);
         cr = -0.5 * (ok ? post_log<TABLOG>(det, tab) : NAN);
         if (WANT_D) {
             // tr(B^-1 dB) = (B11 dB00 - 2 B10 dB10 + B00 dB11) / det
-            const double tr = (B.v[2] * dB.v[0] - 2.0 * B.v[1] * dB.v[1] + B.v[0] * dB.v[2]) * rcp_pos(det);
+            const double tr = (B.v[2] * dB.v[0] - 2.0 * B.v[1] * dB.v[1] + B.v[0] * dB.v[2]) * rcp_fast(det);
             dcr = -0.5 * tr;
         }
     } else {
