@@ -258,7 +258,7 @@ def fp64_roofline(e, d, fit_ms, fp64_peak, flop_tab, flop_src):
            "evaluations_per_step": int(evals), "replicates": d.S, "kernel_ms_per_step": fit_ms,
            "achieved": None, "frac": None, "traffic": None, "flop_source": flop_src}
     if flop_tab is not None and flop_tab.get("S") == d.S:
-        flop = 0.0
+        flop = inst = 0.0
         ok = True
         for ev, p, _ in calls:
             ent = flop_tab["per_design_columns"].get(str(p))
@@ -266,11 +266,17 @@ def fp64_roofline(e, d, fit_ms, fp64_peak, flop_tab, flop_src):
                 ok = False
                 break
             flop += ev * ent["flop_per_evaluation"]
+            inst += ev * ent.get("fp64_instructions_per_evaluation", float("nan"))
         if ok and fit_ms > 0:
             out["achieved"] = flop / (fit_ms * 1e-3) / 1e12
             out["frac"] = out["achieved"] / fp64_peak if fp64_peak else None
             out["algorithmic_flop_per_step"] = flop
             out["flop_per_evaluation"] = {p: v["flop_per_evaluation"] for p, v in flop_tab["per_design_columns"].items()}
+            if fp64_peak and inst == inst:
+                # DFMA, DMUL and DADD all take one slot of the FP64 pipe: its utilisation is what bounds the kernel; the
+                # flop fraction above counts a DADD or DMUL as half a DFMA
+                out["fp64_pipe_frac"] = inst / (fit_ms * 1e-3) / (fp64_peak * 1e12 / 2)
+                out["fma_share_of_fp64_instructions"] = (flop - inst) / inst
     return out
 
 

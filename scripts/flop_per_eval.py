@@ -47,17 +47,22 @@ def main():
            "S": counts["S"], "per_design_columns": {}, "calls": []}
     agg = {}
     for k, c in enumerate(calls):
-        fl = ns = 0.0
+        fl = ns = inst = 0.0
         for nm, m in launches[2 * k: 2 * k + 2]:
-            fl += 2 * m["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"] + m["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] + \
-                m["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+            fma = m["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]
+            other = m["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"] + m["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"]
+            fl += 2 * fma + other
+            inst += fma + other
             ns += m.get("gpu__time_duration.sum", 0.0)
         out["calls"].append({"p": c["p"], "regions": c["regions"], "evaluations": c["evaluations"], "fp64_flop": fl,
-                             "flop_per_evaluation": fl / c["evaluations"], "ncu_ns": ns})
-        a = agg.setdefault(str(c["p"]), [0.0, 0])
-        a[0] += fl; a[1] += c["evaluations"]
-    for p, (fl, ev) in agg.items():
-        out["per_design_columns"][p] = {"flop_per_evaluation": fl / ev, "flop_per_replicate_evaluation": fl / ev / counts["S"]}
+                             "fp64_instructions": inst, "flop_per_evaluation": fl / c["evaluations"], "ncu_ns": ns})
+        a = agg.setdefault(str(c["p"]), [0.0, 0, 0.0])
+        a[0] += fl; a[1] += c["evaluations"]; a[2] += inst
+    # fp64_instructions: DFMA + DMUL + DADD thread instructions; every one of them takes one slot of the FP64 pipe, so
+    # instructions / (peak flop/s / 2) is the pipe's utilisation, which the flop fraction understates when the mix is not all FMA
+    for p, (fl, ev, inst) in agg.items():
+        out["per_design_columns"][p] = {"flop_per_evaluation": fl / ev, "flop_per_replicate_evaluation": fl / ev / counts["S"],
+                                        "fp64_instructions_per_evaluation": inst / ev}
     json.dump(out, open(sys.argv[3], "w"), indent=1)
     print(json.dumps(out["per_design_columns"]))
 
