@@ -115,6 +115,19 @@ alignas(16) static __constant__ double kLogTab[2 * kLogTabN] = {
 #include "log_table.inc"
 };
 
+// the same table in global memory: what the kernels copy to shared memory (coalesced; a constant-memory read with a
+// different index per lane is replayed 32 times)
+#ifdef __CUDACC__
+alignas(16) static __device__ const double kLogTabGlobal[2 * kLogTabN] = {
+#include "log_table.inc"
+};
+// cooperative copy by the whole CTA; the caller synchronises
+__device__ __forceinline__ void load_log_table(double* tab_shared)
+{
+    for (int k = threadIdx.x; k < 2 * kLogTabN; k += blockDim.x) tab_shared[k] = kLogTabGlobal[k];
+}
+#endif
+
 struct alignas(16) LogTabEntry { double rc, lc; };      // one 16-byte shared-memory load per logarithm
 
 // The table as the device code names it: its 32-bit shared-memory address (log_tab_handle), so that the look-up is a

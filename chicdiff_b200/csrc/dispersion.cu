@@ -236,8 +236,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double* pf_prior = pf_init + stride;
     double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
-    if (TABLOG)
-        for (int k = threadIdx.x; k < 2 * kLogTabN; k += blockDim.x) tab[k] = kLogTab[k];
+    if (TABLOG) load_log_table(tab);
     const LogTab tabh = log_tab_handle(tab);
     __syncthreads();
 

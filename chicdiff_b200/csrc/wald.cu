@@ -25,6 +25,7 @@
 // size = 1/alpha is huge, where the lgamma difference cancels: rows with 1/alpha > 1e6 take the
 // saddle-point path (dnbinom_mu_log in common.cuh).
 #include "kernels.h"
+#include "posterior.cuh"
 
 namespace cd {
 
@@ -57,14 +58,16 @@ constexpr double kHugeSize = 1e6;
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
 
-// mu-dependent part of the log density
-__device__ __forceinline__ double nb_logdens(double y, double size, double alpha, double mu, double c)
+// mu-dependent part of the log density; the two logarithms by the table scheme of the line search (common.cuh,
+// log_pos_v2: the kernels below copy the table to shared memory like fit_disp_kernel does)
+__device__ __forceinline__ double nb_logdens(double y, double size, double alpha, double mu, double c, LogTab tab)
 {
     if (size > kHugeSize) return dnbinom_mu_log(y, size, mu);
-    const double l1 = log_pos(1.0 + mu * alpha);
-    const double l2 = log_pos(mu * rcp_pos(size + mu));
+    const double l1 = log_pos_v2(1.0 + mu * alpha, tab);
+    const double l2 = log_pos_v2(mu * rcp_fast(size + mu), tab);
     return (c - size * l1) + y * l2;
 }
+
 
 // ---------------------------------------------------------------------------------------
 // prep
@@ -103,7 +106,7 @@ wald_prep_kernel(int64_t n, int S, int P, const CdDesign* __restrict__ des, cons
 template <int P>
 __device__ __forceinline__ void irls_pass(const double* beta, double alpha, double size, int S, int stride,
                                           const double* ys, const double* nfs, const double* cs, const double* Xs,
-                                          Sym<P>& A, double* b, double& dev)
+                                          LogTab tab, Sym<P>& A, double* b, double& dev)
 {
 #pragma unroll
     for (int k = 0; k < P * (P + 1) / 2; k++) A.v[k] = 0.0;
@@ -119,7 +122,7 @@ __device__ __forceinline__ void irls_pass(const double* beta, double alpha, doub
         double mu = nfj * exp(eta);
         double lmn = eta;
         if (!(mu >= kMinMu)) { mu = kMinMu; lmn = log_pos(kMinMu * rcp_pos(nfj)); }     // fmax(mu, minmu)
-        ll += nb_logdens(yj, size, alpha, mu, cs[j * stride]);
+        ll += nb_logdens(yj, size, alpha, mu, cs[j * stride], tab);
         const double w = mu * rcp_pos(1.0 + alpha * mu);
         const double z = lmn + (yj - mu) * rcp_pos(mu);
 #pragma unroll
@@ -147,8 +150,11 @@ wald_irls_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32
     double* nfs = smem + (size_t)S * stride + threadIdx.x;
     double* cs = smem + (size_t)2 * S * stride + threadIdx.x;
     double* Xs = smem + (size_t)3 * S * stride;
+    __shared__ __align__(16) double tab[2 * kLogTabN];
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
+    load_log_table(tab);
     __syncthreads();
+    const LogTab tabh = log_tab_handle(tab);
     const unsigned lane = threadIdx.x & 31u;
     const double lambda = 1e-6 / (kLn2 * kLn2);
 
@@ -218,7 +224,7 @@ wald_irls_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int32
         __syncwarp();
         // ---- one sweep over the replicates at the current coefficients ----
         double dev = 0.0;
-        if (active && !finished) irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, Xs, A, rhs, dev);
+        if (active && !finished) irls_pass<P>(beta, alpha, size, S, stride, ys, nfs, cs, Xs, tabh, A, rhs, dev);
         __syncwarp();
         if (active && !finished) {
             if (fresh) {
@@ -272,9 +278,12 @@ wald_final_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int3
 {
     __shared__ double Xs[CD_MAXS * CD_MAXP];
     __shared__ int cell[CD_MAXS], cell_size[CD_MAXS];
+    __shared__ __align__(16) double tab[2 * kLogTabN];
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
     for (int k = threadIdx.x; k < S; k += blockDim.x) { cell[k] = des->cell[k]; cell_size[k] = des->cell_size[k]; }
+    load_log_table(tab);
     __syncthreads();
+    const LogTab tabh = log_tab_handle(tab);
     const int ncell = des->ncell, any3 = des->any3;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -320,7 +329,7 @@ wald_final_kernel(int64_t n, int S, const CdDesign* __restrict__ des, const int3
 #pragma unroll
         for (int u = 0; u < P; u++) eta += Xs[j * P + u] * beta[u];
         const double muw = nfj * exp(eta);                   // unfloored, as stored by nbinomWaldTest
-        loglike += nb_logdens(yj, size, alpha, muw, cmat[(int64_t)j * n + i]);
+        loglike += nb_logdens(yj, size, alpha, muw, cmat[(int64_t)j * n + i], tabh);
         const double muc = (P == 1) ? muw : fmax(muw, kMinMu);
         const double w = muc * rcp_pos(1.0 + alpha * muc);
 #pragma unroll
@@ -426,21 +435,41 @@ wald_deviance_p1_kernel(int64_t n, int S, const int32_t* __restrict__ K, const d
                         const double* __restrict__ dispersion, const uint8_t* __restrict__ flags, const double* __restrict__ lfact,
                         double* __restrict__ deviance_out)
 {
+    __shared__ __align__(16) double tab[2 * kLogTabN];
+    load_log_table(tab);
+    __syncthreads();
+    const LogTab tabh = log_tab_handle(tab);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (flags[i] & CD_FLAG_ALLZERO) { deviance_out[i] = NAN; return; }
     const double alpha = dispersion[i];
     const double size = rcp_pos(alpha);
-    const double lgs = lgamma_c_pos(size);
     double qsum = 0.0;
     for (int j = 0; j < S; j++) qsum += (double)K[(int64_t)j * n + i] * rcp_pos(nf[(int64_t)j * n + i]);
     const double beta = log_pos(qsum / S);
     const double eb = exp(beta);
     double loglike = 0.0;
-    for (int j = 0; j < S; j++) {
-        const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
-        const double c = ((lgamma_c_pos(yj + size) - lgs) - lfact_c(yj, lfact)) - kHalfLn2Pi;
-        loglike += nb_logdens(yj, size, alpha, nfj * eb, c);
+    if (size > kHugeSize) {
+        for (int j = 0; j < S; j++)
+            loglike += dnbinom_mu_log((double)K[(int64_t)j * n + i], size, nf[(int64_t)j * n + i] * eb);
+    } else {
+        // lgamma(y + size) - lgamma(size) as in the line search's posterior (posterior.cuh): Stirling parts per sample,
+        // the logarithm of the gamma rationals once for the region
+        const GammaParts gr = gamma_parts<true>(size, tabh);
+        const double inv_den_r = rcp_fast(gr.den);
+        double qprod = 1.0;
+        for (int j = 0; j < S; j++) {
+            const double yj = (double)K[(int64_t)j * n + i], nfj = nf[(int64_t)j * n + i];
+            const GammaParts g = gamma_parts<true>(yj + size, tabh);
+            qprod *= g.den * inv_den_r;
+            if (__double2hiint(qprod) > 0x5fe00000) { loglike -= log_pos_v2(qprod, tabh); qprod = 1.0; }
+            const double c = ((g.st - gr.st) - lfact_c(yj, lfact)) - kHalfLn2Pi;
+            const double mu = nfj * eb;
+            const double l1 = log_pos_v2(1.0 + mu * alpha, tabh);
+            const double l2 = log_pos_v2(mu * rcp_fast(size + mu), tabh);
+            loglike += (c - size * l1) + yj * l2;
+        }
+        loglike -= log_pos_v2(qprod, tabh);
     }
     deviance_out[i] = -2.0 * loglike;
 }
