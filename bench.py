@@ -516,6 +516,11 @@ def main():
         for s in range(S):
             e.set_sample_rows_ptr(s, Rr, N_host[s].data_ptr(), FM_host[s].data_ptr())
 
+    # result columns of a step land in page-locked host memory (allocated once, like the input rows)
+    table_out = {k: torch.empty(n, dtype=torch.float64).pin_memory().numpy() for k in
+                 ("baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "maxCooks")}
+    table_out["flags"] = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+
     def step_e2e(k, steps):
         # batch k's rows were uploaded during batch k-1's region test (or just now for the first batch); batch k+1's
         # upload is issued before this batch's region test and crosses the bus under it
@@ -524,7 +529,7 @@ def main():
         e.aggregate(fetch=False)
         if k + 1 < steps:
             upload()
-        return e.region_test(fetch="table")
+        return e.region_test(fetch="table", out=table_out)
 
     # device-resident steps
     e.set_rows_device(Rr, N_dev.data_ptr(), FM_dev.data_ptr())
@@ -537,15 +542,25 @@ def main():
     launches = (e.launch_count() - launches0) / args.steps
     rendezvous = None
     if world > 1:
-        passes, wait_peers, wait_self = e.last_rendezvous()
+        passes, wait_peers, wait_self, wait_first = e.last_rendezvous()
         mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        launches_trend = 2                      # theta-grid batch + final fit
         rendezvous = {"what": "trend-fit passes of one step: every pass ends with an all-reduce of 8 sums per fit through NVLink peer-memory "
-                              "mailboxes inside the kernel; wait = SM cycles CTA 0 of this rank spent polling for a peer's sequence word "
-                              "(arrival skew of the ranks + store-to-visibility latency), per pass and peer",
-                      "trend_passes_per_step": passes, "ranks": world,
+                              "mailboxes inside the kernel; wait = SM cycles CTA 0 of this rank spent polling for a peer's sequence word, "
+                              "per pass and peer.  The first pass of a launch absorbs the ranks' different arrival times from their line "
+                              "searches (skew); the later passes start together, so their wait is the exchange itself",
+                      "trend_passes_per_step": passes, "trend_launches_per_step": launches_trend, "ranks": world,
                       "mean_wait_us_per_pass_and_peer": wait_peers / max(passes * (world - 1), 1) / mhz,
+                      "first_pass_wait_us_per_launch_and_peer": wait_first / max(launches_trend * (world - 1), 1) / mhz,
+                      "later_pass_wait_us_per_pass_and_peer": (wait_peers - wait_first) / max((passes - launches_trend) * (world - 1), 1) / mhz,
                       "own_slot_us_per_pass": wait_self / max(passes, 1) / mhz,
                       "median_kernel_exchanges_per_step": 8 * 5}
+        # how different the ranks are: the line-search time and the DFMA peak of every rank (the step ends with the slowest)
+        spread = torch.tensor([tm[2], fp64_peak or 0.0, dev_ms], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(spread) for _ in range(world)]
+        R.dist.all_gather(allr, spread)
+        rendezvous["fit_disp_ms_per_rank"] = [round(float(t[0]), 3) for t in allr]
+        rendezvous["fp64_peak_tflops_per_rank"] = [round(float(t[1]), 2) for t in allr]
     flop_tab, flop_src = read_flop_table()
     fp64 = fp64_roofline(e, d, tm[2], fp64_peak, flop_tab, flop_src)
     fp64["kernel"] = "fit_disp_kernel (dispersion line searches: %.0f %% of the step)" % (100.0 * tm[2] / dev_ms)
@@ -556,6 +571,13 @@ def main():
     step_e2e(0, 1)
     step_e2e(0, 1)
     e2e_dev_ms, e2e_wall_ms, _ = R.timed(step_e2e, e2e_steps)
+
+    # the upload alone, all ranks at once: what the host side of this box delivers to N GPUs together (the e2e step cannot
+    # be shorter than this; at N = 8 it is what bounds it)
+    def step_upload(k, steps):
+        upload()
+        e.aggregate(fetch=False)
+    up_ms, _, _ = R.timed(step_upload, 3)
 
     # the same step started one stage earlier: per-replicate CHiCAGO tables -> fused assembly + aggregation
     # (cd_assemble) -> region test.  Reported beside the main line, not instead of it.
@@ -578,7 +600,7 @@ def main():
             for si in range(S):
                 e.set_sample_tables(si, packed[si])
             e.assemble(fetch=False)
-            return e.region_test(fetch="table")
+            return e.region_test(fetch="table", out=table_out)
 
         for _ in range(2):
             step_asm_resident(0, 1)
@@ -638,6 +660,10 @@ def main():
                         "steps": e2e_steps,
                         "h2d_bytes_per_step": int(N_host.numel() * 4 + FM_host.numel() * 8),
                         "d2h_bytes_per_step": int(n * (6 * 8 + 1)),
+                        "upload_alone": {"what": "cd_set_sample_rows of one batch + cd_aggregate and nothing else, all ranks at "
+                                                 "the same time (max over ranks): the floor the host-to-device path sets for a step",
+                                         "ms": up_ms, "gbs_per_gpu": (N_host.numel() * 4 + FM_host.numel() * 8) / (up_ms * 1e-3) / 1e9,
+                                         "gbs_all_gpus": world * (N_host.numel() * 4 + FM_host.numel() * 8) / (up_ms * 1e-3) / 1e9},
                         "pipelined": "the upload of batch k+1 is issued before the region test of batch k (asynchronous "
                                      "cd_set_sample_rows on the context's copy stream, double-buffered rows); every step uploads its "
                                      "own rows inside the timed region"},

@@ -216,7 +216,7 @@ struct cd_ctx {
     unsigned long long eval_counts_host[16] = {0};
     double trend_passes_batch = 0;
     double trend_passes = 0;                       // trend passes (= cross-rank rendezvous of the trend fits) of the last region test
-    unsigned long long wait_host[2] = {0, 0};
+    unsigned long long wait_host[3] = {0, 0, 0};
     DevBuf<int32_t> refit_count;
     DevBuf<int64_t> park_row;
     DevBuf<double> park_d;           // 5 x capacity
@@ -1513,7 +1513,7 @@ int cd_region_test(cd_ctx* ctx, const cd_options* opt, cd_results* out)
 
     CD_CUDA(ctx, ctx->eval_counts.ensure(16));
     CD_CUDA(ctx, cudaMemsetAsync(ctx->eval_counts.p, 0, 16 * sizeof(unsigned long long), st));
-    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 4, 0, 2 * sizeof(unsigned long long), st));
+    CD_CUDA(ctx, cudaMemsetAsync(ctx->counters.p + 4, 0, 3 * sizeof(unsigned long long), st));
     ctx->n_eval_calls = 0;
     ctx->trend_passes = 0;
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -1739,12 +1739,14 @@ int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[1
     return CD_OK;
 }
 
-int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self)
+int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self,
+                       double* wait_cycles_first_pass)
 {
     if (!ctx) return CD_EINVAL;
     if (trend_passes) *trend_passes = ctx->trend_passes;
     if (wait_cycles_peers) *wait_cycles_peers = (double)ctx->wait_host[0];
     if (wait_cycles_self) *wait_cycles_self = (double)ctx->wait_host[1];
+    if (wait_cycles_first_pass) *wait_cycles_first_pass = (double)ctx->wait_host[2];
     return CD_OK;
 }
 

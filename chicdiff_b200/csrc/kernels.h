@@ -189,7 +189,7 @@ struct TrendP2P {
     double* mymail;             // this rank's mailbox: 2 x nranks slots of (8 kMaxBatch + 8) doubles
     unsigned long long epoch;   // distinct per launch, identical on all ranks
     unsigned long long* err;    // device word, never null (see SelP2P)
-    unsigned long long* wait_cycles;   // may be null: [0] += SM cycles CTA 0 waited for peers' sums, [1] += for its own slot
+    unsigned long long* wait_cycles;   // may be null: [0] += SM cycles CTA 0 waited for peers' sums, [1] += for its own slot, [2] += the first-pass part of [0]
 };
 inline size_t trend_p2p_mail_doubles(int nranks) { return (size_t)2 * nranks * (8 * kMaxBatch + 8); }
 // the whole parametricDispersionFit of the G fits of a batch in one cooperative kernel; out[g * 8 + 0..1] coefs,

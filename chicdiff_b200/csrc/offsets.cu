@@ -224,7 +224,12 @@ __device__ __forceinline__ bool p2p_allreduce(const TrendP2P& pp, unsigned long 
         }
         __threadfence_system();
         // how long this rank waited for the slowest peer's sums (CTA 0, per peer): the rendezvous cost the bench reports
-        if (blockIdx.x == 0 && pp.wait_cycles) atomicAdd(pp.wait_cycles + ((int)threadIdx.x == pp.rank ? 1 : 0), (unsigned long long)(clock64() - t0));
+        // ([2]: the part of [0] spent in the first pass of a launch, which absorbs the ranks' different arrival times)
+        if (blockIdx.x == 0 && pp.wait_cycles) {
+            const unsigned long long w = (unsigned long long)(clock64() - t0);
+            atomicAdd(pp.wait_cycles + ((int)threadIdx.x == pp.rank ? 1 : 0), w);
+            if ((int)threadIdx.x != pp.rank && (seq & 0xffffffffull) == 1ull) atomicAdd(pp.wait_cycles + 2, w);
+        }
     }
     __syncthreads();
     if ((int)threadIdx.x < nvals) {

@@ -428,8 +428,10 @@ class Engine:
 
     def region_test(self, norm="combined", theta=None, theta_grid=None, disp_prior_var=None,
                     disp_prior_var_grid=None, disp_grid_len=20, fetch="all", prior_var_fn=None, trend=None,
-                    var_log_disp=None):
+                    var_log_disp=None, out=None):
         """cd_region_test.  fetch: "all" | "table" (columns of the output table only) | "none".
+        out: optional dict of preallocated result arrays by column name (page-locked ones make the device-to-host copies
+        plain DMA transfers; pageable NumPy arrays are staged by the driver at a fraction of the bus rate).
         prior_var_fn(df, residuals) -> dispPriorVar is asked once per dispersion fit whose design has S - p <= 3 and no
         disp_prior_var* given (the place where an R front end evaluates DESeq2's Monte-Carlo rule)."""
         n, S, p = self.n, self.S, self.p
@@ -468,7 +470,14 @@ class Engine:
         else:
             want = []
         for k in want:
-            arrays[k] = np.empty(shapes.get(k, (n,)), dtypes.get(k, np.float64))
+            shape, dtype = shapes.get(k, (n,)), dtypes.get(k, np.float64)
+            if out is not None and k in out:
+                a = out[k]                           # the caller's buffer (e.g. page-locked memory: the copy is a plain DMA then)
+                if a.shape != shape or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("out[%r]: expected a C-contiguous %s array of shape %s" % (k, np.dtype(dtype).name, shape))
+                arrays[k] = a
+            else:
+                arrays[k] = np.empty(shape, dtype)
             setattr(res, k, arrays[k].ctypes.data)
         rc = self._region_test_entry()(self._h, C.byref(opt), C.byref(res))
         if cb_error:
@@ -517,11 +526,12 @@ class Engine:
         return t
 
     def last_rendezvous(self):
-        """(trend passes, SM cycles waited for peers, SM cycles waited for the own slot) of the last region_test"""
-        a, b, c = C.c_double(), C.c_double(), C.c_double()
-        self._L.cd_last_rendezvous.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        self._check(self._L.cd_last_rendezvous(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+        """(trend passes, SM cycles waited for peers, SM cycles waited for the own slot, the first-pass part of the peers'
+        figure) of the last region_test"""
+        a, b, c, d = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self._L.cd_last_rendezvous.argtypes = [C.c_void_p] + [C.POINTER(C.c_double)] * 4
+        self._check(self._L.cd_last_rendezvous(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
 
 
 class MultiEngine(Engine):

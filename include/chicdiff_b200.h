@@ -322,8 +322,11 @@ int cd_last_search_counts(const cd_ctx* ctx, int* n_calls, int64_t evaluations[1
  * pass ends with every rank storing its sums into every peer's mailbox over NVLink and waiting for everybody's), and
  * the SM cycles CTA 0 spent waiting for the peers' sequence words, summed over passes and peers (wait_cycles_self: the
  * same for its own slot, i.e. the cost of the store + fence alone).  wait / (passes x (ranks - 1)) / SM clock = the mean
- * wait per rendezvous and peer: arrival skew of the ranks plus the NVLink store-to-visibility latency. */
-int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self);
+ * wait per rendezvous and peer: arrival skew of the ranks plus the NVLink store-to-visibility latency.
+ * wait_cycles_first_pass: the part of wait_cycles_peers spent in the first pass of each trend kernel (two launches per
+ * cd_region_test with a theta grid), i.e. waiting for the slowest rank to arrive from its line searches. */
+int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cycles_peers, double* wait_cycles_self,
+                       double* wait_cycles_first_pass);
 /* CUDA-event stopwatch on the context's stream (what bench.py brackets its timed region with) */
 int cd_timer_start(cd_ctx* ctx);
 int cd_timer_stop(cd_ctx* ctx, double* ms_out);      /* synchronises */

@@ -787,3 +787,23 @@ def test_prior_variance_callback_for_small_df():
         e.region_test(theta=0.5)
     assert "prior" in str(ei.value)
     e.close()
+
+
+def test_results_into_caller_buffers():
+    """region_test(out=...) fills the caller's (here page-locked) arrays with exactly what it returns otherwise"""
+    import torch
+    d = synth.generate("tiny")
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    e.aggregate(fetch=False)
+    ref = e.region_test(fetch="table")
+    out = {k: torch.empty(d.n, dtype=torch.float64).pin_memory().numpy() for k in ("pvalue", "lfcSE")}
+    got = e.region_test(fetch="table", out=out)
+    assert got["pvalue"] is out["pvalue"]
+    for k in ("baseMean", "log2FoldChange", "lfcSE", "stat", "pvalue", "maxCooks", "flags"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    with pytest.raises(ValueError):
+        e.region_test(fetch="table", out={"pvalue": np.empty(d.n - 1)})
+    e.close()
