@@ -76,6 +76,31 @@ __device__ __forceinline__ double rcp_pos(double b)
     return fma(r, e, r);
 }
 
+// exp(x) for |x| <= 700 (the line search keeps log alpha in [-30, 10]): x = k ln2 + r, |r| <= ln2 / 2, degree-13 Taylor
+// polynomial (the next term is 4e-18 of the result), k by the round-to-nearest trick of adding 1.5 * 2^52, 2^k by an
+// integer add on the exponent.  18 FP64 + 2 integer instructions and no 64-bit literal below 1/10! (the four highest
+// coefficients are rounded to 21 bits: <= 3e-18); libdevice's exp() spends half of its ~90 instructions moving 64-bit
+// literals into registers (profiles/r02_d_fit_disp_source_lines.txt: 6.3 % of the line-search kernel).  <= 2 ulp.
+static __constant__ double kExpC[8] = {1.0 / 2.0, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0,
+                                       1.0 / 362880.0};
+__device__ __forceinline__ double exp_mid(double x)
+{
+    const double magic = 6755399441055744.0;                 // 1.5 * 2^52: the low word of x log2(e) + magic is rint(.)
+    const double t = fma(x, kLog2e, magic);
+    const int k = __double2loint(t);
+    const double dk = t - magic;
+    double r = fma(-dk, kLogC[0], x);                         // k ln2_hi is exact
+    r = fma(-dk, kLogC[1], r);
+    double p = fma(r, 0x1.61246p-33 /* 1/13! */, 0x1.1eed9p-29 /* 1/12! */);
+    p = fma(r, p, 0x1.ae645p-26 /* 1/11! */);
+    p = fma(r, p, 0x1.27e5p-22 /* 1/10! */);
+#pragma unroll
+    for (int j = 7; j >= 0; j--) p = fma(r, p, kExpC[j]);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 // natural log of a positive normal x (< 1 ulp): x = 2^k m with m in [sqrt(1/2), sqrt(2)),
 // log m = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f), f = m - 1   (the classic fdlibm scheme)
 __device__ __forceinline__ double log_pos(double x)

@@ -181,6 +181,8 @@ struct cd_ctx {
     DevBuf<double> FM_rows, FM_rows_alt;
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_copy = nullptr;                 // last upload of the staging round
+    cudaEvent_t ev_tab_copy = nullptr, ev_tab_used = nullptr;   // replicate tables: last upload / compute-stream position at upload time
+    bool tab_copy_pending = false;
     cudaEvent_t ev_read[2] = {nullptr, nullptr};   // last aggregation kernel that read buffer b
     int front = 0;                                 // buffer the last cd_aggregate consumed
     bool front_used = false;
@@ -350,6 +352,8 @@ int cd_create(cd_ctx** out, int device)
     }
     cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_tab_copy, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_tab_used, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&c->ev_read[k], cudaEventDisableTiming);
     for (int k = 0; k < 4; k++) cudaEventCreate(&c->ev[k]);
     for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev_user[k]);
@@ -364,6 +368,8 @@ void cd_destroy(cd_ctx* ctx)
     cudaStreamSynchronize(ctx->st);
     if (ctx->st_copy) { cudaStreamSynchronize(ctx->st_copy); cudaStreamDestroy(ctx->st_copy); }
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->ev_tab_copy) cudaEventDestroy(ctx->ev_tab_copy);
+    if (ctx->ev_tab_used) cudaEventDestroy(ctx->ev_tab_used);
     for (int k = 0; k < 2; k++) if (ctx->ev_read[k]) cudaEventDestroy(ctx->ev_read[k]);
     for (int k = 0; k < 4; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     for (int k = 0; k < 2; k++) if (ctx->ev_user[k]) cudaEventDestroy(ctx->ev_user[k]);
@@ -896,9 +902,15 @@ int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* t)
     off[10] = pos;
     DevBuf<unsigned char>& blob = ctx->tab_blob[(size_t)s];
     CD_CUDA(ctx, blob.ensure(pos));
+    // The copies run on the context's copy stream, like the region rows': cd_assemble is the only reader of these tables
+    // and returns only when its kernel is done, so the tables of the NEXT batch can cross the bus while the region test
+    // of the current one runs.  (Ordered after anything the compute stream still does with this blob:
+    // cd_build_sample_tables, cd_get_sample_tables.)
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev_tab_used, ctx->st));
+    CD_CUDA(ctx, cudaStreamWaitEvent(ctx->st_copy, ctx->ev_tab_used, 0));
     const void* src[10] = {t->s_j, t->tblb, t->s_i, t->tlb, t->tmean, nullptr, t->distfun, t->cnt_off, t->cnt_oe, t->cnt_N};
     for (int k = 0; k < 10; k++)
-        if (src[k] && sizes[k]) CD_CUDA(ctx, cudaMemcpyAsync(blob.p + off[k], src[k], sizes[k], cudaMemcpyHostToDevice, ctx->st));
+        if (src[k] && sizes[k]) CD_CUDA(ctx, cudaMemcpyAsync(blob.p + off[k], src[k], sizes[k], cudaMemcpyHostToDevice, ctx->st_copy));
     AssembleTables& a = ctx->tabs_host[(size_t)s];
     a.s_j = (const double*)(blob.p + off[0]); a.tblb = (const int32_t*)(blob.p + off[1]);
     a.s_i = (const double*)(blob.p + off[2]); a.tlb = (const int32_t*)(blob.p + off[3]);
@@ -906,10 +918,12 @@ int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* t)
     a.distfun = (const double*)(blob.p + off[6]); a.cnt_off = (const int64_t*)(blob.p + off[7]);
     a.cnt_oe = (const int32_t*)(blob.p + off[8]); a.cnt_N = (const int32_t*)(blob.p + off[9]);
     a.n_tblb = t->n_tblb; a.n_tlb = t->n_tlb;
-    CD_LAUNCHN(ctx, 1, launch_tmin(t->n_tblb, t->n_tlb, a.tmean, (double*)(blob.p + off[5]), ctx->st));
+    CD_LAUNCHN(ctx, 1, launch_tmin(t->n_tblb, t->n_tlb, a.tmean, (double*)(blob.p + off[5]), ctx->st_copy));
+    CD_CUDA(ctx, cudaEventRecord(ctx->ev_tab_copy, ctx->st_copy));
+    ctx->tab_copy_pending = true;
     ctx->tab_set[(size_t)s] = 1;
-    ctx->have_agg = false;
-    return CD_OK;           // copies are ordered before cd_assemble on the context's stream
+    // (the matrices of the last cd_assemble stay valid: these tables belong to the NEXT one)
+    return CD_OK;           // asynchronous: the host arrays must stay valid until the next cd_assemble has returned
 }
 
 int cd_build_sample_tables(cd_ctx* ctx, int s, const cd_chicago_table* t)
@@ -924,6 +938,7 @@ int cd_build_sample_tables(cd_ctx* ctx, int s, const cd_chicago_table* t)
         return ctx->fail(CD_EINVAL, "cd_build_sample_tables: null column");
     const bool own_counts = t->cnt_rows == 0;
     if (own_counts && m > 0 && !t->N) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: neither count rows nor the table's N column given");
+    if (ctx->tab_copy_pending) { cudaStreamWaitEvent(ctx->st, ctx->ev_tab_copy, 0); ctx->tab_copy_pending = false; }
     if (!own_counts && (!t->cnt_baitID || !t->cnt_otherEndID || !t->cnt_N)) return ctx->fail(CD_EINVAL, "cd_build_sample_tables: null count column");
     const int64_t mc = own_counts ? m : t->cnt_rows;
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1020,6 +1035,7 @@ int cd_get_sample_tables(cd_ctx* ctx, int s, double* s_j, int32_t* tblb, double*
         return ctx->fail(CD_EINVAL, "cd_get_sample_tables: tables of replicate %d were never set", s);
     CD_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->st;
+    if (ctx->tab_copy_pending) { CD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_tab_copy, 0)); ctx->tab_copy_pending = false; }
     const AssembleTables& a = ctx->tabs_host[(size_t)s];
     const size_t F = (size_t)ctx->F, nt = (size_t)a.n_tblb * (size_t)a.n_tlb;
     int64_t ncnt = 0;
@@ -1064,6 +1080,7 @@ int cd_assemble(cd_ctx* ctx, int keep_rows, int32_t* K_out, double* fullmean_out
         ctx->N_rows_p = ctx->N_rows.p; ctx->FM_rows_p = ctx->FM_rows.p;
     }
     ctx->have_bm_rows = keep_rows != 0;
+    if (ctx->tab_copy_pending) { CD_CUDA(ctx, cudaStreamWaitEvent(ctx->st, ctx->ev_tab_copy, 0)); ctx->tab_copy_pending = false; }
     CD_CUDA(ctx, cudaMemcpyAsync(ctx->tabs_dev.p, ctx->tabs_host.data(), sizeof(AssembleTables) * (size_t)S, cudaMemcpyHostToDevice, ctx->st));
     CD_CUDA(ctx, cudaMemsetAsync(ctx->asm_status.p, 0, sizeof(int32_t), ctx->st));
     CD_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->st));

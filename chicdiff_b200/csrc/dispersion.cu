@@ -179,12 +179,15 @@ cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const double* base
 constexpr int kFitDispThreads = 128;
 constexpr int kFitDispTripCap = 24;     // first pass: a region still searching after this many trips is parked
 
-// dynamic shared memory of the line-search kernels, in doubles: two staging columns and the prefetch slot per lane and
-// the model matrix (the logarithm table is a static array: its address is an instruction immediate)
+// One staged block of a warp: the inputs of 32 consecutive regions, S int32 count rows, S double mean rows, the start
+// values and the prior means (doubles)
+__host__ __device__ static inline size_t fit_disp_block_doubles(int S) { return (size_t)16 * S + (size_t)32 * S + 64; }
+
+// dynamic shared memory of the line-search kernels, in doubles: two staging columns per lane, two staged blocks per warp
+// and the model matrix (the logarithm table is a static array)
 static inline size_t fit_disp_smem_doubles(int S, int P, int threads)
 {
-    return (size_t)2 * S * threads + ((size_t)S * threads + 1) / 2 + (size_t)S * threads + 2 * (size_t)threads +
-           (size_t)S * P;
+    return (size_t)2 * S * threads + (size_t)(threads / 32) * 2 * fit_disp_block_doubles(S) + (size_t)S * P;
 }
 
 // Two passes.  ~2-3 % of the regions run the full 100 trips while the average is below 10; in a
@@ -215,6 +218,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     const double epsilon = 1.0e-4, kappa_0 = 1.0, tol = 1e-6;
     const double min_log_alpha = log(kMinDisp / 10.0);
     const int maxit = 100;
+    const double inv_n_fit = 1.0 / (double)n_fit;
     int64_t n_work = n;
     if (RESUME) {
         const unsigned long long parked = *park.count;
@@ -226,42 +230,55 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
     double a = 0.0, lp = 0.0, lp0 = 0.0, dlp = 0.0, kappa = kappa_0, prior_mean = 0.0, prior_sigmasq = 1.0;   // prior_sigmasq holds 1 / variance
     int iter = 0, iter_accept = 0;
 
-    // First pass: the refill is software-pipelined per lane.  Every lane always owns `pending` (a region whose
-    // replicates are already on their way into its prefetch column by cp.async) and `queued` (a region index claimed
-    // by an atomic whose result is not needed before the lane's next refill), so becoming idle costs one
-    // shared-memory copy.  pf layout per lane: S int32 counts, S double means, start value, prior mean.
-    int* pf_k = reinterpret_cast<int*>(smem + (size_t)2 * S * stride) + threadIdx.x;
-    double* pf_mu = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + threadIdx.x;
-    double* pf_init = pf_mu + (size_t)S * stride;
-    double* pf_prior = pf_init + stride;
-    double* Xs = smem + (size_t)2 * S * stride + (size_t)(S * stride + 1) / 2 + (size_t)S * stride + 2 * (size_t)stride;
+    // First pass: the inputs are staged per WARP.  A warp claims 32 consecutive regions with one atomic and its 32 lanes
+    // copy their rows into a shared-memory block with cp.async (one coalesced request per row, all lanes active); two
+    // blocks per warp, the next one on its way while the lanes draw regions from the current one.  A lane that becomes
+    // idle takes the next unconsumed region of the current block: one shared-memory copy, no address arithmetic and no
+    // global access on the refill path, which runs with 2-3 of 32 lanes on almost every trip (per-lane prefetching cost
+    // 13 % of the kernel's instructions there: profiles/r02_d_fit_disp_source_lines.txt).
+    const size_t blk_doubles = fit_disp_block_doubles(S);
+    double* blk0 = smem + (size_t)2 * S * stride + (size_t)(threadIdx.x >> 5) * 2 * blk_doubles;
+    double* Xs = smem + (size_t)2 * S * stride + (size_t)(kFitDispThreads / 32) * 2 * blk_doubles;
     for (int k = threadIdx.x; k < S * P; k += blockDim.x) Xs[k] = des->X[k];
     if (TABLOG) load_log_table(tab);
     const LogTab tabh = log_tab_handle(tab);
     __syncthreads();
 
-    int64_t pending = 0, queued = 0;
-    auto prefetch = [&](int64_t r) {
+    // block b of this warp: counts [S][32] (int32), means [S][32], start values [32], prior means [32]
+    auto blk_k = [&](int b) { return reinterpret_cast<int*>(blk0 + (size_t)b * blk_doubles); };
+    auto blk_mu = [&](int b) { return blk0 + (size_t)b * blk_doubles + (size_t)16 * S; };
+    auto load_block = [&](int b, int64_t base) {
+        const int64_t r = base + lane;
         if (r < n) {
+            int* kb = blk_k(b) + lane;
+            double* mb = blk_mu(b) + lane;
             const int32_t* kp = K + r;
             const double* mp = mu_g + r;
             for (int j = 0; j < S; j++) {
-                __pipeline_memcpy_async(pf_k + j * stride, kp, sizeof(int32_t));
-                __pipeline_memcpy_async(pf_mu + j * stride, mp, sizeof(double));
+                __pipeline_memcpy_async(kb + j * 32, kp, sizeof(int32_t));
+                __pipeline_memcpy_async(mb + j * 32, mp, sizeof(double));
                 kp += n; mp += n;
             }
-            __pipeline_memcpy_async(pf_init, start_log + r, sizeof(double));
-            if (use_prior) __pipeline_memcpy_async(pf_prior, prior_log_mean + r, sizeof(double));
+            __pipeline_memcpy_async(mb + S * 32, start_log + r, sizeof(double));
+            if (use_prior) __pipeline_memcpy_async(mb + S * 32 + 32, prior_log_mean + r, sizeof(double));
         }
         __pipeline_commit();
     };
-    if (!RESUME) {
+    auto claim32 = [&]() {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 64ull);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        pending = (int64_t)base + lane;
-        queued = (int64_t)base + 32 + lane;
-        prefetch(pending);
+        if (lane == 0) base = atomicAdd(work_counter, 32ull);
+        return (int64_t)__shfl_sync(0xffffffffu, base, 0);
+    };
+    auto valid_in = [&](int64_t base) { return (int)(base >= n ? 0 : (n - base < 32 ? n - base : 32)); };
+    int cur = 0, cur_cnt = 0, cur_pos = 0, next_cnt = 0;      // warp-uniform
+    int64_t cur_base = 0, next_base = 0;
+    if (!RESUME) {
+        cur_base = claim32(); cur_cnt = valid_in(cur_base);
+        load_block(0, cur_base);
+        next_base = claim32(); next_cnt = valid_in(next_base);
+        load_block(1, next_base);
+        __pipeline_wait_prior(1);              // block 0 has landed (this lane's part; __syncwarp for the others')
+        __syncwarp();
     }
 
     while (true) {
@@ -269,49 +286,62 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
         const bool want = !active && !exhausted;
         const unsigned need = __ballot_sync(0xffffffffu, want);
         if (!RESUME) {
-            bool consumed = false;
-            if (want) {
-                if (pending >= n) {
-                    exhausted = true;
-                } else {
+            bool want_now = want;
+            unsigned need_now = need;
+            while (need_now) {                                  // warp-uniform
+                const int avail = cur_cnt - cur_pos;
+                if (avail <= 0) {
+                    // the current block is used up: the next one becomes current, and its buffer is refilled
+                    if (next_cnt <= 0) {                        // the queue is empty
+                        if (want_now) exhausted = true;
+                        break;
+                    }
                     __pipeline_wait_prior(0);
-                    i = pending;
-                    const double a_start = *pf_init;
+                    __syncwarp();                               // every lane's part of the block has landed; all reads of the old one are done
+                    cur ^= 1; cur_base = next_base; cur_cnt = next_cnt; cur_pos = 0;
+                    next_base = claim32(); next_cnt = valid_in(next_base);
+                    load_block(cur ^ 1, next_base);
+                    continue;
+                }
+                const int my_rank = __popc(need_now & ((1u << lane) - 1u));
+                if (want_now && my_rank < avail) {
+                    const int idx = cur_pos + my_rank;
+                    i = cur_base + idx;
+                    const int* kb = blk_k(cur) + idx;
+                    const double* mb = blk_mu(cur) + idx;
+                    const double a_start = mb[S * 32];
                     if (isnan(a_start)) {
-                        // all-zero region: every estimate is NA (its start value was written as NaN upstream)
+                        // all-zero region: every estimate is NA (its start value was written as NaN upstream); the lane
+                        // stays idle and draws again
                         log_alpha_out[i] = NAN; iter_out[i] = 0; initial_lp_out[i] = NAN; last_lp_out[i] = NAN;
                     } else {
                         for (int j = 0; j < S; j++) {
-                            ys[j * stride] = (double)pf_k[j * stride];
-                            mus[j * stride] = pf_mu[j * stride];
+                            ys[j * stride] = (double)kb[j * 32];
+                            mus[j * stride] = mb[j * 32];
                         }
                         // the logarithms of the start value and of the prior mean were taken by the kernels that produced
-                        // them (gene_init / trend_apply): the refill path runs with 2-3 of 32 lanes on almost every trip
+                        // them (gene_init / trend_apply)
                         a = a_start;
                         if (use_prior) {
-                            prior_mean = *pf_prior;
-                            // the fit of virtual region i by counting (<= kMaxBatch fits; this path runs with 2-3 of 32
-                            // lanes on almost every trip, so no division of either kind here); eval_post multiplies
+                            prior_mean = mb[S * 32 + 32];
+                            // the fit of virtual region i (no division of either kind on this path); eval_post multiplies
                             // by the reciprocal of the prior variance, which the launcher took
                             int g = 0;
-                            for (int64_t t = n_fit; t <= i; t += n_fit) g++;
+                            if (n_fit < n) {                 // i / n_fit for i < 2^32 from a double product, corrected at the edges
+                                g = __double2int_rz((double)(unsigned)i * inv_n_fit);
+                                if ((int64_t)(g + 1) * n_fit <= i) g++;
+                                else if ((int64_t)g * n_fit > i) g--;
+                            }
                             prior_sigmasq = prior_inv_sigmasq_g.v[g];
                         }
                         active = true; fresh = true;
                         iter = 0; iter_accept = 0; kappa = kappa_0;
+                        want_now = false;
                     }
-                    pending = queued;
-                    prefetch(pending);
-                    consumed = true;
                 }
-            }
-            const unsigned took = __ballot_sync(0xffffffffu, consumed);
-            if (took) {
-                unsigned long long base = 0;
-                const int leader = __ffs(took) - 1;
-                if ((int)lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(took));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (consumed) queued = (int64_t)(base + __popc(took & ((1u << lane) - 1u)));
+                const int wanted = __popc(need_now);
+                cur_pos += wanted < avail ? wanted : avail;
+                need_now = __ballot_sync(0xffffffffu, want_now);
             }
         } else if (need) {
             unsigned long long base = 0;

@@ -84,7 +84,7 @@ __device__ __forceinline__ void eval_post(double a, const double* ys, const doub
                                           double prior_mean, double prior_inv_sigmasq, bool use_prior,
                                           double& lp_out, double& dlp_out)
 {
-    const double alpha = exp(a);
+    const double alpha = exp_mid(a);
     const double r = rcp_fast(alpha);
     const double log_r = -a;                            // log(1/alpha)
     const GammaParts gr = gamma_parts<TABLOG>(r, tab);

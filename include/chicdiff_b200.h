@@ -146,6 +146,9 @@ int cd_region_universe(cd_ctx* ctx, int64_t m, const int32_t* peak_bait, const i
 int cd_get_region_universe(cd_ctx* ctx, int64_t* row_off_out, int32_t* row_bait_out, int32_t* row_oe_out);
 /* the region universe's rows (RU: baitID, otherEndID), region-contiguous, R = row_off[n] */
 int cd_set_region_rows(cd_ctx* ctx, int64_t R, const int32_t* row_bait, const int32_t* row_oe);
+/* Asynchronous like cd_set_sample_rows: the tables are copied on the context's copy stream and belong to the NEXT
+ * cd_assemble (the matrices of the last one stay valid, so a region test of the current batch can run while the next
+ * batch's tables cross the bus); the host arrays must stay valid until that cd_assemble has returned. */
 int cd_set_sample_tables(cd_ctx* ctx, int s, const cd_sample_tables* tables);
 /* The same tables built ON THE DEVICE from one replicate's raw CHiCAGO columns, replacing the keyed joins / setkey sorts /
  * first-per-group passes of getFullRegionData1 (chicdiff.R:632-634 setkey(x, baitID, otherEndID); :659 first (s_j, tblb)

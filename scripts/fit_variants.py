@@ -40,6 +40,10 @@ for label, env in variants:
     print("%-11s n=%d: %.2f ms/step, %d launches/step | " % (label, d.n, ms, (e.launch_count() - l0) // steps) +
           "  ".join("%s %.2f" % (k, v) for k, v in zip(names, tm)), "| theta", r["theta"], flush=True)
     full = e.region_test(fetch="table")
+    import zlib
+    print("   checksums (bit-level, to compare two builds): pvalue %08x  lfcSE %08x  sum(p) %r" % (
+        zlib.crc32(np.ascontiguousarray(full["pvalue"]).tobytes()), zlib.crc32(np.ascontiguousarray(full["lfcSE"]).tobytes()),
+        float(np.nansum(full["pvalue"]))), flush=True)
     if ref is None:
         ref = full
     else:

@@ -31,6 +31,7 @@ void dm_vec(int what, long n, const double* x, double* out, double* out2)
 {
     for (long i = 0; i < n; i++) {
         if (what == 10) { out[i] = cd::log_pos_v2(x[i], cd::kLogTab); continue; }      // the table-assisted logarithm
+        if (what == 11) { out[i] = cd::exp_mid(x[i]); continue; }                        // the line search's exponential
         if (what == 0) out[i] = cd::log_pos(x[i]);
         else if (what == 1) out[i] = cd::rcp_pos(x[i]);
         else if (what == 2) cd::lgamma_digamma_pos(x[i], out[i], out2[i]);

@@ -217,3 +217,16 @@ def test_table_log(dm):
     err = np.abs(a.astype(np.longdouble) - ref)
     assert float(np.max(err / np.maximum(np.abs(ref), 1.0))) < 3e-16
     assert _vec(dm, 10, np.array([1.0]))[0][0] == 0.0
+
+
+def test_exp_mid(dm):
+    """exp_mid (common.cuh), the exponential of the line search: within 2 ulp over the range the search keeps log alpha in
+    and well beyond it"""
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.uniform(-35, 15, 400000), rng.uniform(-700, 700, 100000), rng.uniform(-1e-3, 1e-3, 50000),
+                        np.array([0.0, -30.0, 10.0, np.log(2) / 2, -np.log(2) / 2, 1e-300])])
+    a, _ = _vec(dm, 11, x)
+    ref = np.exp(x.astype(np.longdouble))
+    err = np.abs(a.astype(np.longdouble) - ref) / np.spacing(ref.astype(np.float64))
+    assert float(np.max(err)) <= 2.0, float(np.max(err))
+    assert _vec(dm, 11, np.array([0.0]))[0][0] == 1.0
