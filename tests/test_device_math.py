@@ -200,6 +200,48 @@ def test_posterior_formulations_are_the_same_function(dm, variant):
         assert worst_dlp < 1e-12, (S, p, worst_dlp)
 
 
+def test_posterior_gamma_rational_overflow_path(dm):
+    """counts in the hundreds of millions at alpha near its cap: the product of the replicates' gamma rationals leaves the
+    double range and eval_post takes one logarithm per replicate instead (posterior.cuh); same function as before"""
+    f = dm.dm_eval_post_variant
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                  C.c_void_p, C.c_void_p]
+    X = np.ascontiguousarray(np.column_stack([np.ones(6), [0, 0, 0, 1, 1, 1]]).astype(float))
+    y = np.array([2.0e9, 1.5e9, 1.9e9, 2.1e9, 1.0e9, 7.0e8])
+    mu = y * np.array([1.1, 0.9, 1.0, 1.2, 0.8, 1.0])
+    for a in (np.log(10.0), np.log(3.0), np.log(0.5)):
+        with np.errstate(over="ignore"):
+            assert np.prod(((y + np.exp(-a)) / np.exp(-a)) ** 10.0) == np.inf   # the single product does overflow
+        out = []
+        for v in (0, 2):
+            lp, dlp = C.c_double(), C.c_double()
+            f(v, 6, 2, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, -2.0, 0.7, 1, C.byref(lp), C.byref(dlp))
+            out.append((lp.value, dlp.value))
+        assert np.isfinite(out[1][0]) and np.isfinite(out[1][1])
+        assert abs(out[0][0] - out[1][0]) <= 5e-15 * np.sum(np.abs(special.gammaln(y + np.exp(-a))))
+        assert abs(out[0][1] - out[1][1]) <= 1e-9 * max(abs(out[0][1]), 1.0)
+    # 16 replicates, three design columns, alpha up to 16: products from far inside the double range to far outside it,
+    # including those that end within a few binades of the largest double
+    rng = np.random.default_rng(11)
+    S = 16
+    X = np.ascontiguousarray(np.column_stack([np.ones(S), np.arange(S) % 2, np.arange(S) >= 8]).astype(float))
+    n_over = 0
+    for _ in range(3000):
+        mu = np.exp(rng.uniform(np.log(0.5), np.log(1e5), S))
+        at = np.exp(rng.uniform(np.log(1e-3), np.log(2.0)))
+        y = rng.negative_binomial(1.0 / at, 1.0 / (1.0 + mu * at)).astype(float)
+        a = rng.uniform(np.log(1e-2), np.log(16.0))
+        out = []
+        for v in (0, 2):
+            lp, dlp = C.c_double(), C.c_double()
+            f(v, S, 3, X.ctypes.data, y.ctypes.data, mu.ctypes.data, a, -2.0, 0.7, 0, C.byref(lp), C.byref(dlp))
+            out.append((lp.value, dlp.value))
+        with np.errstate(over="ignore"):
+            n_over += int(np.prod(((y + np.exp(-a)) / np.exp(-a)) ** 10.0) > 2.0 ** 1000)
+        assert abs(out[0][0] - out[1][0]) <= 5e-15 * (1.0 + np.sum(np.abs(special.gammaln(y + np.exp(-a)))))
+    assert n_over > 100
+
+
 def test_table_log(dm):
     """log_pos_v2 (common.cuh): within 1.5 ulp for every argument >= 1 (all the kernel's logarithms except the determinant's)
     and within 3e-16 of max(1, |log x|) below 1, where the table entry and k ln2 cancel near x = 1."""
