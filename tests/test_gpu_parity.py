@@ -807,3 +807,71 @@ def test_results_into_caller_buffers():
     with pytest.raises(ValueError):
         e.region_test(fetch="table", out={"pvalue": np.empty(d.n - 1)})
     e.close()
+
+
+def test_next_batch_uploads_overlap_the_region_test():
+    """The pipelined call order of bench.py's e2e steps: the rows (or the replicate tables) of batch k+1 are handed over
+    between the aggregation (assembly) and the region test of batch k and travel on the context's copy stream.  Two
+    different batches, alternated: every region test must return exactly what the same batch returns when it is run
+    alone (the upload in flight belongs to the NEXT aggregation and must not touch the matrices of this one)."""
+    import torch
+    d = synth.generate("c1")
+    batches = []
+    rng = np.random.default_rng(3)
+    for b in range(2):
+        N = d.N_rows.copy()
+        if b == 1:
+            N = (N + rng.integers(0, 3, N.shape)).astype(np.int32)        # a second, different batch of the same shape
+        batches.append((torch.from_numpy(N).pin_memory().numpy(), torch.from_numpy(d.FM_rows.copy()).pin_memory().numpy()))
+    kw = dict(disp_prior_var=0.5, disp_prior_var_grid=0.5, fetch="table")
+
+    def alone(N, FM):
+        e = engine.Engine(0)
+        e.set_design(d.X); e.set_regions(d.row_off)
+        for s in range(d.S):
+            e.set_sample_rows(s, N[s], FM[s])
+        e.aggregate(fetch=False)
+        r = e.region_test(**kw)
+        e.close()
+        return r
+    ref = [alone(*b) for b in batches]
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_regions(d.row_off)
+    upload = lambda b: [e.set_sample_rows(s, batches[b][0][s], batches[b][1][s]) for s in range(d.S)]
+    upload(0)
+    for k in range(4):
+        e.aggregate(fetch=False)
+        upload((k + 1) % 2)                                               # next batch on its way ...
+        r = e.region_test(**kw)                                           # ... under this batch's region test
+        for col in ("baseMean", "pvalue", "lfcSE", "flags"):
+            assert np.array_equal(r[col], ref[k % 2][col], equal_nan=True), (k, col)
+    e.close()
+    # the same with the replicate tables of the assembly path
+    tabs = [d.extra["tables"], [dict(t) for t in d.extra["tables"]]]
+    for t in tabs[1]:
+        t["cnt_N"] = (np.asarray(t["cnt_N"]) + 1).astype(np.int32)        # second batch: every observed count one higher
+
+    def alone_asm(tables):
+        e = engine.Engine(0)
+        e.set_design(d.X); e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+        e.set_regions(d.row_off); e.set_region_rows(d.row_bait, d.row_oe)
+        for s in range(d.S):
+            e.set_sample_tables(s, tables[s])
+        e.assemble(fetch=False)
+        r = e.region_test(**kw)
+        e.close()
+        return r
+    ref = [alone_asm(t) for t in tabs]
+    assert not np.array_equal(ref[0]["baseMean"], ref[1]["baseMean"])
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_rmap(d.frag_chr, d.frag_start, d.frag_end, 1)
+    e.set_regions(d.row_off); e.set_region_rows(d.row_bait, d.row_oe)
+    upload = lambda b: [e.set_sample_tables(s, tabs[b][s]) for s in range(d.S)]
+    upload(0)
+    for k in range(4):
+        e.assemble(fetch=False)
+        upload((k + 1) % 2)
+        r = e.region_test(**kw)
+        for col in ("baseMean", "pvalue", "lfcSE", "flags"):
+            assert np.array_equal(r[col], ref[k % 2][col], equal_nan=True), (k, col)
+    e.close()
