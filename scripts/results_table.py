@@ -18,7 +18,7 @@ def last_json_line(path):
 
 def main():
     paths = sys.argv[1:] or [os.path.join(ROOT, "profiles", f) for f in
-                             ("r02_final_bench_1gpu.json", "r02_final_bench_2gpu.json", "r02_final_bench_8gpu.json")]
+                             ("r02_final_bench_1gpu.json", "r02_final_bench_2gpu.json", "r02_final_bench_4gpu.json", "r02_final_bench_8gpu.json")]
     recs = [(p, last_json_line(p)) for p in paths if os.path.exists(p)]
     print("| GPUs | ms/step | regions/s (resident) | e2e ms/step | e2e regions/s | launches/step | fit_disp ms | FP64 flop frac | FP64 pipe frac | strong: ms, speed-up | file |")
     print("|---|---|---|---|---|---|---|---|---|---|---|")
