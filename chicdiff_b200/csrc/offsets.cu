@@ -196,6 +196,7 @@ __device__ __forceinline__ bool trend_grid_barrier(unsigned int* bar, unsigned i
 // ahead, because finishing a pass needs everybody's contribution to it, and CTA 0 contributes to pass k+1 only after
 // the grid barrier of pass k+1, i.e. after all local CTAs have read pass k.  A CTA that gives up raises the error
 // word, which ends every other spin loop (here and in the grid barrier) of this and of the following kernels.
+constexpr int kTrendMaxRanks = 16;                   // peer-memory mailboxes exist for up to 16 ranks (cd_comm_init)
 __device__ __forceinline__ bool p2p_allreduce(const TrendP2P& pp, unsigned long long seq, unsigned int parity, int nvals,
                                               double* sh_tot)
 {
@@ -233,9 +234,15 @@ __device__ __forceinline__ bool p2p_allreduce(const TrendP2P& pp, unsigned long 
     }
     __syncthreads();
     if ((int)threadIdx.x < nvals) {
+        // the slots are final once the sequence words are seen: L2 loads, all in flight, summed in rank order
+        double v[kTrendMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kTrendMaxRanks; r++)
+            v[r] = (r < pp.nranks) ? __ldcg(pp.mymail + ((size_t)parity * pp.nranks + r) * kTrendSlot + threadIdx.x) : 0.0;
         double x = 0.0;
-        for (int r = 0; r < pp.nranks; r++)
-            x += *reinterpret_cast<volatile double*>(pp.mymail + ((size_t)parity * pp.nranks + r) * kTrendSlot + threadIdx.x);
+#pragma unroll
+        for (int r = 0; r < kTrendMaxRanks; r++)
+            if (r < pp.nranks) x += v[r];
         sh_tot[threadIdx.x] = x;
     }
     __syncthreads();

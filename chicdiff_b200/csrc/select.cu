@@ -26,6 +26,7 @@ namespace cd {
 
 constexpr int kSelBins = 2048;
 constexpr int kSelThreads = 256;
+constexpr int kSelMaxRanks = 16;                    // peer-memory mailboxes exist for up to 16 ranks (cd_comm_init)
 constexpr long long kSpinLimit = 20000000000LL;      // ~10 s of SM clocks: a peer died; give up
 
 __device__ __forceinline__ unsigned long long key_of(double x)
@@ -108,10 +109,25 @@ __device__ __forceinline__ bool sel_exchange(const SelP2P& pp, unsigned long lon
     if (threadIdx.x == 0) timed_out = (*reinterpret_cast<volatile unsigned long long*>(pp.err) != 0ull) ? 1 : 0;
     __syncthreads();
     if (timed_out) return false;                  // an earlier exchange already failed: do not wait again
-    for (int r = 0; r < nr; r++) {
-        unsigned long long* dst = pp.peers[r] + my_slot * kSelBins;
-        // (volatile: the counters were accumulated by other SMs' atomics in L2; never read them through this SM's L1)
-        for (int b = threadIdx.x; b < len; b += blockDim.x) dst[b] = *reinterpret_cast<volatile unsigned long long*>(vals + b);
+    // The counters were accumulated by other SMs' atomics in L2: read them there (ld.cg), never through this SM's L1,
+    // once, all loads of a thread in flight together -- and then store them to every peer.  (A volatile load per peer and
+    // word, as in the first version, is one serialised L2 round trip each: ~40 us per exchange at 8 ranks.)
+    {
+        const bool in_global = __isGlobal(vals);      // (the two-word exchange of the last phase hands over shared memory)
+        unsigned long long mine[kSelBins / kSelThreads];
+#pragma unroll
+        for (int k = 0; k < kSelBins / kSelThreads; k++) {
+            const int b = threadIdx.x + k * kSelThreads;
+            mine[k] = (b >= len) ? 0ull : (in_global ? __ldcg(vals + b) : *reinterpret_cast<volatile unsigned long long*>(vals + b));
+        }
+        for (int r = 0; r < nr; r++) {
+            unsigned long long* dst = pp.peers[r] + my_slot * kSelBins;
+#pragma unroll
+            for (int k = 0; k < kSelBins / kSelThreads; k++) {
+                const int b = threadIdx.x + k * kSelThreads;
+                if (b < len) dst[b] = mine[k];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -127,13 +143,18 @@ __device__ __forceinline__ bool sel_exchange(const SelP2P& pp, unsigned long lon
         __threadfence_system();
     }
     __syncthreads();
+    // the peers' slots arrived through NVLink in this GPU's L2 and are final once their sequence words are seen: plain
+    // L2 loads, all ranks' words of a bin in flight together
     for (int b = threadIdx.x; b < len; b += blockDim.x) {
         const bool is_min = b >= min_from;
-        unsigned long long acc = is_min ? ~0ull : 0ull;
-        for (int r = 0; r < nr; r++) {
-            const unsigned long long x = __ldcv(pp.mymail + ((par_base + r) * kSelP2PMaxCols + c) * kSelBins + b);
-            acc = is_min ? (x < acc ? x : acc) : acc + x;
-        }
+        const unsigned long long neutral = is_min ? ~0ull : 0ull;
+        unsigned long long x[kSelMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kSelMaxRanks; r++)
+            x[r] = (r < nr) ? __ldcg(pp.mymail + ((par_base + r) * kSelP2PMaxCols + c) * kSelBins + b) : neutral;
+        unsigned long long acc = neutral;
+#pragma unroll
+        for (int r = 0; r < kSelMaxRanks; r++) acc = is_min ? (x[r] < acc ? x[r] : acc) : acc + x[r];
         vals[b] = acc;
     }
     __syncthreads();
