@@ -169,9 +169,9 @@ cudaError_t launch_gene_init(int64_t n, int64_t n_fit, int S, const double* base
 // ---------------------------------------------------------------------------------------
 // fitDisp line search.  One lane works on one region at a time and the kernel is persistent:
 // iteration counts are very uneven (most regions stop after 5-15 trips, ~2 % run all 100), so
-// a lane that finishes its region immediately pulls the next one from a global work counter
-// (one warp-aggregated atomic per refill) instead of idling until the slowest lane of its warp
-// is done.  Every trip of a lane has the same shape -- one fused posterior + derivative
+// a lane that finishes its region immediately takes the next one -- from the block of 32 consecutive
+// regions its warp has staged in shared memory (one atomic on the global work counter per block) --
+// instead of idling until the slowest lane of its warp is done.  Every trip of a lane has the same shape -- one fused posterior + derivative
 // evaluation -- whether the lane is initialising a fresh region or is inside the line search,
 // so lanes in different states do not serialise each other.
 // The region's replicates (y_j, mu_j) live in a conflict-free shared-memory column per lane.
@@ -208,7 +208,7 @@ fit_disp_kernel(int64_t n, int64_t n_fit, int S, const CdDesign* __restrict__ de
                 unsigned long long* __restrict__ work_counter, FitDispPark park)
 {
     extern __shared__ __align__(16) double smem[];
-    // logarithm table (16-byte aligned: one LDS.128 per logarithm); dynamic part: staging columns, prefetch slots, model matrix
+    // logarithm table (16-byte aligned: one LDS.128 per logarithm); dynamic part: the lanes' columns, the warps' staged blocks, model matrix
     __shared__ __align__(16) double tab[TABLOG ? 2 * kLogTabN : 2];
     const int stride = kFitDispThreads;
     double* ys = smem + threadIdx.x;
