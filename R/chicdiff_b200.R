@@ -219,9 +219,15 @@ getFullRegionData.cuda <- function(chicdiff.settings, RU, RUcontrol, suffix = ""
 ## table with avDist attached (:1965-1967), `distLookup` the table learned from the control set (:2013-2033).
 ## Returns `out` with group, avWeights, weight, weighted_pvalue, weighted_padj, ordered by group like the
 ## reference's merge() leaves it.
-ihwApply.cuda <- function(out, distLookup) {
-  r <- .Call("cdR_ihw_apply", as.numeric(out$avDist), as.numeric(out$pvalue), as.numeric(distLookup$minLogDist),
-             as.numeric(distLookup$maxLogDist), as.numeric(distLookup$avWeights))
+## ctx: a context (cdR_create) to run the n-sized work on its GPU (cdR_ihw_apply_device); NULL = the host routine.
+ihwApply.cuda <- function(out, distLookup, ctx = NULL) {
+  r <- if (is.null(ctx)) {
+    .Call("cdR_ihw_apply", as.numeric(out$avDist), as.numeric(out$pvalue), as.numeric(distLookup$minLogDist),
+          as.numeric(distLookup$maxLogDist), as.numeric(distLookup$avWeights))
+  } else {
+    .Call("cdR_ihw_apply_device", ctx, as.numeric(out$avDist), as.numeric(out$pvalue), as.numeric(distLookup$minLogDist),
+          as.numeric(distLookup$maxLogDist), as.numeric(distLookup$avWeights))
+  }
   out[, avgLogDist := log(abs(avDist))]
   out$group <- r$group
   out$avWeights <- distLookup$avWeights[r$group]

@@ -12,7 +12,8 @@
  *               estimateDispersions / nbinomWaldTest                                    -> cdR_region_test
  *   :1721-1739  results()                                                              -> cdR_results_resident,
  *                                                                                         cdR_results_adjust
- * and, inside IHWcorrection (:2038-2049), the weight application                         -> cdR_ihw_apply
+ * and, inside IHWcorrection (:2038-2049), the weight application                         -> cdR_ihw_apply,
+ *                                                                                         cdR_ihw_apply_device
  */
 #include <R.h>
 #include <Rinternals.h>
@@ -315,6 +316,30 @@ SEXP cdR_ihw_apply(SEXP avDist, SEXP pvalue, SEXP minLogDist, SEXP maxLogDist, S
     if (cd_ihw_apply((int64_t)n, REAL(avDist), REAL(pvalue), G, REAL(minLogDist), REAL(maxLogDist), REAL(avWeights),
                      INTEGER(group), REAL(weight), REAL(wp), REAL(wpadj)) != CD_OK)
         error("chicdiff_b200: cd_ihw_apply: bad arguments or 'breaks' are not unique");
+    SEXP out = PROTECT(allocVector(VECSXP, 4));
+    SET_VECTOR_ELT(out, 0, group); SET_VECTOR_ELT(out, 1, weight); SET_VECTOR_ELT(out, 2, wp); SET_VECTOR_ELT(out, 3, wpadj);
+    SEXP nm = PROTECT(allocVector(STRSXP, 4));
+    SET_STRING_ELT(nm, 0, mkChar("group")); SET_STRING_ELT(nm, 1, mkChar("weight"));
+    SET_STRING_ELT(nm, 2, mkChar("weighted_pvalue")); SET_STRING_ELT(nm, 3, mkChar("weighted_padj"));
+    setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(6);
+    return out;
+}
+
+/* The same on the context's GPU (cd_ihw_apply_device).  avDist = NULL: the avDist column cd_assemble left on the device. */
+SEXP cdR_ihw_apply_device(SEXP ptr, SEXP avDist, SEXP pvalue, SEXP minLogDist, SEXP maxLogDist, SEXP avWeights)
+{
+    cd_ctx* ctx = get_ctx(ptr);
+    R_xlen_t n = XLENGTH(pvalue);
+    int G = (int)XLENGTH(avWeights);
+    if (!isNull(avDist) && XLENGTH(avDist) != n) error("chicdiff_b200: avDist and pvalue differ in length");
+    if (XLENGTH(minLogDist) != G || XLENGTH(maxLogDist) != G) error("chicdiff_b200: the distance lookup must have one row per weight");
+    SEXP group = PROTECT(allocVector(INTSXP, n));
+    SEXP weight = PROTECT(allocVector(REALSXP, n));
+    SEXP wp = PROTECT(allocVector(REALSXP, n));
+    SEXP wpadj = PROTECT(allocVector(REALSXP, n));
+    CD_CHECK(ctx, cd_ihw_apply_device(ctx, (int64_t)n, isNull(avDist) ? NULL : REAL(avDist), REAL(pvalue), G, REAL(minLogDist),
+                                      REAL(maxLogDist), REAL(avWeights), INTEGER(group), REAL(weight), REAL(wp), REAL(wpadj)));
     SEXP out = PROTECT(allocVector(VECSXP, 4));
     SET_VECTOR_ELT(out, 0, group); SET_VECTOR_ELT(out, 1, weight); SET_VECTOR_ELT(out, 2, wp); SET_VECTOR_ELT(out, 3, wpadj);
     SEXP nm = PROTECT(allocVector(STRSXP, 4));

@@ -1767,6 +1767,33 @@ int cd_last_rendezvous(const cd_ctx* ctx, double* trend_passes, double* wait_cyc
     return CD_OK;
 }
 
+int cd_ihw_apply_device(cd_ctx* ctx, int64_t n, const double* avDist, const double* pvalue, int ngroups, const double* minLogDist,
+                        const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
+                        double* weighted_pvalue_out, double* weighted_padj_out)
+{
+    if (!ctx) return CD_EINVAL;
+    if (n < 0 || ngroups < 1 || !minLogDist || !maxLogDist || !avWeights || (n > 0 && !pvalue))
+        return ctx->fail(CD_EINVAL, "cd_ihw_apply_device: bad arguments");
+    if (!avDist && (!ctx->avDist.p || n != ctx->n || !ctx->have_agg))
+        return ctx->fail(CD_EINVAL, "cd_ihw_apply_device: no avDist given and none of %lld regions left on the device by cd_assemble",
+                         (long long)n);
+    CD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    DevBuf<double> in;                                   // pvalue, then avDist when it comes from the host
+    CD_CUDA(ctx, in.ensure((size_t)std::max<int64_t>(2 * n, 1)));
+    if (n > 0) {
+        CD_CUDA(ctx, cudaMemcpyAsync(in.p, pvalue, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (avDist) CD_CUDA(ctx, cudaMemcpyAsync(in.p + n, avDist, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    bool bad_breaks = false;
+    const cudaError_t e = ihw_apply_device(n, avDist ? in.p + n : ctx->avDist.p, in.p, ngroups, minLogDist, maxLogDist, avWeights,
+                                           group_out, weight_out, weighted_pvalue_out, weighted_padj_out, &bad_breaks, st);
+    ctx->launches += (n > 0 && e == cudaSuccess) ? (weighted_padj_out ? 4 : 2) : 0;
+    if (bad_breaks) return ctx->fail(CD_EINVAL, "cd_ihw_apply_device: a break is NaN or 'breaks' are not unique");
+    if (e != cudaSuccess) return ctx->fail(CD_ECUDA, "cd_ihw_apply_device: %s", cudaGetErrorString(e));
+    return CD_OK;
+}
+
 int cd_last_timings(const cd_ctx* ctx, double out_ms[8])
 {
     if (!ctx || !out_ms) return CD_EINVAL;

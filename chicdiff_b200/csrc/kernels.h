@@ -122,6 +122,11 @@ cudaError_t sel_launch_fused(int64_t n, int B, const double* base, int64_t strid
                              int do_exp, double scale, unsigned long long* state, unsigned long long* hist,
                              unsigned long long* aux, unsigned int* bar, const SelP2P& pp, cudaStream_t st);
 
+// ---- IHW weight application on the device (ihw.cu; chicdiff.R:2038-2049) ----
+cudaError_t ihw_apply_device(int64_t n, const double* avDist_dev, const double* pvalue_dev, int ngroups, const double* minLogDist,
+                             const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
+                             double* weighted_pvalue_out, double* weighted_padj_out, bool* bad_breaks, cudaStream_t st);
+
 // ---- results() on resident arrays (results_resident.cu) ----
 // counts: [0] rows with a p-value after the Cook's filter, [1] rows with baseMean == 0
 cudaError_t res_launch_keys(int64_t n, int p, double cutoff, const double* baseMean, const double* maxCooks, const uint8_t* flags,

@@ -254,23 +254,45 @@ extern "C" int cd_results_adjust(int64_t n, int S, int p, const double* baseMean
 // IHWcorrection(), "apply to test data" (chicdiff.R:2038-2049): stratum of every region by cut(log|avDist|, breaks)
 // with breaks half-way between neighbouring strata of the lookup learned on the control set, weight =
 // avWeights[stratum] / mean(avWeights over the rows), weighted p-value, BH.
+namespace cd {
+
+bool ihw_breaks(int ngroups, const double* minLogDist, const double* maxLogDist, std::vector<double>& breaks)
+{
+    breaks.assign((size_t)ngroups + 1, 0.0);
+    for (int k = 0; k <= ngroups; k++) {
+        const double a = k < ngroups ? minLogDist[k] : INFINITY;
+        const double b = k > 0 ? maxLogDist[k - 1] : 0.0;
+        breaks[(size_t)k] = (a + b) / 2;
+        if (std::isnan(breaks[(size_t)k])) return false;
+    }
+    std::sort(breaks.begin(), breaks.end());
+    for (int k = 1; k <= ngroups; k++) if (breaks[(size_t)k] == breaks[(size_t)k - 1]) return false;   // 'breaks' are not unique
+    return true;
+}
+
+double ihw_mean_weight(int64_t n, int ngroups, const unsigned long long* per_group, const double* avWeights)
+{
+    if (n <= 0 || per_group[0] != 0) return NAN;
+    long double sum = 0.0L;
+    for (int g = 1; g <= ngroups; g++)
+        for (unsigned long long c = 0; c < per_group[(size_t)g]; c++) sum += (long double)avWeights[g - 1];
+    long double m = sum / (long double)n, t = 0.0L;
+    for (int g = 1; g <= ngroups; g++)
+        for (unsigned long long c = 0; c < per_group[(size_t)g]; c++) t += ((long double)avWeights[g - 1] - m);
+    return (double)(m + t / (long double)n);
+}
+
+}  // namespace cd
+
 extern "C" int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalue, int ngroups, const double* minLogDist,
                             const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
                             double* weighted_pvalue_out, double* weighted_padj_out)
 {
     if (n < 0 || ngroups < 1 || !minLogDist || !maxLogDist || !avWeights || (n > 0 && (!avDist || !pvalue))) return CD_EINVAL;
-    // breaks <- (c(minLogDist, Inf) + c(0, maxLogDist)) / 2   (:2039); cut() sorts them and refuses duplicates
-    std::vector<double> breaks((size_t)ngroups + 1);
-    for (int k = 0; k <= ngroups; k++) {
-        const double a = k < ngroups ? minLogDist[k] : INFINITY;
-        const double b = k > 0 ? maxLogDist[k - 1] : 0.0;
-        breaks[(size_t)k] = (a + b) / 2;
-        if (std::isnan(breaks[(size_t)k])) return CD_EINVAL;
-    }
-    std::sort(breaks.begin(), breaks.end());
-    for (int k = 1; k <= ngroups; k++) if (breaks[(size_t)k] == breaks[(size_t)k - 1]) return CD_EINVAL;   // 'breaks' are not unique
+    std::vector<double> breaks;
+    if (!cd::ihw_breaks(ngroups, minLogDist, maxLogDist, breaks)) return CD_EINVAL;
     std::vector<int32_t> group((size_t)n);
-    std::vector<int64_t> per_group((size_t)ngroups + 1, 0);               // [0] = NA
+    std::vector<unsigned long long> per_group((size_t)ngroups + 1, 0);    // [0] = NA
     for (int64_t i = 0; i < n; i++) {
         const double x = std::log(std::fabs(avDist[i]));
         int32_t g = INT32_MIN;                                            // NA_integer_
@@ -282,18 +304,7 @@ extern "C" int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalu
         group[(size_t)i] = g;
         per_group[g == INT32_MIN ? 0 : (size_t)g]++;
     }
-    // mean(out$avWeights) over the merged table (rows ordered by stratum; NA strata poison it), R's two-pass
-    // long-double mean
-    double meanw = NAN;
-    if (n > 0 && per_group[0] == 0) {
-        long double sum = 0.0L;
-        for (int g = 1; g <= ngroups; g++)
-            for (int64_t c = 0; c < per_group[(size_t)g]; c++) sum += (long double)avWeights[g - 1];
-        long double m = sum / (long double)n, t = 0.0L;
-        for (int g = 1; g <= ngroups; g++)
-            for (int64_t c = 0; c < per_group[(size_t)g]; c++) t += ((long double)avWeights[g - 1] - m);
-        meanw = (double)(m + t / (long double)n);
-    }
+    const double meanw = cd::ihw_mean_weight(n, ngroups, per_group.data(), avWeights);
     std::vector<double> wp((size_t)n);
     for (int64_t i = 0; i < n; i++) {
         const int32_t g = group[(size_t)i];

@@ -20,7 +20,7 @@ FLAG_ALLZERO, FLAG_GENE_GRID, FLAG_MAP_GRID, FLAG_BETA_NOCONV, FLAG_OUTLIER, FLA
 EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_unique_id", "cd_comm_init", "cd_comm_info", "cd_results_resident", "cd_ihw_apply",
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
-            "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims", "cd_last_rendezvous",
+            "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims", "cd_last_rendezvous", "cd_ihw_apply_device",
             "cd_multi_create", "cd_multi_destroy", "cd_multi_last_error", "cd_multi_gpus", "cd_multi_set_design", "cd_multi_set_regions",
             "cd_multi_get_shards", "cd_multi_set_sample_rows", "cd_multi_aggregate", "cd_multi_region_test", "cd_multi_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
             "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_build_sample_tables", "cd_get_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]
@@ -524,6 +524,22 @@ class Engine:
         t = np.zeros(8, np.float64)
         self._L.cd_last_timings(self._h, _ptr(t))
         return t
+
+    def ihw_apply_device(self, pvalue, minLogDist, maxLogDist, avWeights, avDist=None):
+        """cd_ihw_apply_device: IHWcorrection()'s "apply to test data" block on this context's GPU.  avDist=None uses the
+        avDist column cd_assemble left on the device."""
+        pvalue = np.ascontiguousarray(pvalue, dtype=np.float64)
+        n = len(pvalue)
+        av = None if avDist is None else np.ascontiguousarray(avDist, dtype=np.float64)
+        lo = np.ascontiguousarray(minLogDist, dtype=np.float64)
+        hi = np.ascontiguousarray(maxLogDist, dtype=np.float64)
+        w = np.ascontiguousarray(avWeights, dtype=np.float64)
+        group = np.empty(n, np.int32)
+        weight, wp, wpadj = np.empty(n), np.empty(n), np.empty(n)
+        self._L.cd_ihw_apply_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        self._check(self._L.cd_ihw_apply_device(self._h, n, _ptr(av), _ptr(pvalue), len(w), _ptr(lo), _ptr(hi), _ptr(w),
+                                                _ptr(group), _ptr(weight), _ptr(wp), _ptr(wpadj)))
+        return dict(group=group, weight=weight, weighted_pvalue=wp, weighted_padj=wpadj)
 
     def last_rendezvous(self):
         """(trend passes, SM cycles waited for peers, SM cycles waited for the own slot, the first-pass part of the peers'

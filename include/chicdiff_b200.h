@@ -304,6 +304,15 @@ int cd_ihw_apply(int64_t n, const double* avDist, const double* pvalue, int ngro
                  const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
                  double* weighted_pvalue_out, double* weighted_padj_out);
 
+/* The same block on the device (csrc/ihw.cu): group look-up, weights, weighted p-values and the BH adjustment (one radix
+ * sort + a minimum scan) run on the context's GPU; only the mean weight is taken on the host from the per-group counts
+ * (R's long-double mean).  avDist: n host doubles, or NULL to use the avDist column cd_assemble left on the device
+ * (n must then equal the context's region count).  pvalue: n host doubles.  Outputs as cd_ihw_apply (host, any may be
+ * NULL).  Agrees with cd_ihw_apply bit for bit unless log|avDist| falls within an ulp of a break. */
+int cd_ihw_apply_device(cd_ctx* ctx, int64_t n, const double* avDist, const double* pvalue, int ngroups, const double* minLogDist,
+                        const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
+                        double* weighted_pvalue_out, double* weighted_padj_out);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* sizes of the problem currently set on the context: regions n, samples S, design columns p, region rows R (any pointer
  * may be NULL).  Bindings size their output buffers from these, not from what their caller believes. */

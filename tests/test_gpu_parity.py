@@ -872,3 +872,43 @@ def test_next_batch_uploads_overlap_the_region_test():
         for col in ("baseMean", "pvalue", "lfcSE", "flags"):
             assert np.array_equal(r[col], ref[k % 2][col], equal_nan=True), (k, col)
     e.close()
+
+
+def test_ihw_weight_application_on_the_device():
+    """cd_ihw_apply_device (chicdiff.R:2038-2049 on the GPU: group look-up, weights, weighted p-values, BH by one radix
+    sort and a minimum scan) against the host routine cd_ihw_apply, which the golden table pins: bit for bit, NA rules
+    included, on the golden rows and on a 1.2 M-row synthetic table with ties and NAs."""
+    import os
+    e = engine.Engine(0)
+    cases = []
+    # the golden table of the reference's data package, with the stratum lookup test_golden.py derives from it
+    from test_golden import _lookup_from_golden
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chr19_golden.npz"))
+    glo, ghi, gw = _lookup_from_golden(g)
+    cases.append((g["avDist"], g["pvalue"], glo, ghi, gw))
+    rng = np.random.default_rng(12)
+    n = 1200000
+    av = np.rint(np.exp(rng.uniform(np.log(5e3), np.log(5e7), n))) * rng.choice([-1.0, 1.0], n)
+    pv = rng.uniform(0, 1, n) ** 3
+    pv[rng.integers(0, n, 5000)] = np.nan                               # filtered rows
+    pv[rng.integers(0, n, 2000)] = pv[0]                                # ties
+    pv[rng.integers(0, n, 50)] = 0.0
+    lo = np.array([0.0, 9.5, 11.0, 12.5, 14.0, 15.5])
+    hi = np.array([9.4, 10.9, 12.4, 13.9, 15.4, np.inf])
+    w = np.array([2.1, 1.7, 1.2, 0.8, 0.4, 0.1])
+    cases.append((av, pv, lo, hi, w))
+    av2 = av.copy(); av2[7] = 0.0; av2[11] = np.nan                     # rows without a group poison the mean weight
+    cases.append((av2[:50000], pv[:50000], lo, hi, w))
+    for avd, p, lo_, hi_, w_ in cases:
+        ref = engine.ihw_apply(avd, p, lo_, hi_, w_)
+        got = e.ihw_apply_device(p, lo_, hi_, w_, avDist=avd)
+        for k in ("group", "weight", "weighted_pvalue", "weighted_padj"):
+            assert np.array_equal(got[k], ref[k], equal_nan=(k != "group")), (k, len(p))
+    got = e.ihw_apply_device(g["pvalue"], glo, ghi, gw, avDist=g["avDist"])
+    assert np.array_equal(got["group"], g["group"]) and int((got["weighted_padj"] < 0.05).sum()) == 2759
+    with pytest.raises(engine.ChicdiffError):
+        e.ihw_apply_device(pv[:10], np.array([0.0, 2.0, 2.0]), np.array([2.0, 2.0, np.inf]), w[:3], avDist=av[:10])   # 'breaks' are not unique
+    with pytest.raises(engine.ChicdiffError):
+        e.ihw_apply_device(pv[:10], lo, hi, w)                            # no avDist on the device
+    e.close()
+
