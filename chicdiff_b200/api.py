@@ -12,6 +12,7 @@ Tables are dicts of equally long NumPy columns (the stand-in for data.table).  `
 same adapter written in R for a real drop-in (it can not be executed here); both only marshal columns and
 call the library -- no numerics live on this side.
 """
+import os
 import sys
 
 import numpy as np
@@ -217,6 +218,27 @@ def chicEstimateDistFun(distbin, refBinMean, binsize=20000):
     return np.asarray(out, dtype=np.float64)
 
 
+def read_chicago_tables(files, use_cache=True, columns=None):
+    """The readRDS loop of setChicdiffExperiment() / getFullRegionData1() (chicdiff.R:517-534, 614-623):
+    {condition: [path of a CHiCAGO .Rds (a chicagoData object or its data.table), ...]} -> {condition: [dict of columns,
+    ...]}.  With use_cache the decoded columns are kept as an Arrow file beside each .Rds and memory-mapped on the next
+    run (chicdiff_b200.cache); columns=None keeps every column of the table."""
+    from . import cache, rds
+    out = {}
+    for cond, paths in files.items():
+        out[cond] = []
+        for p in paths:
+            if use_cache:
+                t = dict(cache.load_or_build(p, columns=columns))
+            else:
+                t = rds.chicago_table(p)["columns"]
+                if columns is not None:
+                    t = {k: v for k, v in t.items() if k in columns}
+            t["name"] = os.path.splitext(os.path.basename(p))[0]
+            out[cond].append(t)
+    return out
+
+
 def label_codes(lab):
     """bin labels (R factor / character; None or NaN = NA) -> (int32 codes with -1 = NA, sorted levels)"""
     lab = np.asarray(lab, dtype=object)
@@ -376,13 +398,17 @@ def getFullRegionData(chicdiff_settings, RU, RUcontrol, rmap, chicago_tables, co
     return res
 
 
-def IHWapply(out, distLookup):
+def IHWapply(out, distLookup, engine_obj=None):
     """The "apply to test data" block of IHWcorrection() (chicdiff.R:2038-2049).
 
     out: dict of columns of the DESeq2Wrap table plus "avDist" (:1965-1967); distLookup: dict(minLogDist, maxLogDist,
     avWeights) as learned on the control set (:2013-2033).  Returns a copy of `out` with avgLogDist, group, avWeights,
     weight, weighted_pvalue, weighted_padj, rows ordered by group (NA first) like the reference's merge() leaves them."""
-    r = engine.ihw_apply(out["avDist"], out["pvalue"], distLookup["minLogDist"], distLookup["maxLogDist"], distLookup["avWeights"])
+    if engine_obj is not None:            # the n-sized work on that context's GPU (cd_ihw_apply_device)
+        r = engine_obj.ihw_apply_device(out["pvalue"], distLookup["minLogDist"], distLookup["maxLogDist"], distLookup["avWeights"],
+                                        avDist=out["avDist"])
+    else:
+        r = engine.ihw_apply(out["avDist"], out["pvalue"], distLookup["minLogDist"], distLookup["maxLogDist"], distLookup["avWeights"])
     res = {k: np.asarray(v) for k, v in out.items() if not str(k).startswith("attr_")}
     with np.errstate(divide="ignore", invalid="ignore"):
         res["avgLogDist"] = np.log(np.abs(np.asarray(out["avDist"], dtype=np.float64)))

@@ -16,8 +16,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-from rds_reader import read_rds, data_frame, unwrap  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from chicdiff_b200.rds import read_rds, data_frame, unwrap  # noqa: E402
 
 REF = "/root/reference/ChicdiffData/inst/extdata"
 
