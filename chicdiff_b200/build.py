@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libchicdiff_b200.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["aggregate.cu", "assemble.cu", "tables.cu", "universe.cu", "countput.cu", "chinput.cu", "offsets.cu", "select.cu", "dispersion.cu", "wald.cu", "results_resident.cu", "ihw.cu", "context.cu", "comm.cpp", "results.cpp", "multi.cpp"]
+SOURCES = ["aggregate.cu", "assemble.cu", "tables.cu", "universe.cu", "countput.cu", "chinput.cu", "offsets.cu", "select.cu", "dispersion.cu", "wald.cu", "results_resident.cu", "ihw.cu", "context.cu", "comm.cpp", "results.cpp", "multi.cpp", "priorvar.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-DCD_BUILD"]
 

@@ -1270,11 +1270,10 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
     const int64_t n = ctx->n, nv = (int64_t)G * n;
     cudaStream_t st = ctx->st;
     const int df = S - p;
+    // S - p <= 3: DESeq2's seeded Monte-Carlo rule -- the caller's function if one is given (an R front end evaluates
+    // DESeq2's own code there), else the library's restatement of it (priorvar.cpp)
     const bool ask_caller = std::isnan(prior_var_override) && df <= 3 && opt && opt->prior_var_fn;
-    if (std::isnan(prior_var_override) && df <= 3 && !ask_caller)
-        return ctx->fail(CD_ENUMERIC, "S - p = %d <= 3: DESeq2 estimates the dispersion prior variance by a seeded Monte-Carlo "
-                                      "match here (set.seed(2), rchisq, loess), which is not implemented; pass disp_prior_var "
-                                      "or a prior_var_fn callback", df);
+    const bool small_df_rule = std::isnan(prior_var_override) && df <= 3 && !ask_caller;
     const int32_t* K = (G > 1) ? ctx->Kb.p : ctx->K.p;
     double* baseMean = ctx->g_baseMean.p;
     double* dispGeneEst = ctx->g_dispGeneEst.p;
@@ -1384,6 +1383,25 @@ int run_batch(cd_ctx* ctx, const CdDesign& des, const CdDesign* des_dev, int G, 
             dispPriorVar = opt->prior_var_fn(opt->prior_var_user, df, (int64_t)m, resid.data());
             if (!(dispPriorVar > 0.0) || !std::isfinite(dispPriorVar))
                 return ctx->fail(CD_ENUMERIC, "prior_var_fn returned %g for df = %d (%lld residuals)", dispPriorVar, df, (long long)m);
+        } else if (small_df_rule) {
+            // the rule needs the histogram of the residuals only, and bin counts add up over shards
+            std::vector<double> resid((size_t)n);
+            CD_CUDA(ctx, cudaMemcpyAsync(resid.data(), ctx->g_resid.p + (size_t)g * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+            CD_CUDA(ctx, cudaStreamSynchronize(st));
+            size_t m = 0;
+            for (size_t i = 0; i < (size_t)n; i++) if (std::isfinite(resid[i])) resid[m++] = resid[i];
+            double counts[40];
+            cd_prior_var_hist((int64_t)m, resid.data(), counts);
+            if (ctx->comm.active() && ctx->comm.nranks > 1) {
+                double* c_dev = ctx->scal.p + kScalSums;                  // (free again at this point of the fit)
+                CD_CUDA(ctx, cudaMemcpyAsync(c_dev, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+                CD_COMM(ctx, ctx->comm.allreduce_sum(c_dev, 40, st));
+                CD_CUDA(ctx, cudaMemcpyAsync(counts, c_dev, sizeof(counts), cudaMemcpyDeviceToHost, st));
+                CD_CUDA(ctx, cudaStreamSynchronize(st));
+            }
+            dispPriorVar = cd_prior_var_from_hist(df, counts);
+            if (!(dispPriorVar > 0.0) || !std::isfinite(dispPriorVar))
+                return ctx->fail(CD_ENUMERIC, "dispersion prior variance for S - p = %d: no residual inside (-10, 10) to match", df);
         } else dispPriorVar = std::max(varLogDispEsts - trigamma_host(df / 2.0), 0.25);
         bo.a0[g] = t[0]; bo.a1[g] = t[1]; bo.varLogDispEsts[g] = varLogDispEsts; bo.dispPriorVar[g] = dispPriorVar;
         if (g == 0 || t[4] > ctx->trend_passes_batch) ctx->trend_passes_batch = t[4];

@@ -21,6 +21,7 @@ EXPORTED = ["cd_version", "cd_create", "cd_destroy", "cd_last_error", "cd_comm_u
             "cd_plan_shards", "cd_set_design", "cd_set_regions", "cd_set_sample_rows", "cd_set_rows_device",
             "cd_set_aggregated", "cd_aggregate", "cd_region_test", "cd_results_adjust", "cd_launch_count",
             "cd_device_buffers", "cd_last_timings", "cd_last_search_counts", "cd_get_dims", "cd_last_rendezvous", "cd_ihw_apply_device",
+            "cd_prior_var_small_df", "cd_prior_var_hist", "cd_prior_var_from_hist", "cd_prior_var_debug_stream", "cd_prior_var_debug_curve",
             "cd_multi_create", "cd_multi_destroy", "cd_multi_last_error", "cd_multi_gpus", "cd_multi_set_design", "cd_multi_set_regions",
             "cd_multi_get_shards", "cd_multi_set_sample_rows", "cd_multi_aggregate", "cd_multi_region_test", "cd_multi_last_timings", "cd_timer_start", "cd_timer_stop", "cd_measure_fp64_peak",
             "cd_set_rmap", "cd_set_region_rows", "cd_set_sample_tables", "cd_build_sample_tables", "cd_get_sample_tables", "cd_assemble", "cd_get_sample_rows", "cd_get_sample_bmean", "cd_region_universe", "cd_get_region_universe", "cd_countput", "cd_get_countput", "cd_parse_chinput", "cd_get_chinput"]

@@ -313,6 +313,23 @@ int cd_ihw_apply_device(cd_ctx* ctx, int64_t n, const double* avDist, const doub
                         const double* maxLogDist, const double* avWeights, int32_t* group_out, double* weight_out,
                         double* weighted_pvalue_out, double* weighted_padj_out);
 
+/* ---- dispersion prior variance for 1 <= S - p <= 3 (csrc/priorvar.cpp) ---------------------------------------------- */
+/* DESeq2's estimateDispersionsPriorVar for designs with at most 3 residual degrees of freedom (every 2-vs-2 run; reached
+ * from chicdiff.R:1573, 1603, 1643, 1673): the seeded Monte-Carlo match of the histogram of the dispersion residuals
+ * log(dispGeneEst) - log(dispFit) (set.seed(2), rchisq, rnorm, hist, Kullback-Leibler, loess, floor 0.25).  A host
+ * restatement of R's generators, hist() and loess() -- see the header of priorvar.cpp for what is pinned and what is not.
+ * cd_region_test uses it by itself when S - p <= 3 and neither disp_prior_var* nor prior_var_fn is given; the same
+ * function can be handed to cd_options.prior_var_fn.  resid: the residuals of the regions with dispGeneEst >= 1e-6.
+ * The rule needs only the 40 bin counts of hist(resid, breaks = -20:20/2): cd_prior_var_hist makes them (they add up over
+ * shards), cd_prior_var_from_hist finishes; NaN for df outside 1..3 or an empty histogram. */
+double cd_prior_var_small_df(int df, int64_t n_resid, const double* resid);
+int cd_prior_var_hist(int64_t n_resid, const double* resid, double counts[40]);
+double cd_prior_var_from_hist(int df, const double counts[40]);
+/* test hooks: the first n values after set.seed(seed) of unif_rand (what = 0), norm_rand (1), exp_rand (2),
+ * rgamma(shape, 1) (3); the 200 Kullback-Leibler divergences of a histogram and their loess fit on the 1000-point grid */
+int cd_prior_var_debug_stream(unsigned int seed, int what, double shape, int n, double* out);
+int cd_prior_var_debug_curve(int df, const double counts[40], double kl_out[200], double fitted_out[1000]);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* sizes of the problem currently set on the context: regions n, samples S, design columns p, region rows R (any pointer
  * may be NULL).  Bindings size their output buffers from these, not from what their caller believes. */

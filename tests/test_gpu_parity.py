@@ -76,6 +76,32 @@ def test_c1_shape_2v2_with_given_prior_variance():
     run_and_check(synth.generate("c1"), prior=0.5, prior_grid=0.5)
 
 
+def test_c1_2v2_stand_alone_with_the_small_df_rule():
+    """S - p <= 3 without a given prior variance: the library's restatement of DESeq2's Monte-Carlo rule (csrc/priorvar.cpp)
+    supplies it.  The value must be what the independent restatement (oracle/priorvar.py) makes of the same residuals, the
+    run must equal a run that is handed that value, and that run is held to the oracle as usual.  With the theta grid the
+    five intercept-only fits (S - p = 3) use the rule as well."""
+    from oracle import priorvar as PV
+    d = synth.generate("c1")
+    e = engine.Engine(0)
+    e.set_design(d.X); e.set_regions(d.row_off)
+    for s in range(d.S):
+        e.set_sample_rows(s, d.N_rows[s], d.FM_rows[s])
+    e.aggregate(fetch=False)
+    r = e.region_test(theta=0.5)                                         # no grid: one fit, S - p = 2
+    pv = r["dispPriorVar"]
+    ok = np.isfinite(r["dispGeneEst"]) & (r["dispGeneEst"] >= 1e-6)
+    resid = np.log(r["dispGeneEst"][ok]) - np.log(r["dispFit"][ok])
+    assert pv == PV.prior_var_small_df(2, resid) and pv >= 0.25
+    r2 = e.region_test(theta=0.5, disp_prior_var=pv)
+    for k in ("dispersion", "pvalue", "lfcSE"):
+        assert np.array_equal(r[k], r2[k], equal_nan=True), k
+    rg = e.region_test()                                                 # theta grid: six fits, all through the rule
+    assert rg["theta"] in (0.0, 0.25, 0.5, 0.75, 1.0) and np.isfinite(rg["dispPriorVar"]) and np.isfinite(rg["pvalue"]).any()
+    e.close()
+    run_and_check(d, prior=pv, theta=0.5)
+
+
 def test_c2_one_chromosome_2v2():
     run_and_check(synth.generate("c2"), prior=0.6, prior_grid=0.6)
 
@@ -207,9 +233,8 @@ def test_error_paths():
     for s in range(4):
         e.set_sample_rows(s, np.array([3, 4, 5, 6], np.int32), np.ones(4))
     e.aggregate()
-    with pytest.raises(engine.ChicdiffError) as ei:
-        e.region_test()                                                  # S - p = 2 without a prior variance
-    assert "prior" in str(ei.value)
+    with pytest.raises(engine.ChicdiffError):
+        e.region_test()            # two regions: whatever fails first (trend fit, S - p = 2 rule on an empty histogram), it must say so
     e.close()
 
 
@@ -782,10 +807,9 @@ def test_prior_variance_callback_for_small_df():
         raise KeyError("rule failed")
     with pytest.raises(KeyError):
         e.region_test(theta=0.5, prior_var_fn=boom)
-    # without a rule the old message stays
-    with pytest.raises(engine.ChicdiffError) as ei:
-        e.region_test(theta=0.5)
-    assert "prior" in str(ei.value)
+    # without a caller's rule the library's own restatement of DESeq2's rule answers (csrc/priorvar.cpp)
+    r = e.region_test(theta=0.5)
+    assert r["dispPriorVar"] >= 0.25 and np.isfinite(r["pvalue"]).any()
     e.close()
 
 
