@@ -129,7 +129,7 @@ cudaError_t ihw_apply_device(int64_t n, const double* avDist_dev, const double* 
     std::vector<double> breaks;
     if (!ihw_breaks(ngroups, minLogDist, maxLogDist, breaks)) { *bad_breaks = true; return cudaErrorInvalidValue; }
     if (n == 0) return cudaSuccess;
-    if (n > (int64_t)UINT_MAX) return cudaErrorInvalidValue;
+    if (n > (int64_t)INT_MAX) return cudaErrorInvalidValue;              // row indices are 32-bit; CUB counts in int
     const size_t nn = (size_t)n;
     Scratch s_breaks, s_w, s_counts, s_group, s_weight, s_wp, s_key, s_idx, s_v, s_tmp;
     cudaError_t e;
