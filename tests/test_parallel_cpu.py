@@ -2,7 +2,7 @@
 re-assembly of shard tables, and the PROTOCOL of the global steps as the kernels run it -- exact medians by all-reducing
 2048-bin histogram counters round by round, the parametric trend by all-reducing 8 sums per pass with every rank taking
 the same branch of glm.fit's control flow (tests/protocol_model.py restates both with the all-reduce passed in; here it
-is torch.distributed over gloo).  Nothing is gathered: a rank only ever sees its own regions plus those sums, and the
+is torch.distributed over gloo), the small-df prior-variance rule by all-reducing the 40 bin counts of its histogram.  Nothing is gathered: a rank only ever sees its own regions plus those sums, and the
 results must equal the unsharded oracle's."""
 import os
 import socket
@@ -103,6 +103,29 @@ def _worker(rank, world, port, tmp):
     med = pm.distributed_median(resid, ar_sum, ar_min)
     mad = pm.distributed_median(np.abs(resid - med), ar_sum, ar_min, scale=1.4826)
     assert abs(mad * mad - ro["varLogDispEsts"]) <= 1e-12 * ro["varLogDispEsts"]
+
+    # global step 4, designs with S - p <= 3 only (here exercised on this design's residuals as if it were one): DESeq2's
+    # Monte-Carlo prior-variance rule needs the 40-bin histogram of the residuals, and bin counts add up -- what
+    # cd_region_test all-reduces in a sharded 2-vs-2 run (csrc/priorvar.cpp)
+    import ctypes as C
+    from chicdiff_b200 import engine
+    Lp = engine.load_library()
+    Lp.cd_prior_var_hist.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
+    Lp.cd_prior_var_from_hist.restype = C.c_double
+    Lp.cd_prior_var_from_hist.argtypes = [C.c_int, C.c_void_p]
+    mine = np.ascontiguousarray(resid[np.isfinite(resid)])
+    counts = np.zeros(40)
+    Lp.cd_prior_var_hist(len(mine), mine.ctypes.data, counts.ctypes.data)
+    total = np.ascontiguousarray(ar_sum(counts))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        all_resid = np.where(ro["dispGeneEst"] >= 1e-6, np.log(ro["dispGeneEst"]) - np.log(ro["trend_a0"] + ro["trend_a1"] / ro["baseMean"]), np.inf)
+    all_resid = np.ascontiguousarray(all_resid[np.isfinite(all_resid)])
+    whole = np.zeros(40)
+    Lp.cd_prior_var_hist(len(all_resid), all_resid.ctypes.data, whole.ctypes.data)
+    assert np.array_equal(total, whole) and total.sum() > 0
+    Lp.cd_prior_var_small_df.restype = C.c_double
+    Lp.cd_prior_var_small_df.argtypes = [C.c_int, C.c_int64, C.c_void_p]
+    assert Lp.cd_prior_var_from_hist(2, total.ctypes.data) == Lp.cd_prior_var_small_df(2, len(all_resid), all_resid.ctypes.data)
 
     if rank == 0:
         assert np.array_equal(full["K"], Kf)
