@@ -87,6 +87,17 @@ def test_smoother_reproduces_quadratics_and_follows_the_restatement(L):
     assert np.max(np.abs(fitted - ref)) < 1e-9 * max(1.0, np.max(np.abs(kl)))
     # 33 vertices: 31 median cuts of the 200 grid points down to cells of 6 or 7, and the two ends of the box
     assert len(P.loess_interpolate(grid, kl).x) == 33
+    # the blended surface stays close to the direct one (a local quadratic fit at every point of the fine grid)
+    direct = np.empty(len(fine))
+    for k, z in enumerate(fine):
+        d = np.abs(grid - z)
+        h = np.sort(d)[39]
+        keep = d < h
+        w = np.sqrt((1 - (d[keep] / h) ** 3) ** 3)
+        A = np.vander(grid[keep] - z, 3, increasing=True) * w[:, None]
+        direct[k] = np.linalg.lstsq(A, kl[keep] * w, rcond=None)[0][0]
+    assert np.max(np.abs(fitted - direct)) < 0.02 * (np.max(kl) - np.min(kl))
+    assert abs(fine[np.argmin(fitted)] - fine[np.argmin(direct)]) <= 0.1
 
 
 @pytest.mark.parametrize("df", [2, 3])
